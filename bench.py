@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- measures the hot path on B200 (contract: see DESIGN.md "Measurement").
+
+Default workload = BASELINE.json configs[1]: CTC loss + gradient, batch 256, T=64 frames,
+63-class alphabet, float32.  A "step" is one pass of the path over one batch.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ctc]
+
+Prints ONE JSON line (rank 0).  Keys: metric/value/unit (line-crops/s, whole job, inputs resident
+in HBM), e2e (same metric through the public Python API with host buffers: pinned H2D of the
+logits and labels + D2H of the losses inside the timed region), roofline (dominant kernel,
+algorithmic HBM bytes / CUDA-event time vs MEASURED_PEAKS.json), cpu_baseline (the oracle port on
+the host cores, bounded sample), clocks, gpu_launches.
+`--impl reference` times the reference's CPU path: TensorFlow cannot run here, so
+it is the oracle port (oracle/ctc_oracle.c) on all host threads -- kind "port".
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "line-crops/sec"
+UNIT = "crops/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _traffic(workload):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(workload)
+    return None
+
+
+# --------------------------------------------------------------------------- synthetic inputs
+def make_ctc_batch(seed, T, B, C, max_label=16):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((T, B, C), dtype=np.float32)
+    seq_len = rng.integers(T // 2, T + 1, B).astype(np.int32)
+    lens = np.minimum(rng.integers(1, max_label + 1, B), seq_len // 2).astype(np.int32)
+    lens = np.maximum(lens, 1)
+    off = np.zeros(B + 1, np.int32)
+    off[1:] = np.cumsum(lens)
+    flat = rng.integers(0, C - 1, int(off[-1])).astype(np.int32)
+    rep = rng.random(flat.shape[0]) < 0.15
+    first = np.zeros(flat.shape[0], bool)
+    first[off[:-1]] = True
+    idx = np.nonzero(rep & ~first)[0]
+    flat[idx] = flat[idx - 1]
+    return x, flat, off, seq_len, lens
+
+
+# --------------------------------------------------------------------------- clocks sampler
+class ClockSampler(threading.Thread):
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.period = period
+        self.samples = []  # (t, sm_mhz, reasons_mask)
+        self.max_mhz = None
+        self.ok = False
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.time(), mhz, rs))
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+
+    def summary(self, windows):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        inside = [s for s in self.samples if any(a <= s[0] <= b for a, b in windows)]
+        use = inside if inside else self.samples
+        names = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+                 0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+        mask = 0
+        for s in use:
+            mask |= s[2]
+        reasons = [n for b, n in names.items() if mask & b and n != "gpu_idle"]
+        return {"sm_mhz": statistics.median(s[1] for s in use), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples_under_load": len(inside), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- CPU baseline (oracle port)
+def cpu_baseline_ctc(T, B, C, min_wall=1.5, min_reps=3):
+    from oracle import ctc_oracle
+    ctc_oracle.build()
+    import numpy as np
+    x, flat, off, seq_len, lens = make_ctc_batch(1, T, B, C)
+    labels = [flat[off[b]:off[b + 1]].tolist() for b in range(B)]
+    cores = ctc_oracle.max_threads()
+    ctc_oracle.ctc_loss(x, labels, seq_len, nthreads=cores)  # warm
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        ctc_oracle.ctc_loss(x, labels, seq_len, nthreads=cores)
+        reps += 1
+        dt = time.perf_counter() - t0
+        if reps >= min_reps and dt >= min_wall:
+            break
+    return {"value": B * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d passes over one batch (B=%d,T=%d,C=%d) of oracle/ctc_oracle.c CTC loss+grad, %d threads, %.2f s wall"
+                      % (reps, B, T, C, cores, dt)}
+
+
+def run_reference(args, cfg):
+    """The reference's CPU implementation of the path, on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ctc_oracle
+    ctc_oracle.build()
+    T, B, C = cfg["T"], cfg["B"], cfg["C"]
+    x, flat, off, seq_len, lens = make_ctc_batch(1, T, B, C)
+    labels = [flat[off[b]:off[b + 1]].tolist() for b in range(B)]
+    cores = ctc_oracle.max_threads()
+    for _ in range(max(args.warmup, 1)):
+        ctc_oracle.ctc_loss(x, labels, seq_len, nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctc_oracle.ctc_loss(x, labels, seq_len, nthreads=cores)
+    dt = time.perf_counter() - t0
+    val = B * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg["config"],
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "each step = one batch (B=%d,T=%d,C=%d) through oracle/ctc_oracle.c (TensorFlow "
+                                       "itself cannot run in this image), %d threads" % (B, T, C, cores)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args, cfg):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from cnn_lstm_ctc_ocr_b200 import _lib, ctc
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this framework has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    T, B, C = cfg["T"], cfg["B"], cfg["C"]
+    K, W = args.steps, max(args.warmup, 3)
+    bytes_per_batch = 2 * T * B * C * 4
+    ring_n = max(2, -(-int(2.5 * L2_BYTES) // bytes_per_batch))
+
+    # ---- inputs resident in HBM: a ring of distinct batches larger than L2
+    host = [make_ctc_batch(1000 * rank + i, T, B, C) for i in range(min(ring_n, 8))]
+    ring = []
+    for i in range(ring_n):
+        x, flat, off, seq_len, lens = host[i % len(host)]
+        xt = torch.from_numpy(x).to(dev)
+        if i >= len(host):
+            xt = xt + 1e-3 * i  # distinct memory, same distribution
+        ring.append(dict(x=xt, flat=torch.from_numpy(flat).to(dev), off=torch.from_numpy(off).to(dev),
+                         sl=torch.from_numpy(seq_len).to(dev), Lmax=int(lens.max()),
+                         loss=torch.empty(B, device=dev), grad=torch.empty_like(xt),
+                         status=torch.empty(B, dtype=torch.int32, device=dev)))
+    stream = torch.cuda.Stream(device=dev)
+
+    def step(i, st):
+        r = ring[i % ring_n]
+        _lib.check(lib.ocr_ctc_loss(_lib.ptr(r["x"]), T, B, C, _lib.ptr(r["flat"]), _lib.ptr(r["off"]), _lib.ptr(r["sl"]),
+                                    r["Lmax"], _lib.ptr(r["loss"]), _lib.ptr(r["grad"]), _lib.ptr(r["status"]),
+                                    1.0 / B, None, 0, st), "ocr_ctc_loss")
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    windows = []
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        sh = _lib.stream_handle()
+        n0 = _lib.launch_count()
+        step(0, sh)
+        launches_per_step = _lib.launch_count() - n0
+        for i in range(W):
+            step(i, sh)
+        torch.cuda.synchronize()
+        graph = None
+        if not args.no_graph:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                gh = _lib.stream_handle()
+                for i in range(K):
+                    step(W + i, gh)
+            graph.replay()  # warm the instantiated graph once (untimed)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_a = time.time()
+        e0.record(stream)
+        if graph is not None:
+            graph.replay()
+        else:
+            for i in range(K):
+                step(W + i, sh)
+        e1.record(stream)
+        barrier()
+        t_b = time.time()
+        windows.append((t_a, t_b))
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tm = torch.tensor([ms], device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ms = float(tm.item())
+        value = world * B * K / (ms * 1e-3)
+        kernel_us = ms * 1e3 / (K * launches_per_step)
+        ok_status = int(ring[0]["status"].sum().item()) == 0
+
+        # ---- end to end through the public API with host buffers
+        hx = [torch.from_numpy(h[0]).pin_memory() for h in host]
+        hlab = [(torch.from_numpy(h[1]).pin_memory(), torch.from_numpy(h[4]).pin_memory()) for h in host]
+        hsl = [torch.from_numpy(h[3]).pin_memory() for h in host]
+        hloss = torch.empty(B, dtype=torch.float32).pin_memory()
+        dx = torch.empty((T, B, C), device=dev)
+        dx.requires_grad_(True)
+
+        def e2e_step(i):
+            j = i % len(host)
+            with torch.no_grad():
+                dx.copy_(hx[j], non_blocking=True)
+            loss = ctc.ctc_loss(hlab[j], dx, hsl[j])  # labels/seq_len are host tensors: copied inside
+            hloss.copy_(loss.detach(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return loss
+        for i in range(3):
+            e2e_step(i)
+        KE = max(5, min(K, 200))
+        barrier()
+        t_a = time.time()
+        e0.record(stream)
+        for i in range(KE):
+            e2e_step(i)
+        e1.record(stream)
+        barrier()
+        windows.append((t_a, time.time()))
+        ms_e = e0.elapsed_time(e1)
+        if world > 1:
+            tm = torch.tensor([ms_e], device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ms_e = float(tm.item())
+        h = host[0]
+        e2e = {"value": world * B * KE / (ms_e * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(h[0].nbytes + h[1].nbytes + h[2].nbytes + h[3].nbytes),
+               "d2h_bytes_per_step": int(B * 4), "steps": KE,
+               "api": "cnn_lstm_ctc_ocr_b200.ctc.ctc_loss (loss + gradient), pinned host logits/labels in, losses out"}
+
+        # ---- bandwidth regime of the same kernel (inputs >> L2): where the >=60%-of-HBM target applies
+        bw = None
+        if rank == 0 and not args.skip_bw:
+            try:
+                bw = bandwidth_regime(lib, _lib, dev, T, C, args.bw_batch, windows)
+            except torch.cuda.OutOfMemoryError:
+                bw = {"error": "out of memory"}
+
+    sampler.stop()
+    peak, peak_src = _peaks()
+    if rank == 0:
+        alg_bytes = 2 * T * B * C * 4
+        achieved = alg_bytes / (kernel_us * 1e-6) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": dict(cfg["config"], l2="ring of %d distinct batches (%d MB) > 126 MB L2" % (ring_n, ring_n * bytes_per_batch >> 20),
+                           timed_region="cuda graph of K launches" if graph is not None else "K eager launches",
+                           per_gpu_batch=B),
+            "e2e": e2e,
+            "gpu_launches": K * launches_per_step,
+            "roofline": {"bound": "hbm", "kernel": "ctc_loss_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": _traffic("ctc_cfg2"), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_us": kernel_us,
+                         "note": "cfg2 (8.3 MB, 64-step dependent alpha/beta chains) is latency-bound, see roofline_bw_regime"},
+            "roofline_bw_regime": bw,
+            "clocks": sampler.summary(windows),
+            "parity_status_ok": ok_status,
+        }
+        line["cpu_baseline"] = cpu_baseline_ctc(T, B, C) if world == 1 else None
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bandwidth_regime(lib, _lib, dev, T, C, B, windows):
+    import torch
+    peak, peak_src = _peaks()
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    x = torch.randn((T, B, C), device=dev, generator=g)
+    sl = torch.randint(T // 2, T + 1, (B,), device=dev, generator=g, dtype=torch.int32)
+    lens = torch.minimum(torch.randint(1, 17, (B,), device=dev, generator=g, dtype=torch.int32), sl // 2).clamp_(min=1)
+    off = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+    off[1:] = torch.cumsum(lens, 0)
+    n = int(off[-1].item())
+    flat = torch.randint(0, C - 1, (n,), device=dev, generator=g, dtype=torch.int32)
+    loss = torch.empty(B, device=dev)
+    grad = torch.empty_like(x)
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    sh = _lib.stream_handle()
+
+    def go():
+        _lib.check(lib.ocr_ctc_loss(_lib.ptr(x), T, B, C, _lib.ptr(flat), _lib.ptr(off), _lib.ptr(sl), 16, _lib.ptr(loss),
+                                    _lib.ptr(grad), _lib.ptr(status), 1.0 / B, None, 0, sh), "ocr_ctc_loss")
+    for _ in range(3):
+        go()
+    torch.cuda.synchronize()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_a = time.time()
+    e0.record(torch.cuda.current_stream())
+    for _ in range(reps):
+        go()
+    e1.record(torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    windows.append((t_a, time.time()))
+    us = e0.elapsed_time(e1) * 1e3 / reps
+    alg = 2 * T * B * C * 4
+    ach = alg / (us * 1e-6) / 1e9
+    return {"bound": "hbm", "kernel": "ctc_loss_kernel", "workload": "CTC loss+grad B=%d T=%d C=%d (%.2f GB moved, >> L2)" % (B, T, C, alg / 1e9),
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": _traffic("ctc_bw_regime"),
+            "kernel_us": us, "crops_per_s": B / (us * 1e-6), "peak_source": peak_src}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ctc", choices=["ctc"])
+    ap.add_argument("--no-graph", action="store_true", help="time K eager launches instead of one CUDA graph of K launches")
+    ap.add_argument("--skip-bw", action="store_true", help="skip the bandwidth-regime measurement")
+    ap.add_argument("--bw-batch", type=int, default=65536)
+    args = ap.parse_args()
+    cfg = {"T": 64, "B": 256, "C": 63,
+           "config": {"workload": "BASELINE configs[1]: CTC loss + gradient only, batch 256, T=64 frames, 63-class alphabet "
+                                  "(blank=62), seq_len U{32..64}, label length U{1..16}, fp32 logits ~N(0,1)",
+                      "T": 64, "C": 63, "global_batch": 256 * max(1, int(os.environ.get("WORLD_SIZE", "1"))),
+                      "parallelism": "batch-sharded, no collective (weak scaling)"}}
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

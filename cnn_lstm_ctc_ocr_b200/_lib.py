@@ -1,0 +1,80 @@
+"""ctypes binding of libocr_b200.so (the C ABI declared in include/ocr_b200.h).
+
+There is no CPU fallback and no alternative backend: if the shared library is missing or a call
+fails, this module raises.  Build it with `python -m cnn_lstm_ctc_ocr_b200.build`.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libocr_b200.so")
+
+OCR_OK = 0
+_c = ctypes
+_vp, _i, _f, _sz = _c.c_void_p, _c.c_int, _c.c_float, _c.c_size_t
+
+# name -> (restype, argtypes); mirrors include/ocr_b200.h one to one
+SIGNATURES = {
+    "ocr_last_error": (_c.c_char_p, []),
+    "ocr_version": (_c.c_char_p, []),
+    "ocr_launch_count": (_c.c_uint64, []),
+    "ocr_ctc_loss_workspace_bytes": (_i, [_i, _i, _i, _i, _c.POINTER(_sz)]),
+    "ocr_ctc_loss": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _sz, _vp]),
+    "ocr_ctc_greedy_decode": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "ocr_ctc_beam_search_workspace_bytes": (_i, [_i, _i, _i, _i, _c.POINTER(_sz)]),
+    "ocr_ctc_beam_search": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ocr_edit_distance": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+}
+
+_lib = None
+
+
+class OcrLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libocr_b200.so (no CUDA call is made by loading)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise OcrLibraryError(
+            "libocr_b200.so is not built (%s). Run `python -m cnn_lstm_ctc_ocr_b200.build`. "
+            "This package has no CPU or PyTorch fallback." % SO_PATH)
+    lib = ctypes.CDLL(SO_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != OCR_OK:
+        msg = load().ocr_last_error().decode("utf-8", "replace")
+        raise OcrLibraryError("%s failed (code %d): %s" % (what, rc, msg))
+
+
+def launch_count():
+    return int(load().ocr_launch_count())
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_handle():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise OcrLibraryError("cnn_lstm_ctc_ocr_b200 operates on CUDA tensors only (got a %s tensor); "
+                                  "there is no CPU path" % t.device)

@@ -1,0 +1,104 @@
+/* ocr_b200.h -- C ABI of libocr_b200.so: hand-written sm_100a CUDA kernels for the hot path of
+ * tgialoimtr/cnn_lstm_ctc_ocr (the weinman CNN -> BiLSTM/BiGRU -> CTC line recognizer).
+ *
+ * The reference has no FFI for this path: its boundary is Python functions that add nodes to a
+ * TensorFlow graph.  Each entry point below therefore replaces one TensorFlow op call site in
+ * the reference (cited per function); the Python host layer in cnn_lstm_ctc_ocr_b200/ keeps the
+ * reference's function names on top of these.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless it says "host";
+ *   - the library never allocates or frees device memory and never synchronises the stream:
+ *     all work is enqueued on `stream` (a CUstream / cudaStream_t handle passed as void*);
+ *   - scratch memory comes from the caller: ask ocr_*_workspace_bytes first;
+ *   - return value: OCR_OK (0) or a negative OCR_E* code; ocr_last_error() gives the text of the
+ *     last failure on the calling thread;
+ *   - tensors are dense row-major; logits are time-major [T,B,C] float32 as the reference's
+ *     rnn_logits (src/weinman/model.py:212-221); the CTC blank is class C-1.
+ */
+#ifndef OCR_B200_H
+#define OCR_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCR_OK 0
+#define OCR_EINVAL (-1)     /* bad argument (shape, null pointer, unsupported size) */
+#define OCR_EWORKSPACE (-2) /* workspace too small */
+#define OCR_ECUDA (-3)      /* CUDA launch/runtime error; see ocr_last_error() */
+#define OCR_ENODEVICE (-4)  /* no sm_100 device */
+
+typedef void* ocr_stream_t;
+
+const char* ocr_last_error(void);
+/* "major.minor;sm_100a;<build id>" */
+const char* ocr_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t ocr_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * CTC loss + gradient.  Replaces tf.nn.ctc_loss at src/weinman/model.py:226-227 (defaults:
+ * preprocess_collapse_repeated=False, ctc_merge_repeated=True, time_major=True) and the gradient
+ * TensorFlow registers for it (d loss_b / d logits = softmax - posterior occupancy).
+ *   logits        [T,B,C] f32
+ *   labels        flat int32 label ids, example b owns labels[label_offsets[b] .. label_offsets[b+1])
+ *   label_offsets [B+1] int32
+ *   seq_len       [B] int32, 0 <= seq_len[b] <= T
+ *   loss          [B] f32 out: -log p(labels_b | logits_b); +inf when no alignment exists
+ *   grad          [T,B,C] f32 out (may be NULL): grad_scale * d loss_b / d logits[t,b,:], zero rows
+ *                 for t >= seq_len[b]
+ *   status        [B] int32 out (may be NULL): 0 ok; 1 no valid path (loss=+inf, grad=softmax, as
+ *                 TF's "No valid path found"); 2 labels do not fit in seq_len (TF raises "Not enough
+ *                 time for target transition sequence"; loss=0, grad=0 here and the host layer raises)
+ *   grad_scale    1/B folds the reference's tf.reduce_mean (model.py:228) into the kernel
+ *   max_label_len max over b of the label length (host-known; sizes shared memory)
+ */
+int ocr_ctc_loss_workspace_bytes(int T, int B, int C, int max_label_len, size_t* bytes);
+int ocr_ctc_loss(const float* logits, int T, int B, int C, const int32_t* labels,
+                 const int32_t* label_offsets, const int32_t* seq_len, int max_label_len, float* loss,
+                 float* grad, int32_t* status, float grad_scale, void* workspace, size_t workspace_bytes,
+                 ocr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * CTC greedy decoder.  Replaces tf.nn.ctc_greedy_decoder(merge_repeated=True) at
+ * src/weinman/validate.py:86-90.  Per frame first-maximum arg-max, collapse repeats, drop blank.
+ *   decoded        [B,T] int64 out, -1 padded (sparse_tensor_to_dense(default_value=-1), validate.py:91)
+ *   decoded_len    [B] int32 out
+ *   neg_sum_logits [B] f32 out: -sum_t max_k logits[t,b,k]  (the op's second output)
+ */
+int ocr_ctc_greedy_decode(const float* logits, int T, int B, int C, const int32_t* seq_len,
+                          int merge_repeated, int64_t* decoded, int32_t* decoded_len,
+                          float* neg_sum_logits, ocr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * CTC beam search decoder.  Replaces tf.nn.ctc_beam_search_decoder at src/weinman/test.py:84-88
+ * (beam_width=128, top_paths=1, merge_repeated=True) and src/weinman/client.py:227-231
+ * (merge_repeated=False).
+ *   normalize   1: per-frame log-softmax (newer TF); 0: per-frame max subtraction (older TF 1.x)
+ *   decoded     [B,top_paths,T] int64 out, -1 padded
+ *   decoded_len [B,top_paths] int32 out
+ *   log_prob    [B,top_paths] f32 out
+ * Limits: beam_width in {1..128}, top_paths <= beam_width, C <= 512.
+ */
+int ocr_ctc_beam_search_workspace_bytes(int T, int B, int C, int beam_width, size_t* bytes);
+int ocr_ctc_beam_search(const float* logits, int T, int B, int C, const int32_t* seq_len, int beam_width,
+                        int top_paths, int merge_repeated, int normalize, int64_t* decoded,
+                        int32_t* decoded_len, float* log_prob, void* workspace, size_t workspace_bytes,
+                        ocr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Edit distance.  Replaces tf.edit_distance(hyp, truth, normalize=False) at src/weinman/test.py:90.
+ *   hyp [B,hyp_stride] int64 (-1 padded or with hyp_len), truth flat int32 with offsets [B+1]
+ *   dist [B] f32 out
+ */
+int ocr_edit_distance(const int64_t* hyp, int hyp_stride, const int32_t* hyp_len, const int32_t* truth,
+                      const int32_t* truth_offsets, int B, int max_truth_len, float* dist,
+                      ocr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCR_B200_H */

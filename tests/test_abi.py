@@ -1,0 +1,63 @@
+"""CPU tier: the C-ABI library builds for sm_100a, loads without a GPU and exports every symbol
+include/ocr_b200.h declares; the Python binding table matches the header."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def so_path():
+    from cnn_lstm_ctc_ocr_b200 import build
+    return build.build()
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "ocr_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ocr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(so_path):
+    lib = ctypes.CDLL(so_path)
+    names = _declared()
+    assert len(names) >= 8
+    for n in names:
+        assert hasattr(lib, n), "libocr_b200.so does not export %s" % n
+
+
+def test_binding_table_matches_header(so_path):
+    from cnn_lstm_ctc_ocr_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _declared()
+    lib = _lib.load()
+    assert b"sm_100a" in lib.ocr_version()
+    assert lib.ocr_launch_count() == 0
+
+
+def test_no_cpu_fallback():
+    """Ops refuse CPU tensors instead of silently computing somewhere else."""
+    import torch
+    from cnn_lstm_ctc_ocr_b200 import _lib, ctc
+    with pytest.raises(_lib.OcrLibraryError):
+        ctc.ctc_greedy_decode_raw(torch.zeros(2, 1, 3), torch.tensor([2], dtype=torch.int32))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "cnn_lstm_ctc_ocr_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace("oracle/ctc_oracle.c", "").replace("oracle/det_math.h", ""), f
+
+
+def test_sass_is_sm100a(so_path):
+    import shutil, subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", so_path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out

@@ -1,0 +1,164 @@
+"""GPU tier: the sm_100a CTC kernels, called through the C ABI, against the CPU oracle.
+
+Tolerances (float32 arithmetic on both sides):
+  loss  : rel 1e-5 vs the float64 recursion and vs the TF-faithful float32 oracle;
+  grad  : abs 1e-4 vs the TF-faithful float32 oracle and vs float64 -- the float32 log-domain
+          recursion (TF's, the oracle's and this kernel's alike) carries ~1 ulp(|alpha|) ~ 3e-5 of
+          noise at T=64 (oracle-f32 vs oracle-f64 differ by up to ~8e-5 on the same inputs, asserted
+          in test_oracle_golden.py), so 1e-5 against a float32 reference is not a meaningful bar;
+  decode: bit-exact (labels, lengths, and neg_sum_logits float bits).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from util import cfg2_inputs, make_labels
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "tf_unit_vectors.npz"))
+
+
+def _gpu_loss(x, labels, seq_len, want_grad=True):
+    from cnn_lstm_ctc_ocr_b200 import ctc
+    dev = torch.device("cuda:0")
+    xt = torch.tensor(x, device=dev)
+    flat, off, lengths, _ = ctc._labels_to_flat(labels, x.shape[1], dev)
+    sl = torch.tensor(np.asarray(seq_len, np.int32), device=dev)
+    loss, grad, st = ctc.ctc_loss_raw(xt, flat, off, sl, max(lengths) if lengths else 0, want_grad)
+    torch.cuda.synchronize()
+    return loss.cpu().numpy(), (grad.cpu().numpy() if want_grad else None), st.cpu().numpy()
+
+
+def test_loss_tf_unit_vectors():
+    with np.errstate(divide="ignore"):
+        logits = np.stack([np.log(G["loss_p0"]), np.log(G["loss_p1"])], axis=1)
+    loss, grad, st = _gpu_loss(logits, [G["loss_targets0"].tolist(), G["loss_targets1"].tolist()], [5, 5])
+    assert st.tolist() == [0, 0]
+    np.testing.assert_allclose(loss, [G["loss_value0"], G["loss_value1"]], atol=2e-5)
+    np.testing.assert_allclose(grad[:, 0], G["loss_g0"], atol=2e-6)
+    np.testing.assert_allclose(grad[:, 1], G["loss_g1"], atol=2e-6)
+
+
+@pytest.mark.parametrize("C,ragged,relu", [(63, False, False), (63, True, False), (63, True, True), (96, True, False)])
+def test_loss_cfg2_vs_oracle(oracle, C, ragged, relu):
+    x, labels, seq_len = cfg2_inputs(seed=1, T=64, B=256, C=C, ragged=ragged, relu=relu)
+    loss, grad, st = _gpu_loss(x, labels, seq_len)
+    l32, g32, s32 = oracle.ctc_loss(x, labels, seq_len, nthreads=8)
+    l64, g64, _ = oracle.ctc_loss(x, labels, seq_len, nthreads=8, f64=True)
+    assert (st == s32).all() and (st == 0).all()
+    np.testing.assert_allclose(loss, l64, rtol=1e-5)
+    np.testing.assert_allclose(loss, l32, rtol=1e-5)
+    assert np.abs(grad - g32).max() < 1e-4
+    assert np.abs(grad - g64).max() < 1e-4
+    # size-independent properties: rows inside the sequence sum to zero, rows past it are zero
+    for b in range(0, 256, 17):
+        assert (grad[seq_len[b]:, b] == 0).all()
+        assert np.abs(grad[:seq_len[b], b].sum(-1)).max() < 2e-5
+
+
+def test_loss_edge_cases(oracle):
+    rng = np.random.default_rng(3)
+    T, C = 6, 5
+    x = rng.standard_normal((T, 5, C)).astype(np.float32)
+    labels = [[1, 1, 1], [0], [1, 1, 1], [2], []]
+    sl = [4, 0, 5, 3, 6]
+    loss, grad, st = _gpu_loss(x, labels, sl)
+    lo, go, so = oracle.ctc_loss(x, labels, sl)
+    assert st.tolist() == so.tolist() == [2, 0, 0, 0, 0]
+    np.testing.assert_allclose(loss, lo, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(grad, go, atol=2e-6)
+    x2 = x.copy()
+    x2[0, 2, :] = [0, -np.inf, 0, 0, -np.inf]
+    loss, grad, st = _gpu_loss(x2, labels, sl)
+    lo, go, so = oracle.ctc_loss(x2, labels, sl)
+    assert st[2] == 1 and np.isinf(loss[2]) and so[2] == 1
+    np.testing.assert_allclose(grad[:, 2], go[:, 2], atol=2e-6)  # "no valid path": gradient = softmax
+
+
+def test_loss_long_sequences_use_workspace(oracle):
+    """T=509 (a 1024-px crop), long labels: lattice no longer fits in shared memory."""
+    rng = np.random.default_rng(9)
+    T, B, C = 509, 6, 96
+    x = rng.standard_normal((T, B, C)).astype(np.float32)
+    sl = np.array([509, 400, 509, 37, 255, 509], np.int32)
+    labels = make_labels(rng, B, sl, max_len=120, num_labels=95)
+    labels[0] = [int(v) for v in rng.integers(0, 95, 120)]
+    loss, grad, st = _gpu_loss(x, labels, sl)
+    l64, g64, _ = oracle.ctc_loss(x, labels, sl, f64=True, nthreads=6)
+    assert (st == 0).all()
+    np.testing.assert_allclose(loss, l64, rtol=1e-5)
+    assert np.abs(grad - g64).max() < 5e-4
+
+
+def test_loss_autograd_and_validation():
+    from cnn_lstm_ctc_ocr_b200 import ctc
+    x, labels, seq_len = cfg2_inputs(seed=4, T=32, B=8, C=20)
+    dev = torch.device("cuda:0")
+    xt = torch.tensor(x, device=dev, requires_grad=True)
+    loss = ctc.ctc_loss(labels, xt, torch.tensor(seq_len))
+    loss.mean().backward()
+    ref = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    tl = torch.nn.functional.ctc_loss(torch.log_softmax(ref, -1), torch.tensor(sum(labels, [])),
+                                      torch.tensor(seq_len.astype(np.int64)), torch.tensor([len(l) for l in labels]),
+                                      blank=19, reduction="none")
+    tl.mean().backward()
+    np.testing.assert_allclose(loss.detach().cpu().numpy(), tl.detach().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(xt.grad.cpu().numpy(), ref.grad.numpy(), atol=1e-5)
+    # sparse-triple labels (the reference's SparseTensor), same result
+    idx = torch.tensor([[b, i] for b, l in enumerate(labels) for i in range(len(l))])
+    vals = torch.tensor(sum(labels, []), dtype=torch.int32)
+    loss2 = ctc.ctc_loss((idx, vals, torch.tensor([8, 16])), xt.detach(), torch.tensor(seq_len))
+    assert torch.equal(loss2, loss.detach())
+    with pytest.raises(ValueError, match="Not enough time"):
+        ctc.ctc_loss([[1, 1, 1, 1]] + labels[1:], xt.detach(), torch.tensor([5] + seq_len[1:].tolist()))
+    with pytest.raises(ValueError):
+        ctc.ctc_loss([[19]] + labels[1:], xt.detach(), torch.tensor(seq_len))
+
+
+@pytest.mark.parametrize("C,relu", [(63, False), (96, True), (5, True)])
+def test_greedy_bit_exact(oracle, C, relu):
+    from cnn_lstm_ctc_ocr_b200 import ctc
+    x, _, seq_len = cfg2_inputs(seed=2, T=61, B=300, C=C, relu=relu, scale=0.5 if relu else 1.0)
+    seq_len[3] = 0
+    dev = torch.device("cuda:0")
+    for merge in (True, False):
+        dec, ln, ns = ctc.ctc_greedy_decode_raw(torch.tensor(x, device=dev), torch.tensor(seq_len, device=dev), merge)
+        od, ol, on = oracle.ctc_greedy_decoder(x, seq_len, merge)
+        assert (dec.cpu().numpy() == od).all()
+        assert (ln.cpu().numpy() == ol).all()
+        assert (ns.cpu().numpy().view(np.uint32) == on.ravel().view(np.uint32)).all()  # float bits
+    sp, nsl = ctc.ctc_greedy_decoder(torch.tensor(x, device=dev), torch.tensor(seq_len))
+    dense = ctc.sparse_tensor_to_dense(sp[0], -1).cpu().numpy()
+    assert (dense == oracle.densify(od if False else oracle.ctc_greedy_decoder(x, seq_len, True)[0], oracle.ctc_greedy_decoder(x, seq_len, True)[1])).all()
+    assert nsl.shape == (300, 1)
+
+
+def test_greedy_tf_unit_vectors():
+    from cnn_lstm_ctc_ocr_b200 import ctc
+    with np.errstate(divide="ignore"):
+        logits = np.stack([np.log(G["greedy_p0"]), np.log(G["greedy_p1"])], axis=1)
+    dev = torch.device("cuda:0")
+    dec, ln, ns = ctc.ctc_greedy_decode_raw(torch.tensor(logits, device=dev), torch.tensor([4, 5], dtype=torch.int32, device=dev))
+    assert ln.tolist() == [2, 3]
+    assert dec[0, :2].tolist() == [0, 1] and dec[1, :3].tolist() == [1, 1, 0]
+
+
+def test_edit_distance_vs_oracle(oracle):
+    from cnn_lstm_ctc_ocr_b200 import ctc
+    rng = np.random.default_rng(5)
+    B = 200
+    hyp = [rng.integers(0, 6, rng.integers(0, 70)).tolist() for _ in range(B)]
+    tru = [rng.integers(0, 6, rng.integers(0, 70)).tolist() for _ in range(B)]
+    hyp[0], tru[0] = [], []
+    hyp[1], tru[1] = [1, 2], []
+    hyp[2], tru[2] = [], [3]
+    dev = torch.device("cuda:0")
+
+    def sparse(seqs, dt):
+        idx = torch.tensor([[b, i] for b, l in enumerate(seqs) for i in range(len(l))], dtype=torch.int64).reshape(-1, 2)
+        vals = torch.tensor(sum(seqs, []), dtype=dt)
+        return ctc.SparseTensor(idx.to(dev), vals.to(dev), torch.tensor([len(seqs), max(len(l) for l in seqs)]))
+    d = ctc.edit_distance(sparse(hyp, torch.int64), sparse(tru, torch.int32), normalize=False)
+    assert (d.cpu().numpy() == oracle.edit_distance(hyp, tru)).all()
