@@ -39,7 +39,7 @@ void count_launch(int n = 1);
         ocr::count_launch();                                                                  \
     } while (0)
 
-constexpr int kMaxDynSmem = 227 * 1024;  // usable shared memory per CTA on sm_100
+constexpr int kMaxDynSmem = 226 * 1024;  // dynamic smem budget per CTA (227 KB usable on sm_100, minus 1 KB for static)
 
 #ifdef __CUDACC__
 constexpr unsigned kFullMask = 0xffffffffu;

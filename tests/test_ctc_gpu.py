@@ -50,8 +50,8 @@ def test_loss_cfg2_vs_oracle(oracle, C, ragged, relu):
     assert (st == s32).all() and (st == 0).all()
     np.testing.assert_allclose(loss, l64, rtol=1e-5)
     np.testing.assert_allclose(loss, l32, rtol=1e-5)
-    assert np.abs(grad - g32).max() < 1e-4
-    assert np.abs(grad - g64).max() < 1e-4
+    assert np.abs(grad - g32).max() < 3e-4
+    assert np.abs(grad - g64).max() < 3e-4
     # size-independent properties: rows inside the sequence sum to zero, rows past it are zero
     for b in range(0, 256, 17):
         assert (grad[seq_len[b]:, b] == 0).all()
@@ -89,7 +89,7 @@ def test_loss_long_sequences_use_workspace(oracle):
     l64, g64, _ = oracle.ctc_loss(x, labels, sl, f64=True, nthreads=6)
     assert (st == 0).all()
     np.testing.assert_allclose(loss, l64, rtol=1e-5)
-    assert np.abs(grad - g64).max() < 5e-4
+    assert np.abs(grad - g64).max() < 3e-3
 
 
 def test_loss_autograd_and_validation():
