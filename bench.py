@@ -207,12 +207,16 @@ def run_ours(args, cfg):
                          loss=torch.empty(B, device=dev), grad=torch.empty_like(xt),
                          status=torch.empty(B, dtype=torch.int32, device=dev)))
     stream = torch.cuda.Stream(device=dev)
+    import ctypes
+    need = ctypes.c_size_t(0)
+    _lib.check(lib.ocr_ctc_loss_workspace_bytes(T, B, C, 16, ctypes.byref(need)), "ocr_ctc_loss_workspace_bytes")
+    ws = torch.empty(max(need.value, 1), dtype=torch.uint8, device=dev)
 
     def step(i, st):
         r = ring[i % ring_n]
         _lib.check(lib.ocr_ctc_loss(_lib.ptr(r["x"]), T, B, C, _lib.ptr(r["flat"]), _lib.ptr(r["off"]), _lib.ptr(r["sl"]),
                                     r["Lmax"], _lib.ptr(r["loss"]), _lib.ptr(r["grad"]), _lib.ptr(r["status"]),
-                                    1.0 / B, None, 0, st), "ocr_ctc_loss")
+                                    1.0 / B, _lib.ptr(ws), need.value, st), "ocr_ctc_loss")
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -259,7 +263,9 @@ def run_ours(args, cfg):
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             ms = float(tm.item())
         value = world * B * K / (ms * 1e-3)
-        kernel_us = ms * 1e3 / (K * launches_per_step)
+        # one step = ctc_loss_fast_kernel (the dominant kernel) + the redo gate (a flag read per sequence);
+        # the whole step is charged to the dominant kernel (conservative)
+        kernel_us = ms * 1e3 / K
         ok_status = int(ring[0]["status"].sum().item()) == 0
 
         # ---- end to end through the public API with host buffers
@@ -322,7 +328,7 @@ def run_ours(args, cfg):
                            per_gpu_batch=B),
             "e2e": e2e,
             "gpu_launches": K * launches_per_step,
-            "roofline": {"bound": "hbm", "kernel": "ctc_loss_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "ctc_loss_fast_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": _traffic("ctc_cfg2"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_us": kernel_us,
                          "note": "cfg2 (8.3 MB, 64-step dependent alpha/beta chains) is latency-bound, see roofline_bw_regime"},
@@ -353,10 +359,14 @@ def bandwidth_regime(lib, _lib, dev, T, C, B, windows):
     grad = torch.empty_like(x)
     status = torch.empty(B, dtype=torch.int32, device=dev)
     sh = _lib.stream_handle()
+    import ctypes
+    need = ctypes.c_size_t(0)
+    _lib.check(lib.ocr_ctc_loss_workspace_bytes(T, B, C, 16, ctypes.byref(need)), "ocr_ctc_loss_workspace_bytes")
+    ws = torch.empty(max(need.value, 1), dtype=torch.uint8, device=dev)
 
     def go():
         _lib.check(lib.ocr_ctc_loss(_lib.ptr(x), T, B, C, _lib.ptr(flat), _lib.ptr(off), _lib.ptr(sl), 16, _lib.ptr(loss),
-                                    _lib.ptr(grad), _lib.ptr(status), 1.0 / B, None, 0, sh), "ocr_ctc_loss")
+                                    _lib.ptr(grad), _lib.ptr(status), 1.0 / B, _lib.ptr(ws), need.value, sh), "ocr_ctc_loss")
     for _ in range(3):
         go()
     torch.cuda.synchronize()
@@ -372,9 +382,10 @@ def bandwidth_regime(lib, _lib, dev, T, C, B, windows):
     us = e0.elapsed_time(e1) * 1e3 / reps
     alg = 2 * T * B * C * 4
     ach = alg / (us * 1e-6) / 1e9
-    return {"bound": "hbm", "kernel": "ctc_loss_kernel", "workload": "CTC loss+grad B=%d T=%d C=%d (%.2f GB moved, >> L2)" % (B, T, C, alg / 1e9),
+    return {"bound": "hbm", "kernel": "ctc_loss_fast_kernel", "workload": "CTC loss+grad B=%d T=%d C=%d (%.2f GB moved, >> L2)" % (B, T, C, alg / 1e9),
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": _traffic("ctc_bw_regime"),
-            "kernel_us": us, "crops_per_s": B / (us * 1e-6), "peak_source": peak_src}
+            "kernel_us": us, "crops_per_s": B / (us * 1e-6), "peak_source": peak_src,
+            "redo_sequences": int((status == 100).sum().item())}
 
 
 def main():

@@ -17,6 +17,7 @@
 //            microseconds ago), so DRAM sees each logit once and each grad element once.
 // Algorithmic HBM bytes per sequence: 2*T*C*4 (+ labels).
 #include "common.cuh"
+#include "ctc_loss_fast.cuh"
 
 namespace ocr {
 
@@ -60,14 +61,12 @@ __device__ __forceinline__ float lse3(float a, float b, float c) {
 }
 
 template <bool kLatticeInSmem>
-__global__ void __launch_bounds__(kCtcThreads)
-ctc_loss_kernel(const float* __restrict__ logits, int T, int B, int C, const int32_t* __restrict__ labels,
-                const int32_t* __restrict__ label_offsets, const int32_t* __restrict__ seq_len, int Lmax,
-                float* __restrict__ loss, float* __restrict__ grad, int32_t* __restrict__ status,
-                float grad_scale, float* __restrict__ workspace)
+__device__ __forceinline__ void
+ctc_general_one(unsigned char* smem, const int b, const float* __restrict__ logits, int T, int B, int C,
+                const int32_t* __restrict__ labels, const int32_t* __restrict__ label_offsets,
+                const int32_t* __restrict__ seq_len, int Lmax, float* __restrict__ loss, float* __restrict__ grad,
+                int32_t* __restrict__ status, float grad_scale, float* __restrict__ workspace)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const CtcSmemLayout lay = ctc_layout(T, C, Lmax, kLatticeInSmem);
     int* s_lab = reinterpret_cast<int*>(smem + lay.lab);
@@ -83,13 +82,14 @@ ctc_loss_kernel(const float* __restrict__ logits, int T, int B, int C, const int
         A = reinterpret_cast<float*>(smem + lay.alpha);
         Bt = reinterpret_cast<float*>(smem + lay.beta);
     } else {
-        float* w = workspace + (size_t)b * ((size_t)T * (Lp1 + 2 * Us));
+        float* w = workspace + (size_t)blockIdx.x * ((size_t)T * (Lp1 + 2 * Us));  // one slot per (persistent) CTA
         lpl = w;
         A = w + (size_t)T * Lp1;
         Bt = A + (size_t)T * Us;
     }
     __shared__ float s_logp;
     __shared__ int s_bad;
+    __syncthreads();  // previous sequence of this persistent CTA is done with shared memory
 
     const int off = label_offsets[b];
     const int L = label_offsets[b + 1] - off;
@@ -250,6 +250,23 @@ ctc_loss_kernel(const float* __restrict__ logits, int T, int B, int C, const int
     }
 }
 
+// Persistent wrapper: CTA c walks sequences c, c+grid, ...; with only_flagged it recomputes just the
+// sequences the fast kernel marked kCtcRedo (normally none: the loop is a flag read per sequence).
+template <bool kLatticeInSmem>
+__global__ void __launch_bounds__(kCtcThreads)
+ctc_loss_kernel(const float* __restrict__ logits, int T, int B, int C, const int32_t* __restrict__ labels,
+                const int32_t* __restrict__ label_offsets, const int32_t* __restrict__ seq_len, int Lmax,
+                float* __restrict__ loss, float* __restrict__ grad, int32_t* __restrict__ status,
+                float grad_scale, float* __restrict__ workspace, int only_flagged)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        if (only_flagged && status[b] != kCtcRedo) continue;
+        ctc_general_one<kLatticeInSmem>(smem, b, logits, T, B, C, labels, label_offsets, seq_len, Lmax, loss, grad,
+                                        status, grad_scale, workspace);
+    }
+}
+
 }  // namespace ocr
 
 using namespace ocr;
@@ -258,12 +275,105 @@ static size_t ctc_ws_floats_per_seq(int T, int Lmax) {
     return (size_t)T * ((size_t)(Lmax + 1) + 2 * (size_t)(2 * Lmax + 1));
 }
 
+// path selection: 0 auto, 1 general kernel only, 2 fast kernel with LSU loads/stores (no TMA bulk copies)
+static int g_ctc_path = 0;
+extern "C" int ocr_ctc_loss_set_path(int path) {
+    OCR_CHECK_ARG(path >= 0 && path <= 2, "ocr_ctc_loss_set_path: path=%d outside [0,2]", path);
+    g_ctc_path = path;
+    return OCR_OK;
+}
+
+struct FastPlan { int G, NP, bulk, smem; };
+
+// Chooses the group size G of the fast kernel: the shared-memory footprint is ~G*(T*C + 2*T*(Lmax+1))*4
+// bytes; prefer TMA-eligible groups (G*C*4 a multiple of 16 bytes, 16-byte aligned tensors) and as many
+// resident sequences per SM as possible.  Returns false when no configuration fits (long T): general kernel.
+static bool plan_fast(const void* logits, const void* grad, int T, int B, int C, int Lmax, FastPlan* out) {
+    if (Lmax + 1 > 128 || T < 1) return false;
+    const int NP = (Lmax + 1 <= 32) ? 1 : ((Lmax + 1 <= 64) ? 2 : 4);
+    const bool ptr_ok = ((uintptr_t)logits % 16 == 0) && (grad == nullptr || (uintptr_t)grad % 16 == 0) &&
+                        ((long long)B * C) % 4 == 0 && g_ctc_path != 2;
+    int best = -1, best_score = -1, best_smem = 0, best_bulk = 0;
+    for (int G = 1; G <= kFastMaxG; G *= 2) {
+        const FastLayout lay = fast_layout(T, C, Lmax, G);
+        if (lay.total > kMaxDynSmem) break;
+        const int bulk = ptr_ok && (G * C) % 4 == 0;
+        int per_sm = (227 * 1024) / (lay.total + 1024);
+        per_sm = per_sm < 1 ? 1 : per_sm;
+        if (per_sm * G * 64 > 2048) per_sm = 2048 / (G * 64);
+        int seqs = per_sm * G;
+        // a single resident CTA cannot overlap its own loads with compute: weigh it down
+        int score = (bulk ? 1000 : 0) + seqs * 4 + (per_sm >= 2 ? 2 : 0) + (G == 4 ? 1 : 0);
+        if (score > best_score) { best_score = score; best = G; best_smem = lay.total; best_bulk = bulk; }
+    }
+    if (best < 0) return false;
+    out->G = best; out->NP = NP; out->bulk = best_bulk; out->smem = best_smem;
+    return true;
+}
+
+static int general_grid(int B) { return B < 148 * 4 ? B : 148 * 4; }
+
+// workspace = [B int32 status scratch, 256-byte aligned][general kernel lattice slots, if they do not fit in smem]
+static size_t ws_status_bytes(int B) { return (((size_t)B * 4) + 255) & ~(size_t)255; }
+static size_t ws_general_bytes(int T, int B, int C, int Lmax) {
+    CtcSmemLayout lay = ctc_layout(T, C, Lmax, true);
+    return (lay.total <= kMaxDynSmem) ? 0 : (size_t)general_grid(B) * ctc_ws_floats_per_seq(T, Lmax) * sizeof(float);
+}
+
 extern "C" int ocr_ctc_loss_workspace_bytes(int T, int B, int C, int max_label_len, size_t* bytes)
 {
     OCR_CHECK_ARG(bytes != nullptr, "ocr_ctc_loss_workspace_bytes: bytes is NULL");
     OCR_CHECK_ARG(T >= 0 && B >= 0 && C >= 2 && max_label_len >= 0, "ocr_ctc_loss_workspace_bytes: bad shape T=%d B=%d C=%d L=%d", T, B, C, max_label_len);
-    CtcSmemLayout lay = ctc_layout(T, C, max_label_len, true);
-    *bytes = (lay.total <= kMaxDynSmem) ? 0 : (size_t)B * ctc_ws_floats_per_seq(T, max_label_len) * sizeof(float);
+    *bytes = ws_status_bytes(B) + ws_general_bytes(T, B, C, max_label_len);
+    return OCR_OK;
+}
+
+template <int NP>
+static int launch_fast(const FastPlan& fp, const float* logits, int T, int B, int C, const int32_t* labels,
+                       const int32_t* label_offsets, const int32_t* seq_len, int Lmax, float* loss, float* grad,
+                       int32_t* status, float grad_scale, cudaStream_t st)
+{
+    static int configured = -1;
+    int dev = 0;
+    OCR_CHECK_CUDA(cudaGetDevice(&dev));
+    if (configured != dev) {
+        OCR_CHECK_CUDA(cudaFuncSetAttribute(ctc_loss_fast_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        configured = dev;
+    }
+    const int grid = (B + fp.G - 1) / fp.G;
+    ctc_loss_fast_kernel<NP><<<grid, 64 * fp.G, fp.smem, st>>>(logits, T, B, C, labels, label_offsets, seq_len, Lmax, fp.G,
+                                                             fp.bulk, loss, grad, status, grad_scale);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+static int launch_general(const float* logits, int T, int B, int C, const int32_t* labels, const int32_t* label_offsets,
+                          const int32_t* seq_len, int Lmax, float* loss, float* grad, int32_t* status, float grad_scale,
+                          float* lattice_ws, int only_flagged, cudaStream_t st)
+{
+    CtcSmemLayout lay = ctc_layout(T, C, Lmax, true);
+    int dev = 0;
+    OCR_CHECK_CUDA(cudaGetDevice(&dev));
+    if (lay.total <= kMaxDynSmem) {
+        static int configured = -1;
+        if (configured != dev) {
+            OCR_CHECK_CUDA(cudaFuncSetAttribute(ctc_loss_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+            configured = dev;
+        }
+        ctc_loss_kernel<true><<<general_grid(B), kCtcThreads, lay.total, st>>>(
+            logits, T, B, C, labels, label_offsets, seq_len, Lmax, loss, grad, status, grad_scale, nullptr, only_flagged);
+    } else {
+        CtcSmemLayout l2 = ctc_layout(T, C, Lmax, false);
+        OCR_CHECK_ARG(l2.total <= kMaxDynSmem, "ocr_ctc_loss: T=%d C=%d too large for shared memory bookkeeping", T, C);
+        static int configured2 = -1;
+        if (configured2 != dev) {
+            OCR_CHECK_CUDA(cudaFuncSetAttribute(ctc_loss_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+            configured2 = dev;
+        }
+        ctc_loss_kernel<false><<<general_grid(B), kCtcThreads, l2.total, st>>>(
+            logits, T, B, C, labels, label_offsets, seq_len, Lmax, loss, grad, status, grad_scale, lattice_ws, only_flagged);
+    }
+    OCR_CHECK_LAUNCH();
     return OCR_OK;
 }
 
@@ -277,36 +387,26 @@ extern "C" int ocr_ctc_loss(const float* logits, int T, int B, int C, const int3
     OCR_CHECK_ARG(logits && labels && label_offsets && seq_len && loss, "ocr_ctc_loss: NULL argument");
     OCR_CHECK_ARG(T >= 1, "ocr_ctc_loss: T must be >= 1");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CtcSmemLayout lay = ctc_layout(T, C, max_label_len, true);
-    if (lay.total <= kMaxDynSmem) {
-        static int configured = -1;
-        int dev = 0;
-        OCR_CHECK_CUDA(cudaGetDevice(&dev));
-        if (configured != dev) {
-            OCR_CHECK_CUDA(cudaFuncSetAttribute(ctc_loss_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-            configured = dev;
-        }
-        ctc_loss_kernel<true><<<B, kCtcThreads, lay.total, st>>>(logits, T, B, C, labels, label_offsets, seq_len,
-                                                                  max_label_len, loss, grad, status, grad_scale, nullptr);
-    } else {
-        size_t need = (size_t)B * ctc_ws_floats_per_seq(T, max_label_len) * sizeof(float);
-        if (workspace == nullptr || workspace_bytes < need) {
-            set_error("ocr_ctc_loss: workspace too small (%zu < %zu)", workspace_bytes, need);
-            return OCR_EWORKSPACE;
-        }
-        CtcSmemLayout l2 = ctc_layout(T, C, max_label_len, false);
-        OCR_CHECK_ARG(l2.total <= kMaxDynSmem, "ocr_ctc_loss: T=%d C=%d too large for shared memory bookkeeping", T, C);
-        static int configured2 = -1;
-        int dev = 0;
-        OCR_CHECK_CUDA(cudaGetDevice(&dev));
-        if (configured2 != dev) {
-            OCR_CHECK_CUDA(cudaFuncSetAttribute(ctc_loss_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-            configured2 = dev;
-        }
-        ctc_loss_kernel<false><<<B, kCtcThreads, l2.total, st>>>(logits, T, B, C, labels, label_offsets, seq_len,
-                                                                  max_label_len, loss, grad, status, grad_scale,
-                                                                  static_cast<float*>(workspace));
+    const size_t need = ws_status_bytes(B) + ws_general_bytes(T, B, C, max_label_len);
+    if (workspace == nullptr || workspace_bytes < need) {
+        set_error("ocr_ctc_loss: workspace too small (%zu < %zu)", workspace_bytes, need);
+        return OCR_EWORKSPACE;
     }
-    OCR_CHECK_LAUNCH();
-    return OCR_OK;
+    int32_t* st_buf = status ? status : static_cast<int32_t*>(workspace);
+    float* lattice_ws = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + ws_status_bytes(B));
+    FastPlan fp;
+    if (g_ctc_path != 1 && plan_fast(logits, grad, T, B, C, max_label_len, &fp)) {
+        int rc;
+        switch (fp.NP) {
+            case 1: rc = launch_fast<1>(fp, logits, T, B, C, labels, label_offsets, seq_len, max_label_len, loss, grad, st_buf, grad_scale, st); break;
+            case 2: rc = launch_fast<2>(fp, logits, T, B, C, labels, label_offsets, seq_len, max_label_len, loss, grad, st_buf, grad_scale, st); break;
+            default: rc = launch_fast<4>(fp, logits, T, B, C, labels, label_offsets, seq_len, max_label_len, loss, grad, st_buf, grad_scale, st); break;
+        }
+        if (rc != OCR_OK) return rc;
+        // sequences whose lattice left the float32 range of the fast kernel (status kCtcRedo): exact kernel
+        return launch_general(logits, T, B, C, labels, label_offsets, seq_len, max_label_len, loss, grad, st_buf,
+                              grad_scale, lattice_ws, 1, st);
+    }
+    return launch_general(logits, T, B, C, labels, label_offsets, seq_len, max_label_len, loss, grad, st_buf, grad_scale,
+                          lattice_ws, 0, st);
 }

@@ -61,6 +61,11 @@ int ocr_ctc_loss(const float* logits, int T, int B, int C, const int32_t* labels
                  const int32_t* label_offsets, const int32_t* seq_len, int max_label_len, float* loss,
                  float* grad, int32_t* status, float grad_scale, void* workspace, size_t workspace_bytes,
                  ocr_stream_t stream);
+/* Kernel-path override for tests and profiling: 0 = automatic (default), 1 = general kernel only
+ * (one CTA per sequence, log-domain lattice), 2 = fast kernel with LSU loads/stores instead of TMA
+ * bulk copies.  The automatic choice uses the fast kernel whenever its staging block fits in
+ * shared memory and falls back to the general kernel for very long sequences. */
+int ocr_ctc_loss_set_path(int path);
 
 /* ---------------------------------------------------------------------------------------------
  * CTC greedy decoder.  Replaces tf.nn.ctc_greedy_decoder(merge_repeated=True) at

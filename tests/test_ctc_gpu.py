@@ -1,11 +1,13 @@
 """GPU tier: the sm_100a CTC kernels, called through the C ABI, against the CPU oracle.
 
-Tolerances (float32 arithmetic on both sides):
+Tolerances:
   loss  : rel 1e-5 vs the float64 recursion and vs the TF-faithful float32 oracle;
-  grad  : abs 1e-4 vs the TF-faithful float32 oracle and vs float64 -- the float32 log-domain
-          recursion (TF's, the oracle's and this kernel's alike) carries ~1 ulp(|alpha|) ~ 3e-5 of
-          noise at T=64 (oracle-f32 vs oracle-f64 differ by up to ~8e-5 on the same inputs, asserted
-          in test_oracle_golden.py), so 1e-5 against a float32 reference is not a meaningful bar;
+  grad  : fast kernel (linear-domain lattice, exact power-of-two rescaling): abs 1e-5 vs the float64
+          recursion.  Against the TF-faithful float32 oracle the bar is 3e-4, because THAT recursion
+          (TF's own float32 log-domain arithmetic) carries ~1 ulp(|alpha|) ~ 3e-5 of noise per step
+          (oracle-f32 vs oracle-f64 differ by up to ~1e-4 on the same inputs, asserted in
+          test_oracle_golden.py).  The general (long-sequence) kernel is log-domain float32 like TF
+          and is held to 3e-4 / 3e-3 (T=509);
   decode: bit-exact (labels, lengths, and neg_sum_logits float bits).
 """
 import os
@@ -20,14 +22,16 @@ pytestmark = pytest.mark.gpu
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "tf_unit_vectors.npz"))
 
 
-def _gpu_loss(x, labels, seq_len, want_grad=True):
-    from cnn_lstm_ctc_ocr_b200 import ctc
+def _gpu_loss(x, labels, seq_len, want_grad=True, path=0):
+    from cnn_lstm_ctc_ocr_b200 import ctc, _lib
     dev = torch.device("cuda:0")
+    _lib.check(_lib.load().ocr_ctc_loss_set_path(path), "set_path")
     xt = torch.tensor(x, device=dev)
     flat, off, lengths, _ = ctc._labels_to_flat(labels, x.shape[1], dev)
     sl = torch.tensor(np.asarray(seq_len, np.int32), device=dev)
     loss, grad, st = ctc.ctc_loss_raw(xt, flat, off, sl, max(lengths) if lengths else 0, want_grad)
     torch.cuda.synchronize()
+    _lib.load().ocr_ctc_loss_set_path(0)
     return loss.cpu().numpy(), (grad.cpu().numpy() if want_grad else None), st.cpu().numpy()
 
 
@@ -41,21 +45,67 @@ def test_loss_tf_unit_vectors():
     np.testing.assert_allclose(grad[:, 1], G["loss_g1"], atol=2e-6)
 
 
+@pytest.mark.parametrize("path", [0, 2, 1])
 @pytest.mark.parametrize("C,ragged,relu", [(63, False, False), (63, True, False), (63, True, True), (96, True, False)])
-def test_loss_cfg2_vs_oracle(oracle, C, ragged, relu):
+def test_loss_cfg2_vs_oracle(oracle, C, ragged, relu, path):
     x, labels, seq_len = cfg2_inputs(seed=1, T=64, B=256, C=C, ragged=ragged, relu=relu)
-    loss, grad, st = _gpu_loss(x, labels, seq_len)
+    loss, grad, st = _gpu_loss(x, labels, seq_len, path=path)
     l32, g32, s32 = oracle.ctc_loss(x, labels, seq_len, nthreads=8)
     l64, g64, _ = oracle.ctc_loss(x, labels, seq_len, nthreads=8, f64=True)
     assert (st == s32).all() and (st == 0).all()
     np.testing.assert_allclose(loss, l64, rtol=1e-5)
     np.testing.assert_allclose(loss, l32, rtol=1e-5)
     assert np.abs(grad - g32).max() < 3e-4
-    assert np.abs(grad - g64).max() < 3e-4
+    assert np.abs(grad - g64).max() < (3e-4 if path == 1 else 1e-5)
     # size-independent properties: rows inside the sequence sum to zero, rows past it are zero
     for b in range(0, 256, 17):
         assert (grad[seq_len[b]:, b] == 0).all()
-        assert np.abs(grad[:seq_len[b], b].sum(-1)).max() < 2e-5
+        assert np.abs(grad[:seq_len[b], b].sum(-1)).max() < (3e-4 if path == 1 else 2e-6)
+
+
+@pytest.mark.parametrize("T,B,C,maxlen,path", [
+    (64, 255, 63, 16, 0),    # B*C not a multiple of 4: LSU path, partial last group
+    (64, 8, 63, 16, 0),      # one full TMA group of 8 / two of 4
+    (61, 37, 96, 20, 0),     # partial last group on the TMA path
+    (61, 37, 96, 20, 2),
+    (40, 21, 7, 30, 0),      # labels as long as the sequence allows, tiny alphabet
+    (125, 64, 96, 24, 0),    # cfg3 shape: one sequence per CTA
+    (200, 9, 30, 60, 0),     # 2 label pairs per lane
+    (250, 5, 20, 100, 0),    # 4 label pairs per lane
+    (3, 4, 5, 2, 0), (1, 4, 5, 1, 0), (2, 3, 4, 1, 2),
+])
+def test_loss_shapes_vs_f64(oracle, T, B, C, maxlen, path):
+    rng = np.random.default_rng(T * 1000 + B)
+    x = (rng.standard_normal((T, B, C)) * 2).astype(np.float32)
+    seq_len = rng.integers(max(1, T // 2), T + 1, B).astype(np.int32)
+    seq_len[0] = T
+    labels = make_labels(rng, B, seq_len, max_len=maxlen, num_labels=C - 1, repeat_p=0.3)
+    if B > 2:
+        labels[1] = []          # empty label: only the all-blank alignment
+        seq_len[2] = 0          # zero-length sequence: loss 0, grad 0
+    loss, grad, st = _gpu_loss(x, labels, seq_len, path=path)
+    l64, g64, s64 = oracle.ctc_loss(x, labels, seq_len, nthreads=8, f64=True)
+    assert (st == s64).all()
+    np.testing.assert_allclose(loss, l64, rtol=1e-5, atol=1e-6)
+    assert np.abs(grad - g64).max() < 2e-5
+    loss2, _, _ = _gpu_loss(x, labels, seq_len, want_grad=False, path=path)
+    assert (loss2 == loss).all()
+
+
+def test_loss_extreme_dynamic_range(oracle):
+    """Peaked (confident, often wrong) distributions: per-frame label probabilities down to ~e^-50."""
+    rng = np.random.default_rng(77)
+    T, B, C = 64, 32, 63
+    x = (rng.standard_normal((T, B, C)) * 8).astype(np.float32)
+    seq_len = np.full(B, T, np.int32)
+    labels = make_labels(rng, B, seq_len, max_len=16, num_labels=C - 1)
+    loss, grad, st = _gpu_loss(x, labels, seq_len)
+    l64, g64, s64 = oracle.ctc_loss(x, labels, seq_len, nthreads=8, f64=True)
+    assert (st == 0).all()
+    np.testing.assert_allclose(loss, l64, rtol=1e-5)
+    # sequences whose lattice leaves the float32 range of the linear-domain kernel are recomputed by the
+    # log-domain kernel, which has TF's own float32 noise level (~ulp(|log p|) = 6e-5 per step at |log p| ~ 1000)
+    assert np.abs(grad - g64).max() < 1e-3
 
 
 def test_loss_edge_cases(oracle):
@@ -85,6 +135,11 @@ def test_loss_long_sequences_use_workspace(oracle):
     sl = np.array([509, 400, 509, 37, 255, 509], np.int32)
     labels = make_labels(rng, B, sl, max_len=120, num_labels=95)
     labels[0] = [int(v) for v in rng.integers(0, 95, 120)]
+    from cnn_lstm_ctc_ocr_b200 import _lib
+    import ctypes
+    need = ctypes.c_size_t(0)
+    _lib.load().ocr_ctc_loss_workspace_bytes(T, B, C, 120, ctypes.byref(need))
+    assert need.value > 1 << 20  # no shared-memory configuration fits: general kernel + global lattice workspace
     loss, grad, st = _gpu_loss(x, labels, sl)
     l64, g64, _ = oracle.ctc_loss(x, labels, sl, f64=True, nthreads=6)
     assert (st == 0).all()
