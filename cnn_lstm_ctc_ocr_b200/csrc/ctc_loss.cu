@@ -278,7 +278,7 @@ static size_t ctc_ws_floats_per_seq(int T, int Lmax) {
 // path selection: 0 auto, 1 general kernel only, 2 fast kernel with LSU loads/stores (no TMA bulk copies)
 static int g_ctc_path = 0;
 extern "C" int ocr_ctc_loss_set_path(int path) {
-    OCR_CHECK_ARG(path >= 0 && path <= 2, "ocr_ctc_loss_set_path: path=%d outside [0,2]", path);
+    OCR_CHECK_ARG(path >= 0 && path <= 3, "ocr_ctc_loss_set_path: path=%d outside [0,3]", path);
     g_ctc_path = path;
     return OCR_OK;
 }
@@ -292,7 +292,7 @@ static bool plan_fast(const void* logits, const void* grad, int T, int B, int C,
     if (Lmax + 1 > 128 || T < 1) return false;
     const int NP = (Lmax + 1 <= 32) ? 1 : ((Lmax + 1 <= 64) ? 2 : 4);
     const bool ptr_ok = ((uintptr_t)logits % 16 == 0) && (grad == nullptr || (uintptr_t)grad % 16 == 0) &&
-                        ((long long)B * C) % 4 == 0 && g_ctc_path != 2;
+                        ((long long)B * C) % 4 == 0 && g_ctc_path != 2;  // path 2: LSU loads/stores
     int best = -1, best_score = -1, best_smem = 0, best_bulk = 0;
     for (int G = 1; G <= kFastMaxG; G *= 2) {
         const FastLayout lay = fast_layout(T, C, Lmax, G);
@@ -402,7 +402,7 @@ extern "C" int ocr_ctc_loss(const float* logits, int T, int B, int C, const int3
             case 2: rc = launch_fast<2>(fp, logits, T, B, C, labels, label_offsets, seq_len, max_label_len, loss, grad, st_buf, grad_scale, st); break;
             default: rc = launch_fast<4>(fp, logits, T, B, C, labels, label_offsets, seq_len, max_label_len, loss, grad, st_buf, grad_scale, st); break;
         }
-        if (rc != OCR_OK) return rc;
+        if (rc != OCR_OK || g_ctc_path == 3) return rc;  // path 3 (diagnostics): leave kCtcRedo flags in status
         // sequences whose lattice left the float32 range of the fast kernel (status kCtcRedo): exact kernel
         return launch_general(logits, T, B, C, labels, label_offsets, seq_len, max_label_len, loss, grad, st_buf,
                               grad_scale, lattice_ws, 1, st);

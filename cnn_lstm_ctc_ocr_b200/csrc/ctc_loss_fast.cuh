@@ -11,8 +11,9 @@
 //     block; the finished gradient leaves the same block through cp.async.bulk stores, so
 //     the LSU never issues a global access on the aligned path;
 //   * two warps per sequence.  Softmax statistics are computed "lane per frame" (each lane
-//     walks one logit row in shared memory, skewed so banks never collide), leaving
-//     e = exp(x - max) in place and Z = sum(e);
+//     walks one logit row in shared memory; the row pitch is 4*odd words and lanes are skewed by
+//     lane/8 columns, so the 32 lanes always hit 32 distinct banks), leaving e = exp(x - max) in
+//     place and Z = sum(e);
 //   * the lattice runs in the LINEAR domain on the un-normalised e (the recursion is linear, the
 //     row factors Z cancel in the posterior), register resident: lane i holds the state pair
 //     (blank before label i, label i), one shuffle per frame carries the neighbour state,
@@ -23,13 +24,17 @@
 //   * the alpha warp walks forward while the beta warp walks backward; they meet in the middle:
 //     each stores its half of the lattice, then over the other half multiplies its live values
 //     into what the partner stored, so shared memory holds ONE lattice of products
-//     alpha_t(u)*beta_t(u);
-//   * posterior = product / (row sum of products) (each row normalised by its own total, which
-//     equals p(z|x) up to scaling), scattered "lane per frame" into the staged row, duplicates
-//     handled by plain sequential order, then grad = (e - Z*occ) * (grad_scale / Z).
+//     alpha_t(u)*beta_t(u) (brought back to O(1) by an exact power of two, see prod_exponent);
+//   * posterior = product / (row sum of products), scattered "lane per frame" into the staged
+//     row, duplicates handled by plain sequential order, then grad = (e - Z*occ) * (grad_scale / Z);
+//   * every row of products must sum to the p(z|x) the alpha chain ended with; a sequence where it
+//     does not has lost probability mass to float32 underflow (states more than 2^-126 below the
+//     warp-wide maximum) and is handed to the exact log-domain kernel (status kCtcRedo).
 // Numerics: float32; loss rel. error ~1e-6, gradient abs. error ~1e-6 against the float64
 // recursion (an order of magnitude tighter than the float32 log-domain recursion TF itself runs).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ocr {
@@ -38,25 +43,34 @@ constexpr int kFastMaxG = 8;
 constexpr int kCtcRedo = 100;  // internal status: recompute this sequence with the exact log-domain kernel
 
 struct FastLayout {
-    int RS;        // floats between consecutive frames in the staging block
-    int Lp;        // lattice row length (Lmax + 1)
-    int stage, lat, zz, exr, lab, slz, mbar, total;  // byte offsets
+    int RS;        // floats between consecutive frames in the staging block (4 * odd)
+    int LS;        // floats per lattice row: [trash][state 0 .. 2*Lmax][pad][trash pair][exponent]  (2 * odd)
+    int EX;        // index of the exponent slot inside a lattice row
+    int HI;        // index of the high trash pair
+    int stage, lat, zz, lab, info, zero, mbar, total;  // byte offsets
     int lat_seq;   // floats per sequence in the lattice block
 };
 
 __host__ __device__ inline FastLayout fast_layout(int T, int C, int Lmax, int G) {
     FastLayout f;
-    f.RS = (G * C + 3) & ~3;
-    f.Lp = Lmax + 1;
-    f.lat_seq = T * 2 * f.Lp;
+    int rs4 = (G * C + 3) >> 2;
+    if (!(rs4 & 1)) rs4 += 1;
+    f.RS = rs4 * 4;
+    // positions: 0 low trash, 1+u state u (u <= 2*Lmax), HI,HI+1 high trash, EX exponent
+    int ls2 = Lmax + 3;  // (2*Lmax + 6) / 2
+    if (!(ls2 & 1)) ls2 += 1;
+    f.LS = ls2 * 2;
+    f.HI = 2 * Lmax + 2;
+    f.EX = 2 * Lmax + 4;
+    f.lat_seq = T * f.LS;
     int o = 0;
     f.stage = o; o += T * f.RS * 4;
     f.lat = o;   o += G * f.lat_seq * 4;
     f.zz = o;    o += G * T * 4;
-    f.exr = o;   o += G * T * 4;
-    f.lab = o;   o += G * f.Lp * 4;
-    f.slz = o;   o += G * 8 * 4;  // per sequence: sum(log Z) x2, no-valid flag, log2(pe), Ea, Pt(alpha), Pt(beta), spare
+    f.lab = o;   o += G * (Lmax + 1) * 4;
+    f.info = o;  o += G * 8 * 4;  // per sequence: sum(log Z) x2, no-valid flag, log2(pe), Ea, Pt(alpha), Pt(beta), spare
     o = (o + 15) & ~15;
+    f.zero = o;  o += 16;
     f.mbar = o;  o += 16;
     f.total = o;
     return f;
@@ -93,13 +107,33 @@ __device__ __forceinline__ float fast_ex2(float x) {
 }
 __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
-// exact power-of-two rescale: returns the factor 2^-ex for the warp-wide maximum m (>= 0) and ex
-__device__ __forceinline__ float pow2_rescale(float mloc, int& ex) {
+// shared-memory accesses of the lattice chains by 32-bit shared address (volatile: program order is the schedule)
+__device__ __forceinline__ float lds(unsigned a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds4(unsigned a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+4];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int ldsi(unsigned a) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v)); }
+__device__ __forceinline__ void sts4(unsigned a, float v) { asm volatile("st.shared.f32 [%0+4], %1;" ::"r"(a), "f"(v)); }
+__device__ __forceinline__ void stsi(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v)); }
+
+// Exact power-of-two rescale.  m = warp-wide maximum (>= 0) of the live lattice values; returns 2^(127-e)
+// with e the biased exponent of m, so that m * scale lies in [1,2); ebias = e (the caller sums e - 127).
+// m == 0 gives the finite factor 2^127, which is harmless on an all-zero lattice.
+__device__ __forceinline__ float pow2_rescale(float mloc, int& ebias) {
     const unsigned mb = __reduce_max_sync(kFullMask, __float_as_uint(mloc));
-    const int e = (int)(mb >> 23);
-    if (e == 0 || e == 255) { ex = 0; return 1.0f; }  // zero / denormal / inf: leave alone
-    ex = e - 127;
-    return __uint_as_float((unsigned)(254 - e) << 23);
+    ebias = (int)(mb >> 23);
+    return __uint_as_float(0x7F000000u - (mb & 0x7F800000u));
 }
 
 // The stored lattice halves are scaled: alpha_t = v_t * 2^Ea_t, beta_t = w_t * 2^Eb_t with max(v), max(w) ~ 1,
@@ -113,20 +147,41 @@ __device__ __forceinline__ int prod_exponent(const float (&a0)[NP], const float 
     int k = -100000;
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
-        const int e0a = (int)(__float_as_uint(a0[j]) >> 23), e0b = (int)(__float_as_uint(b0[j]) >> 23);
-        const int e1a = (int)(__float_as_uint(a1[j]) >> 23), e1b = (int)(__float_as_uint(b1[j]) >> 23);
-        if (e0a != 0 && e0b != 0) k = max(k, e0a + e0b - 254);
-        if (e1a != 0 && e1b != 0) k = max(k, e1a + e1b - 254);
+        const int e0a = (int)((__float_as_uint(a0[j]) >> 23) & 0xff), e0b = (int)((__float_as_uint(b0[j]) >> 23) & 0xff);
+        const int e1a = (int)((__float_as_uint(a1[j]) >> 23) & 0xff), e1b = (int)((__float_as_uint(b1[j]) >> 23) & 0xff);
+        if (e0a != 0 && e0b != 0 && e0b != 255) k = max(k, e0a + e0b - 254);
+        if (e1a != 0 && e1b != 0 && e1b != 255) k = max(k, e1a + e1b - 254);
     }
     k = __reduce_max_sync(kFullMask, k);
     return k <= -100000 ? 0 : k;
 }
-// 2^k split into two representable factors (|k| clamped to 240)
-__device__ __forceinline__ void boost_factors(int k, float& f1, float& f2) {
-    k = max(-240, min(240, k));
-    const int k1 = k >> 1, k2 = k - k1;
-    f1 = __uint_as_float((unsigned)(127 + k1) << 23);
-    f2 = __uint_as_float((unsigned)(127 + k2) << 23);
+// product (a * w) * 2^k without leaving the float32 range on the way (|k| clamped to 240)
+struct Boost {
+    float f1, f2;
+    bool split;
+    __device__ __forceinline__ explicit Boost(int k) {
+        k = max(-240, min(240, k));
+        split = (k > 100) || (k < -100);
+        const int k1 = split ? (k >> 1) : k, k2 = k - k1;
+        f1 = __uint_as_float((unsigned)(127 + k1) << 23);
+        f2 = __uint_as_float((unsigned)(127 + k2) << 23);
+    }
+    __device__ __forceinline__ float mul(float a, float w) const { return split ? (a * f1) * (w * f2) : (a * f1) * w; }
+};
+
+// "lane per frame" sweeps over one staged row of C floats, skewed by r columns (r < 4) against bank conflicts
+template <typename F>
+__device__ __forceinline__ void row_sweep(float* row, int C, int r, F&& f) {
+    const int tail = C < 3 ? C : 3;
+    float* p = row + r;
+    const int n = C - tail;
+#pragma unroll 4
+    for (int j = 0; j < n; ++j) f(p[j]);
+    for (int q = 0; q < tail; ++q) {
+        int k = r + n + q;
+        if (k >= C) k -= C;
+        f(row[k]);
+    }
 }
 
 template <int NP>
@@ -141,9 +196,10 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
     const FastLayout lay = fast_layout(T, C, Lmax, G);
     float* stage = reinterpret_cast<float*>(smem + lay.stage);
     float* s_zz = reinterpret_cast<float*>(smem + lay.zz);
-    float* s_slz = reinterpret_cast<float*>(smem + lay.slz);
+    float* s_info = reinterpret_cast<float*>(smem + lay.info);
+    float* s_zero = reinterpret_cast<float*>(smem + lay.zero);
     const unsigned bar = smem_u32(smem + lay.mbar);
-    const int RS = lay.RS, Lp = lay.Lp;
+    const int RS = lay.RS, LS = lay.LS;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = warp >> 1, role = warp & 1;  // role 0: alpha (forward), 1: beta (backward)
@@ -154,28 +210,34 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
     const int b = b0 + s;
     const bool have_seq = s < nb;
 
-    // ---- group frame count, loads
+    // ---- group frame count, TMA loads (warp 0: one bulk copy per frame, spread over the lanes)
     __shared__ int s_tmax;
-    if (tid == 0) {
+    if (warp == 0) {
         int tm = 0;
-        for (int i = 0; i < nb; ++i) tm = max(tm, min(max(seq_len[b0 + i], 0), T));
-        s_tmax = tm;
+        for (int i = lane; i < nb; i += 32) tm = max(tm, min(max(seq_len[b0 + i], 0), T));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tm = max(tm, __shfl_xor_sync(kFullMask, tm, o));
+        if (lane == 0) {
+            s_tmax = tm;
+            s_zero[0] = 0.0f;
+        }
         if (bulk) {
-            mbar_init(bar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            if (tm > 0) {
-                const unsigned row_bytes = (unsigned)(G * C * 4);
-                mbar_expect_tx(bar, row_bytes * (unsigned)tm);
-                const float* src = logits + (size_t)b0 * C;
-                const unsigned dst = smem_u32(stage);
-                for (int t = 0; t < tm; ++t)
-                    bulk_load(dst + (unsigned)t * RS * 4, src + (size_t)t * B * C, row_bytes, bar);
+            const unsigned row_bytes = (unsigned)(G * C * 4);
+            if (lane == 0) {
+                mbar_init(bar, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                if (tm > 0) mbar_expect_tx(bar, row_bytes * (unsigned)tm);
             }
+            __syncwarp();
+            const float* src = logits + (size_t)b0 * C;
+            const unsigned dst = smem_u32(stage);
+            for (int t = lane; t < tm; t += 32)
+                bulk_load(dst + (unsigned)t * RS * 4, src + (size_t)t * B * C, row_bytes, bar);
         }
     }
 
     // ---- labels, feasibility (both warps of a pair compute the same answer)
-    int* s_lab = reinterpret_cast<int*>(smem + lay.lab) + s * Lp;
+    int* s_lab = reinterpret_cast<int*>(smem + lay.lab) + s * (Lmax + 1);
     int off = 0, L = 0, Tb = 0, bad = 0;
     if (have_seq) {
         off = label_offsets[b];
@@ -211,9 +273,11 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
     float* st_s = stage + s * C;  // this sequence's column block
     float* lat = reinterpret_cast<float*>(smem + lay.lat) + s * lay.lat_seq;
     float* zz = s_zz + s * T;
+    float* info = s_info + s * 8;
+    int* infoi = reinterpret_cast<int*>(info);
     const bool run = have_seq && !bad && Tb > 0;
     const int mid = (Tb + 1) >> 1;
-    const int rot = (RS & 1) ? 0 : 1;  // skew so that "lane per frame" accesses hit 32 distinct banks
+    const int skew = (C >= 8) ? (lane >> 3) : 0;  // row pitch is 4*odd words: lanes l, l+8, l+16, l+24 share a bank
     bool novalid = false;
 
     if (run) {
@@ -224,261 +288,279 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
             const int t = t0 + lane;
             if (t < r_hi) {
                 float* row = st_s + t * RS;
-                int k0 = rot ? (lane % C) : 0;
                 float m = -INFINITY;
-                int k = k0;
-#pragma unroll 4
-                for (int j = 0; j < C; ++j) {
-                    m = fmaxf(m, row[k]);
-                    k = (k + 1 == C) ? 0 : k + 1;
-                }
+                row_sweep(row, C, skew, [&](float& v) { m = fmaxf(m, v); });
                 const float ml = m * 1.4426950408889634f;
                 float z = 0.0f;
-                k = k0;
-#pragma unroll 4
-                for (int j = 0; j < C; ++j) {
-                    const float e = fast_ex2(fmaf(row[k], 1.4426950408889634f, -ml));
-                    row[k] = e;
+                row_sweep(row, C, skew, [&](float& v) {
+                    const float e = fast_ex2(fmaf(v, 1.4426950408889634f, -ml));
+                    v = e;
                     z += e;
-                    k = (k + 1 == C) ? 0 : k + 1;
-                }
+                });
                 zz[t] = z;
                 slz += logf(z);
             }
         }
         slz = warp_sum(slz);
-        if (lane == 0) s_slz[s * 8 + role] = slz;
+        if (lane == 0) info[role] = slz;
         pair_barrier(1 + s);  // both halves of the staged block now hold e = exp(x - max)
 
         // ================= pass 2: lattice chains =================
-        float* latB = lat;        // [t][i]   blank state 2i      (i = 0..L)
-        float* latL = lat + Lp;   // [t][i]   label state 2i+1    (i = 0..L-1); row stride 2*Lp
-        const int LS = 2 * Lp;
-        int* exr = reinterpret_cast<int*>(smem + lay.exr) + s * T;  // per-frame scale exponent of the stored half
+        // lattice row t: position 1+u holds state u (blank i -> 1+2i, label i -> 2+2i); positions 0 and HI,HI+1
+        // absorb the stores of lanes that own no state; position EX holds the scale exponent of the stored half.
+        // All chain accesses go through 32-bit shared addresses advanced by a constant per frame.
+        const unsigned a_st = smem_u32(st_s), a_lat = smem_u32(lat), a_zero = smem_u32(s_zero);
+        const unsigned RSB = (unsigned)RS * 4, LSB = (unsigned)LS * 4;
+        const int HI = lay.HI, EX = lay.EX;
         if (role == 0) {
             // pair i = lane*NP + j : (ab = alpha(blank before label i), al = alpha(label i))
             float ab[NP], al[NP], skp[NP];
-            int lb[NP], tdl[NP];
+            unsigned pe[NP], pes[NP], pl[NP];  // e_t(label i) address / stride (0: constant zero), lattice slot
+            int tdl[NP];
+            const float first = lane == 0 ? 0.0f : 1.0f;  // lane 0 has no left neighbour
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
                 const int i = lane * NP + j;
-                const int li = (i < L) ? s_lab[i] : blank;
-                lb[j] = li;
-                skp[j] = (i >= 1 && i < L && s_lab[i - 1] != li) ? 1.0f : 0.0f;
-                tdl[j] = (i < L) ? Tb - (L - i) : (i == L ? Tb : -1);  // label alive iff t <= tdl (i<L); blank alive iff t < tdl
+                const bool hasl = i < L;
+                const int li = hasl ? s_lab[i] : 0;
+                pe[j] = hasl ? a_st + 4u * li : a_zero;
+                pes[j] = hasl ? RSB : 0u;
+                skp[j] = (i >= 1 && hasl && s_lab[i - 1] != li) ? ((j == 0) ? first : 1.0f) : 0.0f;
+                tdl[j] = hasl ? Tb - (L - i) : (i == L ? Tb : -1);  // label alive iff t <= tdl; blank alive iff t < tdl
+                pl[j] = a_lat + 4u * (i <= L ? 1 + 2 * i : HI);
                 ab[j] = 0.0f; al[j] = 0.0f;
             }
+            unsigned pb = a_st + 4u * blank;
+            unsigned pex = a_lat + 4u * EX;
             float sc = 1.0f;
-            int Ea = 0, exn = 0;
-            float eb_n = st_s[blank], el_n[NP];
+            int Ea = 0;  // sum of biased exponents of the applied factors; true exponent = Ea - 127 * (frames done)
+            int ebias = 127;
+            float eb_n = lds(pb), el_n[NP];
 #pragma unroll
-            for (int j = 0; j < NP; ++j) el_n[j] = st_s[lb[j]];
-            // one forward step: alpha_t from alpha_{t-1}; stored value v_t = alpha_t * 2^-Ea
-            auto step = [&](int t) {
-                const float eb = eb_n;
-                float el[NP];
+            for (int j = 0; j < NP; ++j) el_n[j] = lds(pe[j]);
+            // one forward step: alpha_t from alpha_{t-1}; stored value v_t = alpha_t * 2^-(Ea - 127 (t+1))
+            auto step = [&](int t, auto masked) {
+                const float ebs = eb_n * sc;
+                float els[NP];
 #pragma unroll
-                for (int j = 0; j < NP; ++j) el[j] = el_n[j];
-                if (t + 1 < Tb) {
-                    const float* nrow = st_s + (t + 1) * RS;
-                    eb_n = nrow[blank];
+                for (int j = 0; j < NP; ++j) els[j] = el_n[j] * sc;
+                Ea += ebias;
+                pb += RSB;  // prefetch e_{t+1} (row Tb is never consumed; the read stays inside the CTA's shared memory)
+                eb_n = lds(pb);
 #pragma unroll
-                    for (int j = 0; j < NP; ++j) el_n[j] = nrow[lb[j]];
-                }
+                for (int j = 0; j < NP; ++j) { pe[j] += pes[j]; el_n[j] = lds(pe[j]); }
+                const float up = __shfl_up_sync(kFullMask, al[NP - 1], 1);
                 float nbv[NP], nlv[NP];
-                if (t == 0) {
 #pragma unroll
-                    for (int j = 0; j < NP; ++j) {
-                        const int i = lane * NP + j;
-                        nbv[j] = (i == 0) ? eb : 0.0f;
-                        nlv[j] = (i == 0) ? el[j] : 0.0f;
-                    }
-                } else {
-                    float up = __shfl_up_sync(kFullMask, al[NP - 1], 1);
-                    if (lane == 0) up = 0.0f;
-#pragma unroll
-                    for (int j = 0; j < NP; ++j) {
-                        const float pl = (j == 0) ? up : al[j - 1];
-                        nbv[j] = eb * (ab[j] + pl);
-                        nlv[j] = el[j] * (al[j] + ab[j] + skp[j] * pl);
-                    }
+                for (int j = 0; j < NP; ++j) {
+                    const float pv = (j == 0) ? up : al[j - 1];
+                    const float t1 = al[j] + ab[j];
+                    nbv[j] = ebs * ((j == 0) ? fmaf(pv, first, ab[j]) : (ab[j] + pv));
+                    nlv[j] = els[j] * fmaf(pv, skp[j], t1);
                 }
                 float mloc = 0.0f;
 #pragma unroll
                 for (int j = 0; j < NP; ++j) {
-                    const int i = lane * NP + j;
-                    ab[j] = (t < tdl[j]) ? nbv[j] * sc : 0.0f;
-                    al[j] = (t <= tdl[j] && i < L) ? nlv[j] * sc : 0.0f;
+                    if constexpr (decltype(masked)::value) {
+                        ab[j] = (t < tdl[j]) ? nbv[j] : 0.0f;
+                        al[j] = (t <= tdl[j]) ? nlv[j] : 0.0f;
+                    } else {
+                        ab[j] = nbv[j];
+                        al[j] = nlv[j];
+                    }
                     mloc = fmaxf(mloc, fmaxf(ab[j], al[j]));
                 }
-                Ea += exn;
-                sc = pow2_rescale(mloc, exn);
+                sc = pow2_rescale(mloc, ebias);
             };
-            for (int t = 0; t < mid; ++t) {
-                step(t);
-                float* rb = latB + t * LS;
-                float* rl = latL + t * LS;
+            auto store = [&]() {
+#pragma unroll
+                for (int j = 0; j < NP; ++j) { sts(pl[j], ab[j]); sts4(pl[j], al[j]); pl[j] += LSB; }
+                stsi(pex, Ea);
+                pex += LSB;
+            };
+            // t = 0: alpha_0(blank 0) = e_0(blank), alpha_0(label 0) = e_0(label 0)
+            {
+                const float eb0 = eb_n;
+                pb += RSB;
+                eb_n = lds(pb);
 #pragma unroll
                 for (int j = 0; j < NP; ++j) {
                     const int i = lane * NP + j;
-                    if (i <= L) rb[i] = ab[j];
-                    if (i < L) rl[i] = al[j];
+                    const float el0 = el_n[j];
+                    pe[j] += pes[j];
+                    el_n[j] = lds(pe[j]);
+                    ab[j] = (i == 0 && 0 < tdl[j]) ? eb0 : 0.0f;
+                    al[j] = (i == 0 && 0 <= tdl[j] && L > 0) ? el0 : 0.0f;
                 }
-                if (lane == 0) exr[t] = Ea;
+                float mloc = 0.0f;
+#pragma unroll
+                for (int j = 0; j < NP; ++j) mloc = fmaxf(mloc, fmaxf(ab[j], al[j]));
+                Ea += ebias;
+                sc = pow2_rescale(mloc, ebias);
             }
+            const int tm0 = max(1, Tb - L);  // states start dying (cannot reach the end any more) at t = Tb - L
+            int t = 1;
+            store();  // mid >= 1
+            for (; t < min(mid, tm0); ++t) { step(t, std::false_type()); store(); }
+            for (; t < mid; ++t) { step(t, std::true_type()); store(); }
             pair_barrier(1 + s);  // partner has stored beta_t (and its exponents) for t >= mid
             int Pt = 0;
-            for (int t = mid; t < Tb; ++t) {
-                step(t);
-                float* rb = latB + t * LS;
-                float* rl = latL + t * LS;
+            bool first_consume = true;
+            auto consume = [&]() {
                 float wb[NP], wl[NP];
 #pragma unroll
-                for (int j = 0; j < NP; ++j) {
-                    const int i = lane * NP + j;
-                    wb[j] = (i <= L) ? rb[i] : 0.0f;
-                    wl[j] = (i < L) ? rl[i] : 0.0f;
-                }
-                const int Es = Ea + exr[t];
-                if (t == mid) Pt = Es + prod_exponent<NP>(ab, al, wb, wl);
-                float f1, f2;
-                boost_factors(Es - Pt, f1, f2);
+                for (int j = 0; j < NP; ++j) { wb[j] = lds(pl[j]); wl[j] = lds4(pl[j]); }
+                const int Es = Ea + ldsi(pex);
+                if (first_consume) { Pt = Es + prod_exponent<NP>(ab, al, wb, wl); first_consume = false; }
+                const Boost bo(Es - Pt);
 #pragma unroll
                 for (int j = 0; j < NP; ++j) {
-                    const int i = lane * NP + j;
-                    if (i <= L) rb[i] = (ab[j] * f1) * (wb[j] * f2);
-                    if (i < L) rl[i] = (al[j] * f1) * (wl[j] * f2);
+                    sts(pl[j], bo.mul(ab[j], wb[j]));
+                    sts4(pl[j], bo.mul(al[j], wl[j]));
+                    pl[j] += LSB;
                 }
-            }
+                pex += LSB;
+            };
+            for (; t < min(Tb, tm0); ++t) { step(t, std::false_type()); consume(); }
+            for (; t < Tb; ++t) { step(t, std::true_type()); consume(); }
             // p(z|x) in e-units: alpha(2L) + alpha(2L-1) at the last frame
             float up = __shfl_up_sync(kFullMask, al[NP - 1], 1);
             if (lane == 0) up = 0.0f;
-            float pe = 0.0f;
+            float pev = 0.0f;
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
                 const int i = lane * NP + j;
-                const float pl = (j == 0) ? up : al[j - 1];
-                if (i == L) pe = ab[j] + pl;
+                const float pv = (j == 0) ? up : al[j - 1];
+                if (i == L) pev = ab[j] + pv;
             }
-            pe = __shfl_sync(kFullMask, pe, L / NP);
+            pev = __shfl_sync(kFullMask, pev, L / NP);
             pair_barrier(1 + s);  // both chains done: products complete, partner's sum(log Z) visible
-            novalid = !(pe > 0.0f);
+            novalid = !(pev > 0.0f);
             if (lane == 0) {
-                const float sumlz = s_slz[s * 8] + s_slz[s * 8 + 1];
-                const float lp = novalid ? -INFINITY : (logf(pe) + (float)Ea * 0.6931471805599453f - sumlz);
+                const float sumlz = info[0] + info[1];
+                const int Etrue = Ea - 127 * Tb;  // Tb factors were applied (the first one is 2^0)
+                const float lp = novalid ? -INFINITY : (logf(pev) + (float)Etrue * 0.6931471805599453f - sumlz);
                 loss[b] = -lp;
                 status[b] = novalid ? kCtcRedo : 0;  // an all-zero lattice may be underflow: the exact kernel decides
-                s_slz[s * 8 + 2] = novalid ? 1.0f : 0.0f;
-                s_slz[s * 8 + 3] = novalid ? 0.0f : log2f(pe);
-                reinterpret_cast<int*>(s_slz)[s * 8 + 4] = Ea;
-                reinterpret_cast<int*>(s_slz)[s * 8 + 5] = Pt;
+                info[2] = novalid ? 1.0f : 0.0f;
+                info[3] = novalid ? 0.0f : log2f(pev);
+                infoi[4] = Ea;
+                infoi[5] = Pt;
             }
         } else {
             // pair i = lane*NP + j : (bl = beta(label i-1), bb = beta(blank after label i-1))
-            float bb[NP], bl[NP], skp[NP];
-            int lb[NP], tbl[NP], tbb[NP];
+            float bb[NP], bl[NP], skp[NP], c1[NP];
+            unsigned pe[NP], pes[NP], pl[NP];
+            int tbl[NP], tbb[NP];
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
                 const int i = lane * NP + j;
-                const int li = (i >= 1 && i <= L) ? s_lab[i - 1] : blank;
-                lb[j] = li;
-                skp[j] = (i >= 1 && i < L && s_lab[i] != li) ? 1.0f : 0.0f;
-                tbl[j] = (i >= 1 && i <= L) ? i - 1 : 0x7fffffff;  // label i-1 alive iff t >= i-1
-                tbb[j] = (i <= L) ? i : 0x7fffffff;                // blank i alive iff t >= i
+                const bool hasl = i >= 1 && i <= L;
+                const int li = hasl ? s_lab[i - 1] : 0;
+                pe[j] = hasl ? a_st + (unsigned)(Tb - 1) * RSB + 4u * li : a_zero;
+                pes[j] = hasl ? RSB : 0u;
+                skp[j] = (hasl && i < L && s_lab[i] != li) ? 1.0f : 0.0f;
+                c1[j] = hasl ? 1.0f : 0.0f;
+                tbl[j] = hasl ? i - 1 : 0x7fffffff;   // label i-1 alive iff t >= i-1
+                tbb[j] = (i <= L) ? i : 0x7fffffff;   // blank i alive iff t >= i
+                pl[j] = a_lat + (unsigned)(Tb - 1) * LSB + 4u * (i <= L ? 2 * i : HI);
                 bb[j] = 0.0f; bl[j] = 0.0f;
             }
+            unsigned pb = a_st + (unsigned)(Tb - 1) * RSB + 4u * blank;
+            unsigned pex = a_lat + (unsigned)(Tb - 1) * LSB + 4u * EX;
             float sc = 1.0f;
-            int Eb = 0, exn = 0;
-            float eb_n = 0.0f, el_n[NP];
+            int Eb = 0, ebias = 127;
+            float eb_n = lds(pb), el_n[NP];  // e_{Tb-1}: consumed by the step that produces beta_{Tb-2}
 #pragma unroll
-            for (int j = 0; j < NP; ++j) el_n[j] = 0.0f;
-            // one backward step: beta_t from beta_{t+1} and e_{t+1}; stored value w_t = beta_t * 2^-Eb
-            auto step = [&](int t) {
-                const float eb = eb_n;
-                float el[NP];
+            for (int j = 0; j < NP; ++j) el_n[j] = lds(pe[j]);
+            // one backward step: beta_t from beta_{t+1} and e_{t+1}; stored value w_t = beta_t * 2^-(Eb - 127 (Tb-t))
+            auto step = [&](int t, auto masked) {
+                const float ebs = eb_n * sc;
+                float els[NP];
 #pragma unroll
-                for (int j = 0; j < NP; ++j) el[j] = el_n[j];
-                {   // e_t, needed by the NEXT step (t-1)
-                    const float* nrow = st_s + t * RS;
-                    eb_n = nrow[blank];
+                for (int j = 0; j < NP; ++j) els[j] = el_n[j] * sc;
+                Eb += ebias;
+                if (t > 0) {  // prefetch e_t for the next step
+                    pb -= RSB;
+                    eb_n = lds(pb);
 #pragma unroll
-                    for (int j = 0; j < NP; ++j) el_n[j] = nrow[lb[j]];
+                    for (int j = 0; j < NP; ++j) { pe[j] -= pes[j]; el_n[j] = lds(pe[j]); }
                 }
-                float nbb[NP], nbl[NP];
-                if (t == Tb - 1) {
+                float wb[NP], wl[NP];
 #pragma unroll
-                    for (int j = 0; j < NP; ++j) {
-                        const int i = lane * NP + j;
-                        nbb[j] = (i == L) ? 1.0f : 0.0f;
-                        nbl[j] = (i == L && L >= 1) ? 1.0f : 0.0f;
-                    }
-                } else {
-                    float wb[NP], wl[NP];
-#pragma unroll
-                    for (int j = 0; j < NP; ++j) {
-                        wb[j] = bb[j] * eb;
-                        wl[j] = bl[j] * el[j];
-                    }
-                    float dn = __shfl_down_sync(kFullMask, wl[0], 1);
-                    if (lane == 31) dn = 0.0f;
-#pragma unroll
-                    for (int j = 0; j < NP; ++j) {
-                        const float nx = (j == NP - 1) ? dn : wl[j + 1];
-                        nbb[j] = wb[j] + nx;
-                        nbl[j] = wl[j] + wb[j] + skp[j] * nx;
-                    }
+                for (int j = 0; j < NP; ++j) {
+                    wb[j] = bb[j] * ebs;
+                    wl[j] = bl[j] * els[j];
                 }
+                float dn = __shfl_down_sync(kFullMask, wl[0], 1);
+                if (lane == 31) dn = 0.0f;
                 float mloc = 0.0f;
 #pragma unroll
                 for (int j = 0; j < NP; ++j) {
-                    bb[j] = (t >= tbb[j]) ? nbb[j] * sc : 0.0f;
-                    bl[j] = (t >= tbl[j]) ? nbl[j] * sc : 0.0f;
+                    const float nx = (j == NP - 1) ? dn : wl[j + 1];
+                    const float nbb = wb[j] + nx;
+                    const float nbl = fmaf(skp[j], nx, fmaf(c1[j], wb[j], wl[j]));
+                    if constexpr (decltype(masked)::value) {
+                        bb[j] = (t >= tbb[j]) ? nbb : 0.0f;
+                        bl[j] = (t >= tbl[j]) ? nbl : 0.0f;
+                    } else {
+                        bb[j] = nbb;
+                        bl[j] = nbl;
+                    }
                     mloc = fmaxf(mloc, fmaxf(bb[j], bl[j]));
                 }
-                Eb += exn;
-                sc = pow2_rescale(mloc, exn);
+                sc = pow2_rescale(mloc, ebias);
             };
-            for (int t = Tb - 1; t >= mid; --t) {
-                step(t);
-                float* rb = latB + t * LS;
-                float* rl = latL + t * LS;
+            auto store = [&]() {
 #pragma unroll
-                for (int j = 0; j < NP; ++j) {
-                    const int i = lane * NP + j;
-                    if (i <= L) rb[i] = bb[j];
-                    if (i >= 1 && i <= L) rl[i - 1] = bl[j];
-                }
-                if (lane == 0) exr[t] = Eb;
+                for (int j = 0; j < NP; ++j) { sts(pl[j], bl[j]); sts4(pl[j], bb[j]); pl[j] -= LSB; }
+                stsi(pex, Eb);
+                pex -= LSB;
+            };
+            // t = Tb-1: beta(last blank) = beta(last label) = 1
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                const int i = lane * NP + j;
+                bb[j] = (i == L && Tb - 1 >= tbb[j]) ? 1.0f : 0.0f;
+                bl[j] = (i == L && L >= 1 && Tb - 1 >= tbl[j]) ? 1.0f : 0.0f;
             }
-            pair_barrier(1 + s);  // partner has stored alpha_t (and its exponents) for t < mid
+            Eb += ebias;  // the factor 2^0 of the first frame
             int Pt = 0;
-            for (int t = mid - 1; t >= 0; --t) {
-                step(t);
-                float* rb = latB + t * LS;
-                float* rl = latL + t * LS;
-                float vb[NP], vl[NP];
+            bool first_consume = true;
+            auto consume = [&]() {
+                float vl[NP], vb[NP];
+#pragma unroll
+                for (int j = 0; j < NP; ++j) { vl[j] = lds(pl[j]); vb[j] = lds4(pl[j]); }
+                const int Es = Eb + ldsi(pex);
+                if (first_consume) { Pt = Es + prod_exponent<NP>(bb, bl, vb, vl); first_consume = false; }
+                const Boost bo(Es - Pt);
 #pragma unroll
                 for (int j = 0; j < NP; ++j) {
-                    const int i = lane * NP + j;
-                    vb[j] = (i <= L) ? rb[i] : 0.0f;
-                    vl[j] = (i >= 1 && i <= L) ? rl[i - 1] : 0.0f;
+                    sts(pl[j], bo.mul(bl[j], vl[j]));
+                    sts4(pl[j], bo.mul(bb[j], vb[j]));
+                    pl[j] -= LSB;
                 }
-                const int Es = Eb + exr[t];
-                if (t == mid - 1) Pt = Es + prod_exponent<NP>(bb, bl, vb, vl);
-                float f1, f2;
-                boost_factors(Es - Pt, f1, f2);
-#pragma unroll
-                for (int j = 0; j < NP; ++j) {
-                    const int i = lane * NP + j;
-                    if (i <= L) rb[i] = (bb[j] * f1) * (vb[j] * f2);
-                    if (i >= 1 && i <= L) rl[i - 1] = (bl[j] * f1) * (vl[j] * f2);
-                }
+                pex -= LSB;
+            };
+            int t = Tb - 1;
+            if (t >= mid) {
+                store();
+                --t;
+                for (; t >= max(mid, L); --t) { step(t, std::false_type()); store(); }
+                for (; t >= mid; --t) { step(t, std::true_type()); store(); }
+                pair_barrier(1 + s);  // partner has stored alpha_t (and its exponents) for t < mid
+            } else {
+                pair_barrier(1 + s);  // Tb == 1: the only frame belongs to the partner's half
+                consume();
+                --t;
             }
-            if (lane == 0) reinterpret_cast<int*>(s_slz)[s * 8 + 6] = Pt;
+            for (; t >= L; --t) { step(t, std::false_type()); consume(); }
+            for (; t >= 0; --t) { step(t, std::true_type()); consume(); }
+            if (lane == 0) infoi[6] = Pt;
             pair_barrier(1 + s);
         }
         pair_barrier(1 + s);  // flags / log2 p written by the alpha warp
-        novalid = s_slz[s * 8 + 2] != 0.0f;
+        novalid = info[2] != 0.0f;
     } else if (have_seq && role == 0 && lane == 0) {
         // TF: zero-length sequence -> loss 0, grad 0.  Infeasible / invalid -> flagged, zero outputs.
         loss[b] = 0.0f;
@@ -486,18 +568,15 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
     }
 
     // ================= pass 3: posterior scatter + gradient rows, lane per frame =================
-    // Every row of products must sum to the same p(z|x) the alpha chain ended with; a row that does not has
-    // lost probability mass to float32 underflow somewhere in the chains (states more than 2^-126 below the
-    // warp-wide maximum are flushed).  Such sequences are handed to the exact log-domain kernel (kCtcRedo).
     if (have_seq) {
-        const int Tr = run ? Tb : 0;
-        const int r_lo = role == 0 ? 0 : mid, r_hi = role == 0 ? mid : Tr;
-        const float* latB = lat;
-        const float* latL = lat + Lp;
-        const int LS = 2 * Lp;
-        const float l2pe = s_slz[s * 8 + 3];
-        const float dexp = (float)(reinterpret_cast<const int*>(s_slz)[s * 8 + (role == 0 ? 6 : 5)] -
-                                   reinterpret_cast<const int*>(s_slz)[s * 8 + 4]);
+        const int Tr = run ? Tb : 0, midr = run ? mid : 0;
+        const int r_lo = role == 0 ? 0 : midr, r_hi = role == 0 ? midr : Tr;
+        // Rows below mid carry Pt of the beta warp (it formed those products), rows above Pt of the alpha warp.
+        // All exponents are sums of biased exponents: a row's products carry 127*(Tb+1), the alpha chain 127*Tb.
+        const float l2pe = info[3];
+        const float dexp = (float)(infoi[role == 0 ? 6 : 5] - infoi[4] - 127);
+        // rounding noise of the two chains grows with T (~1e-7 per frame); anything above it is lost mass
+        const float thr = 1.0e-5f + 4.0e-7f * (float)T;
         bool lost = false;
         for (int t0 = r_lo; t0 < r_hi; t0 += 32) {
             const int t = t0 + lane;
@@ -505,36 +584,24 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 float* row = st_s + t * RS;
                 const float z = zz[t];
                 if (!novalid) {
-                    const float* rb = latB + t * LS;
-                    const float* rl = latL + t * LS;
+                    const float* rp = lat + (size_t)t * LS + 1;  // rp[u] = product at state u
                     float S = 0.0f, Bs = 0.0f;
-                    int i = lane % (L + 1);
-                    for (int j = 0; j <= L; ++j) {
-                        const float pb = rb[i];
-                        Bs += pb;
-                        if (i < L) S += rl[i];
-                        i = (i == L) ? 0 : i + 1;
+                    for (int i = 0; i < L; ++i) {
+                        Bs += rp[2 * i];
+                        S += rp[2 * i + 1];
                     }
+                    Bs += rp[2 * L];
                     S += Bs;
-                    lost = lost || !(fabsf(log2f(S) - l2pe + dexp) < 9.765625e-4f);
-                    if (!grad) continue;
-                    const float r = (S > 0.0f) ? z / S : 0.0f;
-                    row[blank] -= Bs * r;
-                    if (L > 0) {
-                        i = lane % L;
-                        for (int j = 0; j < L; ++j) {
-                            row[s_lab[i]] -= rl[i] * r;
-                            i = (i + 1 == L) ? 0 : i + 1;
-                        }
+                    lost = lost || !(fabsf(log2f(S) - l2pe + dexp) < thr);
+                    if (grad) {
+                        const float r = (S > 0.0f) ? z / S : 0.0f;
+                        row[blank] -= Bs * r;
+                        for (int i = 0; i < L; ++i) row[s_lab[i]] -= rp[2 * i + 1] * r;
                     }
                 }
-                if (!grad) continue;
-                const float gs = grad_scale / z;
-                int k = rot ? (lane % C) : 0;
-#pragma unroll 4
-                for (int j = 0; j < C; ++j) {
-                    row[k] *= gs;
-                    k = (k + 1 == C) ? 0 : k + 1;
+                if (grad) {
+                    const float gs = grad_scale / z;
+                    row_sweep(row, C, skew, [&](float& v) { v *= gs; });
                 }
             }
         }
@@ -542,29 +609,21 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
     }
     if (!grad) return;
     if (have_seq) {
+        // frames past the sequence end: zero gradient (both warps, lane per class: conflict-free)
         const int Tr = run ? Tb : 0;
-        // frames past the sequence end: zero gradient
-        const int zr = T - Tr;
-        for (int t0 = Tr + role * ((zr + 1) >> 1), te = role == 0 ? Tr + ((zr + 1) >> 1) : T; t0 < te; t0 += 32) {
-            const int t = t0 + lane;
-            if (t < te) {
-                float* row = st_s + t * RS;
-                int k = rot ? (lane % C) : 0;
-                for (int j = 0; j < C; ++j) {
-                    row[k] = 0.0f;
-                    k = (k + 1 == C) ? 0 : k + 1;
-                }
-            }
+        for (int t = Tr + role; t < T; t += 2) {
+            float* row = st_s + t * RS;
+            for (int k = lane; k < C; k += 32) row[k] = 0.0f;
         }
     }
     if (bulk) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
             const unsigned row_bytes = (unsigned)(G * C * 4);
             float* dst = grad + (size_t)b0 * C;
             const unsigned src = smem_u32(stage);
-            for (int t = 0; t < T; ++t) bulk_store(dst + (size_t)t * B * C, src + (unsigned)t * RS * 4, row_bytes);
+            for (int t = lane; t < T; t += 32) bulk_store(dst + (size_t)t * B * C, src + (unsigned)t * RS * 4, row_bytes);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
