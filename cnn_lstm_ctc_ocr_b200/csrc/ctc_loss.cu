@@ -283,7 +283,14 @@ extern "C" int ocr_ctc_loss_set_path(int path) {
     return OCR_OK;
 }
 
-struct FastPlan { int G, NP, bulk, smem; };
+// Tuning aid: buffer of clock64() stamps, kCtcTimelineSlots per warp of every CTA of the fast kernel
+// (NULL switches it off).  The caller sizes it for ceil(B/G) CTAs x 2G warps.
+extern "C" int ocr_debug_ctc_timeline(long long* device_buffer) {
+    OCR_CHECK_CUDA(cudaMemcpyToSymbol(g_ctc_timeline, &device_buffer, sizeof(device_buffer)));
+    return OCR_OK;
+}
+
+struct FastPlan { int G, NP, CR, bulk, smem; };
 
 // Chooses the group size G of the fast kernel: the shared-memory footprint is ~G*(T*C + 2*T*(Lmax+1))*4
 // bytes; prefer TMA-eligible groups (G*C*4 a multiple of 16 bytes, 16-byte aligned tensors) and as many
@@ -291,10 +298,12 @@ struct FastPlan { int G, NP, bulk, smem; };
 static bool plan_fast(const void* logits, const void* grad, int T, int B, int C, int Lmax, FastPlan* out) {
     if (Lmax + 1 > 128 || T < 1) return false;
     const int NP = (Lmax + 1 <= 32) ? 1 : ((Lmax + 1 <= 64) ? 2 : 4);
+    const int CR = (C <= 64) ? 64 : ((C <= 128) ? 128 : 0);  // softmax rows held in registers up to 128 classes
+    const int maxG = (CR == 128) ? 4 : kFastMaxG;              // 128-register rows: 256-thread CTAs
     const bool ptr_ok = ((uintptr_t)logits % 16 == 0) && (grad == nullptr || (uintptr_t)grad % 16 == 0) &&
                         ((long long)B * C) % 4 == 0 && g_ctc_path != 2;  // path 2: LSU loads/stores
     int best = -1, best_score = -1, best_smem = 0, best_bulk = 0;
-    for (int G = 1; G <= kFastMaxG; G *= 2) {
+    for (int G = 1; G <= maxG; G *= 2) {
         const FastLayout lay = fast_layout(T, C, Lmax, G);
         if (lay.total > kMaxDynSmem) break;
         const int bulk = ptr_ok && (G * C) % 4 == 0;
@@ -307,7 +316,7 @@ static bool plan_fast(const void* logits, const void* grad, int T, int B, int C,
         if (score > best_score) { best_score = score; best = G; best_smem = lay.total; best_bulk = bulk; }
     }
     if (best < 0) return false;
-    out->G = best; out->NP = NP; out->bulk = best_bulk; out->smem = best_smem;
+    out->G = best; out->NP = NP; out->CR = CR; out->bulk = best_bulk; out->smem = best_smem;
     return true;
 }
 
@@ -328,7 +337,7 @@ extern "C" int ocr_ctc_loss_workspace_bytes(int T, int B, int C, int max_label_l
     return OCR_OK;
 }
 
-template <int NP>
+template <int NP, int CR>
 static int launch_fast(const FastPlan& fp, const float* logits, int T, int B, int C, const int32_t* labels,
                        const int32_t* label_offsets, const int32_t* seq_len, int Lmax, float* loss, float* grad,
                        int32_t* status, float grad_scale, cudaStream_t st)
@@ -337,11 +346,11 @@ static int launch_fast(const FastPlan& fp, const float* logits, int T, int B, in
     int dev = 0;
     OCR_CHECK_CUDA(cudaGetDevice(&dev));
     if (configured != dev) {
-        OCR_CHECK_CUDA(cudaFuncSetAttribute(ctc_loss_fast_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        OCR_CHECK_CUDA(cudaFuncSetAttribute(ctc_loss_fast_kernel<NP, CR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
         configured = dev;
     }
     const int grid = (B + fp.G - 1) / fp.G;
-    ctc_loss_fast_kernel<NP><<<grid, 64 * fp.G, fp.smem, st>>>(logits, T, B, C, labels, label_offsets, seq_len, Lmax, fp.G,
+    ctc_loss_fast_kernel<NP, CR><<<grid, 64 * fp.G, fp.smem, st>>>(logits, T, B, C, labels, label_offsets, seq_len, Lmax, fp.G,
                                                              fp.bulk, loss, grad, status, grad_scale);
     OCR_CHECK_LAUNCH();
     return OCR_OK;
@@ -395,13 +404,14 @@ extern "C" int ocr_ctc_loss(const float* logits, int T, int B, int C, const int3
     int32_t* st_buf = status ? status : static_cast<int32_t*>(workspace);
     float* lattice_ws = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + ws_status_bytes(B));
     FastPlan fp;
-    if (g_ctc_path != 1 && plan_fast(logits, grad, T, B, C, max_label_len, &fp)) {
+    // the fast kernel stages y * grad_scale and runs its lattice on it: it needs a positive scale
+    if (g_ctc_path != 1 && grad_scale > 0.0f && plan_fast(logits, grad, T, B, C, max_label_len, &fp)) {
         int rc;
-        switch (fp.NP) {
-            case 1: rc = launch_fast<1>(fp, logits, T, B, C, labels, label_offsets, seq_len, max_label_len, loss, grad, st_buf, grad_scale, st); break;
-            case 2: rc = launch_fast<2>(fp, logits, T, B, C, labels, label_offsets, seq_len, max_label_len, loss, grad, st_buf, grad_scale, st); break;
-            default: rc = launch_fast<4>(fp, logits, T, B, C, labels, label_offsets, seq_len, max_label_len, loss, grad, st_buf, grad_scale, st); break;
-        }
+#define OCR_FAST(NP_, CR_) rc = launch_fast<NP_, CR_>(fp, logits, T, B, C, labels, label_offsets, seq_len, max_label_len, loss, grad, st_buf, grad_scale, st)
+        if (fp.CR == 64) { if (fp.NP == 1) OCR_FAST(1, 64); else if (fp.NP == 2) OCR_FAST(2, 64); else OCR_FAST(4, 64); }
+        else if (fp.CR == 128) { if (fp.NP == 1) OCR_FAST(1, 128); else if (fp.NP == 2) OCR_FAST(2, 128); else OCR_FAST(4, 128); }
+        else { if (fp.NP == 1) OCR_FAST(1, 0); else if (fp.NP == 2) OCR_FAST(2, 0); else OCR_FAST(4, 0); }
+#undef OCR_FAST
         if (rc != OCR_OK || g_ctc_path == 3) return rc;  // path 3 (diagnostics): leave kCtcRedo flags in status
         // sequences whose lattice left the float32 range of the fast kernel (status kCtcRedo): exact kernel
         return launch_general(logits, T, B, C, labels, label_offsets, seq_len, max_label_len, loss, grad, st_buf,

@@ -10,12 +10,12 @@
 //     (cp.async.bulk -> shared memory, completion on an mbarrier) into a [T][G][C] staging
 //     block; the finished gradient leaves the same block through cp.async.bulk stores, so
 //     the LSU never issues a global access on the aligned path;
-//   * two warps per sequence.  Softmax statistics are computed "lane per frame" (each lane
-//     walks one logit row in shared memory; the row pitch is 4*odd words and lanes are skewed by
-//     lane/8 columns, so the 32 lanes always hit 32 distinct banks), leaving e = exp(x - max) in
-//     place and Z = sum(e);
-//   * the lattice runs in the LINEAR domain on the un-normalised e (the recursion is linear, the
-//     row factors Z cancel in the posterior), register resident: lane i holds the state pair
+//   * two warps per sequence.  The softmax is computed "lane per frame": each lane pulls one logit
+//     row out of shared memory into registers (the row pitch is 4*odd words and lanes are skewed by
+//     lane/8 columns, so the 32 lanes always hit 32 distinct banks), reduces max and sum(exp) there
+//     and writes y * grad_scale back -- one read and one write of the staged block, which is already
+//     the gradient of every class the label does not contain;
+//   * the lattice runs in the LINEAR domain on y, register resident: lane i holds the state pair
 //     (blank before label i, label i), one shuffle per frame carries the neighbour state,
 //     the chain per frame is shuffle + 3 dependent FP ops.  Dynamic range is handled with an
 //     exact power-of-two rescale every frame (warp max by one redux.sync, applied one frame
@@ -25,8 +25,8 @@
 //     each stores its half of the lattice, then over the other half multiplies its live values
 //     into what the partner stored, so shared memory holds ONE lattice of products
 //     alpha_t(u)*beta_t(u) (brought back to O(1) by an exact power of two, see prod_exponent);
-//   * posterior = product / (row sum of products), scattered "lane per frame" into the staged
-//     row, duplicates handled by plain sequential order, then grad = (e - Z*occ) * (grad_scale / Z);
+//   * posterior = product / (row sum of products), subtracted "lane per frame" from the label and
+//     blank columns of the staged row (duplicates handled by plain sequential order);
 //   * every row of products must sum to the p(z|x) the alpha chain ended with; a sequence where it
 //     does not has lost probability mass to float32 underflow (states more than 2^-126 below the
 //     warp-wide maximum) and is handed to the exact log-domain kernel (status kCtcRedo).
@@ -42,12 +42,20 @@ namespace ocr {
 constexpr int kFastMaxG = 8;
 constexpr int kCtcRedo = 100;  // internal status: recompute this sequence with the exact log-domain kernel
 
+// Optional phase timeline for tuning (ocr_debug_ctc_timeline): per warp, clock64() at up to 12 phase boundaries.
+__device__ long long* g_ctc_timeline = nullptr;
+constexpr int kCtcTimelineSlots = 12;
+__device__ __forceinline__ void ctc_mark(long long* tl, int slot) {
+    if (tl != nullptr && (threadIdx.x & 31) == 0)
+        tl[((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kCtcTimelineSlots + slot] = clock64();
+}
+
 struct FastLayout {
     int RS;        // floats between consecutive frames in the staging block (4 * odd)
     int LS;        // floats per lattice row: [trash][state 0 .. 2*Lmax][pad][trash pair][exponent]  (2 * odd)
     int EX;        // index of the exponent slot inside a lattice row
     int HI;        // index of the high trash pair
-    int stage, lat, zz, lab, info, zero, mbar, total;  // byte offsets
+    int stage, lat, lab, info, zero, mbar, total;  // byte offsets
     int lat_seq;   // floats per sequence in the lattice block
 };
 
@@ -63,12 +71,11 @@ __host__ __device__ inline FastLayout fast_layout(int T, int C, int Lmax, int G)
     f.HI = 2 * Lmax + 2;
     f.EX = 2 * Lmax + 4;
     f.lat_seq = T * f.LS;
-    int o = 0;
+    int o = f.RS * 4;  // one pad row: the beta chain prefetches e_{t-1} unconditionally
     f.stage = o; o += T * f.RS * 4;
-    f.lat = o;   o += G * f.lat_seq * 4;
-    f.zz = o;    o += G * T * 4;
+    f.lat = o;   o += (G * f.lat_seq + f.LS) * 4;  // + one row: the alpha warp's look-ahead read past the last frame
     f.lab = o;   o += G * (Lmax + 1) * 4;
-    f.info = o;  o += G * 8 * 4;  // per sequence: sum(log Z) x2, no-valid flag, log2(pe), Ea, Pt(alpha), Pt(beta), spare
+    f.info = o;  o += G * 8 * 4;  // per sequence: [2] no-valid flag, [3] log2(pe), [4] Ea, [5] Pt(alpha), [6] Pt(beta)
     o = (o + 15) & ~15;
     f.zero = o;  o += 16;
     f.mbar = o;  o += 16;
@@ -127,14 +134,24 @@ __device__ __forceinline__ void sts(unsigned a, float v) { asm volatile("st.shar
 __device__ __forceinline__ void sts4(unsigned a, float v) { asm volatile("st.shared.f32 [%0+4], %1;" ::"r"(a), "f"(v)); }
 __device__ __forceinline__ void stsi(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v)); }
 
-// Exact power-of-two rescale.  m = warp-wide maximum (>= 0) of the live lattice values; returns 2^(127-e)
-// with e the biased exponent of m, so that m * scale lies in [1,2); ebias = e (the caller sums e - 127).
-// m == 0 gives the finite factor 2^127, which is harmless on an all-zero lattice.
-__device__ __forceinline__ float pow2_rescale(float mloc, int& ebias) {
-    const unsigned mb = __reduce_max_sync(kFullMask, __float_as_uint(mloc));
-    ebias = (int)(mb >> 23);
-    return __uint_as_float(0x7F000000u - (mb & 0x7F800000u));
-}
+// Exact power-of-two rescaling of a lattice chain.  The stored values are v_t = value_t * 2^-E_t.  The warp-wide
+// maximum of frame t-1 (one redux.sync, issued a whole frame before it is read, so it never sits on the
+// dependency chain) and the factor already applied to frame t fix the factor of frame t+1:
+//   c_{t+1} = x_{t-1} - c_t   (x = exponent of the maximum)   =>   x_{t+1} = growth_t + growth_{t+1}  (deadbeat).
+// Factors are exact powers of two and E is an integer, so the scaling adds no rounding error.
+struct Rescale {
+    float sc = 1.0f;             // factor for the frame being computed (2^-c)
+    int c = 0;                   // its exponent
+    int E = 0;                   // sum of the exponents applied so far: value = stored * 2^E
+    unsigned mb = 0x3F800000u;   // bits of the previous frame's maximum
+    __device__ __forceinline__ void next(float mloc) {
+        E += c;
+        const int x = (int)(mb >> 23) - 127;
+        c = max(-126, min(126, x - c));
+        sc = __uint_as_float((unsigned)(127 - c) << 23);
+        mb = __reduce_max_sync(kFullMask, __float_as_uint(mloc));
+    }
+};
 
 // The stored lattice halves are scaled: alpha_t = v_t * 2^Ea_t, beta_t = w_t * 2^Eb_t with max(v), max(w) ~ 1,
 // but the two maxima usually sit on different states, so v*w at the states that matter can be far below the
@@ -155,37 +172,62 @@ __device__ __forceinline__ int prod_exponent(const float (&a0)[NP], const float 
     k = __reduce_max_sync(kFullMask, k);
     return k <= -100000 ? 0 : k;
 }
-// product (a * w) * 2^k without leaving the float32 range on the way (|k| clamped to 240)
+// product (a * w) * 2^k without leaving the float32 range on the way: one factor while |k| <= 100 (the usual
+// case, a warp-uniform branch), two half factors up to |k| = 240.  Beyond that the row sum misses p(z|x) and
+// the sequence goes to the exact kernel.
 struct Boost {
     float f1, f2;
     bool split;
     __device__ __forceinline__ explicit Boost(int k) {
-        k = max(-240, min(240, k));
         split = (k > 100) || (k < -100);
-        const int k1 = split ? (k >> 1) : k, k2 = k - k1;
-        f1 = __uint_as_float((unsigned)(127 + k1) << 23);
-        f2 = __uint_as_float((unsigned)(127 + k2) << 23);
+        if (split) {
+            k = max(-240, min(240, k));
+            const int k1 = k >> 1;
+            f1 = __uint_as_float((unsigned)(127 + k1) << 23);
+            f2 = __uint_as_float((unsigned)(127 + k - k1) << 23);
+        } else {
+            f1 = __uint_as_float((unsigned)(127 + k) << 23);
+            f2 = 1.0f;
+        }
     }
-    __device__ __forceinline__ float mul(float a, float w) const { return split ? (a * f1) * (w * f2) : (a * f1) * w; }
 };
-
 // "lane per frame" sweeps over one staged row of C floats, skewed by r columns (r < 4) against bank conflicts
 template <typename F>
 __device__ __forceinline__ void row_sweep(float* row, int C, int r, F&& f) {
     const int tail = C < 3 ? C : 3;
     float* p = row + r;
     const int n = C - tail;
-#pragma unroll 4
-    for (int j = 0; j < n; ++j) f(p[j]);
+    int j = 0;
+    for (; j + 8 <= n; j += 8) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) f(p[j + q], q);
+    }
+    for (; j < n; ++j) f(p[j], 0);
     for (int q = 0; q < tail; ++q) {
         int k = r + n + q;
         if (k >= C) k -= C;
-        f(row[k]);
+        f(row[k], 0);
     }
 }
 
-template <int NP>
-__global__ void __launch_bounds__(64 * kFastMaxG)
+// f(k) for k in [0, n) with k a compile-time constant after unrolling (register-array indexing); n <= CR
+template <int CR, typename F>
+__device__ __forceinline__ void for_row(int n, F&& f) {
+#pragma unroll
+    for (int kb = 0; kb < CR; kb += 8) {
+        if (kb + 8 <= n) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f(kb + q);
+        } else if (kb < n) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (kb + q < n) f(kb + q);
+        }
+    }
+}
+
+template <int NP, int CR>
+__global__ void __launch_bounds__(CR > 64 ? 64 * 4 : 64 * kFastMaxG)
 ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, const int32_t* __restrict__ labels,
                      const int32_t* __restrict__ label_offsets, const int32_t* __restrict__ seq_len, int Lmax, int G,
                      int use_bulk, float* __restrict__ loss, float* __restrict__ grad, int32_t* __restrict__ status,
@@ -195,7 +237,6 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
     unsigned char* smem = smem_f;
     const FastLayout lay = fast_layout(T, C, Lmax, G);
     float* stage = reinterpret_cast<float*>(smem + lay.stage);
-    float* s_zz = reinterpret_cast<float*>(smem + lay.zz);
     float* s_info = reinterpret_cast<float*>(smem + lay.info);
     float* s_zero = reinterpret_cast<float*>(smem + lay.zero);
     const unsigned bar = smem_u32(smem + lay.mbar);
@@ -203,6 +244,8 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = warp >> 1, role = warp & 1;  // role 0: alpha (forward), 1: beta (backward)
+    long long* const tl = g_ctc_timeline;
+    ctc_mark(tl, 0);
     const int b0 = blockIdx.x * G;
     const int nb = min(G, B - b0);
     const bool bulk = use_bulk && nb == G;
@@ -269,10 +312,10 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
     } else if (tmax > 0) {
         mbar_wait(bar, 0);
     }
+    ctc_mark(tl, 1);
 
     float* st_s = stage + s * C;  // this sequence's column block
     float* lat = reinterpret_cast<float*>(smem + lay.lat) + s * lay.lat_seq;
-    float* zz = s_zz + s * T;
     float* info = s_info + s * 8;
     int* infoi = reinterpret_cast<int*>(info);
     const bool run = have_seq && !bad && Tb > 0;
@@ -281,35 +324,67 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
     bool novalid = false;
 
     if (run) {
-        // ================= pass 1: softmax statistics, lane per frame =================
+        // ================= pass 1: softmax, lane per frame; the staged row becomes y * grad_scale =================
         const int r_lo = role == 0 ? 0 : mid, r_hi = role == 0 ? mid : Tb;
-        float slz = 0.0f;
         for (int t0 = r_lo; t0 < r_hi; t0 += 32) {
             const int t = t0 + lane;
             if (t < r_hi) {
                 float* row = st_s + t * RS;
-                float m = -INFINITY;
-                row_sweep(row, C, skew, [&](float& v) { m = fmaxf(m, v); });
-                const float ml = m * 1.4426950408889634f;
-                float z = 0.0f;
-                row_sweep(row, C, skew, [&](float& v) {
-                    const float e = fast_ex2(fmaf(v, 1.4426950408889634f, -ml));
-                    v = e;
-                    z += e;
-                });
-                zz[t] = z;
-                slz += logf(z);
+                if constexpr (CR > 0) {
+                    // the whole row lives in registers between the one read and the one write
+                    const int tail = C < 3 ? C : 3, n = C - tail;
+                    float* p = row + skew;
+                    int kt[3];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { int k = skew + n + q; kt[q] = (k >= C) ? k - C : k; }
+                    float x[CR], xt[3];
+                    for_row<CR>(n, [&](int k) { x[k] = p[k]; });
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) xt[q] = (q < tail) ? row[kt[q]] : -INFINITY;
+                    float m[4] = {xt[0], xt[1], xt[2], -INFINITY};
+                    for_row<CR>(n, [&](int k) { m[k & 3] = fmaxf(m[k & 3], x[k]); });
+                    const float ml = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])) * 1.4426950408889634f;
+                    float z[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                    for_row<CR>(n, [&](int k) {
+                        x[k] = fast_ex2(fmaf(x[k], 1.4426950408889634f, -ml));
+                        z[k & 3] += x[k];
+                    });
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        xt[q] = (q < tail) ? fast_ex2(fmaf(xt[q], 1.4426950408889634f, -ml)) : 0.0f;
+                        z[q] += xt[q];
+                    }
+                    const float gz = grad_scale / ((z[0] + z[1]) + (z[2] + z[3]));
+                    for_row<CR>(n, [&](int k) { p[k] = x[k] * gz; });
+#pragma unroll
+                    for (int q = 0; q < 3; ++q)
+                        if (q < tail) row[kt[q]] = xt[q] * gz;
+                } else {
+                    // rows wider than the register budget: three sweeps over shared memory
+                    float m0 = -INFINITY, m1 = -INFINITY;
+                    row_sweep(row, C, skew, [&](float& v, int q) { if (q & 1) m1 = fmaxf(m1, v); else m0 = fmaxf(m0, v); });
+                    const float ml = fmaxf(m0, m1) * 1.4426950408889634f;
+                    float z0 = 0.0f, z1 = 0.0f;
+                    row_sweep(row, C, skew, [&](float& v, int q) {
+                        const float e = fast_ex2(fmaf(v, 1.4426950408889634f, -ml));
+                        v = e;
+                        if (q & 1) z1 += e; else z0 += e;
+                    });
+                    const float gz = grad_scale / (z0 + z1);
+                    row_sweep(row, C, skew, [&](float& v, int) { v *= gz; });
+                }
             }
         }
-        slz = warp_sum(slz);
-        if (lane == 0) info[role] = slz;
-        pair_barrier(1 + s);  // both halves of the staged block now hold e = exp(x - max)
+        ctc_mark(tl, 2);
+        pair_barrier(1 + s);  // both halves of the staged block now hold y * grad_scale
+        ctc_mark(tl, 3);
 
         // ================= pass 2: lattice chains =================
         // lattice row t: position 1+u holds state u (blank i -> 1+2i, label i -> 2+2i); positions 0 and HI,HI+1
         // absorb the stores of lanes that own no state; position EX holds the scale exponent of the stored half.
         // All chain accesses go through 32-bit shared addresses advanced by a constant per frame.
         const unsigned a_st = smem_u32(st_s), a_lat = smem_u32(lat), a_zero = smem_u32(s_zero);
+        const float kinv = 1.0f / grad_scale;
         const unsigned RSB = (unsigned)RS * 4, LSB = (unsigned)LS * 4;
         const int HI = lay.HI, EX = lay.EX;
         if (role == 0) {
@@ -332,19 +407,17 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
             }
             unsigned pb = a_st + 4u * blank;
             unsigned pex = a_lat + 4u * EX;
-            float sc = 1.0f;
-            int Ea = 0;  // sum of biased exponents of the applied factors; true exponent = Ea - 127 * (frames done)
-            int ebias = 127;
+            Rescale rs;
             float eb_n = lds(pb), el_n[NP];
 #pragma unroll
             for (int j = 0; j < NP; ++j) el_n[j] = lds(pe[j]);
-            // one forward step: alpha_t from alpha_{t-1}; stored value v_t = alpha_t * 2^-(Ea - 127 (t+1))
+            // one forward step: alpha_t from alpha_{t-1}; stored value v_t = alpha_t * 2^-E
             auto step = [&](int t, auto masked) {
-                const float ebs = eb_n * sc;
+                const float sck = rs.sc * kinv;  // staged rows hold y * grad_scale
+                const float ebs = eb_n * sck;
                 float els[NP];
 #pragma unroll
-                for (int j = 0; j < NP; ++j) els[j] = el_n[j] * sc;
-                Ea += ebias;
+                for (int j = 0; j < NP; ++j) els[j] = el_n[j] * sck;
                 pb += RSB;  // prefetch e_{t+1} (row Tb is never consumed; the read stays inside the CTA's shared memory)
                 eb_n = lds(pb);
 #pragma unroll
@@ -370,12 +443,12 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                     }
                     mloc = fmaxf(mloc, fmaxf(ab[j], al[j]));
                 }
-                sc = pow2_rescale(mloc, ebias);
+                rs.next(mloc);
             };
             auto store = [&]() {
 #pragma unroll
                 for (int j = 0; j < NP; ++j) { sts(pl[j], ab[j]); sts4(pl[j], al[j]); pl[j] += LSB; }
-                stsi(pex, Ea);
+                stsi(pex, rs.E);
                 pex += LSB;
             };
             // t = 0: alpha_0(blank 0) = e_0(blank), alpha_0(label 0) = e_0(label 0)
@@ -389,35 +462,53 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                     const float el0 = el_n[j];
                     pe[j] += pes[j];
                     el_n[j] = lds(pe[j]);
-                    ab[j] = (i == 0 && 0 < tdl[j]) ? eb0 : 0.0f;
-                    al[j] = (i == 0 && 0 <= tdl[j] && L > 0) ? el0 : 0.0f;
+                    ab[j] = (i == 0 && 0 < tdl[j]) ? eb0 * kinv : 0.0f;
+                    al[j] = (i == 0 && 0 <= tdl[j] && L > 0) ? el0 * kinv : 0.0f;
                 }
                 float mloc = 0.0f;
 #pragma unroll
                 for (int j = 0; j < NP; ++j) mloc = fmaxf(mloc, fmaxf(ab[j], al[j]));
-                Ea += ebias;
-                sc = pow2_rescale(mloc, ebias);
+                rs.next(mloc);
             }
             const int tm0 = max(1, Tb - L);  // states start dying (cannot reach the end any more) at t = Tb - L
             int t = 1;
             store();  // mid >= 1
             for (; t < min(mid, tm0); ++t) { step(t, std::false_type()); store(); }
             for (; t < mid; ++t) { step(t, std::true_type()); store(); }
+            ctc_mark(tl, 4);
             pair_barrier(1 + s);  // partner has stored beta_t (and its exponents) for t >= mid
+            ctc_mark(tl, 5);
             int Pt = 0;
             bool first_consume = true;
+            // the partner's beta_t for the frame about to be consumed is fetched one frame ahead
+            float wb_n[NP], wl_n[NP];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) { wb_n[j] = lds(pl[j]); wl_n[j] = lds4(pl[j]); }
+            int ex_n = ldsi(pex);
             auto consume = [&]() {
                 float wb[NP], wl[NP];
 #pragma unroll
-                for (int j = 0; j < NP; ++j) { wb[j] = lds(pl[j]); wl[j] = lds4(pl[j]); }
-                const int Es = Ea + ldsi(pex);
+                for (int j = 0; j < NP; ++j) { wb[j] = wb_n[j]; wl[j] = wl_n[j]; }
+                const int Es = rs.E + ex_n;
+#pragma unroll
+                for (int j = 0; j < NP; ++j) { wb_n[j] = lds(pl[j] + LSB); wl_n[j] = lds4(pl[j] + LSB); }
+                ex_n = ldsi(pex + LSB);  // one row past the sequence on the last frame: inside the CTA's shared memory
                 if (first_consume) { Pt = Es + prod_exponent<NP>(ab, al, wb, wl); first_consume = false; }
                 const Boost bo(Es - Pt);
+                if (bo.split) {
 #pragma unroll
-                for (int j = 0; j < NP; ++j) {
-                    sts(pl[j], bo.mul(ab[j], wb[j]));
-                    sts4(pl[j], bo.mul(al[j], wl[j]));
-                    pl[j] += LSB;
+                    for (int j = 0; j < NP; ++j) {
+                        sts(pl[j], (ab[j] * bo.f1) * (wb[j] * bo.f2));
+                        sts4(pl[j], (al[j] * bo.f1) * (wl[j] * bo.f2));
+                        pl[j] += LSB;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NP; ++j) {
+                        sts(pl[j], (ab[j] * bo.f1) * wb[j]);
+                        sts4(pl[j], (al[j] * bo.f1) * wl[j]);
+                        pl[j] += LSB;
+                    }
                 }
                 pex += LSB;
             };
@@ -434,17 +525,16 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 if (i == L) pev = ab[j] + pv;
             }
             pev = __shfl_sync(kFullMask, pev, L / NP);
-            pair_barrier(1 + s);  // both chains done: products complete, partner's sum(log Z) visible
+            ctc_mark(tl, 6);
+            pair_barrier(1 + s);  // both chains done: products complete
             novalid = !(pev > 0.0f);
             if (lane == 0) {
-                const float sumlz = info[0] + info[1];
-                const int Etrue = Ea - 127 * Tb;  // Tb factors were applied (the first one is 2^0)
-                const float lp = novalid ? -INFINITY : (logf(pev) + (float)Etrue * 0.6931471805599453f - sumlz);
+                const float lp = novalid ? -INFINITY : (logf(pev) + (float)rs.E * 0.6931471805599453f);
                 loss[b] = -lp;
                 status[b] = novalid ? kCtcRedo : 0;  // an all-zero lattice may be underflow: the exact kernel decides
                 info[2] = novalid ? 1.0f : 0.0f;
                 info[3] = novalid ? 0.0f : log2f(pev);
-                infoi[4] = Ea;
+                infoi[4] = rs.E;
                 infoi[5] = Pt;
             }
         } else {
@@ -468,24 +558,21 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
             }
             unsigned pb = a_st + (unsigned)(Tb - 1) * RSB + 4u * blank;
             unsigned pex = a_lat + (unsigned)(Tb - 1) * LSB + 4u * EX;
-            float sc = 1.0f;
-            int Eb = 0, ebias = 127;
+            Rescale rs;
             float eb_n = lds(pb), el_n[NP];  // e_{Tb-1}: consumed by the step that produces beta_{Tb-2}
 #pragma unroll
             for (int j = 0; j < NP; ++j) el_n[j] = lds(pe[j]);
-            // one backward step: beta_t from beta_{t+1} and e_{t+1}; stored value w_t = beta_t * 2^-(Eb - 127 (Tb-t))
+            // one backward step: beta_t from beta_{t+1} and y_{t+1}; stored value w_t = beta_t * 2^-E
             auto step = [&](int t, auto masked) {
-                const float ebs = eb_n * sc;
+                const float sck = rs.sc * kinv;  // staged rows hold y * grad_scale
+                const float ebs = eb_n * sck;
                 float els[NP];
 #pragma unroll
-                for (int j = 0; j < NP; ++j) els[j] = el_n[j] * sc;
-                Eb += ebias;
-                if (t > 0) {  // prefetch e_t for the next step
-                    pb -= RSB;
-                    eb_n = lds(pb);
+                for (int j = 0; j < NP; ++j) els[j] = el_n[j] * sck;
+                pb -= RSB;  // prefetch e_t for the next step (t = 0 reads the pad row; never consumed)
+                eb_n = lds(pb);
 #pragma unroll
-                    for (int j = 0; j < NP; ++j) { pe[j] -= pes[j]; el_n[j] = lds(pe[j]); }
-                }
+                for (int j = 0; j < NP; ++j) { pe[j] -= pes[j]; el_n[j] = lds(pe[j]); }
                 float wb[NP], wl[NP];
 #pragma unroll
                 for (int j = 0; j < NP; ++j) {
@@ -509,12 +596,12 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                     }
                     mloc = fmaxf(mloc, fmaxf(bb[j], bl[j]));
                 }
-                sc = pow2_rescale(mloc, ebias);
+                rs.next(mloc);
             };
             auto store = [&]() {
 #pragma unroll
                 for (int j = 0; j < NP; ++j) { sts(pl[j], bl[j]); sts4(pl[j], bb[j]); pl[j] -= LSB; }
-                stsi(pex, Eb);
+                stsi(pex, rs.E);
                 pex -= LSB;
             };
             // t = Tb-1: beta(last blank) = beta(last label) = 1
@@ -524,21 +611,40 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 bb[j] = (i == L && Tb - 1 >= tbb[j]) ? 1.0f : 0.0f;
                 bl[j] = (i == L && L >= 1 && Tb - 1 >= tbl[j]) ? 1.0f : 0.0f;
             }
-            Eb += ebias;  // the factor 2^0 of the first frame
+            rs.next(1.0f);
             int Pt = 0;
             bool first_consume = true;
+            float vl_n[NP], vb_n[NP];
+            int ex_n = 0;
+            auto consume_prefetch = [&]() {  // the partner's alpha_t of the first frame to be consumed
+#pragma unroll
+                for (int j = 0; j < NP; ++j) { vl_n[j] = lds(pl[j]); vb_n[j] = lds4(pl[j]); }
+                ex_n = ldsi(pex);
+            };
             auto consume = [&]() {
                 float vl[NP], vb[NP];
 #pragma unroll
-                for (int j = 0; j < NP; ++j) { vl[j] = lds(pl[j]); vb[j] = lds4(pl[j]); }
-                const int Es = Eb + ldsi(pex);
+                for (int j = 0; j < NP; ++j) { vl[j] = vl_n[j]; vb[j] = vb_n[j]; }
+                const int Es = rs.E + ex_n;
+#pragma unroll
+                for (int j = 0; j < NP; ++j) { vl_n[j] = lds(pl[j] - LSB); vb_n[j] = lds4(pl[j] - LSB); }
+                ex_n = ldsi(pex - LSB);  // one row before the sequence on the last frame: inside the CTA's shared memory
                 if (first_consume) { Pt = Es + prod_exponent<NP>(bb, bl, vb, vl); first_consume = false; }
                 const Boost bo(Es - Pt);
+                if (bo.split) {
 #pragma unroll
-                for (int j = 0; j < NP; ++j) {
-                    sts(pl[j], bo.mul(bl[j], vl[j]));
-                    sts4(pl[j], bo.mul(bb[j], vb[j]));
-                    pl[j] -= LSB;
+                    for (int j = 0; j < NP; ++j) {
+                        sts(pl[j], (bl[j] * bo.f1) * (vl[j] * bo.f2));
+                        sts4(pl[j], (bb[j] * bo.f1) * (vb[j] * bo.f2));
+                        pl[j] -= LSB;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NP; ++j) {
+                        sts(pl[j], (bl[j] * bo.f1) * vl[j]);
+                        sts4(pl[j], (bb[j] * bo.f1) * vb[j]);
+                        pl[j] -= LSB;
+                    }
                 }
                 pex -= LSB;
             };
@@ -548,18 +654,24 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 --t;
                 for (; t >= max(mid, L); --t) { step(t, std::false_type()); store(); }
                 for (; t >= mid; --t) { step(t, std::true_type()); store(); }
+                ctc_mark(tl, 4);
                 pair_barrier(1 + s);  // partner has stored alpha_t (and its exponents) for t < mid
+                ctc_mark(tl, 5);
+                consume_prefetch();
             } else {
                 pair_barrier(1 + s);  // Tb == 1: the only frame belongs to the partner's half
+                consume_prefetch();
                 consume();
                 --t;
             }
             for (; t >= L; --t) { step(t, std::false_type()); consume(); }
             for (; t >= 0; --t) { step(t, std::true_type()); consume(); }
             if (lane == 0) infoi[6] = Pt;
+            ctc_mark(tl, 6);
             pair_barrier(1 + s);
         }
         pair_barrier(1 + s);  // flags / log2 p written by the alpha warp
+        ctc_mark(tl, 7);
         novalid = info[2] != 0.0f;
     } else if (have_seq && role == 0 && lane == 0) {
         // TF: zero-length sequence -> loss 0, grad 0.  Infeasible / invalid -> flagged, zero outputs.
@@ -572,9 +684,8 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
         const int Tr = run ? Tb : 0, midr = run ? mid : 0;
         const int r_lo = role == 0 ? 0 : midr, r_hi = role == 0 ? midr : Tr;
         // Rows below mid carry Pt of the beta warp (it formed those products), rows above Pt of the alpha warp.
-        // All exponents are sums of biased exponents: a row's products carry 127*(Tb+1), the alpha chain 127*Tb.
         const float l2pe = info[3];
-        const float dexp = (float)(infoi[role == 0 ? 6 : 5] - infoi[4] - 127);
+        const float dexp = (float)(infoi[role == 0 ? 6 : 5] - infoi[4]);
         // rounding noise of the two chains grows with T (~1e-7 per frame); anything above it is lost mass
         const float thr = 1.0e-5f + 4.0e-7f * (float)T;
         bool lost = false;
@@ -582,7 +693,6 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
             const int t = t0 + lane;
             if (t < r_hi) {
                 float* row = st_s + t * RS;
-                const float z = zz[t];
                 if (!novalid) {
                     const float* rp = lat + (size_t)t * LS + 1;  // rp[u] = product at state u
                     float S = 0.0f, Bs = 0.0f;
@@ -594,31 +704,29 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                     S += Bs;
                     lost = lost || !(fabsf(log2f(S) - l2pe + dexp) < thr);
                     if (grad) {
-                        const float r = (S > 0.0f) ? z / S : 0.0f;
+                        const float r = (S > 0.0f) ? grad_scale / S : 0.0f;
                         row[blank] -= Bs * r;
                         for (int i = 0; i < L; ++i) row[s_lab[i]] -= rp[2 * i + 1] * r;
                     }
-                }
-                if (grad) {
-                    const float gs = grad_scale / z;
-                    row_sweep(row, C, skew, [&](float& v) { v *= gs; });
                 }
             }
         }
         if (run && !novalid && __any_sync(kFullMask, lost) && lane == 0) status[b] = kCtcRedo;
     }
+    ctc_mark(tl, 8);
     if (!grad) return;
     if (have_seq) {
         // frames past the sequence end: zero gradient (both warps, lane per class: conflict-free)
         const int Tr = run ? Tb : 0;
-        for (int t = Tr + role; t < T; t += 2) {
-            float* row = st_s + t * RS;
-            for (int k = lane; k < C; k += 32) row[k] = 0.0f;
-        }
+        float* p = st_s + (size_t)(Tr + role) * RS + lane;
+        for (int t = Tr + role; t < T; t += 2, p += 2 * RS)
+            for (int k = 0; k + lane < C; k += 32) p[k] = 0.0f;
     }
+    ctc_mark(tl, 9);
     if (bulk) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
+        ctc_mark(tl, 10);
         if (warp == 0) {
             const unsigned row_bytes = (unsigned)(G * C * 4);
             float* dst = grad + (size_t)b0 * C;
@@ -627,6 +735,7 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
+        ctc_mark(tl, 11);
     } else {
         __syncthreads();
         const int n = nb * C;

@@ -67,6 +67,9 @@ int ocr_ctc_loss(const float* logits, int T, int B, int C, const int32_t* labels
  * The automatic choice uses the fast kernel whenever its staging block fits in
  * shared memory and falls back to the general kernel for very long sequences. */
 int ocr_ctc_loss_set_path(int path);
+/* Tuning aid: per-warp clock64() stamps at the fast kernel's phase boundaries (12 int64 per warp, CTA-major);
+ * pass NULL to switch it off.  Not part of the product path. */
+int ocr_debug_ctc_timeline(long long* device_buffer);
 
 /* ---------------------------------------------------------------------------------------------
  * CTC greedy decoder.  Replaces tf.nn.ctc_greedy_decoder(merge_repeated=True) at
