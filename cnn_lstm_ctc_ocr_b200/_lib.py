@@ -25,6 +25,7 @@ SIGNATURES = {
     "ocr_ctc_greedy_decode": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "ocr_ctc_beam_search_workspace_bytes": (_i, [_i, _i, _i, _i, _c.POINTER(_sz)]),
     "ocr_ctc_beam_search": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ocr_gemm_tf32": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ocr_edit_distance": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
 }
 

@@ -1,0 +1,274 @@
+// TF32 tensor-core GEMM with fused bias / ReLU epilogue for sm_100a:  D[M,N] = act(A[M,K] * W[N,K]^T + bias[N]).
+//
+// The dense contractions of the recognizer -- the 3x3 convolutions as (im2col patches) x (filters)
+// (/root/reference/src/weinman/model.py:84-109, tf.layers.conv2d), the LSTM/GRU input projections
+// (model.py:167-199, the [x, h] * kernel product of tf.contrib.rnn cells split into its x part) and the
+// logits layer (model.py:216-220, tf.layers.dense + ReLU) -- all have this shape with K-major operands.
+//
+// Blackwell mapping (one 128 x BN output tile per CTA, 6 warps, warp specialised):
+//   warp 0 / one lane : TMA producer.  cp.async.bulk.tensor.2d loads a 128x32 fp32 box of A and a BNx32 box of W
+//                       per k-step into a 128B-swizzled shared-memory stage; completion on the stage's mbarrier.
+//   warp 1            : allocates BN TMEM columns; one lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8, four per
+//                       k-step, shared-memory descriptors, fp32 accumulator in TMEM) and tcgen05.commit's the stage
+//                       back to the producer; the last commit signals the epilogue.
+//   warps 2..5        : epilogue.  tcgen05.ld (32 lanes x 32 columns per warp) -> registers -> + bias, ReLU ->
+//                       128-byte row segments to global memory.
+// Out-of-range rows / columns / k are zero-filled by TMA, so M, N, K need no padding (K*4 bytes must be a
+// multiple of 16 for the tensor map).  TF32 keeps fp32 storage end to end: activations and weights stay the
+// reference's float32 tensors, products are rounded to 10-bit mantissas inside the tensor core, sums are fp32.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace ocr {
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmBK = 32;  // fp32 elements = one 128-byte swizzle row
+constexpr int kGemmThreads = 192;
+
+__device__ __forceinline__ unsigned g_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void g_mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void g_mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void g_mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    for (unsigned it = 0; it < (1u << 28); ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* tm, int c0, int c1, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows of 128 bytes, 8-row atoms 1024 bytes apart
+__device__ __forceinline__ unsigned long long umma_desc_k128(unsigned smem_addr) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((smem_addr >> 4) & 0x3FFF);
+    d |= (unsigned long long)1 << 16;               // leading byte offset (unused for swizzled K-major)
+    d |= (unsigned long long)(1024 >> 4) << 32;     // stride byte offset: next 8-row atom
+    d |= (unsigned long long)1 << 46;               // descriptor version (sm_100)
+    d |= (unsigned long long)2 << 61;               // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc, unsigned acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+template <int BN, int STAGES>
+struct GemmSmem {
+    static constexpr int kA = kGemmBM * kGemmBK * 4;
+    static constexpr int kB = BN * kGemmBK * 4;
+    static constexpr int kStage = kA + kB;
+    static constexpr int kBars = STAGES * kStage;
+    static constexpr int kTotal = kBars + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const float* __restrict__ bias, float* __restrict__ D, int M, int N, int K, int ldd, int relu)
+{
+    using S = GemmSmem<BN, STAGES>;
+    extern __shared__ unsigned char gemm_smem_raw[];
+    // 128-byte swizzle wants 1024-byte aligned tiles
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~(uintptr_t)1023);
+    const unsigned s_base = g_smem_u32(smem);
+    const unsigned bar_full = s_base + S::kBars;
+    const unsigned bar_empty = bar_full + STAGES * 8;
+    const unsigned bar_acc = bar_empty + STAGES * 8;
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + S::kBars + (2 * STAGES + 1) * 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kGemmBM, n0 = blockIdx.y * BN;
+    const int nk = (K + kGemmBK - 1) / kGemmBK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { g_mbar_init(bar_full + s * 8, 1); g_mbar_init(bar_empty + s * 8, 1); }
+        g_mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)), "r"((unsigned)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_d = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int k = 0; k < nk; ++k) {
+                const int s = k % STAGES;
+                if (k >= STAGES) g_mbar_wait(bar_empty + s * 8, ((k / STAGES) - 1) & 1);
+                g_mbar_expect_tx(bar_full + s * 8, (unsigned)S::kStage);
+                tma_load_2d(s_base + s * S::kStage, &tmA, k * kGemmBK, m0, bar_full + s * 8);
+                tma_load_2d(s_base + s * S::kStage + S::kA, &tmB, k * kGemmBK, n0, bar_full + s * 8);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: fp32 accumulate, tf32 x tf32, both K-major, N = BN, M = 128
+            const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(kGemmBM >> 4) << 24);
+            for (int k = 0; k < nk; ++k) {
+                const int s = k % STAGES;
+                g_mbar_wait(bar_full + s * 8, (k / STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned a_addr = s_base + s * S::kStage, b_addr = a_addr + S::kA;
+                const unsigned long long da = umma_desc_k128(a_addr), db = umma_desc_k128(b_addr);
+#pragma unroll
+                for (int kk = 0; kk < kGemmBK / 8; ++kk)  // 8 tf32 = 32 bytes per MMA: advance the start address inside the swizzle row
+                    umma_tf32(tmem_d, da + (unsigned long long)(kk * 2), db + (unsigned long long)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+                umma_commit(bar_empty + s * 8);  // frees the stage when the MMAs that read it retire
+            }
+            umma_commit(bar_acc);
+        }
+    } else {
+        // epilogue warps 2..5: TMEM lane quarter = warp % 4
+        const int q = warp & 3;
+        g_mbar_wait(bar_acc, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            unsigned r[32];
+            const unsigned taddr = tmem_d + ((unsigned)(q * 32) << 16) + (unsigned)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < M) {
+                float* drow = D + (size_t)row * ldd + n0 + c0;
+                const bool vec = ((reinterpret_cast<uintptr_t>(drow) & 15) == 0) && (n0 + c0 + 32 <= N);
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(r[j]);
+                    const int col = n0 + c0 + j;
+                    if (bias != nullptr && col < N) x += __ldg(bias + col);
+                    v[j] = relu ? fmaxf(x, 0.0f) : x;
+                }
+                if (vec) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(drow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + c0 + j < N) drow[j] = v[j];
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((unsigned)BN) : "memory");
+    }
+}
+
+}  // namespace ocr
+
+using namespace ocr;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor [rows, K] row-major with row pitch ld elements; box = [box_rows, 32 floats], 128-byte swizzle
+static int make_map(CUtensorMap* tm, const float* base, long long rows, long long K, long long ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (enc == nullptr) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return OCR_ECUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kGemmBK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld K=%lld ld=%lld", (int)r, rows, K, ld); return OCR_ECUDA; }
+    return OCR_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const float* A, int lda, const float* W, int ldw, const float* bias, float* D, int ldd, int M, int N, int K,
+                       int relu, cudaStream_t st)
+{
+    using S = GemmSmem<BN, STAGES>;
+    CUtensorMap tmA, tmB;
+    int rc = make_map(&tmA, A, M, K, lda, kGemmBM);
+    if (rc != OCR_OK) return rc;
+    rc = make_map(&tmB, W, N, K, ldw, BN);
+    if (rc != OCR_OK) return rc;
+    static int configured = -1;
+    int dev = 0;
+    OCR_CHECK_CUDA(cudaGetDevice(&dev));
+    if (configured != dev) {
+        OCR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        configured = dev;
+    }
+    dim3 grid((M + kGemmBM - 1) / kGemmBM, (N + BN - 1) / BN);
+    gemm_tf32_kernel<BN, STAGES><<<grid, kGemmThreads, S::kTotal, st>>>(tmA, tmB, bias, D, M, N, K, ldd, relu);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+extern "C" int ocr_gemm_tf32(const float* A, int lda, const float* W, int ldw, const float* bias, float* D, int ldd, int M, int N,
+                             int K, int relu, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(M >= 0 && N >= 0 && K >= 1, "ocr_gemm_tf32: bad shape M=%d N=%d K=%d", M, N, K);
+    if (M == 0 || N == 0) return OCR_OK;
+    OCR_CHECK_ARG(A && W && D, "ocr_gemm_tf32: NULL argument");
+    OCR_CHECK_ARG(lda >= K && ldw >= K && ldd >= N, "ocr_gemm_tf32: leading dimensions too small");
+    OCR_CHECK_ARG((lda % 4) == 0 && (ldw % 4) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0,
+                  "ocr_gemm_tf32: A and W need 16-byte aligned rows (pointer and leading dimension * 4 bytes)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long mt = (M + kGemmBM - 1) / kGemmBM;
+    // widest tile that still gives the 148 SMs something to do
+    int bn = 32;
+    if (N > 32) bn = 64;
+    if (N > 64 && mt * ((N + 127) / 128) >= 120) bn = 128;
+    if (N > 128 && mt * ((N + 255) / 256) >= 120) bn = 256;
+    switch (bn) {
+        case 32: return launch_gemm<32, 8>(A, lda, W, ldw, bias, D, ldd, M, N, K, relu, st);
+        case 64: return launch_gemm<64, 6>(A, lda, W, ldw, bias, D, ldd, M, N, K, relu, st);
+        case 128: return launch_gemm<128, 5>(A, lda, W, ldw, bias, D, ldd, M, N, K, relu, st);
+        default: return launch_gemm<256, 4>(A, lda, W, ldw, bias, D, ldd, M, N, K, relu, st);
+    }
+}

@@ -107,6 +107,16 @@ int ocr_edit_distance(const int64_t* hyp, int hyp_stride, const int32_t* hyp_len
                       const int32_t* truth_offsets, int B, int max_truth_len, float* dist,
                       ocr_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Dense contraction D[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) on the tcgen05 tensor cores (TF32 products,
+ * fp32 accumulation in TMEM, TMA-fed).  The shape of tf.layers.conv2d on im2col patches (model.py:97-104),
+ * of the x-part of the tf.contrib.rnn cell kernels (model.py:173-192) and of tf.layers.dense (model.py:216-220).
+ *   A [M,K] fp32 row-major, row pitch lda;  W [N,K] fp32 row-major (K-major weights), row pitch ldw;
+ *   bias [N] or NULL;  D [M,N] fp32, row pitch ldd;  relu != 0 applies max(x,0).
+ * A and W rows must be 16-byte aligned (pointer % 16 == 0, lda % 4 == 0, ldw % 4 == 0). */
+int ocr_gemm_tf32(const float* A, int lda, const float* W, int ldw, const float* bias, float* D, int ldd, int M,
+                  int N, int K, int relu, ocr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,64 @@
+"""GPU tier: the tcgen05/TMA TF32 GEMM (ocr_gemm_tf32) against a plain float64 reference of the same op.
+Tolerance: TF32 rounds each operand to a 10-bit mantissa (relative 2^-11 per factor) and accumulates in fp32:
+|error| <= ~1e-3 * sum_k |a_k w_k|; the test bounds it by 2e-3 * (|A| @ |W|^T)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _gemm(A, W, bias, relu, ldd=None):
+    from cnn_lstm_ctc_ocr_b200 import _lib
+    lib = _lib.load()
+    M, K = A.shape
+    N = W.shape[0]
+    ldd = ldd or N
+    D = torch.full((M, ldd), float("nan"), device=A.device)
+    _lib.check(lib.ocr_gemm_tf32(_lib.ptr(A), A.stride(0), _lib.ptr(W), W.stride(0), _lib.ptr(bias), _lib.ptr(D), ldd, M, N, K,
+                                 int(relu), _lib.stream_handle()), "ocr_gemm_tf32")
+    torch.cuda.synchronize()
+    return D
+
+
+@pytest.mark.parametrize("M,N,K,relu,use_bias", [
+    (128, 32, 32, False, False),      # one tile, one k-step
+    (128, 64, 288, True, True),       # conv2-like K
+    (3780, 32, 288, True, True),      # conv2 of one 32x128 crop
+    (945, 64, 576, True, True),       # conv4
+    (183 * 32, 256, 2304, True, True),  # conv8, batch 32
+    (1952, 4096, 256, False, True),   # BiLSTM layer-1 input projection (T=61, B=32, both directions)
+    (1952, 96, 1024, True, True),     # logits
+    (1952, 63, 1024, True, True),     # N not a multiple of anything
+    (200, 130, 36, False, True),      # ragged everything (K tail zero-filled by TMA)
+    (1, 1, 4, False, False),
+])
+def test_gemm_tf32_matches_reference(M, N, K, relu, use_bias):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(M * 7 + N)
+    A = torch.randn((M, K), device="cuda", generator=g)
+    W = torch.randn((N, K), device="cuda", generator=g) * 0.1
+    bias = torch.randn((N,), device="cuda", generator=g) if use_bias else None
+    D = _gemm(A, W, bias, relu)
+    ref = A.double() @ W.double().t()
+    if use_bias:
+        ref = ref + bias.double()
+    if relu:
+        ref = ref.clamp_min(0)
+    bound = 2e-3 * (A.abs().double() @ W.abs().double().t()) + 1e-6
+    err = (D.double() - ref).abs()
+    assert torch.isfinite(D).all()
+    assert bool((err <= bound).all()), "max err %.3g (bound %.3g)" % (err.max().item(), bound.max().item())
+
+
+def test_gemm_tf32_strided_operands_and_padding():
+    """Row pitches larger than K / N; columns beyond N must stay untouched."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    Abuf = torch.randn((300, 72), device="cuda", generator=g)
+    Wbuf = torch.randn((50, 80), device="cuda", generator=g)
+    A, W = Abuf[:, :68], Wbuf[:, :68]
+    D = _gemm(A, W, None, False, ldd=64)
+    ref = A.double() @ W.double().t()
+    assert (D[:, :50].double() - ref).abs().max() < 0.1
+    assert torch.isnan(D[:, 50:]).all()
