@@ -8,5 +8,6 @@ There is no CPU path: importing works anywhere, calling an op needs the built li
 """
 from . import _lib  # noqa: F401
 from . import ctc  # noqa: F401
+from . import model  # noqa: F401
 
 __version__ = "0.1.0"

@@ -16,9 +16,7 @@
 // Out-of-range rows / columns / k are zero-filled by TMA, so M, N, K need no padding (K*4 bytes must be a
 // multiple of 16 for the tensor map).  TF32 keeps fp32 storage end to end: activations and weights stay the
 // reference's float32 tensors, products are rounded to 10-bit mantissas inside the tensor core, sums are fp32.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "gemm_tf32.cuh"
 
 namespace ocr {
 
@@ -227,15 +225,9 @@ static int make_map(CUtensorMap* tm, const float* base, long long rows, long lon
 }
 
 template <int BN, int STAGES>
-static int launch_gemm(const float* A, int lda, const float* W, int ldw, const float* bias, float* D, int ldd, int M, int N, int K,
-                       int relu, cudaStream_t st)
+static int launch_planned(const GemmPlan& p, cudaStream_t st)
 {
     using S = GemmSmem<BN, STAGES>;
-    CUtensorMap tmA, tmB;
-    int rc = make_map(&tmA, A, M, K, lda, kGemmBM);
-    if (rc != OCR_OK) return rc;
-    rc = make_map(&tmB, W, N, K, ldw, BN);
-    if (rc != OCR_OK) return rc;
     static int configured = -1;
     int dev = 0;
     OCR_CHECK_CUDA(cudaGetDevice(&dev));
@@ -243,32 +235,53 @@ static int launch_gemm(const float* A, int lda, const float* W, int ldw, const f
         OCR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
         configured = dev;
     }
-    dim3 grid((M + kGemmBM - 1) / kGemmBM, (N + BN - 1) / BN);
-    gemm_tf32_kernel<BN, STAGES><<<grid, kGemmThreads, S::kTotal, st>>>(tmA, tmB, bias, D, M, N, K, ldd, relu);
+    dim3 grid((p.M + kGemmBM - 1) / kGemmBM, (p.N + BN - 1) / BN);
+    gemm_tf32_kernel<BN, STAGES><<<grid, kGemmThreads, S::kTotal, st>>>(p.tmA, p.tmB, p.bias, p.D, p.M, p.N, p.K, p.ldd, p.relu);
     OCR_CHECK_LAUNCH();
     return OCR_OK;
 }
 
-extern "C" int ocr_gemm_tf32(const float* A, int lda, const float* W, int ldw, const float* bias, float* D, int ldd, int M, int N,
-                             int K, int relu, ocr_stream_t stream)
+namespace ocr {
+
+int gemm_plan(GemmPlan* p, const float* A, int lda, const float* W, int ldw, const float* bias, float* D, int ldd, int M, int N,
+              int K, int relu)
 {
-    OCR_CHECK_ARG(M >= 0 && N >= 0 && K >= 1, "ocr_gemm_tf32: bad shape M=%d N=%d K=%d", M, N, K);
-    if (M == 0 || N == 0) return OCR_OK;
-    OCR_CHECK_ARG(A && W && D, "ocr_gemm_tf32: NULL argument");
-    OCR_CHECK_ARG(lda >= K && ldw >= K && ldd >= N, "ocr_gemm_tf32: leading dimensions too small");
+    OCR_CHECK_ARG(M >= 1 && N >= 1 && K >= 1, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+    OCR_CHECK_ARG(A && W && D, "gemm: NULL argument");
+    OCR_CHECK_ARG(lda >= K && ldw >= K && ldd >= N, "gemm: leading dimensions too small");
     OCR_CHECK_ARG((lda % 4) == 0 && (ldw % 4) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0,
-                  "ocr_gemm_tf32: A and W need 16-byte aligned rows (pointer and leading dimension * 4 bytes)");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+                  "gemm: A and W need 16-byte aligned rows (pointer and leading dimension * 4 bytes)");
     const long long mt = (M + kGemmBM - 1) / kGemmBM;
     // widest tile that still gives the 148 SMs something to do
     int bn = 32;
     if (N > 32) bn = 64;
     if (N > 64 && mt * ((N + 127) / 128) >= 120) bn = 128;
     if (N > 128 && mt * ((N + 255) / 256) >= 120) bn = 256;
-    switch (bn) {
-        case 32: return launch_gemm<32, 8>(A, lda, W, ldw, bias, D, ldd, M, N, K, relu, st);
-        case 64: return launch_gemm<64, 6>(A, lda, W, ldw, bias, D, ldd, M, N, K, relu, st);
-        case 128: return launch_gemm<128, 5>(A, lda, W, ldw, bias, D, ldd, M, N, K, relu, st);
-        default: return launch_gemm<256, 4>(A, lda, W, ldw, bias, D, ldd, M, N, K, relu, st);
+    p->bn = bn; p->bias = bias; p->D = D; p->M = M; p->N = N; p->K = K; p->ldd = ldd; p->relu = relu;
+    int rc = make_map(&p->tmA, A, M, K, lda, kGemmBM);
+    if (rc != OCR_OK) return rc;
+    return make_map(&p->tmB, W, N, K, ldw, bn);
+}
+
+int gemm_run(const GemmPlan& p, cudaStream_t st)
+{
+    switch (p.bn) {
+        case 32: return launch_planned<32, 8>(p, st);
+        case 64: return launch_planned<64, 6>(p, st);
+        case 128: return launch_planned<128, 5>(p, st);
+        default: return launch_planned<256, 4>(p, st);
     }
+}
+
+}  // namespace ocr
+
+extern "C" int ocr_gemm_tf32(const float* A, int lda, const float* W, int ldw, const float* bias, float* D, int ldd, int M, int N,
+                             int K, int relu, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(M >= 0 && N >= 0 && K >= 1, "ocr_gemm_tf32: bad shape M=%d N=%d K=%d", M, N, K);
+    if (M == 0 || N == 0) return OCR_OK;
+    GemmPlan p;
+    int rc = gemm_plan(&p, A, lda, W, ldw, bias, D, ldd, M, N, K, relu);
+    if (rc != OCR_OK) return rc;
+    return gemm_run(p, static_cast<cudaStream_t>(stream));
 }

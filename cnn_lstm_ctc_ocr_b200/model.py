@@ -1,0 +1,205 @@
+"""The weinman CNN -> bidirectional LSTM/GRU -> logits graph of the reference on B200 (INFER mode).
+
+Mirrors the reference's Python-level interface (src/weinman/model.py, model_bu.py, validate.py):
+
+  convnet_layers(inputs, widths, mode)                    model.py:126-165
+  rnn_layers(features, sequence_length, num_classes)      model.py:202-221  (GRU 512/256)  /  model_bu.py:202-221 (LSTM 512/512)
+  preprocess_image(image)                                 validate.py:56-68
+  get_output(rnn_logits, sequence_length)                 validate.py:81-92 (greedy decode, dense, -1 padded)
+  get_string(labels), out_charset, num_classes()          validate.py:126-129, mjsynth.py:23-26
+
+TensorFlow keeps the weights in variable scopes; here a `Model` object holds them under the same variable
+names ("convnet/conv1/kernel", "rnn/bdrnn1/fw/lstm_cell/kernel", ... SURVEY.md App. A.8), importable from /
+exportable to an .npz keyed by those names.  All arithmetic runs in libocr_b200.so: the convolutions, the RNN
+input / recurrent projections and the logits layer on the tcgen05 tensor cores (TF32 products, fp32 sums),
+the rest as coalesced CUDA kernels.  There is no CPU path.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, ctc
+
+# mjsynth.py:23-26
+out_charset = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789 `~!@#$%^&*()-=_+[]{};'\\:\"|,./<>?"
+
+
+def num_classes():
+    return len(out_charset)
+
+
+class ModeKeys:  # tf.contrib.learn.ModeKeys
+    TRAIN = "train"
+    EVAL = "eval"
+    INFER = "infer"
+
+
+# (filters, kernel, padding, name, batch_norm)  -- model.py:47-54
+LAYER_PARAMS = [(32, 3, "valid", "conv1", False), (32, 3, "same", "conv2", True),
+                (64, 3, "same", "conv3", False), (64, 3, "same", "conv4", True),
+                (128, 3, "same", "conv5", False), (128, 3, "same", "conv6", True),
+                (256, 3, "same", "conv7", False), (256, 3, "same", "conv8", True)]
+# max-pool applied to the INPUT of each 'same' convolution (model.py:134-144): (window_h, window_w, stride_h, stride_w)
+_POOL_BEFORE = {"conv2": (1, 1, 1, 1), "conv3": (2, 2, 2, 2), "conv4": (1, 1, 1, 1), "conv5": (2, 2, 2, 1),
+                "conv6": (1, 1, 1, 1), "conv7": (2, 2, 2, 1), "conv8": (1, 1, 1, 1)}
+BN_EPS = 1e-3
+
+
+def preprocess_image(image):
+    """validate._preprocess_image: uint8 -> float32 in [-0.5, 0.5].  (Model.convnet_layers also accepts the uint8
+    tensor directly and fuses this into conv1.)"""
+    return image.to(torch.float32) / 255.0 - 0.5
+
+
+def get_string(labels):
+    """validate._get_string: label ids -> text."""
+    return "".join(out_charset[int(c)] for c in labels)
+
+
+class Model:
+    """Weights of the recognizer + the reference's graph-building functions as methods."""
+
+    def __init__(self, params, cell_type="lstm", rnn_sizes=(512, 512), device="cuda"):
+        if cell_type not in ("lstm", "gru"):
+            raise ValueError("cell_type must be 'lstm' (model_bu.py) or 'gru' (model.py)")
+        self.cell_type = cell_type
+        self.rnn_sizes = tuple(rnn_sizes)
+        self.device = torch.device(device)
+        self.params = {k: torch.as_tensor(np.asarray(v), dtype=torch.float32).to(self.device) for k, v in params.items()}
+        self._prepare()
+
+    # ------------------------------------------------------------------ weights
+    @classmethod
+    def load_npz(cls, path, **kw):
+        with np.load(path) as z:
+            return cls({k: z[k] for k in z.files}, **kw)
+
+    def save_npz(self, path):
+        np.savez(path, **{k: v.cpu().numpy() for k, v in self.params.items()})
+
+    def _prepare(self):
+        """Kernel-side layouts: BN folded into filters/biases, filters as K-major [Cout, 9*Cin], RNN kernels split
+        into x / h parts, transposed to [N, K] and stacked fw | bw."""
+        p = self.params
+        self.conv = {}
+        for (filters, k, padding, name, bn) in LAYER_PARAMS:
+            w = p["convnet/%s/kernel" % name].double()   # [3,3,Cin,Cout]
+            b = p["convnet/%s/bias" % name].double()
+            if bn:
+                q = "convnet/%s/batch_norm/" % name
+                scale = p[q + "gamma"].double() / torch.sqrt(p[q + "moving_variance"].double() + BN_EPS)
+                w = w * scale
+                b = (b - p[q + "moving_mean"].double()) * scale + p[q + "beta"].double()
+            if name == "conv1":
+                self.conv[name] = (w.float().contiguous(), b.float().contiguous())
+            else:
+                self.conv[name] = (w.reshape(-1, filters).t().float().contiguous(), b.float().contiguous())
+        self.rnn = []
+        I = 256
+        for scope, H in (("bdrnn1", self.rnn_sizes[0]), ("bdrnn2", self.rnn_sizes[1])):
+            if self.cell_type == "lstm":
+                ks = [p["rnn/%s/%s/lstm_cell/kernel" % (scope, d)] for d in ("fw", "bw")]
+                wx = torch.cat([k[:I].t() for k in ks], 0).contiguous()          # [8H, I]
+                wh = torch.cat([k[I:].t() for k in ks], 0).contiguous()          # [8H, H]
+                bias = torch.cat([p["rnn/%s/%s/lstm_cell/bias" % (scope, d)] for d in ("fw", "bw")]).contiguous()
+                self.rnn.append(dict(I=I, H=H, wx=wx, wh=wh, wh2=None, bias=bias))
+            else:
+                gk = [p["rnn/%s/%s/gru_cell/gates/kernel" % (scope, d)] for d in ("fw", "bw")]
+                ck = [p["rnn/%s/%s/gru_cell/candidate/kernel" % (scope, d)] for d in ("fw", "bw")]
+                wx = torch.cat([torch.cat([g[:I].t(), c[:I].t()], 0) for g, c in zip(gk, ck)], 0).contiguous()   # [6H, I]
+                wh = torch.cat([g[I:].t() for g in gk], 0).contiguous()          # [4H, H]
+                wh2 = torch.cat([c[I:].t() for c in ck], 0).contiguous()         # [2H, H]
+                bias = torch.cat([torch.cat([p["rnn/%s/%s/gru_cell/gates/bias" % (scope, d)],
+                                             p["rnn/%s/%s/gru_cell/candidate/bias" % (scope, d)]]) for d in ("fw", "bw")]).contiguous()
+                self.rnn.append(dict(I=I, H=H, wx=wx, wh=wh, wh2=wh2, bias=bias))
+            I = 2 * H
+        self.logits_w = p["rnn/logits/kernel"].t().contiguous()   # [C, 2H]
+        self.logits_b = p["rnn/logits/bias"].contiguous()
+
+    # ------------------------------------------------------------------ graph
+    def convnet_layers(self, inputs, widths, mode=ModeKeys.INFER):
+        """inputs [B,32,W,1] float32 NHWC (preprocessed) or uint8 (preprocessing fused), widths [B] int32
+        -> (features [B,T,256], sequence_length [B] int32).   model.py:126-165"""
+        if mode == ModeKeys.TRAIN:
+            raise NotImplementedError("TRAIN mode (batch statistics, backward) is not built yet; see DESIGN.md section 0")
+        _lib.require_cuda(inputs)
+        lib = _lib.load()
+        sh = _lib.stream_handle()
+        B, H, W, one = inputs.shape
+        if one != 1:
+            raise ValueError("inputs must be [B, H, W, 1]")
+        x = inputs.contiguous()
+        is_u8 = x.dtype == torch.uint8
+        if not is_u8:
+            x = x.float()
+        dev = x.device
+        w1, b1 = self.conv["conv1"]
+        a = torch.empty((B, H - 2, W - 2, w1.shape[-1]), dtype=torch.float32, device=dev)
+        _lib.check(lib.ocr_conv1_3x3_valid(_lib.ptr(x), int(is_u8), B, H, W, _lib.ptr(w1), _lib.ptr(b1), w1.shape[-1], _lib.ptr(a), sh),
+                   "ocr_conv1_3x3_valid")
+        for (filters, k, padding, name, bn) in LAYER_PARAMS[1:]:
+            ph, pw, s_h, s_w = _POOL_BEFORE[name]
+            Bn, Hn, Wn, Cn = a.shape
+            Hp, Wp = (Hn - ph) // s_h + 1, (Wn - pw) // s_w + 1
+            if Hp < 1 or Wp < 1:
+                raise ValueError("image too small for the convolutional stack (need height 32, width >= 8)")
+            patches = torch.empty((Bn * Hp * Wp, 9 * Cn), dtype=torch.float32, device=dev)
+            _lib.check(lib.ocr_im2col3x3_same(_lib.ptr(a), Bn, Hn, Wn, Cn, ph, pw, s_h, s_w, _lib.ptr(patches), sh), "ocr_im2col3x3_same")
+            wk, bk = self.conv[name]
+            a = torch.empty((Bn, Hp, Wp, filters), dtype=torch.float32, device=dev)
+            _lib.check(lib.ocr_gemm_tf32(_lib.ptr(patches), 9 * Cn, _lib.ptr(wk), 9 * Cn, _lib.ptr(bk), _lib.ptr(a), filters,
+                                         Bn * Hp * Wp, filters, 9 * Cn, 1, sh), "ocr_gemm_tf32")
+            del patches
+        Bn, Hn, Wn, Cn = a.shape
+        seq = torch.empty((Wn, Bn, Cn), dtype=torch.float32, device=dev)   # pool8 (all Hn = 3 rows) + squeeze, time-major
+        _lib.check(lib.ocr_rows_max_to_seq(_lib.ptr(a), Bn, Hn, Wn, Cn, _lib.ptr(seq), sh), "ocr_rows_max_to_seq")
+        widths = torch.as_tensor(widths).to(device=dev, dtype=torch.int32)
+        sequence_length = torch.div(widths - 2, 2, rounding_mode="floor") - 2   # model.py:152-163
+        return seq.transpose(0, 1), sequence_length.to(torch.int32)
+
+    def rnn_layer(self, seq, sequence_length, layer):
+        """seq [T,B,I] time-major -> [T,B,2H]   (model.py:167-199)"""
+        lib = _lib.load()
+        L = self.rnn[layer]
+        T, B, I = seq.shape
+        H = L["H"]
+        cell = 0 if self.cell_type == "lstm" else 1
+        need = ctypes.c_size_t(0)
+        _lib.check(lib.ocr_birnn_workspace_bytes(cell, T, B, H, ctypes.byref(need)), "ocr_birnn_workspace_bytes")
+        ws = torch.empty(need.value, dtype=torch.uint8, device=seq.device)
+        out = torch.empty((T, B, 2 * H), dtype=torch.float32, device=seq.device)
+        _lib.check(lib.ocr_birnn_layer(cell, _lib.ptr(seq), T, B, I, H, _lib.ptr(sequence_length), _lib.ptr(L["wx"]), _lib.ptr(L["wh"]),
+                                       _lib.ptr(L["wh2"]), _lib.ptr(L["bias"]), _lib.ptr(out), _lib.ptr(ws), need.value,
+                                       _lib.stream_handle()), "ocr_birnn_layer")
+        return out
+
+    def rnn_layers(self, features, sequence_length, num_classes=None):
+        """features [B,T,256], sequence_length [B] -> logits [T,B,num_classes+1] (dense + ReLU).   model.py:202-221"""
+        _lib.require_cuda(features)
+        lib = _lib.load()
+        C = self.logits_w.shape[0]
+        if num_classes is not None and num_classes + 1 != C:
+            raise ValueError("this model's logits layer has %d outputs, not num_classes+1 = %d" % (C, num_classes + 1))
+        seq = features.transpose(0, 1).contiguous().float()   # time-major (model.py:212)
+        sl = sequence_length.to(device=seq.device, dtype=torch.int32).contiguous()
+        r1 = self.rnn_layer(seq, sl, 0)
+        r2 = self.rnn_layer(r1, sl, 1)
+        T, B, F = r2.shape
+        logits = torch.empty((T, B, C), dtype=torch.float32, device=seq.device)
+        _lib.check(lib.ocr_gemm_tf32(_lib.ptr(r2), F, _lib.ptr(self.logits_w), F, _lib.ptr(self.logits_b), _lib.ptr(logits), C,
+                                     T * B, C, F, 1, _lib.stream_handle()), "ocr_gemm_tf32")
+        return logits
+
+    def get_output(self, rnn_logits, sequence_length):
+        """validate._get_output: greedy CTC decode -> [dense int64 [B,Lmax], -1 padded]."""
+        predictions, _ = ctc.ctc_greedy_decoder(rnn_logits, sequence_length, merge_repeated=True)
+        return [ctc.sparse_tensor_to_dense(predictions[0], default_value=-1)]
+
+    def recognize(self, images, widths):
+        """images [B,32,W,1] uint8 or float -> list of strings: the graph LocalServer.run builds (server.py:80-89)
+        plus its post-processing (server.py:134-138)."""
+        features, sl = self.convnet_layers(images, widths, ModeKeys.INFER)
+        logits = self.rnn_layers(features, sl)
+        dense = self.get_output(logits, sl)[0].cpu().numpy()
+        return [get_string([c for c in row if c >= 0]) for row in dense]

@@ -117,6 +117,31 @@ int ocr_edit_distance(const int64_t* hyp, int hyp_stride, const int32_t* hyp_len
 int ocr_gemm_tf32(const float* A, int lda, const float* W, int ldw, const float* bias, float* D, int ldd, int M,
                   int N, int K, int relu, ocr_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Recognizer layers around the GEMM (INFER mode; batch-norm folded into filters/biases by the caller).
+ *
+ * ocr_conv1_3x3_valid: conv1 of convnet_layers (model.py:47,134; 3x3 'valid', ONE input channel, ReLU) with
+ *   validate._preprocess_image (validate.py:56-68: u8/255 - 0.5) fused in when in_is_u8 != 0.
+ *   in [B,H,W] u8 or f32;  w [3,3,1,Cout] (HWIO);  out [B,H-2,W-2,Cout] f32 NHWC.  Cout % 4 == 0.
+ * ocr_im2col3x3_same: patches of a 3x3 'same' convolution (model.py:97-104) taken from max_pool(in)
+ *   (model.py:111-116; window pool_h x pool_w, strides stride_h x stride_w, 'valid'; 1,1,1,1 = no pooling):
+ *   in [B,H,W,C] f32 NHWC -> out [B*Hp*Wp, 9*C], column order (kh, kw, c).  C % 4 == 0.
+ * ocr_rows_max_to_seq: pool8 + squeeze + time-major transpose (model.py:145-147,212): in [B,H,W,C] -> out [W,B,C].
+ * ocr_birnn_layer: one tf.nn.bidirectional_dynamic_rnn layer, time-major, per-example sequence_length
+ *   (model.py:167-199 GRUCell; model_bu.py:167-199 LSTMCell): zero outputs past the length, the backward
+ *   direction starts at frame len-1.  x [T,B,I] -> out [T,B,2H] (fw | bw).
+ *   cell 0 = LSTM: wx [8H,I] (rows fw i,j,f,o then bw), wh [8H,H], wh2 unused, bias [8H]; forget_bias 1.0
+ *   cell 1 = GRU : wx [6H,I] (rows per direction r,u,candidate), wh [4H,H] (r,u per direction), wh2 [2H,H], bias [6H] */
+int ocr_conv1_3x3_valid(const void* in, int in_is_u8, int B, int H, int W, const float* w, const float* bias, int Cout,
+                        float* out, ocr_stream_t stream);
+int ocr_im2col3x3_same(const float* in, int B, int H, int W, int C, int pool_h, int pool_w, int stride_h, int stride_w,
+                       float* out, ocr_stream_t stream);
+int ocr_rows_max_to_seq(const float* in, int B, int H, int W, int C, float* out, ocr_stream_t stream);
+int ocr_birnn_workspace_bytes(int cell, int T, int B, int H, size_t* bytes);
+int ocr_birnn_layer(int cell, const float* x, int T, int B, int I, int H, const int32_t* seq_len, const float* wx,
+                    const float* wh, const float* wh2, const float* bias, float* out, void* workspace,
+                    size_t workspace_bytes, ocr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

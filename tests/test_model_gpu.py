@@ -1,0 +1,88 @@
+"""GPU tier: the recognizer graph (conv stack -> BiLSTM / BiGRU -> logits -> greedy decode) on B200 against the
+float64 numpy oracle (oracle/model_oracle.py).
+
+Tolerance.  The contractions run as TF32 tensor-core products (each factor rounded to 10 mantissa bits, sums in
+fp32): relative error per product <= 2^-10, accumulated over K <= 2304 terms of mixed sign and eight conv layers +
+two recurrent layers it stays at the 1e-3 level relative to the activation scale.  Asserted: features within
+5e-3 * max|features|, logits within 1e-2 * max|logits| of the float64 reference.  Decodes are compared on the
+kernel's OWN logits (bit-exact against the CTC oracle); decode equality against the float64 graph is reported,
+not required, because ReLU logits have near-ties that a 1e-3 perturbation may flip."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(B, W, seed):
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (B, 32, W, 1)).astype(np.uint8)
+    widths = np.full(B, W, np.int32)
+    return img, widths
+
+
+@pytest.mark.parametrize("cell,sizes", [("lstm", (512, 512)), ("gru", (512, 256))])
+def test_full_graph_vs_oracle(cell, sizes):
+    from cnn_lstm_ctc_ocr_b200 import model
+    B, W = 4, 128
+    params = mo.init_params(seed=0, cell_type=cell, sizes=sizes, num_classes=95, dtype=np.float64, randomize_bn=True)
+    img, widths = _inputs(B, W, 1)
+    widths[1], widths[3] = 100, 41                     # ragged true widths inside the padded bucket (server.py:30)
+    feats_ref, sl_ref = mo.convnet_layers(mo.preprocess_image(img), widths, params)
+    logits_ref = mo.rnn_layers(feats_ref, sl_ref, params, cell, sizes)
+
+    m = model.Model(params, cell_type=cell, rnn_sizes=sizes)
+    dev = torch.device("cuda:0")
+    feats, sl = m.convnet_layers(torch.tensor(img, device=dev), torch.tensor(widths), model.ModeKeys.INFER)
+    assert sl.cpu().tolist() == sl_ref.tolist() == [61, 47, 61, 17]
+    f = feats.cpu().numpy()
+    assert f.shape == feats_ref.shape == (B, 61, 256)
+    assert np.abs(f - feats_ref).max() <= 5e-3 * np.abs(feats_ref).max()
+    # float input path (validate._preprocess_image applied by the caller): same features up to TF32 rounding noise
+    # (last-bit differences of the preprocessed pixels land on different TF32 roundings downstream)
+    feats2, _ = m.convnet_layers(model.preprocess_image(torch.tensor(img, device=dev)), torch.tensor(widths))
+    assert np.abs(feats2.cpu().numpy() - f).max() <= 2e-3 * np.abs(f).max()
+
+    logits = m.rnn_layers(feats, sl, 95)
+    lg = logits.cpu().numpy()
+    assert lg.shape == logits_ref.shape == (61, B, 96) and (lg >= 0).all()
+    for b in range(B):   # frames past the sequence length are relu(bias) on both sides; compare the live part
+        n = sl_ref[b]
+        assert np.abs(lg[:n, b] - logits_ref[:n, b]).max() <= 1e-2 * np.abs(logits_ref).max()
+    # decode of the kernel's own logits: bit-exact against the CTC oracle
+    from oracle import ctc_oracle
+    dense = m.get_output(logits, sl)[0].cpu().numpy()
+    od, ol, _ = ctc_oracle.ctc_greedy_decoder(lg, sl_ref)
+    assert (dense == ctc_oracle.densify(od, ol)).all()
+    texts = m.recognize(torch.tensor(img, device=dev), torch.tensor(widths))
+    assert len(texts) == B and all(isinstance(t, str) for t in texts)
+
+
+def test_rnn_layer_masks_and_directions():
+    """Per-example lengths: zeros past the length, backward direction starts at len-1 (bidirectional_dynamic_rnn)."""
+    from cnn_lstm_ctc_ocr_b200 import model
+    rng = np.random.default_rng(5)
+    params = mo.init_params(seed=2, cell_type="lstm", sizes=(512, 512), dtype=np.float64)
+    for k in list(params):
+        if "lstm_cell/kernel" in k:
+            params[k] = params[k] * 8      # make the recurrence matter (TruncNormal(0.01) is nearly linear)
+    T, B = 12, 5
+    feats = rng.standard_normal((B, T, 256))
+    sl = np.array([12, 1, 7, 0, 12], np.int32)
+    ref = mo.rnn_layer(np.transpose(feats, (1, 0, 2)), sl, params, "bdrnn1", "lstm", 512)
+    m = model.Model(params, cell_type="lstm", rnn_sizes=(512, 512))
+    dev = torch.device("cuda:0")
+    out = m.rnn_layer(torch.tensor(feats, device=dev, dtype=torch.float32).transpose(0, 1).contiguous(), torch.tensor(sl, device=dev), 0)
+    o = out.cpu().numpy()
+    assert np.abs(o - ref).max() <= 5e-3 * np.abs(ref).max()
+    for b in range(B):
+        assert (o[sl[b]:, b] == 0).all()
+
+
+def test_train_mode_not_built_yet():
+    from cnn_lstm_ctc_ocr_b200 import model
+    m = model.Model(mo.init_params(0, dtype=np.float32))
+    with pytest.raises(NotImplementedError):
+        m.convnet_layers(torch.zeros((1, 32, 64, 1), device="cuda"), torch.tensor([64]), model.ModeKeys.TRAIN)
