@@ -327,6 +327,9 @@ def run_ours(args, cfg):
                 bw = bandwidth_regime(lib, _lib, dev, T, C, args.bw_batch, windows)
             except torch.cuda.OutOfMemoryError:
                 bw = {"error": "out of memory"}
+        infer = None
+        if not args.skip_infer:
+            infer = inference_block(dev, world, windows, with_cpu=(rank == 0 and world == 1))
 
     sampler.stop()
     peak, peak_src = _peaks()
@@ -347,6 +350,7 @@ def run_ours(args, cfg):
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_us": kernel_us,
                          "note": "one step = ctc_loss_fast_kernel + the redo gate; cfg2 (8.3 MB, L2 resident, 64 CTAs of 2x24 dependent lattice frames) is latency-bound, see roofline_bw_regime"},
             "roofline_bw_regime": bw,
+            "inference": infer,
             "clocks": sampler.summary(windows),
             "parity_status_ok": ok_status,
         }
@@ -355,6 +359,100 @@ def run_ours(args, cfg):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------- recognizer inference (BASELINE configs[0])
+INFER_FLOP_PER_CROP = {("lstm", 128): 1855.5e6, ("gru", 128): 1225.9e6}  # forward FLOPs, SURVEY.md section 8(d)
+
+
+def inference_block(dev, world, windows, B=32, W=128, cell="lstm", steps=20, with_cpu=True):
+    """configs[0]: weinman CNN-BiLSTM-CTC inference, batch 32 synthetic 32x128 grayscale crops, greedy decode,
+    random-init weights.  value = graph replay with the crops resident in HBM; e2e = Model.recognize() from pinned
+    host uint8 crops to host strings."""
+    import numpy as np
+    import torch
+    from cnn_lstm_ctc_ocr_b200 import _lib, model
+    from oracle import model_oracle as mo   # parameter initialiser + CPU baseline only
+    sizes = (512, 512) if cell == "lstm" else (512, 256)
+    params = mo.init_params(0, cell, sizes, 95, np.float32)
+    m = model.Model(params, cell_type=cell, rnn_sizes=sizes, device=dev)
+    rng = np.random.default_rng(0)
+    host_img = torch.from_numpy(rng.integers(0, 256, (B, 32, W, 1)).astype(np.uint8)).pin_memory()
+    host_w = torch.full((B,), W, dtype=torch.int32).pin_memory()
+    img = host_img.to(dev)
+    widths = host_w.to(dev)
+
+    def fwd():
+        f, sl = m.convnet_layers(img, widths)
+        lg = m.rnn_layers(f, sl)
+        return m.get_output(lg, sl)
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            fwd()
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        fwd()
+        launches = _lib.launch_count() - n0
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            f, sl = m.convnet_layers(img, widths)
+            lg = m.rnn_layers(f, sl)
+            dec, ln, ns = __import__("cnn_lstm_ctc_ocr_b200").ctc.ctc_greedy_decode_raw(lg, sl)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_a = time.time()
+        e0.record(stream)
+        for _ in range(steps):
+            g.replay()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        windows.append((t_a, time.time()))
+        ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / steps
+        # end to end: host crops -> strings
+        for _ in range(2):
+            m.recognize(host_img.to(dev, non_blocking=True), host_w)
+        torch.cuda.synchronize()
+        t_a = time.time()
+        e0.record(stream)
+        for _ in range(steps):
+            texts = m.recognize(host_img.to(dev, non_blocking=True), host_w)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        windows.append((t_a, time.time()))
+        ms_e = max_over_ranks(e0.elapsed_time(e1), world, dev) / steps
+    flop = INFER_FLOP_PER_CROP.get((cell, W))
+    peaks = {}
+    pth = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pth):
+        with open(pth) as fjs:
+            peaks = json.load(fjs)
+    tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
+    out = {"workload": "BASELINE configs[0]: weinman CNN-Bi%s-CTC inference, batch %d synthetic 32x%d grayscale crops, greedy CTC decode, "
+                       "random-init weights, 96 logits" % (cell.upper(), B, W),
+           "value": world * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "gpu_launches_per_step": launches,
+           "timed_region": "cuda graph replay of the whole forward + greedy decode, crops resident in HBM",
+           "dtype": "tf32 products, fp32 accumulate/storage",
+           "e2e": {"value": world * B / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(host_img.numel() + host_w.numel() * 4),
+                   "d2h_bytes_per_step": int(B * 61 * 8), "api": "cnn_lstm_ctc_ocr_b200.model.Model.recognize (uint8 crops -> strings)"},
+           "roofline": {"bound": "tensor", "achieved": (flop * B / (ms * 1e-3) / 1e12) if flop else None, "peak": tf32_peak, "unit": "TFLOP/s",
+                        "frac": (flop * B / (ms * 1e-3) / 1e12 / tf32_peak) if flop else None, "traffic": None,
+                        "peak_source": "half of the measured sustained bf16 GEMM peak (TF32 runs at half the bf16 rate); "
+                                       "the step is launch/latency bound by the %d-frame recurrence, not tensor bound" % 61}}
+    if with_cpu:
+        t0 = time.perf_counter()
+        p64 = {k: v.astype(np.float32) for k, v in params.items()}
+        x = mo.preprocess_image(host_img.numpy()).astype(np.float32)
+        feats, sl_ = mo.convnet_layers(x, np.full(B, W), p64)
+        logits = mo.rnn_layers(feats, sl_, p64, cell, sizes)
+        from oracle import ctc_oracle
+        ctc_oracle.ctc_greedy_decoder(logits.astype(np.float32), sl_)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": B / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                               "sample": "one batch of %d crops through oracle/model_oracle.py (numpy float32, BLAS threads) + "
+                                         "the C greedy decoder, %.1f s wall (TensorFlow itself cannot run in this image)" % (B, dt)}
+    return out
 
 
 def bandwidth_regime(lib, _lib, dev, T, C, B, windows):
@@ -412,6 +510,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time K eager launches instead of one CUDA graph of K launches")
     ap.add_argument("--skip-bw", action="store_true", help="skip the bandwidth-regime measurement")
     ap.add_argument("--bw-batch", type=int, default=65536)
+    ap.add_argument("--skip-infer", action="store_true", help="skip the recognizer-inference block (BASELINE configs[0])")
     args = ap.parse_args()
     cfg = {"T": 64, "B": 256, "C": 63,
            "config": {"workload": "BASELINE configs[1]: CTC loss + gradient only, batch 256, T=64 frames, 63-class alphabet "
