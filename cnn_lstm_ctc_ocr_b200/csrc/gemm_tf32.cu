@@ -20,55 +20,7 @@
 
 namespace ocr {
 
-constexpr int kGemmBM = 128;
-constexpr int kGemmBK = 32;  // fp32 elements = one 128-byte swizzle row
 constexpr int kGemmThreads = 192;
-
-__device__ __forceinline__ unsigned g_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void g_mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void g_mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// bounded wait: a protocol bug traps instead of hanging the GPU
-__device__ __forceinline__ void g_mbar_wait(unsigned bar, unsigned parity) {
-    unsigned done = 0;
-    for (unsigned it = 0; it < (1u << 28); ++it) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return;
-    }
-    __trap();
-}
-__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* tm, int c0, int c1, unsigned bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-// shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows of 128 bytes, 8-row atoms 1024 bytes apart
-__device__ __forceinline__ unsigned long long umma_desc_k128(unsigned smem_addr) {
-    unsigned long long d = 0;
-    d |= (unsigned long long)((smem_addr >> 4) & 0x3FFF);
-    d |= (unsigned long long)1 << 16;               // leading byte offset (unused for swizzled K-major)
-    d |= (unsigned long long)(1024 >> 4) << 32;     // stride byte offset: next 8-row atom
-    d |= (unsigned long long)1 << 46;               // descriptor version (sm_100)
-    d |= (unsigned long long)2 << 61;               // SWIZZLE_128B
-    return d;
-}
-__device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc, unsigned acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u) : "memory");
-}
-__device__ __forceinline__ void umma_commit(unsigned bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
 
 template <int BN, int STAGES>
 struct GemmSmem {
@@ -210,7 +162,8 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 tensor [rows, K] row-major with row pitch ld elements; box = [box_rows, 32 floats], 128-byte swizzle
-static int make_map(CUtensorMap* tm, const float* base, long long rows, long long K, long long ld, int box_rows) {
+namespace ocr {
+int tma_map_2d(CUtensorMap* tm, const float* base, long long rows, long long K, long long ld, int box_rows) {
     EncodeTiledFn enc = get_encode();
     if (enc == nullptr) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return OCR_ECUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -223,6 +176,7 @@ static int make_map(CUtensorMap* tm, const float* base, long long rows, long lon
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld K=%lld ld=%lld", (int)r, rows, K, ld); return OCR_ECUDA; }
     return OCR_OK;
 }
+}  // namespace ocr
 
 template <int BN, int STAGES>
 static int launch_planned(const GemmPlan& p, cudaStream_t st)
@@ -258,9 +212,9 @@ int gemm_plan(GemmPlan* p, const float* A, int lda, const float* W, int ldw, con
     if (N > 64 && mt * ((N + 127) / 128) >= 120) bn = 128;
     if (N > 128 && mt * ((N + 255) / 256) >= 120) bn = 256;
     p->bn = bn; p->bias = bias; p->D = D; p->M = M; p->N = N; p->K = K; p->ldd = ldd; p->relu = relu;
-    int rc = make_map(&p->tmA, A, M, K, lda, kGemmBM);
+    int rc = tma_map_2d(&p->tmA, A, M, K, lda, kGemmBM);
     if (rc != OCR_OK) return rc;
-    return make_map(&p->tmB, W, N, K, ldw, bn);
+    return tma_map_2d(&p->tmB, W, N, K, ldw, bn);
 }
 
 int gemm_run(const GemmPlan& p, cudaStream_t st)

@@ -1,0 +1,291 @@
+// Persistent bidirectional LSTM recurrence for sm_100a: the frame loop of tf.nn.bidirectional_dynamic_rnn over
+// tf.contrib.rnn.LSTMCell (/root/reference/src/weinman/model_bu.py:167-199) as ONE kernel launch per layer.
+//
+// The per-frame product h_{t-1} * W_h^T is tiny (M = batch, N = 4H, K = H) and strictly sequential in t: as a
+// stream of per-frame GEMM launches it is bound by launch + ramp-up latency.  Here the recurrent weights never
+// leave the chip:
+//   * CTA (d, j) owns direction d and hidden units [j*hs, (j+1)*hs): its 4*hs gate rows of W_h (gate-major) are
+//     TMA-loaded ONCE into shared memory (128 KB for hs = 16, H = 512, TF32) as 128B-swizzled K-major tiles;
+//   * every frame, the previous hidden state of the direction ([B, H], global/L2) streams through a 4-stage TMA
+//     ring as the A operand; tcgen05.mma.kind::tf32 (M = 128 batch rows, N = 4*hs, K = 8) accumulates the gate
+//     pre-activations of the CTA's units into TMEM;
+//   * TMEM lane = batch row, so one epilogue thread holds all four gates of all hs units of its example: it adds
+//     the input projection, applies the cell update with the cell state c kept in REGISTERS for the whole sequence,
+//     and writes h_t (next frame's operand, double buffered) and the layer output;
+//   * the CTAs of a direction meet at a per-frame grid barrier (global atomic counter; cooperative launch
+//     guarantees co-residency), both directions run concurrently in the same launch.
+// Per-example sequence lengths follow dynamic_rnn: an example is updated only while s < len (its state is carried
+// unchanged afterwards, outputs past the length stay zero); the backward direction visits frame len-1-s at step s.
+#include "gemm_tf32.cuh"
+
+namespace ocr {
+
+constexpr int kRnnMaxStages = 32;
+constexpr int kRnnThreads = 192;
+
+// one MUFU each (tanh.approx: max relative error 2^-11, the same order as the TF32 rounding of the operands)
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigm(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+
+// bounded spin on a global counter (acquire)
+__device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned target) {
+    for (unsigned it = 0; it < (1u << 27); ++it) {
+        unsigned v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        if (v >= target) return;
+        __nanosleep(20);
+    }
+    __trap();
+}
+
+template <int HS>  // hidden units per CTA; N = 4*HS gate columns
+__global__ void __launch_bounds__(kRnnThreads, 1)
+lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH00,
+                       const __grid_constant__ CUtensorMap tmH01, const __grid_constant__ CUtensorMap tmH10,
+                       const __grid_constant__ CUtensorMap tmH11, const float* __restrict__ xp, const int32_t* __restrict__ seq_len,
+                       float* __restrict__ hbuf /*[2 parity][2 dir][B][H]*/, float* __restrict__ out /*[T,B,2H]*/,
+                       unsigned* __restrict__ counters /*[2]*/, int T, int B, int H, int NS, int a_rows, int n_stages)
+{
+    constexpr int N = 4 * HS;
+    const int nk = H / kGemmBK;
+    extern __shared__ unsigned char rnn_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(rnn_smem_raw) + 1023) & ~(uintptr_t)1023);
+    const unsigned s_base = g_smem_u32(smem);
+    const unsigned w_bytes = (unsigned)N * kGemmBK * 4;          // one k-chunk of the weight slice
+    // one k-chunk of h: only the a_rows (>= B, multiple of 8) real batch rows are fetched; the MMA still reads 128
+    // rows, the rest is whatever follows in shared memory and lands in TMEM lanes no thread looks at
+    const unsigned a_bytes = (unsigned)a_rows * kGemmBK * 4;
+    const unsigned s_w = s_base;                                 // nk resident weight tiles
+    const unsigned s_a = s_w + (unsigned)nk * w_bytes;           // ring of kRnnStages h tiles
+    const unsigned s_bar = s_a + (unsigned)n_stages * a_bytes + kGemmBM * kGemmBK * 4;  // + one full tile of slack for the 128-row read
+    const unsigned bar_full = s_bar, bar_empty = s_bar + kRnnMaxStages * 8, bar_w = bar_empty + kRnnMaxStages * 8, bar_acc = bar_w + 8;
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + (s_bar - s_base) + (2 * kRnnMaxStages + 2) * 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = blockIdx.x / NS, j = blockIdx.x % NS;  // direction, hidden slice
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < n_stages; ++s) { g_mbar_init(bar_full + s * 8, 1); g_mbar_init(bar_empty + s * 8, 1); }
+        g_mbar_init(bar_w, 1);
+        g_mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)), "r"((unsigned)(N < 32 ? 32 : N)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_d = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // resident weight slice: rows [(d*NS + j)*N, +N) of the gate-major permuted W_h
+            g_mbar_expect_tx(bar_w, (unsigned)nk * w_bytes);
+            for (int k = 0; k < nk; ++k) tma_load_2d(s_w + k * w_bytes, &tmW, k * kGemmBK, (d * NS + j) * N, bar_w);
+            int it = 0;
+            for (int s = 0; s < T; ++s) {
+                if (s > 0) {
+                    wait_counter(counters + d, (unsigned)NS * (unsigned)s);   // every slice of this direction wrote h_s
+                    asm volatile("fence.proxy.async;" ::: "memory");          // generic-proxy writes -> async-proxy (TMA) reads
+                }
+                const CUtensorMap* tm = (s & 1) ? (d ? &tmH11 : &tmH10) : (d ? &tmH01 : &tmH00);
+                for (int k = 0; k < nk; ++k, ++it) {
+                    const int st = it % n_stages;
+                    if (it >= n_stages) g_mbar_wait(bar_empty + st * 8, ((it / n_stages) - 1) & 1);
+                    g_mbar_expect_tx(bar_full + st * 8, a_bytes);
+                    tma_load_2d(s_a + st * a_bytes, tm, k * kGemmBK, 0, bar_full + st * 8);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(kGemmBM >> 4) << 24);
+            g_mbar_wait(bar_w, 0);
+            int it = 0;
+            for (int s = 0; s < T; ++s) {
+                for (int k = 0; k < nk; ++k, ++it) {
+                    const int st = it % n_stages;
+                    g_mbar_wait(bar_full + st * 8, (it / n_stages) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const unsigned long long da = umma_desc_k128(s_a + st * a_bytes), db = umma_desc_k128(s_w + k * w_bytes);
+#pragma unroll
+                    for (int kk = 0; kk < kGemmBK / 8; ++kk)
+                        umma_tf32(tmem_d, da + (unsigned long long)(kk * 2), db + (unsigned long long)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+                    umma_commit(bar_empty + st * 8);
+                }
+                umma_commit(bar_acc);   // gate pre-activations of frame step s are in TMEM
+                // the next frame's first MMA overwrites TMEM; it cannot start before the epilogue has read this frame:
+                // its operand h_{s+1} only exists after every CTA (this one included) passed the grid barrier
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;           // batch row = TMEM lane
+        const bool live_row = r < B;
+        const int len = live_row ? min(max(seq_len[r], 0), T) : 0;
+        float c[HS], h[HS];
+#pragma unroll
+        for (int u = 0; u < HS; ++u) { c[u] = 0.0f; h[u] = 0.0f; }
+        for (int s = 0; s < T; ++s) {
+            // the input projection of this frame does not depend on the recurrent product: fetch it while the MMAs run
+            const bool upd = live_row && s < len;
+            const int t = d ? len - 1 - s : s;
+            float xi[HS], xj[HS], xf[HS], xo[HS];
+            if (upd) {
+                const float* x = xp + ((size_t)t * B + r) * 8 * H + (size_t)d * 4 * H + j * HS;
+#pragma unroll
+                for (int u = 0; u < HS; u += 4) {
+                    *reinterpret_cast<float4*>(xi + u) = __ldg(reinterpret_cast<const float4*>(x + u));
+                    *reinterpret_cast<float4*>(xj + u) = __ldg(reinterpret_cast<const float4*>(x + H + u));
+                    *reinterpret_cast<float4*>(xf + u) = __ldg(reinterpret_cast<const float4*>(x + 2 * H + u));
+                    *reinterpret_cast<float4*>(xo + u) = __ldg(reinterpret_cast<const float4*>(x + 3 * H + u));
+                }
+            }
+            g_mbar_wait(bar_acc, s & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            unsigned g[N];
+#pragma unroll
+            for (int c0 = 0; c0 < N; c0 += 16) {
+                const unsigned taddr = tmem_d + ((unsigned)(q * 32) << 16) + (unsigned)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(g[c0 + 0]), "=r"(g[c0 + 1]), "=r"(g[c0 + 2]), "=r"(g[c0 + 3]), "=r"(g[c0 + 4]), "=r"(g[c0 + 5]), "=r"(g[c0 + 6]),
+                      "=r"(g[c0 + 7]), "=r"(g[c0 + 8]), "=r"(g[c0 + 9]), "=r"(g[c0 + 10]), "=r"(g[c0 + 11]), "=r"(g[c0 + 12]),
+                      "=r"(g[c0 + 13]), "=r"(g[c0 + 14]), "=r"(g[c0 + 15])
+                    : "r"(taddr) : "memory");
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (live_row) {
+                float* hn = hbuf + (((size_t)((s + 1) & 1) * 2 + d) * B + r) * H + j * HS;
+                if (upd) {
+#pragma unroll
+                    for (int u = 0; u < HS; ++u) {
+                        const float zi = __uint_as_float(g[u]) + xi[u];
+                        const float zj = __uint_as_float(g[HS + u]) + xj[u];
+                        const float zf = __uint_as_float(g[2 * HS + u]) + xf[u];
+                        const float zo = __uint_as_float(g[3 * HS + u]) + xo[u];
+                        c[u] = sigm(zf + 1.0f) * c[u] + sigm(zi) * tanh_fast(zj);
+                        h[u] = sigm(zo) * tanh_fast(c[u]);
+                    }
+                    float* o = out + ((size_t)t * B + r) * 2 * H + (size_t)d * H + j * HS;
+#pragma unroll
+                    for (int u = 0; u < HS; u += 4) *reinterpret_cast<float4*>(o + u) = make_float4(h[u], h[u + 1], h[u + 2], h[u + 3]);
+                }
+                // carried or updated, the state is the next frame's operand
+#pragma unroll
+                for (int u = 0; u < HS; u += 4) *reinterpret_cast<float4*>(hn + u) = make_float4(h[u], h[u + 1], h[u + 2], h[u + 3]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps: their h stores are ordered before...
+            if (warp == 2 && lane == 0)                      // ...this gpu-scope release (cumulative) that publishes the slice
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counters + d) : "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((unsigned)(N < 32 ? 32 : N)) : "memory");
+    }
+}
+
+// gate-major permutation of the recurrent weights: row ((d*NS + j)*4 + g)*HS + u  <-  wh[d*4H + g*H + j*HS + u]
+__global__ void permute_wh_kernel(const float* __restrict__ wh, float* __restrict__ whp, int H, int HS, int NS)
+{
+    const long long total = (long long)8 * H * H;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(idx % H);
+        long long row = idx / H;
+        const int u = (int)(row % HS); row /= HS;
+        const int g = (int)(row % 4); row /= 4;
+        const int j = (int)(row % NS);
+        const int d = (int)(row / NS);
+        whp[idx] = wh[((size_t)d * 4 * H + (size_t)g * H + j * HS + u) * H + k];
+    }
+}
+
+}  // namespace ocr
+
+using namespace ocr;
+
+constexpr int kHS = 16;
+
+namespace ocr {
+
+bool lstm_persistent_supported(int T, int B, int H) {
+    if (B > kGemmBM || (H % kGemmBK) != 0 || (H % kHS) != 0) return false;
+    const int NS = H / kHS;
+    if (2 * NS > 148) return false;   // one CTA per SM, all co-resident
+    if (H / kGemmBK > kRnnMaxStages) return false;
+    const size_t w = (size_t)H / kGemmBK * (4 * kHS) * kGemmBK * 4;
+    const size_t a = (size_t)((B + 7) / 8 * 8) * kGemmBK * 4;
+    // weights + at least 2 stages of h + the slack tile + barriers + alignment
+    return w + 2 * a + kGemmBM * kGemmBK * 4 + 1024 + 1024 <= (size_t)kMaxDynSmem && T >= 1;
+}
+
+size_t lstm_persistent_workspace_floats(int B, int H) {
+    // permuted W_h [8H, H] + h double buffer [2][2][B][H] + counters (64 floats)
+    return (size_t)8 * H * H + (size_t)4 * B * H + 64;
+}
+
+// xp [T*B, 8H] (input projection + bias), wh [8H, H] (fw i,j,f,o | bw), out [T,B,2H] (pre-zeroed by this call)
+int lstm_persistent_run(const float* xp, const float* wh, const int32_t* seq_len, int T, int B, int H, float* out, float* ws,
+                        cudaStream_t st)
+{
+    const int NS = H / kHS;
+    float* whp = ws;
+    float* hbuf = whp + (size_t)8 * H * H;
+    unsigned* counters = reinterpret_cast<unsigned*>(hbuf + (size_t)4 * B * H);
+    {
+        const long long total = (long long)8 * H * H;
+        long long gsz = (total + 255) / 256;
+        permute_wh_kernel<<<(int)(gsz > 148 * 16 ? 148 * 16 : gsz), 256, 0, st>>>(wh, whp, H, kHS, NS);
+        OCR_CHECK_LAUNCH();
+    }
+    OCR_CHECK_CUDA(cudaMemsetAsync(hbuf, 0, sizeof(float) * ((size_t)4 * B * H + 64), st));
+    OCR_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)T * B * 2 * H, st));
+    const int nk = H / kGemmBK;
+    const int a_rows = (B + 7) / 8 * 8;
+    const size_t w_bytes = (size_t)nk * (4 * kHS) * kGemmBK * 4, a_bytes = (size_t)a_rows * kGemmBK * 4;
+    const size_t fixed = w_bytes + kGemmBM * kGemmBK * 4 + 1024 + 1024;
+    int n_stages = (int)(((size_t)kMaxDynSmem - fixed) / a_bytes);
+    n_stages = n_stages > nk ? nk : n_stages;   // the whole h row block in flight when it fits
+    CUtensorMap tmW, tmH[2][2];
+    int rc = tma_map_2d(&tmW, whp, (long long)8 * H, H, H, 4 * kHS);
+    if (rc != OCR_OK) return rc;
+    for (int p = 0; p < 2; ++p)
+        for (int d = 0; d < 2; ++d) {
+            rc = tma_map_2d(&tmH[p][d], hbuf + ((size_t)p * 2 + d) * B * H, B, H, H, a_rows);
+            if (rc != OCR_OK) return rc;
+        }
+    const size_t smem = fixed + (size_t)n_stages * a_bytes;
+    static int configured = -1;
+    int dev = 0;
+    OCR_CHECK_CUDA(cudaGetDevice(&dev));
+    if (configured != dev) {
+        OCR_CHECK_CUDA(cudaFuncSetAttribute(lstm_persistent_kernel<kHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        configured = dev;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * NS);
+    cfg.blockDim = dim3(kRnnThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: they wait on each other every frame
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_persistent_kernel<kHS>, tmW, tmH[0][0], tmH[0][1], tmH[1][0], tmH[1][1], xp, seq_len, hbuf, out,
+                                      counters, T, B, H, NS, a_rows, n_stages));
+    count_launch();
+    return OCR_OK;
+}
+
+}  // namespace ocr

@@ -172,6 +172,12 @@ gru_cell_kernel(const float* __restrict__ ch, const float* __restrict__ xp, cons
     }
 }
 
+// lstm_persistent.cu
+bool lstm_persistent_supported(int T, int B, int H);
+size_t lstm_persistent_workspace_floats(int B, int H);
+int lstm_persistent_run(const float* xp, const float* wh, const int32_t* seq_len, int T, int B, int H, float* out, float* ws,
+                        cudaStream_t st);
+
 static inline int grid_for(long long total, int threads = 256) {
     long long g = (total + threads - 1) / threads;
     const long long cap = 148LL * 16;
@@ -220,12 +226,22 @@ extern "C" int ocr_rows_max_to_seq(const float* in, int B, int H, int W, int C, 
     return OCR_OK;
 }
 
+// 0 = automatic (persistent LSTM kernel when the shape allows), 1 = frame-by-frame launches only
+static int g_birnn_path = 0;
+extern "C" int ocr_birnn_set_path(int path) {
+    OCR_CHECK_ARG(path == 0 || path == 1, "ocr_birnn_set_path: path=%d outside [0,1]", path);
+    g_birnn_path = path;
+    return OCR_OK;
+}
+
 extern "C" int ocr_birnn_workspace_bytes(int cell, int T, int B, int H, size_t* bytes)
 {
     OCR_CHECK_ARG(bytes != nullptr && (cell == 0 || cell == 1) && T >= 0 && B >= 0 && H >= 1, "ocr_birnn_workspace_bytes: bad argument");
     const size_t G = (cell == 0) ? 4 : 3;
     // xp [T*B, 2*G*H] + gh [2B, 2*(cell?2:4)*H] + h, c/u, rh [2B,H] each + ch [2B,2H]
-    *bytes = sizeof(float) * ((size_t)T * B * 2 * G * H + (size_t)2 * B * 8 * H + (size_t)2 * B * H * 3 + (size_t)2 * B * 2 * H) + 256;
+    size_t step = (size_t)2 * B * 8 * H + (size_t)2 * B * H * 3 + (size_t)2 * B * 2 * H;
+    if (cell == 0 && lstm_persistent_supported(T, B, H)) step = step > lstm_persistent_workspace_floats(B, H) ? step : lstm_persistent_workspace_floats(B, H);
+    *bytes = sizeof(float) * ((size_t)T * B * 2 * G * H + step) + 256;
     return OCR_OK;
 }
 
@@ -257,6 +273,8 @@ extern "C" int ocr_birnn_layer(int cell, const float* x, int T, int B, int I, in
     // input projection of every frame and both directions, bias folded in
     int rc = ocr_gemm_tf32(x, I, wx, I, bias, xp, 2 * G * H, T * B, 2 * G * H, I, 0, stream);
     if (rc != OCR_OK) return rc;
+    if (cell == 0 && g_birnn_path == 0 && lstm_persistent_supported(T, B, H))
+        return lstm_persistent_run(xp, wh, seq_len, T, B, H, out, gh, st);   // one launch for all T frames
     OCR_CHECK_CUDA(cudaMemsetAsync(h, 0, sizeof(float) * (size_t)2 * B * H * 3, st));
     OCR_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)T * B * 2 * H, st));
     const int cg = grid_for((long long)2 * B * H);

@@ -138,6 +138,9 @@ int ocr_im2col3x3_same(const float* in, int B, int H, int W, int C, int pool_h, 
                        float* out, ocr_stream_t stream);
 int ocr_rows_max_to_seq(const float* in, int B, int H, int W, int C, float* out, ocr_stream_t stream);
 int ocr_birnn_workspace_bytes(int cell, int T, int B, int H, size_t* bytes);
+/* Kernel-path override for tests: 0 = automatic (LSTM layers with B <= 128, H <= 512 run as ONE persistent
+ * tcgen05 kernel for all frames), 1 = one recurrent GEMM + one cell kernel per frame. */
+int ocr_birnn_set_path(int path);
 int ocr_birnn_layer(int cell, const float* x, int T, int B, int I, int H, const int32_t* seq_len, const float* wx,
                     const float* wh, const float* wh2, const float* bias, float* out, void* workspace,
                     size_t workspace_bytes, ocr_stream_t stream);

@@ -60,9 +60,12 @@ def test_full_graph_vs_oracle(cell, sizes):
     assert len(texts) == B and all(isinstance(t, str) for t in texts)
 
 
-def test_rnn_layer_masks_and_directions():
-    """Per-example lengths: zeros past the length, backward direction starts at len-1 (bidirectional_dynamic_rnn)."""
-    from cnn_lstm_ctc_ocr_b200 import model
+@pytest.mark.parametrize("path", [0, 1])
+def test_rnn_layer_masks_and_directions(path):
+    """Per-example lengths: zeros past the length, backward direction starts at len-1 (bidirectional_dynamic_rnn).
+    path 0 = persistent tcgen05 LSTM kernel, path 1 = frame-by-frame launches."""
+    from cnn_lstm_ctc_ocr_b200 import model, _lib
+    _lib.check(_lib.load().ocr_birnn_set_path(path), "ocr_birnn_set_path")
     rng = np.random.default_rng(5)
     params = mo.init_params(seed=2, cell_type="lstm", sizes=(512, 512), dtype=np.float64)
     for k in list(params):
@@ -76,6 +79,7 @@ def test_rnn_layer_masks_and_directions():
     dev = torch.device("cuda:0")
     out = m.rnn_layer(torch.tensor(feats, device=dev, dtype=torch.float32).transpose(0, 1).contiguous(), torch.tensor(sl, device=dev), 0)
     o = out.cpu().numpy()
+    _lib.load().ocr_birnn_set_path(0)
     assert np.abs(o - ref).max() <= 5e-3 * np.abs(ref).max()
     for b in range(B):
         assert (o[sl[b]:, b] == 0).all()
