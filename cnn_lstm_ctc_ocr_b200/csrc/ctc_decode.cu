@@ -5,8 +5,8 @@
 // App. A.5): per frame first-maximum arg-max (ties -> lowest class index; they are real here
 // because the logits come out of a ReLU, model.py:206,216), neg_sum_logits accumulated in frame
 // order, emit unless blank or equal to the previous frame's class.
-// One warp per sequence: HBM-bound read-once scan of T*C*4 bytes per sequence; four rows are kept
-// in flight per warp to cover DRAM latency.
+// One CTA (4 warps) per sequence: HBM-bound read-once scan of T*C*4 bytes per sequence; sixteen rows are kept
+// in flight per CTA to cover DRAM latency.
 //
 // Edit distance: replaces tf.edit_distance(normalize=False) at src/weinman/test.py:90.  One warp
 // per pair, anti-diagonal Levenshtein wavefront in shared memory.
@@ -21,23 +21,26 @@ __device__ __forceinline__ void argmax_combine(float& v, int& i, float ov, int o
     if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
 }
 
+// One CTA (4 warps) per sequence.  Phase 1: the warps take the frames round-robin, four rows in flight each, and
+// leave the per-frame arg-max (class, value) in shared memory.  Phase 2: warp 0 collapses repeats / drops blanks with
+// ballot prefix counts (order-preserving compaction) and lane 0 adds the maxima in frame order (bit-exact float sum).
 __global__ void __launch_bounds__(kGreedyWarps * 32)
 ctc_greedy_kernel(const float* __restrict__ logits, int T, int B, int C, const int32_t* __restrict__ seq_len,
                   int merge_repeated, int64_t* __restrict__ decoded, int32_t* __restrict__ decoded_len,
                   float* __restrict__ neg_sum_logits)
 {
-    const int lane = threadIdx.x & 31;
-    const int b = blockIdx.x * kGreedyWarps + (threadIdx.x >> 5);
-    if (b >= B) return;
+    extern __shared__ unsigned char greedy_smem[];
+    int* s_idx = reinterpret_cast<int*>(greedy_smem);          // [T]
+    float* s_val = reinterpret_cast<float*>(s_idx + T);        // [T]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.x;
     const int Tb = min(max(seq_len[b], 0), T);
     const int blank = C - 1;
     const size_t rstride = (size_t)B * C;
     const float* xb = logits + (size_t)b * C;
     int64_t* out = decoded + (size_t)b * T;
-    int prev = -1, n = 0;
-    float acc = 0.0f;
-    constexpr int R = 4;  // rows in flight
-    for (int t0 = 0; t0 < Tb; t0 += R) {
+    constexpr int R = 4;  // rows in flight per warp
+    for (int t0 = warp * R; t0 < Tb; t0 += kGreedyWarps * R) {
         float bv[R];
         int bi[R];
 #pragma unroll
@@ -61,22 +64,29 @@ ctc_greedy_kernel(const float* __restrict__ logits, int T, int B, int C, const i
                 int oi = __shfl_xor_sync(kFullMask, bi[r], o);
                 argmax_combine(bv[r], bi[r], ov, oi);
             }
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if (t0 + r < Tb) {
-                    acc += -bv[r];
-                    const int c = bi[r];
-                    if (c != blank && !(merge_repeated && c == prev)) out[n++] = c;
-                    prev = c;
-                }
-            }
+            if (lane == 0 && t0 + r < Tb) { s_idx[t0 + r] = bi[r]; s_val[t0 + r] = bv[r]; }
         }
     }
-    n = __shfl_sync(kFullMask, n, 0);
+    __syncthreads();
+    if (warp != 0) return;
+    int n = 0;
+    for (int t0 = 0; t0 < Tb; t0 += 32) {
+        const int t = t0 + lane;
+        bool keep = false;
+        int c = 0;
+        if (t < Tb) {
+            c = s_idx[t];
+            const int prev = t > 0 ? s_idx[t - 1] : -1;
+            keep = c != blank && !(merge_repeated && c == prev);
+        }
+        const unsigned m = __ballot_sync(kFullMask, keep);
+        if (keep) out[n + __popc(m & ((1u << lane) - 1))] = c;
+        n += __popc(m);
+    }
     for (int t = n + lane; t < T; t += 32) out[t] = -1;
     if (lane == 0) {
+        float acc = 0.0f;
+        for (int t = 0; t < Tb; ++t) acc += -s_val[t];
         decoded_len[b] = n;
         neg_sum_logits[b] = acc;
     }
@@ -151,8 +161,8 @@ extern "C" int ocr_ctc_greedy_decode(const float* logits, int T, int B, int C, c
     OCR_CHECK_ARG(T >= 1 && B >= 0 && C >= 2, "ocr_ctc_greedy_decode: bad shape T=%d B=%d C=%d", T, B, C);
     if (B == 0) return OCR_OK;
     OCR_CHECK_ARG(logits && seq_len && decoded && decoded_len && neg_sum_logits, "ocr_ctc_greedy_decode: NULL argument");
-    const int grid = (B + kGreedyWarps - 1) / kGreedyWarps;
-    ctc_greedy_kernel<<<grid, kGreedyWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+    OCR_CHECK_ARG((size_t)T * 8 <= 48 * 1024, "ocr_ctc_greedy_decode: T=%d too large", T);
+    ctc_greedy_kernel<<<B, kGreedyWarps * 32, (size_t)T * 8, static_cast<cudaStream_t>(stream)>>>(
         logits, T, B, C, seq_len, merge_repeated, decoded, decoded_len, neg_sum_logits);
     OCR_CHECK_LAUNCH();
     return OCR_OK;

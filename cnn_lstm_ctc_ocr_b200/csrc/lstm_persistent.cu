@@ -235,18 +235,28 @@ size_t lstm_persistent_workspace_floats(int B, int H) {
 }
 
 // xp [T*B, 8H] (input projection + bias), wh [8H, H] (fw i,j,f,o | bw), out [T,B,2H] (pre-zeroed by this call)
-int lstm_persistent_run(const float* xp, const float* wh, const int32_t* seq_len, int T, int B, int H, float* out, float* ws,
-                        cudaStream_t st)
+int lstm_permute_wh(const float* wh, int H, float* whp, cudaStream_t st)
+{
+    const long long total = (long long)8 * H * H;
+    long long gsz = (total + 255) / 256;
+    permute_wh_kernel<<<(int)(gsz > 148 * 16 ? 148 * 16 : gsz), 256, 0, st>>>(wh, whp, H, kHS, H / kHS);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+// wh_perm: gate-major permuted recurrent weights from lstm_permute_wh, or NULL to permute wh into the workspace now
+int lstm_persistent_run(const float* xp, const float* wh, const float* wh_perm, const int32_t* seq_len, int T, int B, int H,
+                        float* out, float* ws, cudaStream_t st)
 {
     const int NS = H / kHS;
-    float* whp = ws;
-    float* hbuf = whp + (size_t)8 * H * H;
+    float* whp_ws = ws;
+    float* hbuf = whp_ws + (size_t)8 * H * H;
     unsigned* counters = reinterpret_cast<unsigned*>(hbuf + (size_t)4 * B * H);
-    {
-        const long long total = (long long)8 * H * H;
-        long long gsz = (total + 255) / 256;
-        permute_wh_kernel<<<(int)(gsz > 148 * 16 ? 148 * 16 : gsz), 256, 0, st>>>(wh, whp, H, kHS, NS);
-        OCR_CHECK_LAUNCH();
+    const float* whp = wh_perm;
+    if (whp == nullptr) {
+        int rc0 = lstm_permute_wh(wh, H, whp_ws, st);
+        if (rc0 != OCR_OK) return rc0;
+        whp = whp_ws;
     }
     OCR_CHECK_CUDA(cudaMemsetAsync(hbuf, 0, sizeof(float) * ((size_t)4 * B * H + 64), st));
     OCR_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)T * B * 2 * H, st));

@@ -175,8 +175,9 @@ gru_cell_kernel(const float* __restrict__ ch, const float* __restrict__ xp, cons
 // lstm_persistent.cu
 bool lstm_persistent_supported(int T, int B, int H);
 size_t lstm_persistent_workspace_floats(int B, int H);
-int lstm_persistent_run(const float* xp, const float* wh, const int32_t* seq_len, int T, int B, int H, float* out, float* ws,
-                        cudaStream_t st);
+int lstm_permute_wh(const float* wh, int H, float* whp, cudaStream_t st);
+int lstm_persistent_run(const float* xp, const float* wh, const float* wh_perm, const int32_t* seq_len, int T, int B, int H,
+                        float* out, float* ws, cudaStream_t st);
 
 static inline int grid_for(long long total, int threads = 256) {
     long long g = (total + threads - 1) / threads;
@@ -248,6 +249,12 @@ extern "C" int ocr_birnn_workspace_bytes(int cell, int T, int B, int H, size_t* 
 // One bidirectional recurrent layer (time-major).
 //   cell 0 = LSTM: wx [8H, I] (rows: fw i,j,f,o | bw i,j,f,o), wh [8H, H], bias [8H]
 //   cell 1 = GRU : wx [6H, I] (rows per direction: r,u,cand), whg [4H, H] (r,u per direction), whc [2H, H], bias [6H]
+extern "C" int ocr_lstm_prepare_wh(const float* wh, int H, float* wh_perm, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(wh && wh_perm && H >= 16 && (H % 16) == 0, "ocr_lstm_prepare_wh: bad argument (H=%d)", H);
+    return lstm_permute_wh(wh, H, wh_perm, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int ocr_birnn_layer(int cell, const float* x, int T, int B, int I, int H, const int32_t* seq_len, const float* wx,
                                const float* wh, const float* wh2, const float* bias, float* out, void* workspace,
                                size_t workspace_bytes, ocr_stream_t stream)
@@ -274,7 +281,7 @@ extern "C" int ocr_birnn_layer(int cell, const float* x, int T, int B, int I, in
     int rc = ocr_gemm_tf32(x, I, wx, I, bias, xp, 2 * G * H, T * B, 2 * G * H, I, 0, stream);
     if (rc != OCR_OK) return rc;
     if (cell == 0 && g_birnn_path == 0 && lstm_persistent_supported(T, B, H))
-        return lstm_persistent_run(xp, wh, seq_len, T, B, H, out, gh, st);   // one launch for all T frames
+        return lstm_persistent_run(xp, wh, cell == 0 ? wh2 : nullptr, seq_len, T, B, H, out, gh, st);   // one launch for all T frames
     OCR_CHECK_CUDA(cudaMemsetAsync(h, 0, sizeof(float) * (size_t)2 * B * H * 3, st));
     OCR_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)T * B * 2 * H, st));
     const int cg = grid_for((long long)2 * B * H);

@@ -57,6 +57,26 @@ def get_string(labels):
     return "".join(out_charset[int(c)] for c in labels)
 
 
+def ctc_loss_layer(rnn_logits, sequence_labels, sequence_length):
+    """model.ctc_loss_layer (model.py:224-229): mean over the batch of tf.nn.ctc_loss(time_major=True)."""
+    return ctc.ctc_loss(sequence_labels, rnn_logits, sequence_length, time_major=True).mean()
+
+
+def get_testing(rnn_logits, sequence_length, label, label_length):
+    """test._get_testing (test.py:75-104) -> (loss, label_error, sequence_error), all scalars:
+    CTC loss; beam search (width 128, top path, merge_repeated=True); label_error = sum of edit distances / sum of
+    label lengths; sequence_error = fraction of sequences with a non-zero edit distance.
+    label: SparseTensor-like triple (indices [N,2], values [N], dense_shape [2]); label_length [B]."""
+    loss = ctc_loss_layer(rnn_logits, label, sequence_length)
+    predictions, _ = ctc.ctc_beam_search_decoder(rnn_logits, sequence_length, beam_width=128, top_paths=1, merge_repeated=True)
+    truth = ctc.SparseTensor(label[0].to(rnn_logits.device), label[1].to(rnn_logits.device), label[2])
+    label_errors = ctc.edit_distance(predictions[0], truth, normalize=False)
+    total_labels = torch.as_tensor(label_length).to(label_errors.device).sum().to(torch.float32)
+    label_error = label_errors.sum() / total_labels
+    sequence_error = (label_errors != 0).sum().to(torch.float32) / label_errors.numel()
+    return loss, label_error, sequence_error
+
+
 class Model:
     """Weights of the recognizer + the reference's graph-building functions as methods."""
 
@@ -103,7 +123,12 @@ class Model:
                 wx = torch.cat([k[:I].t() for k in ks], 0).contiguous()          # [8H, I]
                 wh = torch.cat([k[I:].t() for k in ks], 0).contiguous()          # [8H, H]
                 bias = torch.cat([p["rnn/%s/%s/lstm_cell/bias" % (scope, d)] for d in ("fw", "bw")]).contiguous()
-                self.rnn.append(dict(I=I, H=H, wx=wx, wh=wh, wh2=None, bias=bias))
+                wh2 = None
+                if self.device.type == "cuda" and H % 16 == 0:
+                    # recurrent weights pre-arranged (gate-major hidden slices) for the persistent kernel, once
+                    wh2 = torch.empty_like(wh)
+                    _lib.check(_lib.load().ocr_lstm_prepare_wh(_lib.ptr(wh), H, _lib.ptr(wh2), _lib.stream_handle()), "ocr_lstm_prepare_wh")
+                self.rnn.append(dict(I=I, H=H, wx=wx, wh=wh, wh2=wh2, bias=bias))
             else:
                 gk = [p["rnn/%s/%s/gru_cell/gates/kernel" % (scope, d)] for d in ("fw", "bw")]
                 ck = [p["rnn/%s/%s/gru_cell/candidate/kernel" % (scope, d)] for d in ("fw", "bw")]

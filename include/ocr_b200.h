@@ -130,7 +130,8 @@ int ocr_gemm_tf32(const float* A, int lda, const float* W, int ldw, const float*
  * ocr_birnn_layer: one tf.nn.bidirectional_dynamic_rnn layer, time-major, per-example sequence_length
  *   (model.py:167-199 GRUCell; model_bu.py:167-199 LSTMCell): zero outputs past the length, the backward
  *   direction starts at frame len-1.  x [T,B,I] -> out [T,B,2H] (fw | bw).
- *   cell 0 = LSTM: wx [8H,I] (rows fw i,j,f,o then bw), wh [8H,H], wh2 unused, bias [8H]; forget_bias 1.0
+ *   cell 0 = LSTM: wx [8H,I] (rows fw i,j,f,o then bw), wh [8H,H], bias [8H]; forget_bias 1.0; wh2 = NULL or the
+ *            [8H,H] output of ocr_lstm_prepare_wh(wh) (weights pre-arranged for the persistent kernel, do it once)
  *   cell 1 = GRU : wx [6H,I] (rows per direction r,u,candidate), wh [4H,H] (r,u per direction), wh2 [2H,H], bias [6H] */
 int ocr_conv1_3x3_valid(const void* in, int in_is_u8, int B, int H, int W, const float* w, const float* bias, int Cout,
                         float* out, ocr_stream_t stream);
@@ -138,6 +139,7 @@ int ocr_im2col3x3_same(const float* in, int B, int H, int W, int C, int pool_h, 
                        float* out, ocr_stream_t stream);
 int ocr_rows_max_to_seq(const float* in, int B, int H, int W, int C, float* out, ocr_stream_t stream);
 int ocr_birnn_workspace_bytes(int cell, int T, int B, int H, size_t* bytes);
+int ocr_lstm_prepare_wh(const float* wh, int H, float* wh_perm, ocr_stream_t stream);
 /* Kernel-path override for tests: 0 = automatic (LSTM layers with B <= 128, H <= 512 run as ONE persistent
  * tcgen05 kernel for all frames), 1 = one recurrent GEMM + one cell kernel per frame. */
 int ocr_birnn_set_path(int path);

@@ -90,3 +90,23 @@ def test_train_mode_not_built_yet():
     m = model.Model(mo.init_params(0, dtype=np.float32))
     with pytest.raises(NotImplementedError):
         m.convnet_layers(torch.zeros((1, 32, 64, 1), device="cuda"), torch.tensor([64]), model.ModeKeys.TRAIN)
+
+
+def test_get_testing_metrics():
+    """test._get_testing (test.py:75-104): loss, label_error, sequence_error against the oracles."""
+    from cnn_lstm_ctc_ocr_b200 import model
+    from oracle import ctc_oracle
+    from util import cfg2_inputs
+    x, labels, seq_len = cfg2_inputs(seed=11, T=40, B=24, C=30, scale=3.0)
+    dev = torch.device("cuda:0")
+    idx = torch.tensor([[b, i] for b, l in enumerate(labels) for i in range(len(l))], dtype=torch.int64)
+    vals = torch.tensor(sum(labels, []), dtype=torch.int32)
+    label = (idx, vals, torch.tensor([24, 16]))
+    lens = torch.tensor([len(l) for l in labels])
+    loss, le, se = model.get_testing(torch.tensor(x, device=dev), torch.tensor(seq_len), label, lens)
+    l64, _, _ = ctc_oracle.ctc_loss(x, labels, seq_len, f64=True, want_grad=False)
+    od, ol, _ = ctc_oracle.ctc_beam_search_decoder(x, seq_len, 128, 1, True, nthreads=8)
+    d = ctc_oracle.edit_distance([od[b, 0, :ol[b, 0]].tolist() for b in range(24)], labels)
+    assert abs(float(loss) - l64.mean()) < 1e-4 * l64.mean()
+    assert abs(float(le) - d.sum() / sum(len(l) for l in labels)) < 1e-6
+    assert abs(float(se) - np.count_nonzero(d) / 24.0) < 1e-6
