@@ -29,6 +29,8 @@ SIGNATURES = {
     "ocr_conv1_3x3_valid": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "ocr_im2col3x3_same": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "ocr_rows_max_to_seq": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "ocr_conv3x3_same": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
+    "ocr_maxpool": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "ocr_birnn_workspace_bytes": (_i, [_i, _i, _i, _i, _c.POINTER(_sz)]),
     "ocr_birnn_set_path": (_i, [_i]),
     "ocr_lstm_prepare_wh": (_i, [_vp, _i, _vp, _vp]),

@@ -1,0 +1,222 @@
+// 3x3 'same' convolution as an IMPLICIT GEMM on the tcgen05 tensor cores (sm_100a): the im2col patch matrix is
+// never written to memory.  Replaces tf.layers.conv2d(+ folded batch-norm)(+ ReLU) of the reference's conv2..conv8
+// (/root/reference/src/weinman/model.py:84-109,134-144), and the 2x2 max-pools between them (model.py:111-116).
+//
+//   out[(b,y,x), co] = relu(bias[co] + sum_{tap, c} in[b, y+dy(tap), x+dx(tap), c] * w[co, tap, c])
+//
+// One 128-pixel x BN-filter tile per CTA, 10 warps:
+//   warp 0 / one lane : TMA (cp.async.bulk.tensor.2d) loads the BN x 32 filter box of each k-step (k-step = 32 channels
+//                       of one tap) into a 128B-swizzled stage.
+//   warps 6..9        : patch gatherers, one thread per output pixel: cp.async (16-byte, zero-fill for the padding
+//                       ring) copies the pixel's 32 channels of the current tap straight from the NHWC activation
+//                       into the same swizzle pattern TMA would have produced; completion is signalled with
+//                       cp.async.mbarrier.arrive.noinc, so many k-steps are in flight per thread without registers.
+//   warp 1            : tcgen05.mma.kind::tf32 issue (after a proxy fence: the patch tile was written by the generic
+//                       proxy), accumulator in TMEM, tcgen05.commit frees the stage.
+//   warps 2..5        : epilogue (TMEM -> bias -> ReLU -> NHWC rows).
+// Every activation element is read 9 x (Cout / BN) times, but from L2/L1, and nothing but the output is written:
+// DRAM traffic drops from (input + 2 x 9 x input + output) with explicit im2col to (input + output).
+#include "gemm_tf32.cuh"
+
+namespace ocr {
+
+constexpr int kConvThreads = 320;
+
+__device__ __forceinline__ void cp_async16_zfill(unsigned dst, const void* src, unsigned src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(unsigned bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+template <int BN, int STAGES>
+struct ConvSmem {
+    static constexpr int kA = kGemmBM * kGemmBK * 4;
+    static constexpr int kB = BN * kGemmBK * 4;
+    static constexpr int kStage = kA + kB;
+    static constexpr int kBars = STAGES * kStage;
+    static constexpr int kTotal = kBars + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kConvThreads)
+conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ in, int B, int H, int W, int C,
+                     const float* __restrict__ bias, float* __restrict__ out, int Cout, int relu)
+{
+    using S = ConvSmem<BN, STAGES>;
+    extern __shared__ unsigned char conv_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(conv_smem_raw) + 1023) & ~(uintptr_t)1023);
+    const unsigned s_base = g_smem_u32(smem);
+    const unsigned bar_full = s_base + S::kBars;
+    const unsigned bar_empty = bar_full + STAGES * 8;
+    const unsigned bar_acc = bar_empty + STAGES * 8;
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + S::kBars + (2 * STAGES + 1) * 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int M = B * H * W;
+    const int m0 = blockIdx.x * kGemmBM, n0 = blockIdx.y * BN;
+    const int cpt = C / kGemmBK;      // k-steps per tap
+    const int nk = 9 * cpt;
+
+    if (threadIdx.x == 0) {
+        // full: one arrive.expect_tx by the TMA lane + 128 cp.async completions of the gatherers
+        for (int s = 0; s < STAGES; ++s) { g_mbar_init(bar_full + s * 8, 1 + 128); g_mbar_init(bar_empty + s * 8, 1); }
+        g_mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)), "r"((unsigned)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_d = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int k = 0; k < nk; ++k) {
+                const int s = k % STAGES;
+                if (k >= STAGES) g_mbar_wait(bar_empty + s * 8, ((k / STAGES) - 1) & 1);
+                g_mbar_expect_tx(bar_full + s * 8, (unsigned)S::kB);
+                tma_load_2d(s_base + s * S::kStage + S::kA, &tmW, k * kGemmBK, n0, bar_full + s * 8);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(kGemmBM >> 4) << 24);
+            for (int k = 0; k < nk; ++k) {
+                const int s = k % STAGES;
+                g_mbar_wait(bar_full + s * 8, (k / STAGES) & 1);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // patch tile: generic-proxy writes -> async-proxy reads
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned a_addr = s_base + s * S::kStage, b_addr = a_addr + S::kA;
+                const unsigned long long da = umma_desc_k128(a_addr), db = umma_desc_k128(b_addr);
+#pragma unroll
+                for (int kk = 0; kk < kGemmBK / 8; ++kk)
+                    umma_tf32(tmem_d, da + (unsigned long long)(kk * 2), db + (unsigned long long)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+                umma_commit(bar_empty + s * 8);
+            }
+            umma_commit(bar_acc);
+        }
+    } else if (warp < 6) {
+        const int q = warp & 3;
+        g_mbar_wait(bar_acc, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        gemm_epilogue<BN>(tmem_d, q, lane, m0, n0, M, Cout, bias, out, Cout, relu);
+    } else {
+        // patch gatherers: thread pr owns tile row pr = output pixel m0 + pr
+        const int pr = threadIdx.x - 192;
+        const int m = m0 + pr;
+        const bool valid = m < M;
+        int x = 0, y = 0, b = 0;
+        if (valid) { x = m % W; const int t = m / W; y = t % H; b = t / H; }
+        const unsigned row_off = (unsigned)(pr >> 3) * 1024u + (unsigned)(pr & 7) * 128u;
+        const unsigned sw = (unsigned)(pr & 7);
+        for (int k = 0; k < nk; ++k) {
+            const int s = k % STAGES;
+            if (k >= STAGES) g_mbar_wait(bar_empty + s * 8, ((k / STAGES) - 1) & 1);
+            const int tap = k / cpt, c0 = (k - tap * cpt) * kGemmBK;
+            const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+            const bool inb = valid && yy >= 0 && yy < H && xx >= 0 && xx < W;
+            const float* src = inb ? in + (((size_t)b * H + yy) * W + xx) * C + c0 : in;
+            const unsigned nbytes = inb ? 16u : 0u;   // 0 source bytes = zero fill (padding ring, rows past M)
+            const unsigned dst = s_base + s * S::kStage + row_off;
+#pragma unroll
+            for (unsigned j = 0; j < 8; ++j) cp_async16_zfill(dst + ((j ^ sw) << 4), src + j * 4, nbytes);
+            cp_async_arrive_noinc(bar_full + s * 8);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((unsigned)BN) : "memory");
+    }
+}
+
+// 'valid' max-pool, NHWC, one thread per float4 of channels
+__global__ void __launch_bounds__(256)
+maxpool_kernel(const float* __restrict__ in, int B, int H, int W, int C, int ph, int pw, int sh, int sw, int Hp, int Wp, float* __restrict__ out)
+{
+    const int c4n = C >> 2;
+    const long long total = (long long)B * Hp * Wp * c4n;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % c4n);
+        long long p = idx / c4n;
+        const int x = (int)(p % Wp); p /= Wp;
+        const int y = (int)(p % Hp);
+        const int b = (int)(p / Hp);
+        float4 v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        for (int dy = 0; dy < ph; ++dy)
+            for (int dx = 0; dx < pw; ++dx) {
+                const float4 u = __ldg(reinterpret_cast<const float4*>(in + (((size_t)b * H + (y * sh + dy)) * W + (x * sw + dx)) * C) + c4);
+                v.x = fmaxf(v.x, u.x); v.y = fmaxf(v.y, u.y); v.z = fmaxf(v.z, u.z); v.w = fmaxf(v.w, u.w);
+            }
+        reinterpret_cast<float4*>(out)[idx] = v;
+    }
+}
+
+}  // namespace ocr
+
+using namespace ocr;
+
+template <int BN, int STAGES>
+static int launch_conv(const float* in, int B, int H, int W, int C, const float* w, const float* bias, int Cout, int relu, float* out,
+                       cudaStream_t st)
+{
+    using S = ConvSmem<BN, STAGES>;
+    CUtensorMap tmW;
+    int rc = tma_map_2d(&tmW, w, Cout, 9 * C, 9 * C, BN);
+    if (rc != OCR_OK) return rc;
+    static int configured = -1;
+    int dev = 0;
+    OCR_CHECK_CUDA(cudaGetDevice(&dev));
+    if (configured != dev) {
+        OCR_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_igemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        configured = dev;
+    }
+    const long long M = (long long)B * H * W;
+    dim3 grid((unsigned)((M + kGemmBM - 1) / kGemmBM), (unsigned)((Cout + BN - 1) / BN));
+    conv3x3_igemm_kernel<BN, STAGES><<<grid, kConvThreads, S::kTotal, st>>>(tmW, in, B, H, W, C, bias, out, Cout, relu);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+extern "C" int ocr_conv3x3_same(const float* in, int B, int H, int W, int C, const float* w, const float* bias, int Cout, int relu,
+                                float* out, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(B >= 0 && H >= 1 && W >= 1 && C >= 32 && (C % 32) == 0 && Cout >= 1, "ocr_conv3x3_same: bad shape B=%d H=%d W=%d C=%d Cout=%d (C must be a multiple of 32)", B, H, W, C, Cout);
+    if (B == 0) return OCR_OK;
+    OCR_CHECK_ARG(in && w && bias && out, "ocr_conv3x3_same: NULL argument");
+    OCR_CHECK_ARG(((uintptr_t)in % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)out % 16) == 0, "ocr_conv3x3_same: pointers must be 16-byte aligned");
+    OCR_CHECK_ARG((long long)B * H * W < 0x7fffffffLL, "ocr_conv3x3_same: too many output pixels");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long mt = ((long long)B * H * W + kGemmBM - 1) / kGemmBM;
+    int bn = 32;
+    if (Cout > 32) bn = 64;
+    if (Cout > 64 && mt * ((Cout + 127) / 128) >= 120) bn = 128;
+    if (Cout > 128 && mt * ((Cout + 255) / 256) >= 120) bn = 256;
+    switch (bn) {
+        case 32: return launch_conv<32, 8>(in, B, H, W, C, w, bias, Cout, relu, out, st);
+        case 64: return launch_conv<64, 6>(in, B, H, W, C, w, bias, Cout, relu, out, st);
+        case 128: return launch_conv<128, 5>(in, B, H, W, C, w, bias, Cout, relu, out, st);
+        default: return launch_conv<256, 4>(in, B, H, W, C, w, bias, Cout, relu, out, st);
+    }
+}
+
+extern "C" int ocr_maxpool(const float* in, int B, int H, int W, int C, int pool_h, int pool_w, int stride_h, int stride_w, float* out,
+                           ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(B >= 0 && C >= 4 && (C % 4) == 0 && pool_h >= 1 && pool_w >= 1 && stride_h >= 1 && stride_w >= 1 && H >= pool_h && W >= pool_w,
+                  "ocr_maxpool: bad shape B=%d H=%d W=%d C=%d pool %dx%d stride %dx%d", B, H, W, C, pool_h, pool_w, stride_h, stride_w);
+    if (B == 0) return OCR_OK;
+    OCR_CHECK_ARG(in && out, "ocr_maxpool: NULL argument");
+    const int Hp = (H - pool_h) / stride_h + 1, Wp = (W - pool_w) / stride_w + 1;
+    const long long total = (long long)B * Hp * Wp * (C / 4);
+    long long g = (total + 255) / 256;
+    maxpool_kernel<<<(int)(g > 148 * 16 ? 148 * 16 : (g < 1 ? 1 : g)), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, B, H, W, C, pool_h, pool_w,
+                                                                                                           stride_h, stride_w, Hp, Wp, out);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}

@@ -72,6 +72,50 @@ __device__ __forceinline__ void umma_commit(unsigned bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// accumulator tile (TMEM lanes q*32.., BN columns) -> + bias, ReLU -> global rows; called by the four epilogue warps
+template <int BN>
+__device__ __forceinline__ void gemm_epilogue(unsigned tmem_d, int q, int lane, int m0, int n0, int M, int N,
+                                              const float* __restrict__ bias, float* __restrict__ D, int ldd, int relu)
+{
+    const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        unsigned r[32];
+        const unsigned taddr = tmem_d + ((unsigned)(q * 32) << 16) + (unsigned)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < M) {
+            float* drow = D + (size_t)row * ldd + n0 + c0;
+            const bool vec = ((reinterpret_cast<uintptr_t>(drow) & 15) == 0) && (n0 + c0 + 32 <= N);
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float x = __uint_as_float(r[j]);
+                const int col = n0 + c0 + j;
+                if (bias != nullptr && col < N) x += __ldg(bias + col);
+                v[j] = relu ? fmaxf(x, 0.0f) : x;
+            }
+            if (vec) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(drow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (n0 + c0 + j < N) drow[j] = v[j];
+            }
+        }
+    }
+}
+
 #endif
 
 }  // namespace ocr

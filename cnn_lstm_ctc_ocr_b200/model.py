@@ -80,7 +80,9 @@ def get_testing(rnn_logits, sequence_length, label, label_length):
 class Model:
     """Weights of the recognizer + the reference's graph-building functions as methods."""
 
-    def __init__(self, params, cell_type="lstm", rnn_sizes=(512, 512), device="cuda"):
+    def __init__(self, params, cell_type="lstm", rnn_sizes=(512, 512), device="cuda", conv_path="igemm"):
+        # conv_path: "igemm" = implicit GEMM (patches gathered inside the kernel); "im2col" = explicit patch matrix + GEMM
+        self.conv_path = conv_path
         if cell_type not in ("lstm", "gru"):
             raise ValueError("cell_type must be 'lstm' (model_bu.py) or 'gru' (model.py)")
         self.cell_type = cell_type
@@ -169,13 +171,23 @@ class Model:
             Hp, Wp = (Hn - ph) // s_h + 1, (Wn - pw) // s_w + 1
             if Hp < 1 or Wp < 1:
                 raise ValueError("image too small for the convolutional stack (need height 32, width >= 8)")
-            patches = torch.empty((Bn * Hp * Wp, 9 * Cn), dtype=torch.float32, device=dev)
-            _lib.check(lib.ocr_im2col3x3_same(_lib.ptr(a), Bn, Hn, Wn, Cn, ph, pw, s_h, s_w, _lib.ptr(patches), sh), "ocr_im2col3x3_same")
             wk, bk = self.conv[name]
-            a = torch.empty((Bn, Hp, Wp, filters), dtype=torch.float32, device=dev)
-            _lib.check(lib.ocr_gemm_tf32(_lib.ptr(patches), 9 * Cn, _lib.ptr(wk), 9 * Cn, _lib.ptr(bk), _lib.ptr(a), filters,
-                                         Bn * Hp * Wp, filters, 9 * Cn, 1, sh), "ocr_gemm_tf32")
-            del patches
+            if self.conv_path == "igemm":
+                if (ph, pw, s_h, s_w) != (1, 1, 1, 1):
+                    pooled = torch.empty((Bn, Hp, Wp, Cn), dtype=torch.float32, device=dev)
+                    _lib.check(lib.ocr_maxpool(_lib.ptr(a), Bn, Hn, Wn, Cn, ph, pw, s_h, s_w, _lib.ptr(pooled), sh), "ocr_maxpool")
+                    a = pooled
+                out = torch.empty((Bn, Hp, Wp, filters), dtype=torch.float32, device=dev)
+                _lib.check(lib.ocr_conv3x3_same(_lib.ptr(a), Bn, Hp, Wp, Cn, _lib.ptr(wk), _lib.ptr(bk), filters, 1, _lib.ptr(out), sh),
+                           "ocr_conv3x3_same")
+                a = out
+            else:
+                patches = torch.empty((Bn * Hp * Wp, 9 * Cn), dtype=torch.float32, device=dev)
+                _lib.check(lib.ocr_im2col3x3_same(_lib.ptr(a), Bn, Hn, Wn, Cn, ph, pw, s_h, s_w, _lib.ptr(patches), sh), "ocr_im2col3x3_same")
+                a = torch.empty((Bn, Hp, Wp, filters), dtype=torch.float32, device=dev)
+                _lib.check(lib.ocr_gemm_tf32(_lib.ptr(patches), 9 * Cn, _lib.ptr(wk), 9 * Cn, _lib.ptr(bk), _lib.ptr(a), filters,
+                                             Bn * Hp * Wp, filters, 9 * Cn, 1, sh), "ocr_gemm_tf32")
+                del patches
         Bn, Hn, Wn, Cn = a.shape
         seq = torch.empty((Wn, Bn, Cn), dtype=torch.float32, device=dev)   # pool8 (all Hn = 3 rows) + squeeze, time-major
         _lib.check(lib.ocr_rows_max_to_seq(_lib.ptr(a), Bn, Hn, Wn, Cn, _lib.ptr(seq), sh), "ocr_rows_max_to_seq")

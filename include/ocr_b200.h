@@ -138,6 +138,15 @@ int ocr_conv1_3x3_valid(const void* in, int in_is_u8, int B, int H, int W, const
 int ocr_im2col3x3_same(const float* in, int B, int H, int W, int C, int pool_h, int pool_w, int stride_h, int stride_w,
                        float* out, ocr_stream_t stream);
 int ocr_rows_max_to_seq(const float* in, int B, int H, int W, int C, float* out, ocr_stream_t stream);
+/* ocr_conv3x3_same: conv2..conv8 of convnet_layers (model.py:84-109; tf.layers.conv2d 3x3 'same' + bias, batch-norm
+ *   folded, optional ReLU) as an implicit GEMM on tcgen05: the patches are gathered by cp.async straight into the
+ *   swizzled operand tiles, no im2col matrix in memory.  in [B,H,W,C] f32 NHWC (C % 32 == 0), w [Cout, 9*C] K-major
+ *   (column order kh, kw, c), out [B,H,W,Cout].
+ * ocr_maxpool: tf.layers.max_pooling2d 'valid' (model.py:111-116): in [B,H,W,C] -> out [B,Hp,Wp,C]. */
+int ocr_conv3x3_same(const float* in, int B, int H, int W, int C, const float* w, const float* bias, int Cout, int relu,
+                     float* out, ocr_stream_t stream);
+int ocr_maxpool(const float* in, int B, int H, int W, int C, int pool_h, int pool_w, int stride_h, int stride_w, float* out,
+                ocr_stream_t stream);
 int ocr_birnn_workspace_bytes(int cell, int T, int B, int H, size_t* bytes);
 int ocr_lstm_prepare_wh(const float* wh, int H, float* wh_perm, ocr_stream_t stream);
 /* Kernel-path override for tests: 0 = automatic (LSTM layers with B <= 128, H <= 512 run as ONE persistent

@@ -85,6 +85,18 @@ def test_rnn_layer_masks_and_directions(path):
         assert (o[sl[b]:, b] == 0).all()
 
 
+def test_conv_paths_agree():
+    """Implicit GEMM (default) and explicit im2col + GEMM are the same contraction in the same order of k."""
+    from cnn_lstm_ctc_ocr_b200 import model
+    params = mo.init_params(seed=4, dtype=np.float32, randomize_bn=True)
+    img, widths = _inputs(3, 75, 2)      # odd width: ragged tiles on every layer
+    dev = torch.device("cuda:0")
+    f1, _ = model.Model(params, conv_path="igemm").convnet_layers(torch.tensor(img, device=dev), torch.tensor(widths))
+    f2, _ = model.Model(params, conv_path="im2col").convnet_layers(torch.tensor(img, device=dev), torch.tensor(widths))
+    assert f1.shape == f2.shape
+    assert torch.equal(f1, f2)
+
+
 def test_train_mode_not_built_yet():
     from cnn_lstm_ctc_ocr_b200 import model
     m = model.Model(mo.init_params(0, dtype=np.float32))
