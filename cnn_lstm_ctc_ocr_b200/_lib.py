@@ -11,7 +11,7 @@ SO_PATH = os.path.join(_HERE, "libocr_b200.so")
 
 OCR_OK = 0
 _c = ctypes
-_vp, _i, _f, _sz = _c.c_void_p, _c.c_int, _c.c_float, _c.c_size_t
+_vp, _i, _f, _sz, _ll = _c.c_void_p, _c.c_int, _c.c_float, _c.c_size_t, _c.c_longlong
 
 # name -> (restype, argtypes); mirrors include/ocr_b200.h one to one
 SIGNATURES = {
@@ -36,6 +36,29 @@ SIGNATURES = {
     "ocr_lstm_prepare_wh": (_i, [_vp, _i, _vp, _vp]),
     "ocr_birnn_layer": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ocr_edit_distance": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    # training step
+    "ocr_transpose": (_i, [_vp, _ll, _i, _i, _vp, _ll, _ll, _vp]),
+    "ocr_planar_pad_pitch": (_i, [_i]),
+    "ocr_nhwc_to_planar_pad": (_i, [_vp, _i, _i, _i, _i, _vp, _ll, _i, _ll, _vp]),
+    "ocr_gemm_wgrad_scratch_bytes": (_i, [_i, _i, _ll, _i, _c.POINTER(_sz)]),
+    "ocr_gemm_tf32_wgrad": (_i, [_vp, _ll, _vp, _ll, _vp, _i, _ll, _i, _i, _ll, _i, _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32), _ll, _vp, _sz, _vp]),
+    "ocr_bn_batch_sums": (_i, [_vp, _ll, _i, _vp, _vp]),
+    "ocr_bn_finalize": (_i, [_vp, _ll, _i, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "ocr_bn_relu_apply": (_i, [_vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ocr_bn_relu_bwd_sums": (_i, [_vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ocr_bn_relu_bwd_apply": (_i, [_vp, _vp, _ll, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ocr_copy_2d": (_i, [_vp, _ll, _vp, _ll, _ll, _ll, _vp]),
+    "ocr_relu_bwd_bias": (_i, [_vp, _vp, _ll, _i, _vp, _vp, _vp, _vp]),
+    "ocr_colsum": (_i, [_vp, _ll, _i, _i, _vp, _vp, _vp]),
+    "ocr_relu_bwd": (_i, [_vp, _vp, _ll, _vp, _vp]),
+    "ocr_maxpool_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ocr_rows_max_to_seq_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "ocr_conv1_wgrad": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
+    "ocr_conv_filter_layouts": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
+    "ocr_adam_step": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _vp]),
+    "ocr_birnn_lstm_train_workspace_bytes": (_i, [_i, _i, _i, _c.POINTER(_sz)]),
+    "ocr_birnn_lstm_train_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ocr_birnn_lstm_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None

@@ -22,6 +22,12 @@ namespace ocr {
 
 constexpr int kGemmThreads = 192;
 
+struct GemmSplit {
+    int ksteps_per_split, nbatch;
+    int a_shift[9], a_row[9];
+    long long split_stride, batch_stride;
+};
+
 template <int BN, int STAGES>
 struct GemmSmem {
     static constexpr int kA = kGemmBM * kGemmBK * 4;
@@ -34,7 +40,8 @@ struct GemmSmem {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const float* __restrict__ bias, float* __restrict__ D, int M, int N, int K, int ldd, int relu)
+                 const float* __restrict__ bias, float* __restrict__ D, int M, int N, int K, int ldd, int relu,
+                 const GemmSplit sp)
 {
     using S = GemmSmem<BN, STAGES>;
     extern __shared__ unsigned char gemm_smem_raw[];
@@ -47,8 +54,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + S::kBars + (2 * STAGES + 1) * 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * kGemmBM, n0 = blockIdx.y * BN;
-    const int nk = (K + kGemmBK - 1) / kGemmBK;
+    // blockIdx.x = m-tile * nbatch + batch (the batches of one tile run side by side and share operand tiles in L2)
+    const int batch = blockIdx.x % sp.nbatch;
+    const int m0 = (blockIdx.x / sp.nbatch) * kGemmBM, n0 = blockIdx.y * BN;
+    const int nk_all = (K + kGemmBK - 1) / kGemmBK;
+    const int k_begin = sp.ksteps_per_split > 0 ? blockIdx.z * sp.ksteps_per_split : 0;
+    const int nk = sp.ksteps_per_split > 0 ? min(sp.ksteps_per_split, nk_all - k_begin) : nk_all;
+    const int a_shift = sp.a_shift[batch], a_row = sp.a_row[batch];
+    D += (size_t)batch * sp.batch_stride + (size_t)blockIdx.z * sp.split_stride;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { g_mbar_init(bar_full + s * 8, 1); g_mbar_init(bar_empty + s * 8, 1); }
@@ -70,8 +83,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int s = k % STAGES;
                 if (k >= STAGES) g_mbar_wait(bar_empty + s * 8, ((k / STAGES) - 1) & 1);
                 g_mbar_expect_tx(bar_full + s * 8, (unsigned)S::kStage);
-                tma_load_2d(s_base + s * S::kStage, &tmA, k * kGemmBK, m0, bar_full + s * 8);
-                tma_load_2d(s_base + s * S::kStage + S::kA, &tmB, k * kGemmBK, n0, bar_full + s * 8);
+                tma_load_2d(s_base + s * S::kStage, &tmA, (k_begin + k) * kGemmBK + a_shift, m0 + a_row, bar_full + s * 8);
+                tma_load_2d(s_base + s * S::kStage + S::kA, &tmB, (k_begin + k) * kGemmBK, n0, bar_full + s * 8);
             }
         }
     } else if (warp == 1) {
@@ -153,8 +166,14 @@ static int launch_planned(const GemmPlan& p, cudaStream_t st)
         OCR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
         configured = dev;
     }
-    dim3 grid((p.M + kGemmBM - 1) / kGemmBM, (p.N + BN - 1) / BN);
-    gemm_tf32_kernel<BN, STAGES><<<grid, kGemmThreads, S::kTotal, st>>>(p.tmA, p.tmB, p.bias, p.D, p.M, p.N, p.K, p.ldd, p.relu);
+    dim3 grid(((p.M + kGemmBM - 1) / kGemmBM) * p.nbatch, (p.N + BN - 1) / BN, p.splits);
+    GemmSplit sp;
+    sp.ksteps_per_split = p.splits > 1 ? p.ksteps_per_split : 0;
+    sp.nbatch = p.nbatch;
+    for (int i = 0; i < 9; ++i) { sp.a_shift[i] = p.a_shift[i]; sp.a_row[i] = p.a_row[i]; }
+    sp.split_stride = p.split_stride;
+    sp.batch_stride = p.batch_stride;
+    gemm_tf32_kernel<BN, STAGES><<<grid, kGemmThreads, S::kTotal, st>>>(p.tmA, p.tmB, p.bias, p.D, p.M, p.N, p.K, p.ldd, p.relu, sp);
     OCR_CHECK_LAUNCH();
     return OCR_OK;
 }
@@ -189,6 +208,71 @@ int gemm_run(const GemmPlan& p, cudaStream_t st)
         case 128: return launch_planned<128, 5>(p, st);
         default: return launch_planned<256, 4>(p, st);
     }
+}
+
+// D[b][i] = sum_z partials[b][z][i] in a fixed order (deterministic split-K)
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partials, int splits, int M, int N, int ldd, long long batch_stride, int nbatch,
+                     float* __restrict__ D)
+{
+    const long long per = (long long)M * N, total = per * nbatch;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(idx / per);
+        const long long i = idx - (long long)b * per;
+        const float* src = partials + (size_t)b * splits * per + i;
+        float acc = 0.0f;
+        for (int z = 0; z < splits; ++z) acc += src[(size_t)z * per];
+        D[(size_t)b * batch_stride + (size_t)(i / N) * ldd + (i % N)] = acc;
+    }
+}
+
+static int wgrad_splits(int M, int N, long long R, int nbatch, int* ksteps_per_split) {
+    const long long nk = (R + kGemmBK - 1) / kGemmBK;
+    const int bn = N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
+    const long long tiles = (long long)((M + kGemmBM - 1) / kGemmBM) * ((N + bn - 1) / bn) * nbatch;
+    long long want = (2 * 148 + tiles - 1) / tiles;            // about two waves of CTAs
+    if (want > nk / 8) want = nk / 8;                           // at least 8 k-steps per split
+    if (want < 1) want = 1;
+    const long long kps = (nk + want - 1) / want;
+    *ksteps_per_split = (int)kps;
+    return (int)((nk + kps - 1) / kps);
+}
+
+size_t gemm_wgrad_scratch_floats(int M, int N, long long R, int nbatch) {
+    int kps;
+    const int splits = wgrad_splits(M, N, R, nbatch, &kps);
+    return (size_t)splits * nbatch * M * N;
+}
+
+int gemm_wgrad(const float* A, long long lda, const float* W, long long ldw, float* D, int ldd, long long batch_stride, int M, int N,
+               long long R, int nbatch, const int* a_shift, const int* a_row, long long a_rows, float* partials, cudaStream_t st)
+{
+    OCR_CHECK_ARG(M >= 1 && N >= 1 && R >= 1 && nbatch >= 1 && nbatch <= 9, "gemm_wgrad: bad shape M=%d N=%d R=%lld nbatch=%d", M, N, R, nbatch);
+    OCR_CHECK_ARG(A && W && D && partials, "gemm_wgrad: NULL argument");
+    OCR_CHECK_ARG((lda % 4) == 0 && (ldw % 4) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0 && R < 0x7fffffffLL,
+                  "gemm_wgrad: operands need 16-byte aligned rows");
+    GemmPlan p;
+    p.bn = N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
+    p.bias = nullptr; p.M = M; p.N = N; p.K = (int)R; p.relu = 0;
+    p.splits = wgrad_splits(M, N, R, nbatch, &p.ksteps_per_split);
+    p.nbatch = nbatch;
+    for (int i = 0; i < nbatch; ++i) { p.a_shift[i] = a_shift ? a_shift[i] : 0; p.a_row[i] = a_row ? a_row[i] : 0; }
+    // partial tiles are dense M x N
+    p.D = partials; p.ldd = N;
+    p.split_stride = (long long)M * N;
+    p.batch_stride = (long long)p.splits * M * N;
+    int rc = tma_map_2d(&p.tmA, A, a_rows, R, lda, kGemmBM);
+    if (rc != OCR_OK) return rc;
+    rc = tma_map_2d(&p.tmB, W, N, R, ldw, p.bn);
+    if (rc != OCR_OK) return rc;
+    if (p.splits == 1) p.ksteps_per_split = 0;
+    rc = gemm_run(p, st);
+    if (rc != OCR_OK) return rc;
+    const long long total = (long long)M * N * nbatch;
+    long long g = (total + 255) / 256;
+    splitk_reduce_kernel<<<(int)(g > 148 * 8 ? 148 * 8 : g), 256, 0, st>>>(partials, p.splits, M, N, ldd, batch_stride, nbatch, D);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
 }
 
 }  // namespace ocr

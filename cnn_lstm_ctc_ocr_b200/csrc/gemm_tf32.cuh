@@ -12,12 +12,25 @@ struct GemmPlan {
     const float* bias;
     float* D;
     int M, N, K, ldd, relu, bn;
+    // split-K / shifted-operand form used by the weight-gradient contractions (gemm_plan_wgrad):
+    //   D[batch][split] (M x N) = sum over the split's k range of A[m, k + a_shift[batch]] * W[n, k]
+    int splits = 1, ksteps_per_split = 0, nbatch = 1;
+    int a_shift[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, a_row[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long split_stride = 0, batch_stride = 0;   // elements between the partial outputs of consecutive splits / batches
 };
 
 // D[M,N] = act(A[M,K] * W[N,K]^T + bias[N]); see ocr_gemm_tf32 in include/ocr_b200.h for the operand rules
 int gemm_plan(GemmPlan* p, const float* A, int lda, const float* W, int ldw, const float* bias, float* D, int ldd, int M, int N,
               int K, int relu);
 int gemm_run(const GemmPlan& p, cudaStream_t st);
+// Weight-gradient contraction over a long row dimension R (both operands R-contiguous, i.e. transposed activations):
+//   D[batch] (M x N, row pitch ldd, batches batch_stride apart) = sum_r A[a_row[batch] + m, r + a_shift[batch]] * W[n, r]
+// (A has a_rows rows in total; a_shift must be a multiple of 4: TMA box origins are 16-byte aligned)
+// split over the CTAs along R; partial tiles go to `partials` ([nbatch][splits][M][N], caller scratch) and a second
+// kernel adds them up in a fixed order (deterministic).  Out-of-range r (negative too) reads as zero (TMA fill).
+size_t gemm_wgrad_scratch_floats(int M, int N, long long R, int nbatch);
+int gemm_wgrad(const float* A, long long lda, const float* W, long long ldw, float* D, int ldd, long long batch_stride, int M, int N,
+               long long R, int nbatch, const int* a_shift, const int* a_row, long long a_rows, float* partials, cudaStream_t st);
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 32;  // fp32 elements = one 128-byte swizzle row

@@ -1,0 +1,728 @@
+// Training-step kernels of the recognizer (sm_100a): everything train.py's graph adds around the dense contractions.
+//
+//   batch-norm with BATCH statistics + moving-average update     model.py:118-123 (training=True), train.py:116-118
+//   gradients of ReLU / bias-add / max-pool / pool8+squeeze        model.py:97-116,145-147 (TensorFlow's registered gradients)
+//   LSTMCell frames that keep what back-propagation through time needs, and the BPTT frame loop
+//                                                                   model_bu.py:167-199 (bidirectional_dynamic_rnn)
+//   weight-gradient contractions on tcgen05 (split-K over the long pixel / frame dimension, operands transposed so
+//   that the contraction index is contiguous; the 9 filter taps are 9 shifted views of ONE padded planar copy)
+//   Adam (tf.train.AdamOptimizer) over one flat parameter buffer     train.py:128-137
+//
+// The memory-bound kernels are coalesced grid-stride loops; per-channel reductions accumulate float partials per thread,
+// combine them per CTA in shared memory and finish in double-precision atomics (order-independent to ~1e-16).
+#include "gemm_tf32.cuh"
+
+namespace ocr {
+
+static inline int grid_cap(long long total, int threads = 256, int waves = 16) {
+    long long g = (total + threads - 1) / threads;
+    const long long cap = 148LL * waves;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// transposes: out[c][r] = src[r + src_shift][c] (zero when r + src_shift is outside [0, rows)), src [rows, cols]
+// row-major, out row pitch ld.  PAD: `rows` counts the pixels of a zero-ringed grid [B, H+2, Wp] (Wp = W+2 rounded up to
+// a multiple of 4, so that whole-row shifts of the planar copy stay 16-byte aligned for TMA); ring pixels read as zero,
+// interior pixels come from the dense NHWC tensor.  blockIdx.z selects one of the pre-shifted copies (src_shift + z).
+template <bool PAD>
+__global__ void __launch_bounds__(256)
+transpose_kernel(const float* __restrict__ in, long long rows, int cols, int ld_in, float* __restrict__ out, long long ld, int H, int W, int Wp,
+                 long long src_shift, long long copy_stride)
+{
+    __shared__ float tile[32][33];
+    const long long r0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    src_shift += blockIdx.z;
+    out += (size_t)blockIdx.z * copy_stride;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long r = r0 + ty + i * 8 + src_shift;
+        const int c = c0 + tx;
+        float v = 0.0f;
+        if (r >= 0 && r < rows && c < cols) {
+            if (PAD) {
+                const int Hp = H + 2;
+                const int xp = (int)(r % Wp);
+                const long long q = r / Wp;
+                const int yp = (int)(q % Hp);
+                const long long b = q / Hp;
+                if (xp >= 1 && xp <= W && yp >= 1 && yp <= H) v = __ldg(in + (((size_t)b * H + (yp - 1)) * W + (xp - 1)) * ld_in + c);
+            } else {
+                v = __ldg(in + (size_t)r * ld_in + c);
+            }
+        }
+        tile[ty + i * 8][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + i * 8;
+        const long long r = r0 + tx;
+        if (c < cols && r < rows) out[(size_t)c * ld + r] = tile[tx][ty + i * 8];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-channel reductions over the rows of x [rows, C].  One CTA = 8 warps x 32 channels (blockIdx.y = channel group);
+// warp w walks rows w, w + 8*gridDim.x, ...; lane = channel.  MODE selects what is summed:
+//   0: s0 = sum x, s1 = sum x^2                                        (batch-norm statistics)
+//   1: s0 = sum x                                                      (bias gradient)
+//   2: dz = g * (z > 0), z = gamma*(x-mean)*inv_std+beta: s0 = sum dz, s1 = sum dz * xhat   (batch-norm backward)
+//   3: dy = g * (x > 0) written to out; s0 = sum dy                    (ReLU backward + bias gradient; x = layer output)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+channel_reduce_kernel(const float* __restrict__ x, const float* __restrict__ g, long long rows, int C, int ldx, const float* __restrict__ mean,
+                      const float* __restrict__ inv_std, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      float* __restrict__ out, double* __restrict__ sums /*[2][C]*/)
+{
+    __shared__ float red[2][8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.y * 32 + lane;
+    const bool ok = c < C;
+    float mu = 0.f, is = 0.f, ga = 0.f, be = 0.f;
+    if (MODE == 2 && ok) { mu = mean[c]; is = inv_std[c]; ga = gamma[c]; be = beta[c]; }
+    float s0 = 0.f, s1 = 0.f, k0 = 0.f, k1 = 0.f;   // Kahan-compensated partial sums
+    for (long long r = (long long)blockIdx.x * 8 + warp; r < rows; r += (long long)gridDim.x * 8) {
+        if (!ok) continue;
+        const size_t o = (size_t)r * ldx + c;
+        float a0 = 0.f, a1 = 0.f;
+        if (MODE == 0) { const float v = x[o]; a0 = v; a1 = v * v; }
+        if (MODE == 1) { a0 = x[o]; }
+        if (MODE == 2) {
+            const float xh = (x[o] - mu) * is;
+            const float dz = (ga * xh + be > 0.f) ? g[o] : 0.f;
+            a0 = dz; a1 = dz * xh;
+        }
+        if (MODE == 3) {
+            const float dy = x[o] > 0.f ? g[o] : 0.f;
+            out[o] = dy;
+            a0 = dy;
+        }
+        { const float y = a0 - k0; const float t = s0 + y; k0 = (t - s0) - y; s0 = t; }
+        if (MODE == 0 || MODE == 2) { const float y = a1 - k1; const float t = s1 + y; k1 = (t - s1) - y; s1 = t; }
+    }
+    red[0][warp][lane] = s0;
+    red[1][warp][lane] = s1;
+    __syncthreads();
+    if (warp == 0 && ok) {
+        double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { t0 += (double)red[0][w][lane]; t1 += (double)red[1][w][lane]; }
+        atomicAdd(sums + c, t0);
+        if (MODE == 0 || MODE == 2) atomicAdd(sums + C + c, t1);
+    }
+}
+
+// batch statistics -> mean, inv_std; moving averages (tf.layers.batch_normalization, momentum 0.99; the fused kernel
+// feeds the UNBIASED batch variance to the moving variance).
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, long long n, int C, float eps, float momentum, float* __restrict__ mean,
+                                   float* __restrict__ inv_std, float* __restrict__ moving_mean, float* __restrict__ moving_var)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double m = sums[c] / (double)n;
+    double var = sums[C + c] / (double)n - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[c] = (float)m;
+    inv_std[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (moving_mean != nullptr) {
+        const double unb = n > 1 ? var * ((double)n / (double)(n - 1)) : var;
+        moving_mean[c] = (float)((double)momentum * moving_mean[c] + (1.0 - (double)momentum) * m);
+        moving_var[c] = (float)((double)momentum * moving_var[c] + (1.0 - (double)momentum) * unb);
+    }
+}
+__global__ void sums_to_float_kernel(const double* __restrict__ sums, int n, float* __restrict__ o0, float* __restrict__ o1)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    if (o0) o0[c] = (float)sums[c];
+    if (o1) o1[c] = (float)sums[n + c];
+}
+
+// out = relu(gamma * (y - mean) * inv_std + beta), float4 over channels
+__global__ void __launch_bounds__(256)
+bn_relu_apply_kernel(const float* __restrict__ y, long long rows, int C, const float* __restrict__ mean, const float* __restrict__ inv_std,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out)
+{
+    const int c4n = C >> 2;
+    const long long total = rows * c4n;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % c4n) * 4;
+        const float4 v = reinterpret_cast<const float4*>(y)[idx];
+        const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(inv_std + c);
+        const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+        float4 o;
+        o.x = fmaxf(ga.x * ((v.x - mu.x) * is.x) + be.x, 0.f);
+        o.y = fmaxf(ga.y * ((v.y - mu.y) * is.y) + be.y, 0.f);
+        o.z = fmaxf(ga.z * ((v.z - mu.z) * is.z) + be.z, 0.f);
+        o.w = fmaxf(ga.w * ((v.w - mu.w) * is.w) + be.w, 0.f);
+        reinterpret_cast<float4*>(out)[idx] = o;
+    }
+}
+
+// dy = gamma * inv_std * (dz - dbeta/n - xhat * dgamma/n), dz = g * (z > 0)
+__global__ void __launch_bounds__(256)
+bn_relu_bwd_apply_kernel(const float* __restrict__ y, const float* __restrict__ g, long long rows, long long n, int C, const float* __restrict__ mean,
+                         const float* __restrict__ inv_std, const float* __restrict__ gamma, const float* __restrict__ beta,
+                         const double* __restrict__ sums, float* __restrict__ dy)
+{
+    const long long total = rows * C;
+    const double inv_n = 1.0 / (double)n;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C);
+        const float is = inv_std[c], ga = gamma[c];
+        const float xh = (y[idx] - mean[c]) * is;
+        const float dz = (ga * xh + beta[c] > 0.f) ? g[idx] : 0.f;
+        const float db = (float)(sums[c] * inv_n), dg = (float)(sums[C + c] * inv_n);
+        dy[idx] = ga * is * (dz - db - xh * dg);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// max-pool gradient (gather form, no atomics): the gradient of a window goes to its FIRST maximum in row-major window
+// order (TensorFlow's MaxPoolGrad / the arg-max of the forward pass).
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const float* __restrict__ in, const float* __restrict__ dout, int B, int H, int W, int C, int ph, int pw, int sh, int sw,
+                   int Hp, int Wp, float* __restrict__ din)
+{
+    const long long total = (long long)B * H * W * C;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C);
+        long long p = idx / C;
+        const int x = (int)(p % W); p /= W;
+        const int y = (int)(p % H);
+        const int b = (int)(p / H);
+        const float v = in[idx];
+        float acc = 0.f;
+        // windows (oy, ox) with oy*sh <= y < oy*sh + ph
+        const int oy_lo = max(0, (y - ph + sh) / sh), oy_hi = min(Hp - 1, y / sh);
+        const int ox_lo = max(0, (x - pw + sw) / sw), ox_hi = min(Wp - 1, x / sw);
+        for (int oy = oy_lo; oy <= oy_hi; ++oy)
+            for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+                if (oy * sh + ph <= y || ox * sw + pw <= x) continue;
+                // is (y, x) the first maximum of this window?
+                bool first = true;
+                for (int dy = 0; dy < ph && first; ++dy)
+                    for (int dx = 0; dx < pw; ++dx) {
+                        const int yy = oy * sh + dy, xx = ox * sw + dx;
+                        if (yy == y && xx == x) continue;
+                        const float u = __ldg(in + (((size_t)b * H + yy) * W + xx) * C + c);
+                        const bool before = (yy < y) || (yy == y && xx < x);
+                        if (u > v || (before && u == v)) { first = false; break; }
+                    }
+                if (first) acc += __ldg(dout + (((size_t)b * Hp + oy) * Wp + ox) * C + c);
+            }
+        din[idx] = acc;
+    }
+}
+
+// pool8 + squeeze + time-major transpose backward: in [B,H,W,C], dseq [W,B,C] -> din (first maximum over the H rows)
+__global__ void __launch_bounds__(256)
+rows_max_bwd_kernel(const float* __restrict__ in, const float* __restrict__ dseq, int B, int H, int W, int C, float* __restrict__ din)
+{
+    const long long total = (long long)B * W * C;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C);
+        long long p = idx / C;
+        const int x = (int)(p % W);
+        const int b = (int)(p / W);
+        int best = 0;
+        float bv = in[(((size_t)b * H) * W + x) * C + c];
+        for (int y = 1; y < H; ++y) {
+            const float u = in[(((size_t)b * H + y) * W + x) * C + c];
+            if (u > bv) { bv = u; best = y; }
+        }
+        const float gd = dseq[((size_t)x * B + b) * C + c];
+        for (int y = 0; y < H; ++y) din[(((size_t)b * H + y) * W + x) * C + c] = (y == best) ? gd : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LSTM frames for training.  Same state-row convention as model_ops.cu (rows [0,B) forward, [B,2B) backward; frame of
+// step s: forward t = s, backward t = len-1-s).  The pre-activations in xp [T*B, 8H] are REPLACED by the gate
+// activations (i, tanh j, f, o) and the cell state of every visited frame is kept in cs [T,B,2H].
+__global__ void __launch_bounds__(256)
+lstm_cell_train_kernel(const float* __restrict__ gh, float* __restrict__ xp, const int32_t* __restrict__ seq_len, int s, int T, int B, int H,
+                       float* __restrict__ h, float* __restrict__ c, float* __restrict__ out /*[T,B,2H]*/, float* __restrict__ cs /*[T,B,2H]*/)
+{
+    const int total = 2 * B * H;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int j = idx % H;
+        const int r = idx / H;
+        const int dir = r >= B, b = dir ? r - B : r;
+        const int len = min(seq_len[b], T);
+        if (s >= len) continue;
+        const int t = dir ? len - 1 - s : s;
+        const float* g = gh + (size_t)r * 8 * H + dir * 4 * H;
+        float* x = xp + ((size_t)t * B + b) * 8 * H + dir * 4 * H;
+        const float gi = sigm(g[j] + x[j]), gj = tanhf(g[H + j] + x[H + j]);
+        const float gf = sigm(g[2 * H + j] + x[2 * H + j] + 1.0f), go = sigm(g[3 * H + j] + x[3 * H + j]);
+        const float cn = gf * c[idx] + gi * gj;
+        const float hn = go * tanhf(cn);
+        x[j] = gi; x[H + j] = gj; x[2 * H + j] = gf; x[3 * H + j] = go;
+        c[idx] = cn;
+        h[idx] = hn;
+        const size_t o = ((size_t)t * B + b) * 2 * H + dir * H + j;
+        out[o] = hn;
+        cs[o] = cn;
+    }
+}
+
+// One BPTT frame.  act [T*B, 8H]: gate activations in, gate PRE-activation gradients out (in place).  dh_rec [2B, 2H]
+// is the product dG_step * W_h of the step processed just before (columns dir*H.. of row r); dh, dc [2B,H] carry the
+// state gradients; dgs [2B, 4H] receives this step's gate gradients as the A operand of the next recurrent product
+// (zero rows for examples that are past their length).
+__global__ void __launch_bounds__(256)
+lstm_cell_bwd_kernel(float* __restrict__ act, const float* __restrict__ cs, const float* __restrict__ dout, const float* __restrict__ dh_rec,
+                     const int32_t* __restrict__ seq_len, int s, int last, int T, int B, int H, float* __restrict__ dh, float* __restrict__ dc,
+                     float* __restrict__ dgs)
+{
+    const int total = 2 * B * H;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int j = idx % H;
+        const int r = idx / H;
+        const int dir = r >= B, b = dir ? r - B : r;
+        const int len = min(seq_len[b], T);
+        float* gs = dgs + (size_t)r * 4 * H;
+        // gradient flowing into h_s from step s+1 (only if that step was live for this example)
+        float dhv = 0.f, dcv = 0.f;
+        if (!last && s + 1 < len) { dhv = dh_rec[(size_t)r * 2 * H + dir * H + j]; dcv = dc[idx]; }
+        if (s >= len) { gs[j] = 0.f; gs[H + j] = 0.f; gs[2 * H + j] = 0.f; gs[3 * H + j] = 0.f; continue; }
+        const int t = dir ? len - 1 - s : s;
+        const size_t o = ((size_t)t * B + b) * 2 * H + dir * H + j;
+        float* a = act + ((size_t)t * B + b) * 8 * H + dir * 4 * H;
+        const float gi = a[j], gj = a[H + j], gf = a[2 * H + j], go = a[3 * H + j];
+        const float cn = cs[o];
+        float cprev = 0.f;
+        if (s > 0) { const int tp = dir ? t + 1 : t - 1; cprev = cs[((size_t)tp * B + b) * 2 * H + dir * H + j]; }
+        const float tc = tanhf(cn);
+        const float dht = dout[o] + dhv;
+        const float d_o = dht * tc * go * (1.f - go);
+        const float dct = dcv + dht * go * (1.f - tc * tc);
+        const float d_i = dct * gj * gi * (1.f - gi);
+        const float d_j = dct * gi * (1.f - gj * gj);
+        const float d_f = dct * cprev * gf * (1.f - gf);
+        a[j] = d_i; a[H + j] = d_j; a[2 * H + j] = d_f; a[3 * H + j] = d_o;
+        gs[j] = d_i; gs[H + j] = d_j; gs[2 * H + j] = d_f; gs[3 * H + j] = d_o;
+        dc[idx] = dct * gf;
+        dh[idx] = dht;   // kept for inspection; the recurrent product is taken from dgs
+    }
+}
+
+// rows (t, b) with t >= len_b were never visited: their slots still hold input-projection values; their gradient is 0
+__global__ void __launch_bounds__(256)
+zero_past_len_kernel(float* __restrict__ a, const int32_t* __restrict__ seq_len, int T, int B, int cols4)
+{
+    const long long total = (long long)T * B * cols4;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long row = idx / cols4;
+        const int b = (int)(row % B), t = (int)(row / B);
+        if (t >= seq_len[b]) reinterpret_cast<float4*>(a)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// conv1 weight gradient: dw[tap, co] = sum_pixels dy[pix, co] * img[pix + tap].  One input channel, so this is a
+// reduction, not a contraction: lane = output channel (blockIdx.y = 32-channel group), a warp walks pixels.
+template <bool kU8>
+__global__ void __launch_bounds__(256)
+conv1_wgrad_kernel(const void* __restrict__ in_, int B, int H, int W, const float* __restrict__ dy, int Co, double* __restrict__ sums /*[9][Co]*/)
+{
+    __shared__ float red[8][9][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int co = blockIdx.y * 32 + lane;
+    const int Ho = H - 2, Wo = W - 2;
+    const long long npix = (long long)B * Ho * Wo;
+    float acc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+    for (long long p = (long long)blockIdx.x * 8 + warp; p < npix; p += (long long)gridDim.x * 8) {
+        const int x = (int)(p % Wo);
+        const long long q = p / Wo;
+        const int y = (int)(q % Ho);
+        const int b = (int)(q / Ho);
+        const float g = co < Co ? dy[(size_t)p * Co + co] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int jx = 0; jx < 3; ++jx) {
+                const size_t o = ((size_t)b * H + (y + i)) * W + (x + jx);
+                float v;
+                if (kU8) v = (float)__ldg(reinterpret_cast<const unsigned char*>(in_) + o) / 255.0f - 0.5f;
+                else v = __ldg(reinterpret_cast<const float*>(in_) + o);
+                acc[i * 3 + jx] = fmaf(g, v, acc[i * 3 + jx]);
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) red[warp][k][lane] = acc[k];
+    __syncthreads();
+    for (int k = warp; k < 9; k += 8) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += (double)red[w][k][lane];
+        if (co < Co) atomicAdd(sums + (size_t)k * Co + co, t);
+    }
+}
+
+// filter layouts derived from the master HWIO tensor w [3,3,C,Co]:
+//   w_fwd [Co, 9*C]:  w_fwd[co, tap*C + c]        = w[tap, c, co]     (K-major operand of the forward implicit GEMM)
+//   w_dgr [C, 9*Co]:  w_dgr[c, (8-tap)*Co + co]   = w[tap, c, co]     (the input gradient is a 3x3 'same' convolution of dy
+//                                                                        with the filter rotated by 180 degrees)
+__global__ void __launch_bounds__(256)
+conv_filter_layouts_kernel(const float* __restrict__ w, int C, int Co, float* __restrict__ w_fwd, float* __restrict__ w_dgr)
+{
+    const int total = 9 * C * Co;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int co = idx % Co;
+        const int c = (idx / Co) % C;
+        const int tap = idx / (Co * C);
+        const float v = w[idx];
+        if (w_fwd) w_fwd[(size_t)co * 9 * C + tap * C + c] = v;
+        if (w_dgr) w_dgr[(size_t)c * 9 * Co + (8 - tap) * Co + co] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tf.train.AdamOptimizer over a flat buffer: m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr_t m / (sqrt(v) + eps),
+// lr_t = lr sqrt(1-b2^t) / (1-b1^t) computed by the host.  float4, grid-stride.
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, float lr_t,
+            float b1, float b2, float eps, float gscale)
+{
+    const long long n4 = n >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+        const float4 gg = reinterpret_cast<const float4*>(g)[i];
+#define OCR_ADAM1(f)                                              \
+        {                                                         \
+            const float gr = gg.f * gscale;                       \
+            mm.f = b1 * mm.f + (1.f - b1) * gr;                   \
+            vv.f = b2 * vv.f + (1.f - b2) * gr * gr;              \
+            pp.f -= lr_t * mm.f / (sqrtf(vv.f) + eps);            \
+        }
+        OCR_ADAM1(x) OCR_ADAM1(y) OCR_ADAM1(z) OCR_ADAM1(w)
+#undef OCR_ADAM1
+        reinterpret_cast<float4*>(p)[i] = pp;
+        reinterpret_cast<float4*>(m)[i] = mm;
+        reinterpret_cast<float4*>(v)[i] = vv;
+    }
+    // tail
+    for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gr = g[i] * gscale;
+        const float mn = b1 * m[i] + (1.f - b1) * gr, vn = b2 * v[i] + (1.f - b2) * gr * gr;
+        m[i] = mn; v[i] = vn;
+        p[i] -= lr_t * mn / (sqrtf(vn) + eps);
+    }
+}
+
+// dz = g * (z > 0) for a ReLU whose OUTPUT z is given (logits layer), float4
+__global__ void __launch_bounds__(256)
+relu_bwd_kernel(const float* __restrict__ z, const float* __restrict__ g, long long n, float* __restrict__ dz)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dz[i] = z[i] > 0.f ? g[i] : 0.f;
+}
+
+}  // namespace ocr
+
+using namespace ocr;
+
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" int ocr_transpose(const float* in, long long rows, int cols, int ld_in, float* out, long long ld_out, long long src_shift,
+                             ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(rows >= 0 && cols >= 1 && ld_in >= cols && ld_out >= rows, "ocr_transpose: bad shape rows=%lld cols=%d ld_in=%d ld_out=%lld", rows, cols, ld_in, ld_out);
+    if (rows == 0) return OCR_OK;
+    OCR_CHECK_ARG(in && out, "ocr_transpose: NULL argument");
+    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
+    transpose_kernel<false><<<grid, 256, 0, ST(stream)>>>(in, rows, cols, ld_in, out, ld_out, 0, 0, 0, src_shift, 0);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+extern "C" int ocr_planar_pad_pitch(int W) { return (W + 2 + 3) & ~3; }
+
+extern "C" int ocr_nhwc_to_planar_pad(const float* in, int B, int H, int W, int C, float* out, long long ld_out, int ncopies,
+                                      long long copy_stride, ocr_stream_t stream)
+{
+    const int Wp = ocr_planar_pad_pitch(W);
+    const long long rows = (long long)B * (H + 2) * Wp;
+    OCR_CHECK_ARG(B >= 0 && H >= 1 && W >= 1 && C >= 1 && ld_out >= rows && (ncopies == 1 || ncopies == 3) && (ncopies == 1 || copy_stride >= (long long)C * ld_out),
+                  "ocr_nhwc_to_planar_pad: bad shape B=%d H=%d W=%d C=%d ld=%lld ncopies=%d", B, H, W, C, ld_out, ncopies);
+    if (B == 0) return OCR_OK;
+    OCR_CHECK_ARG(in && out, "ocr_nhwc_to_planar_pad: NULL argument");
+    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)ncopies);
+    transpose_kernel<true><<<grid, 256, 0, ST(stream)>>>(in, rows, C, C, out, ld_out, H, W, Wp, ncopies == 3 ? -1 : 0, copy_stride);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+extern "C" int ocr_gemm_wgrad_scratch_bytes(int M, int N, long long R, int nbatch, size_t* bytes)
+{
+    OCR_CHECK_ARG(bytes && M >= 1 && N >= 1 && R >= 1 && nbatch >= 1 && nbatch <= 9, "ocr_gemm_wgrad_scratch_bytes: bad argument");
+    *bytes = gemm_wgrad_scratch_floats(M, N, R, nbatch) * sizeof(float);
+    return OCR_OK;
+}
+
+extern "C" int ocr_gemm_tf32_wgrad(const float* At, long long lda, const float* Wt, long long ldw, float* D, int ldd, long long batch_stride,
+                                   int M, int N, long long R, int nbatch, const int32_t* a_shift_host, const int32_t* a_row_host,
+                                   long long a_rows, void* scratch, size_t scratch_bytes, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(M >= 1 && N >= 1 && R >= 1 && nbatch >= 1 && nbatch <= 9, "ocr_gemm_tf32_wgrad: bad shape");
+    if (scratch == nullptr || scratch_bytes < gemm_wgrad_scratch_floats(M, N, R, nbatch) * sizeof(float)) {
+        set_error("ocr_gemm_tf32_wgrad: scratch too small");
+        return OCR_EWORKSPACE;
+    }
+    int sh[9] = {0}, ar[9] = {0};
+    for (int i = 0; i < nbatch; ++i) {
+        sh[i] = a_shift_host ? a_shift_host[i] : 0;
+        ar[i] = a_row_host ? a_row_host[i] : 0;
+        OCR_CHECK_ARG((sh[i] % 4) == 0, "ocr_gemm_tf32_wgrad: a_shift[%d] = %d is not a multiple of 4 (TMA needs 16-byte aligned box origins)", i, sh[i]);
+        OCR_CHECK_ARG(ar[i] >= 0 && ar[i] + M <= (a_rows > 0 ? a_rows : M), "ocr_gemm_tf32_wgrad: a_row[%d] = %d outside the operand", i, ar[i]);
+    }
+    return gemm_wgrad(At, lda, Wt, ldw, D, ldd, batch_stride, M, N, R, nbatch, sh, ar, a_rows > 0 ? a_rows : M, reinterpret_cast<float*>(scratch), ST(stream));
+}
+
+template <int MODE>
+static int launch_reduce(const float* x, const float* g, long long rows, int C, int ldx, const float* mean, const float* inv_std,
+                         const float* gamma, const float* beta, float* out, double* sums, cudaStream_t st)
+{
+    OCR_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+    const int gy = (C + 31) / 32;
+    long long gx = (rows + 7) / 8;
+    const long long cap = (148LL * 8 + gy - 1) / gy;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    channel_reduce_kernel<MODE><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, st>>>(x, g, rows, C, ldx, mean, inv_std, gamma, beta, out, sums);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+// sums [2][C] doubles: per-channel sum and sum of squares of THIS replica's rows.  A data-parallel job that wants the
+// statistics of the global batch all-reduces `sums` (and adds up the row counts) before ocr_bn_finalize.
+extern "C" int ocr_bn_batch_sums(const float* y, long long rows, int C, void* sums, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(rows >= 1 && C >= 1 && y && sums, "ocr_bn_batch_sums: bad argument");
+    return launch_reduce<0>(y, nullptr, rows, C, C, nullptr, nullptr, nullptr, nullptr, nullptr, reinterpret_cast<double*>(sums), ST(stream));
+}
+
+extern "C" int ocr_bn_finalize(const void* sums, long long n, int C, float eps, float momentum, float* mean, float* inv_std,
+                               float* moving_mean, float* moving_var, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(n >= 1 && C >= 1 && sums && mean && inv_std && ((moving_mean == nullptr) == (moving_var == nullptr)), "ocr_bn_finalize: bad argument");
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(reinterpret_cast<const double*>(sums), n, C, eps, momentum, mean, inv_std, moving_mean, moving_var);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+extern "C" int ocr_bn_relu_apply(const float* y, long long rows, int C, const float* mean, const float* inv_std, const float* gamma,
+                                 const float* beta, float* out, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(rows >= 1 && C >= 4 && (C % 4) == 0 && y && mean && inv_std && gamma && beta && out, "ocr_bn_relu_apply: bad argument");
+    bn_relu_apply_kernel<<<grid_cap(rows * (C / 4)), 256, 0, ST(stream)>>>(y, rows, C, mean, inv_std, gamma, beta, out);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+// sums [2][C] doubles out: sum dz and sum dz*xhat over this replica's rows (dz = dout where the ReLU was active);
+// dgamma = sum dz*xhat, dbeta = sum dz (this replica's share of the parameter gradients).
+extern "C" int ocr_bn_relu_bwd_sums(const float* y, const float* dout, long long rows, int C, const float* mean, const float* inv_std,
+                                    const float* gamma, const float* beta, void* sums, float* dgamma, float* dbeta, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(rows >= 1 && C >= 1 && y && dout && mean && inv_std && gamma && beta && dgamma && dbeta && sums, "ocr_bn_relu_bwd_sums: bad argument");
+    int rc = launch_reduce<2>(y, dout, rows, C, C, mean, inv_std, gamma, beta, nullptr, reinterpret_cast<double*>(sums), ST(stream));
+    if (rc != OCR_OK) return rc;
+    sums_to_float_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(reinterpret_cast<const double*>(sums), C, dbeta, dgamma);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+// dy = gamma * inv_std * (dz - sums[0]/n - xhat * sums[1]/n); n = rows the statistics were taken over (global batch when
+// `sums` was all-reduced)
+extern "C" int ocr_bn_relu_bwd_apply(const float* y, const float* dout, long long rows, long long n, int C, const float* mean,
+                                     const float* inv_std, const float* gamma, const float* beta, const void* sums, float* dy,
+                                     ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(rows >= 1 && n >= rows && C >= 1 && y && dout && mean && inv_std && gamma && beta && sums && dy, "ocr_bn_relu_bwd_apply: bad argument");
+    bn_relu_bwd_apply_kernel<<<grid_cap(rows * C), 256, 0, ST(stream)>>>(y, dout, rows, n, C, mean, inv_std, gamma, beta, reinterpret_cast<const double*>(sums), dy);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+extern "C" int ocr_copy_2d(const float* src, long long ld_src, float* dst, long long ld_dst, long long rows, long long cols, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(rows >= 0 && cols >= 0 && ld_src >= cols && ld_dst >= cols, "ocr_copy_2d: bad shape");
+    if (rows == 0 || cols == 0) return OCR_OK;
+    OCR_CHECK_ARG(src && dst, "ocr_copy_2d: NULL argument");
+    OCR_CHECK_CUDA(cudaMemcpy2DAsync(dst, (size_t)ld_dst * 4, src, (size_t)ld_src * 4, (size_t)cols * 4, (size_t)rows, cudaMemcpyDeviceToDevice, ST(stream)));
+    return OCR_OK;
+}
+
+extern "C" int ocr_relu_bwd_bias(const float* out, const float* dout, long long rows, int C, float* dy, float* dbias, void* scratch,
+                                 ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(rows >= 1 && C >= 1 && out && dout && dy && dbias && scratch, "ocr_relu_bwd_bias: bad argument");
+    double* sums = reinterpret_cast<double*>(scratch);
+    int rc = launch_reduce<3>(out, dout, rows, C, C, nullptr, nullptr, nullptr, nullptr, dy, sums, ST(stream));
+    if (rc != OCR_OK) return rc;
+    sums_to_float_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(sums, C, dbias, nullptr);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+extern "C" int ocr_colsum(const float* x, long long rows, int C, int ldx, float* out, void* scratch, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(rows >= 1 && C >= 1 && ldx >= C && x && out && scratch, "ocr_colsum: bad argument");
+    double* sums = reinterpret_cast<double*>(scratch);
+    int rc = launch_reduce<1>(x, nullptr, rows, C, ldx, nullptr, nullptr, nullptr, nullptr, nullptr, sums, ST(stream));
+    if (rc != OCR_OK) return rc;
+    sums_to_float_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(sums, C, out, nullptr);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+extern "C" int ocr_relu_bwd(const float* z, const float* g, long long n, float* dz, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(n >= 0 && (n == 0 || (z && g && dz)), "ocr_relu_bwd: bad argument");
+    if (n == 0) return OCR_OK;
+    relu_bwd_kernel<<<grid_cap(n), 256, 0, ST(stream)>>>(z, g, n, dz);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+extern "C" int ocr_maxpool_bwd(const float* in, const float* dout, int B, int H, int W, int C, int pool_h, int pool_w, int stride_h, int stride_w,
+                               float* din, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(B >= 1 && C >= 1 && pool_h >= 1 && pool_w >= 1 && stride_h >= 1 && stride_w >= 1 && H >= pool_h && W >= pool_w && in && dout && din,
+                  "ocr_maxpool_bwd: bad argument");
+    const int Hp = (H - pool_h) / stride_h + 1, Wp = (W - pool_w) / stride_w + 1;
+    maxpool_bwd_kernel<<<grid_cap((long long)B * H * W * C), 256, 0, ST(stream)>>>(in, dout, B, H, W, C, pool_h, pool_w, stride_h, stride_w, Hp, Wp, din);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+extern "C" int ocr_rows_max_to_seq_bwd(const float* in, const float* dseq, int B, int H, int W, int C, float* din, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(B >= 1 && H >= 1 && W >= 1 && C >= 1 && in && dseq && din, "ocr_rows_max_to_seq_bwd: bad argument");
+    rows_max_bwd_kernel<<<grid_cap((long long)B * W * C), 256, 0, ST(stream)>>>(in, dseq, B, H, W, C, din);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+extern "C" int ocr_conv1_wgrad(const void* in, int in_is_u8, int B, int H, int W, const float* dy, int Cout, float* dw, void* scratch,
+                               ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(B >= 1 && H >= 3 && W >= 3 && Cout >= 1 && in && dy && dw && scratch, "ocr_conv1_wgrad: bad argument");
+    double* sums = reinterpret_cast<double*>(scratch);
+    OCR_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * 9 * Cout, ST(stream)));
+    const int gy = (Cout + 31) / 32;
+    const long long npix = (long long)B * (H - 2) * (W - 2);
+    long long gx = (npix + 7) / 8;
+    if (gx > 148 * 8) gx = 148 * 8;
+    if (in_is_u8) conv1_wgrad_kernel<true><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, ST(stream)>>>(in, B, H, W, dy, Cout, sums);
+    else conv1_wgrad_kernel<false><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, ST(stream)>>>(in, B, H, W, dy, Cout, sums);
+    OCR_CHECK_LAUNCH();
+    sums_to_float_kernel<<<(9 * Cout + 127) / 128, 128, 0, ST(stream)>>>(sums, 9 * Cout, dw, nullptr);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+extern "C" int ocr_conv_filter_layouts(const float* w_hwio, int C, int Cout, float* w_fwd, float* w_dgrad, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(C >= 1 && Cout >= 1 && w_hwio && (w_fwd || w_dgrad), "ocr_conv_filter_layouts: bad argument");
+    conv_filter_layouts_kernel<<<grid_cap(9LL * C * Cout), 256, 0, ST(stream)>>>(w_hwio, C, Cout, w_fwd, w_dgrad);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+extern "C" int ocr_adam_step(float* params, const float* grads, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
+                             float eps, float grad_scale, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(n >= 0 && (n == 0 || (params && grads && m && v)), "ocr_adam_step: bad argument");
+    OCR_CHECK_ARG(((uintptr_t)params % 16) == 0 && ((uintptr_t)grads % 16) == 0 && ((uintptr_t)m % 16) == 0 && ((uintptr_t)v % 16) == 0,
+                  "ocr_adam_step: buffers must be 16-byte aligned");
+    if (n == 0) return OCR_OK;
+    adam_kernel<<<grid_cap((n + 3) / 4, 256, 8), 256, 0, ST(stream)>>>(params, grads, m, v, n, lr_t, beta1, beta2, eps, grad_scale);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// bidirectional LSTM layer, training form (frame by frame; keeps gate activations and cell states)
+extern "C" int ocr_birnn_lstm_train_workspace_bytes(int T, int B, int H, size_t* bytes)
+{
+    OCR_CHECK_ARG(bytes && T >= 0 && B >= 0 && H >= 1, "ocr_birnn_lstm_train_workspace_bytes: bad argument");
+    // gh [2B, 8H] + h, c [2B,H] + dgs [2B,4H] + dh_rec [2B,2H] + dh, dc
+    *bytes = sizeof(float) * ((size_t)2 * B * 8 * H + (size_t)2 * B * H * 4 + (size_t)2 * B * 4 * H + (size_t)2 * B * 2 * H) + 256;
+    return OCR_OK;
+}
+
+extern "C" int ocr_birnn_lstm_train_fwd(const float* x, int T, int B, int I, int H, const int32_t* seq_len, const float* wx, const float* wh,
+                                        const float* bias, float* out, float* gates, float* cstate, void* workspace, size_t workspace_bytes,
+                                        ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(T >= 1 && B >= 1 && I >= 4 && (I % 4) == 0 && H >= 4 && (H % 4) == 0, "ocr_birnn_lstm_train_fwd: bad shape T=%d B=%d I=%d H=%d", T, B, I, H);
+    OCR_CHECK_ARG(x && seq_len && wx && wh && bias && out && gates && cstate, "ocr_birnn_lstm_train_fwd: NULL argument");
+    size_t need = 0;
+    ocr_birnn_lstm_train_workspace_bytes(T, B, H, &need);
+    if (workspace == nullptr || workspace_bytes < need) { set_error("ocr_birnn_lstm_train_fwd: workspace too small"); return OCR_EWORKSPACE; }
+    cudaStream_t st = ST(stream);
+    float* ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    float* gh = ws;
+    float* h = gh + (size_t)2 * B * 8 * H;
+    float* c = h + (size_t)2 * B * H;
+    int rc = ocr_gemm_tf32(x, I, wx, I, bias, gates, 8 * H, T * B, 8 * H, I, 0, stream);
+    if (rc != OCR_OK) return rc;
+    OCR_CHECK_CUDA(cudaMemsetAsync(h, 0, sizeof(float) * (size_t)2 * B * H * 2, st));
+    OCR_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)T * B * 2 * H, st));
+    OCR_CHECK_CUDA(cudaMemsetAsync(cstate, 0, sizeof(float) * (size_t)T * B * 2 * H, st));
+    OCR_CHECK_CUDA(cudaMemsetAsync(gh, 0, sizeof(float) * (size_t)2 * B * 8 * H, st));
+    GemmPlan p1;
+    rc = gemm_plan(&p1, h, H, wh, H, nullptr, gh, 8 * H, 2 * B, 8 * H, H, 0);
+    if (rc != OCR_OK) return rc;
+    const int cg = grid_cap((long long)2 * B * H);
+    for (int s = 0; s < T; ++s) {
+        if (s > 0) { rc = gemm_run(p1, st); if (rc != OCR_OK) return rc; }
+        lstm_cell_train_kernel<<<cg, 256, 0, st>>>(gh, gates, seq_len, s, T, B, H, h, c, out, cstate);
+        OCR_CHECK_LAUNCH();
+    }
+    return OCR_OK;
+}
+
+// wh_rows [2H, 4H]: the h-part of the TensorFlow kernels (rows = hidden unit, columns = gates i,j,f,o), forward
+// direction's H rows then the backward direction's.  gates: activations in, d(pre-activation) out.
+extern "C" int ocr_birnn_lstm_bwd(const float* dout, int T, int B, int H, const int32_t* seq_len, float* gates, const float* cstate,
+                                  const float* wh_rows, void* workspace, size_t workspace_bytes, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(T >= 1 && B >= 1 && H >= 4 && (H % 4) == 0, "ocr_birnn_lstm_bwd: bad shape T=%d B=%d H=%d", T, B, H);
+    OCR_CHECK_ARG(dout && seq_len && gates && cstate && wh_rows, "ocr_birnn_lstm_bwd: NULL argument");
+    size_t need = 0;
+    ocr_birnn_lstm_train_workspace_bytes(T, B, H, &need);
+    if (workspace == nullptr || workspace_bytes < need) { set_error("ocr_birnn_lstm_bwd: workspace too small"); return OCR_EWORKSPACE; }
+    cudaStream_t st = ST(stream);
+    float* ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    float* gh = ws;
+    float* dh = gh + (size_t)2 * B * 8 * H;
+    float* dc = dh + (size_t)2 * B * H;
+    float* dgs = dc + (size_t)2 * B * H * 3;          // [2B, 4H]
+    float* dh_rec = dgs + (size_t)2 * B * 4 * H;      // [2B, 2H]
+    OCR_CHECK_CUDA(cudaMemsetAsync(dh, 0, sizeof(float) * (size_t)2 * B * H * 2, st));
+    zero_past_len_kernel<<<grid_cap((long long)T * B * 2 * H), 256, 0, st>>>(gates, seq_len, T, B, 2 * H);
+    OCR_CHECK_LAUNCH();
+    GemmPlan p1;
+    // dh_rec[r, n] = sum_g dgs[r, g] * wh_rows[n, g]
+    int rc = gemm_plan(&p1, dgs, 4 * H, wh_rows, 4 * H, nullptr, dh_rec, 2 * H, 2 * B, 2 * H, 4 * H, 0);
+    if (rc != OCR_OK) return rc;
+    const int cg = grid_cap((long long)2 * B * H);
+    for (int s = T - 1; s >= 0; --s) {
+        lstm_cell_bwd_kernel<<<cg, 256, 0, st>>>(gates, cstate, dout, dh_rec, seq_len, s, s == T - 1 ? 1 : 0, T, B, H, dh, dc, dgs);
+        OCR_CHECK_LAUNCH();
+        if (s > 0) { rc = gemm_run(p1, st); if (rc != OCR_OK) return rc; }
+    }
+    return OCR_OK;
+}

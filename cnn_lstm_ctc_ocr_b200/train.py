@@ -1,0 +1,427 @@
+"""The reference's training step on B200 (src/weinman/train.py), replayed on libocr_b200.so.
+
+  Trainer(params, ...)                       the variables of scope "convnet|rnn" (train.py:105-111) + Adam slots
+  Trainer.train_step(image, width, label)    one `sess.run(train_op)` (train.py:175-199):
+        convnet_layers(mode=TRAIN)  model.py:126-165   batch-norm with batch statistics, moving averages updated
+        rnn_layers                  model_bu.py:202-221 (bidirectional LSTM 512/512)
+        ctc_loss_layer              model.py:224-229
+        _get_training               train.py:101-141   exponential_decay (non-staircase) + AdamOptimizer(beta1=momentum)
+  learning_rate(step)                        tf.train.exponential_decay as configured by train.py:36-45,120-126
+
+TensorFlow derives the backward graph by itself; here it is written out: every line below is one call into the C ABI
+(include/ocr_b200.h, "Training step").  All trainable variables live in ONE flat float32 buffer in TensorFlow layout
+(ordered logits, bdrnn2, bdrnn1, conv8 .. conv1 = the order their gradients become available), with gradients and the
+Adam slots in matching flat buffers: Adam is one kernel launch, and data-parallel training all-reduces two contiguous
+buckets over NCCL (RNN + logits as soon as the recurrent layers are done, the convolutional stack at the end) while the
+remaining backward pass is still running.  Per-replica batch-norm statistics by default (as TensorFlow towers would);
+sync_bn=True all-reduces the per-channel sums so that N replicas reproduce the single-GPU step exactly.
+PyTorch supplies device memory, streams and torch.distributed only.  There is no CPU path.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, ctc
+from .model import BN_EPS, LAYER_PARAMS, _POOL_BEFORE, Model, ModeKeys
+
+BN_MOMENTUM = 0.99   # tf.layers.batch_normalization default (model.py:120)
+
+
+def learning_rate(step, learning_rate=1e-4, decay_steps=2 ** 16, decay_rate=0.9, staircase=False):
+    """tf.train.exponential_decay (train.py:120-126; flags train.py:36-45)."""
+    e = step / float(decay_steps)
+    if staircase:
+        e = math.floor(e)
+    return learning_rate * decay_rate ** e
+
+
+def _is_trainable(name):
+    return "moving_mean" not in name and "moving_variance" not in name
+
+
+def _param_order(cell_type):
+    names = ["rnn/logits/kernel", "rnn/logits/bias"]
+    for scope in ("bdrnn2", "bdrnn1"):
+        names += ["rnn/%s/fw/lstm_cell/kernel" % scope, "rnn/%s/bw/lstm_cell/kernel" % scope,
+                  "rnn/%s/fw/lstm_cell/bias" % scope, "rnn/%s/bw/lstm_cell/bias" % scope]
+    n_rnn = len(names)
+    for (filters, k, padding, name, bn) in reversed(LAYER_PARAMS):
+        names += ["convnet/%s/kernel" % name, "convnet/%s/bias" % name]
+        if bn:
+            names += ["convnet/%s/batch_norm/gamma" % name, "convnet/%s/batch_norm/beta" % name]
+    return names, n_rnn
+
+
+class Trainer:
+    def __init__(self, params, cell_type="lstm", rnn_sizes=(512, 512), device="cuda", learning_rate=1e-4, momentum=0.9,
+                 decay_rate=0.9, decay_steps=2 ** 16, decay_staircase=False, beta2=0.999, epsilon=1e-8,
+                 process_group=None, sync_bn=False, global_step=0):
+        if cell_type != "lstm":
+            raise NotImplementedError("the training step is built for the LSTM model (model_bu.py); GRU training is not built")
+        self.cell_type = cell_type
+        self.rnn_sizes = tuple(rnn_sizes)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.OcrLibraryError("Trainer needs a CUDA device; there is no CPU path")
+        self.lib = _lib.load()
+        self.hp = dict(learning_rate=learning_rate, decay_steps=decay_steps, decay_rate=decay_rate, staircase=decay_staircase)
+        self.beta1, self.beta2, self.epsilon = momentum, beta2, epsilon
+        self.global_step = int(global_step)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(process_group if process_group is not True else None)
+        self.sync_bn = bool(sync_bn) and self.world > 1
+
+        names, n_rnn = _param_order(cell_type)
+        missing = [n for n in names if n not in params]
+        if missing:
+            raise KeyError("parameters missing: %s" % missing[:3])
+        self.names = names
+        self.shapes = {n: tuple(np.asarray(params[n]).shape) for n in names}
+        self.offsets = {}
+        off = 0
+        for i, n in enumerate(names):
+            if i == n_rnn:
+                self.n_rnn_floats = off
+            self.offsets[n] = off
+            off += (int(np.prod(self.shapes[n])) + 63) // 64 * 64     # 256-byte aligned slots (TMA operands, float4)
+        self.n_floats = off
+        dev = self.device
+        self.theta = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.adam_m = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.adam_v = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.params, self.grads = {}, {}
+        for n in names:
+            o, sz = self.offsets[n], int(np.prod(self.shapes[n]))
+            self.params[n] = self.theta[o:o + sz].view(self.shapes[n])
+            self.grads[n] = self.grad[o:o + sz].view(self.shapes[n])
+            self.params[n].copy_(torch.as_tensor(np.asarray(params[n]), dtype=torch.float32))
+        self.stats = {n: torch.as_tensor(np.asarray(v), dtype=torch.float32).to(dev).contiguous() for n, v in params.items() if not _is_trainable(n)}
+        self.scratch = torch.zeros(16 * 9 * 4096, dtype=torch.uint8, device=dev)   # double sums: up to 8H = 4096 columns x 2
+        self.zero_bias = torch.zeros(1024, dtype=torch.float32, device=dev)
+        self.wscratch = None
+        self._alloc_derived()
+        self.derive_layouts()
+
+    # ------------------------------------------------------------------ helpers
+    def _c(self, rc, what):
+        _lib.check(rc, what)
+
+    def _sh(self):
+        return _lib.stream_handle()
+
+    def _new(self, *shape):
+        return torch.empty(shape, dtype=torch.float32, device=self.device)
+
+    def all_params(self):
+        """name -> tensor in TensorFlow variable naming (trainable variables + batch-norm moving statistics)."""
+        d = dict(self.params)
+        d.update(self.stats)
+        return d
+
+    def to_model(self, **kw):
+        """An inference Model over (a copy of) the current variables."""
+        return Model({k: v.detach().cpu().numpy() for k, v in self.all_params().items()}, cell_type=self.cell_type,
+                     rnn_sizes=self.rnn_sizes, device=self.device, **kw)
+
+    def save_npz(self, path):
+        np.savez(path, global_step=np.int64(self.global_step), **{k: v.detach().cpu().numpy() for k, v in self.all_params().items()})
+
+    # ------------------------------------------------------------------ kernel-side weight layouts
+    def _alloc_derived(self):
+        self.conv_w = {}
+        cin = 1
+        for (filters, k, padding, name, bn) in LAYER_PARAMS:
+            if name != "conv1":
+                self.conv_w[name] = (self._new(filters, 9 * cin), self._new(cin, 9 * filters))
+            cin = filters
+        self.rnn_w = []
+        I = 256
+        for H in self.rnn_sizes:
+            self.rnn_w.append(dict(I=I, H=H, wx=self._new(8 * H, I), wh=self._new(8 * H, H), wxcat=self._new(I, 8 * H), wh_rows=self._new(2 * H, 4 * H)))
+            I = 2 * H
+        C = self.shapes["rnn/logits/kernel"][1]
+        self.logits_w = self._new(C, I)
+
+    def derive_layouts(self):
+        """Re-derive the operand layouts of the kernels from the TensorFlow-layout variables (after every update)."""
+        lib, sh = self.lib, self._sh()
+        cin = 1
+        for (filters, k, padding, name, bn) in LAYER_PARAMS:
+            if name != "conv1":
+                wf, wd = self.conv_w[name]
+                self._c(lib.ocr_conv_filter_layouts(_lib.ptr(self.params["convnet/%s/kernel" % name]), cin, filters, _lib.ptr(wf), _lib.ptr(wd), sh),
+                        "ocr_conv_filter_layouts")
+            cin = filters
+        for scope, L in zip(("bdrnn1", "bdrnn2"), self.rnn_w):
+            I, H = L["I"], L["H"]
+            for d, dn in enumerate(("fw", "bw")):
+                kern = self.params["rnn/%s/%s/lstm_cell/kernel" % (scope, dn)]      # [I+H, 4H]
+                kp = kern.data_ptr()
+                # x part [I,4H] -> wx rows d*4H.. ([4H, I]);  h part [H,4H] -> wh rows d*4H.. ([4H, H])
+                self._c(lib.ocr_transpose(ctypes.c_void_p(kp), I, 4 * H, 4 * H, ctypes.c_void_p(L["wx"].data_ptr() + d * 4 * H * I * 4), I, 0, sh), "ocr_transpose")
+                self._c(lib.ocr_transpose(ctypes.c_void_p(kp + I * 4 * H * 4), H, 4 * H, 4 * H, ctypes.c_void_p(L["wh"].data_ptr() + d * 4 * H * H * 4), H, 0, sh), "ocr_transpose")
+                self._c(lib.ocr_copy_2d(ctypes.c_void_p(kp), 4 * H, ctypes.c_void_p(L["wxcat"].data_ptr() + d * 4 * H * 4), 8 * H, I, 4 * H, sh), "ocr_copy_2d")
+                self._c(lib.ocr_copy_2d(ctypes.c_void_p(kp + I * 4 * H * 4), 4 * H, ctypes.c_void_p(L["wh_rows"].data_ptr() + d * H * 4 * H * 4), 4 * H, H, 4 * H, sh), "ocr_copy_2d")
+        kl = self.params["rnn/logits/kernel"]                                        # [2H, C]
+        self._c(lib.ocr_transpose(_lib.ptr(kl), kl.shape[0], kl.shape[1], kl.shape[1], _lib.ptr(self.logits_w), kl.shape[0], 0, sh), "ocr_transpose")
+
+    # ------------------------------------------------------------------ building blocks
+    def _conv(self, x, w, bias, cout, relu):
+        B, H, W, C = x.shape
+        out = self._new(B, H, W, cout)
+        self._c(self.lib.ocr_conv3x3_same(_lib.ptr(x), B, H, W, C, _lib.ptr(w), _lib.ptr(bias), cout, int(relu), _lib.ptr(out), self._sh()), "ocr_conv3x3_same")
+        return out
+
+    def _pool(self, x, ph, pw, s_h, s_w):
+        B, H, W, C = x.shape
+        Hp, Wp = (H - ph) // s_h + 1, (W - pw) // s_w + 1
+        if Hp < 1 or Wp < 1:
+            raise ValueError("image too small for the convolutional stack (need height 32, width >= 8)")
+        out = self._new(B, Hp, Wp, C)
+        self._c(self.lib.ocr_maxpool(_lib.ptr(x), B, H, W, C, ph, pw, s_h, s_w, _lib.ptr(out), self._sh()), "ocr_maxpool")
+        return out
+
+    def _wgrad(self, At, lda, Wt, ldw, D, ldd, batch_stride, M, N, R, shifts=(0,), a_rows=0, a_row=None):
+        nb = len(shifts)
+        need = ctypes.c_size_t(0)
+        self._c(self.lib.ocr_gemm_wgrad_scratch_bytes(M, N, R, nb, ctypes.byref(need)), "ocr_gemm_wgrad_scratch_bytes")
+        if self.wscratch is None or self.wscratch.numel() < need.value:
+            self.wscratch = torch.empty(max(need.value, 1 << 24), dtype=torch.uint8, device=self.device)
+        arr = (ctypes.c_int32 * nb)(*shifts)
+        rows = (ctypes.c_int32 * nb)(*(a_row if a_row is not None else [0] * nb))
+        self._c(self.lib.ocr_gemm_tf32_wgrad(At, lda, Wt, ldw, D, ldd, batch_stride, M, N, R, nb, arr, rows, a_rows, _lib.ptr(self.wscratch),
+                                             self.wscratch.numel(), self._sh()), "ocr_gemm_tf32_wgrad")
+
+    def _transposed(self, x2d, src_shift=0):
+        """[R, C] -> [C, ld] with the long dimension contiguous (ld = R rounded up to 4); out[c, r] = x[r + src_shift, c]."""
+        R, C = x2d.shape
+        ld = (R + 3) // 4 * 4
+        out = self._new(C, ld)
+        self._c(self.lib.ocr_transpose(_lib.ptr(x2d), R, C, x2d.stride(0), _lib.ptr(out), ld, src_shift, self._sh()), "ocr_transpose")
+        return out, ld
+
+    def _planar(self, x, ncopies=1):
+        B, H, W, C = x.shape
+        R = B * (H + 2) * self.lib.ocr_planar_pad_pitch(W)      # a multiple of 4
+        out = self._new(ncopies, C, R)
+        self._c(self.lib.ocr_nhwc_to_planar_pad(_lib.ptr(x), B, H, W, C, _lib.ptr(out), R, ncopies, C * R, self._sh()), "ocr_nhwc_to_planar_pad")
+        return out, R
+
+    def _conv_wgrad(self, x, dy, name):
+        """d kernel [3,3,C,Cout] = sum over pixels of (3x3 patch of x) x dy.  Tap (i, j) is the zero-ringed planar copy of x
+        shifted by j-1 pixels (three copies: TMA box origins must be 16-byte aligned) and by i-1 padded rows (a multiple of
+        four elements): nine views, one launch."""
+        B, H, W, C = x.shape
+        Co = dy.shape[3]
+        Wp = self.lib.ocr_planar_pad_pitch(W)
+        xp, R = self._planar(x, 3)
+        dyp, _ = self._planar(dy, 1)
+        shifts = [(i - 1) * Wp for i in range(3) for j in range(3)]
+        a_row = [j * C for i in range(3) for j in range(3)]
+        self._wgrad(_lib.ptr(xp), R, _lib.ptr(dyp), R, _lib.ptr(self.grads["convnet/%s/kernel" % name]), Co, C * Co, C, Co, R, shifts, 3 * C, a_row)
+
+    def _allreduce(self, t, async_op=False):
+        import torch.distributed as dist
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=None if self.pg is True else self.pg, async_op=async_op)
+
+    # ------------------------------------------------------------------ the step
+    def forward_backward(self, image, width, label):
+        """Forward in TRAIN mode + backward; fills self.grad (gradient of the MEAN CTC loss over this replica's batch).
+        Returns the per-example losses [B] (device)."""
+        lib, sh = self.lib, self._sh()
+        _lib.require_cuda(image)
+        B, Hh, Ww, one = image.shape
+        if one != 1:
+            raise ValueError("image must be [B, H, W, 1]")
+        x = image.contiguous()
+        is_u8 = x.dtype == torch.uint8
+        if not is_u8:
+            x = x.float()
+        P, G = self.params, self.grads
+        scr = _lib.ptr(self.scratch)
+        saved = {}
+        # ---------------- forward: convnet_layers(mode=TRAIN)
+        w1, b1 = P["convnet/conv1/kernel"], P["convnet/conv1/bias"]
+        a = self._new(B, Hh - 2, Ww - 2, w1.shape[-1])
+        self._c(lib.ocr_conv1_3x3_valid(_lib.ptr(x), int(is_u8), B, Hh, Ww, _lib.ptr(w1), _lib.ptr(b1), w1.shape[-1], _lib.ptr(a), sh), "ocr_conv1_3x3_valid")
+        saved["conv1"] = dict(out=a)
+        for (filters, k, padding, name, bn) in LAYER_PARAMS[1:]:
+            S = {}
+            ph, pw, s_h, s_w = _POOL_BEFORE[name]
+            if (ph, pw, s_h, s_w) != (1, 1, 1, 1):
+                S["pool_in"], S["pool"] = a, (ph, pw, s_h, s_w)
+                a = self._pool(a, ph, pw, s_h, s_w)
+            S["x"] = a
+            wf, _ = self.conv_w[name]
+            bias = P["convnet/%s/bias" % name]
+            if not bn:
+                a = self._conv(a, wf, bias, filters, relu=True)
+                S["out"] = a
+            else:
+                y = self._conv(a, wf, bias, filters, relu=False)
+                rows = y.numel() // filters
+                q = "convnet/%s/batch_norm/" % name
+                sums = torch.empty(2 * filters, dtype=torch.float64, device=self.device)
+                self._c(lib.ocr_bn_batch_sums(_lib.ptr(y), rows, filters, _lib.ptr(sums), sh), "ocr_bn_batch_sums")
+                n_stat = rows
+                if self.sync_bn:
+                    self._allreduce(sums)
+                    n_stat = rows * self.world
+                mean, inv_std = self._new(filters), self._new(filters)
+                self._c(lib.ocr_bn_finalize(_lib.ptr(sums), n_stat, filters, BN_EPS, BN_MOMENTUM, _lib.ptr(mean), _lib.ptr(inv_std),
+                                            _lib.ptr(self.stats[q + "moving_mean"]), _lib.ptr(self.stats[q + "moving_variance"]), sh), "ocr_bn_finalize")
+                a = self._new(*y.shape)
+                self._c(lib.ocr_bn_relu_apply(_lib.ptr(y), rows, filters, _lib.ptr(mean), _lib.ptr(inv_std), _lib.ptr(P[q + "gamma"]),
+                                              _lib.ptr(P[q + "beta"]), _lib.ptr(a), sh), "ocr_bn_relu_apply")
+                S.update(y=y, mean=mean, inv_std=inv_std, out=a, n_stat=n_stat)
+            saved[name] = S
+        Bn, Hn, Wn, Cn = a.shape
+        seq = self._new(Wn, Bn, Cn)
+        self._c(lib.ocr_rows_max_to_seq(_lib.ptr(a), Bn, Hn, Wn, Cn, _lib.ptr(seq), sh), "ocr_rows_max_to_seq")
+        T = Wn
+        if torch.is_tensor(width) and width.is_cuda:
+            seq_len = (torch.div(width.to(torch.int32) - 2, 2, rounding_mode="floor") - 2).to(torch.int32).contiguous()
+            seq_len_host = seq_len.tolist()
+        else:   # host widths (the usual case): no device round trip for the label validation
+            seq_len_host = ((np.asarray(width, dtype=np.int64).reshape(-1) - 2) // 2 - 2).tolist()          # model.py:152-163
+            seq_len = torch.tensor(seq_len_host, dtype=torch.int32).to(self.device, non_blocking=True)
+        if len(seq_len_host) != B:
+            raise ValueError("width must have one entry per image")
+        # ---------------- forward: rnn_layers
+        need = ctypes.c_size_t(0)
+        Hmax = max(self.rnn_sizes)
+        self._c(lib.ocr_birnn_lstm_train_workspace_bytes(T, B, Hmax, ctypes.byref(need)), "ocr_birnn_lstm_train_workspace_bytes")
+        ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
+        rnn_saved = []
+        xin = seq
+        for scope, L in zip(("bdrnn1", "bdrnn2"), self.rnn_w):
+            I, H = L["I"], L["H"]
+            out, gates, cs = self._new(T, B, 2 * H), self._new(T * B, 8 * H), self._new(T, B, 2 * H)
+            o = self.offsets["rnn/%s/fw/lstm_cell/bias" % scope]
+            bias8 = self.theta[o:o + 8 * H]     # fw | bw biases are adjacent in the flat buffer
+            self._c(lib.ocr_birnn_lstm_train_fwd(_lib.ptr(xin), T, B, I, H, _lib.ptr(seq_len), _lib.ptr(L["wx"]), _lib.ptr(L["wh"]), _lib.ptr(bias8),
+                                                 _lib.ptr(out), _lib.ptr(gates), _lib.ptr(cs), _lib.ptr(ws), need.value, sh), "ocr_birnn_lstm_train_fwd")
+            rnn_saved.append(dict(x=xin, out=out, gates=gates, cs=cs))
+            xin = out
+        F = xin.shape[2]
+        C = self.logits_w.shape[0]
+        R = T * B
+        logits = self._new(T, B, C)
+        self._c(lib.ocr_gemm_tf32(_lib.ptr(xin), F, _lib.ptr(self.logits_w), F, _lib.ptr(P["rnn/logits/bias"]), _lib.ptr(logits), C, R, C, F, 1, sh), "ocr_gemm_tf32")
+        # ---------------- ctc_loss_layer: mean over the batch (model.py:224-229); the kernel returns d mean / d logits
+        flat, offsets, lengths, flat_host = ctc._labels_to_flat(label, B, self.device)
+        ctc._validate_ctc(flat_host, lengths, seq_len_host, T, C, False)
+        losses, dlog, _ = ctc.ctc_loss_raw(logits, flat, offsets, seq_len, max(lengths) if lengths else 0, want_grad=True, grad_scale=1.0 / B)
+        self.last_logits, self.last_seq_len = logits, seq_len
+        # ---------------- backward: logits layer (dense + ReLU, model.py:216-220)
+        self._c(lib.ocr_relu_bwd(_lib.ptr(logits), _lib.ptr(dlog), dlog.numel(), _lib.ptr(dlog), sh), "ocr_relu_bwd")
+        dz = dlog.view(R, C)
+        self._c(lib.ocr_colsum(_lib.ptr(dz), R, C, C, _lib.ptr(G["rnn/logits/bias"]), scr, sh), "ocr_colsum")
+        dzT, ldz = self._transposed(dz)
+        outT, ldo = self._transposed(rnn_saved[-1]["out"].view(R, F))
+        self._wgrad(_lib.ptr(outT), ldo, _lib.ptr(dzT), ldz, _lib.ptr(G["rnn/logits/kernel"]), C, 0, F, C, R, [0])
+        dout = self._new(T, B, F)
+        self._c(lib.ocr_gemm_tf32(_lib.ptr(dz), C, _lib.ptr(P["rnn/logits/kernel"]), C, None, _lib.ptr(dout), F, R, F, C, 0, sh), "ocr_gemm_tf32")
+        del dzT
+        # ---------------- backward: recurrent layers (BPTT), last layer first
+        for li in (1, 0):
+            scope = ("bdrnn1", "bdrnn2")[li]
+            L, S = self.rnn_w[li], rnn_saved[li]
+            I, H = L["I"], L["H"]
+            self._c(lib.ocr_birnn_lstm_bwd(_lib.ptr(dout), T, B, H, _lib.ptr(seq_len), _lib.ptr(S["gates"]), _lib.ptr(S["cs"]), _lib.ptr(L["wh_rows"]),
+                                           _lib.ptr(ws), need.value, sh), "ocr_birnn_lstm_bwd")
+            dG = S["gates"]                                   # [R, 8H] gradient of the gate pre-activations
+            o = self.offsets["rnn/%s/fw/lstm_cell/bias" % scope]
+            self._c(lib.ocr_colsum(_lib.ptr(dG), R, 8 * H, 8 * H, _lib.ptr(self.grad[o:o + 8 * H]), scr, sh), "ocr_colsum")
+            dGT, ldg = self._transposed(dG)
+            xT, ldx = self._transposed(S["x"].reshape(R, I))
+            for d, dn in enumerate(("fw", "bw")):
+                gk = G["rnn/%s/%s/lstm_cell/kernel" % (scope, dn)]                 # [I+H, 4H]
+                Wt = ctypes.c_void_p(dGT.data_ptr() + d * 4 * H * ldg * 4)
+                self._wgrad(_lib.ptr(xT), ldx, Wt, ldg, _lib.ptr(gk), 4 * H, 0, I, 4 * H, R, [0])
+                # h_{prev}: the layer's own output one frame earlier (forward) / later (backward direction)
+                shift = -B if d == 0 else B
+                if B % 4 == 0:      # a frame shift of the transposed output is an aligned TMA coordinate offset
+                    At, lda, shifts = ctypes.c_void_p(outT.data_ptr() + d * H * ldo * 4), ldo, [shift]
+                else:
+                    hprevT, lda = self._transposed(S["out"].view(R, 2 * H)[:, d * H:(d + 1) * H], shift)
+                    At, shifts = _lib.ptr(hprevT), [0]
+                self._wgrad(At, lda, Wt, ldg, ctypes.c_void_p(gk.data_ptr() + I * 4 * H * 4), 4 * H, 0, H, 4 * H, R, shifts)
+            dx = self._new(T, B, I)
+            self._c(lib.ocr_gemm_tf32(_lib.ptr(dG), 8 * H, _lib.ptr(L["wxcat"]), 8 * H, None, _lib.ptr(dx), I, R, I, 8 * H, 0, sh), "ocr_gemm_tf32")
+            dout = dx
+            outT, ldo = xT, ldx          # the input of layer 2 is the output of layer 1
+            del dGT
+            S.clear()
+        # the RNN + logits bucket of the flat gradient is complete: start its all-reduce behind the conv backward
+        works = []
+        if self.world > 1:
+            works.append(self._allreduce(self.grad[:self.n_rnn_floats], async_op=True))
+        # ---------------- backward: convolutional stack
+        S = saved["conv8"]
+        a8 = S["out"]
+        da = self._new(*a8.shape)
+        self._c(lib.ocr_rows_max_to_seq_bwd(_lib.ptr(a8), _lib.ptr(dout), Bn, Hn, Wn, Cn, _lib.ptr(da), sh), "ocr_rows_max_to_seq_bwd")
+        for (filters, k, padding, name, bn) in reversed(LAYER_PARAMS[1:]):
+            S = saved[name]
+            xin = S["x"]
+            rows = da.numel() // filters
+            if bn:
+                q = "convnet/%s/batch_norm/" % name
+                sums = torch.empty(2 * filters, dtype=torch.float64, device=self.device)
+                args = (_lib.ptr(S["mean"]), _lib.ptr(S["inv_std"]), _lib.ptr(P[q + "gamma"]), _lib.ptr(P[q + "beta"]))
+                self._c(lib.ocr_bn_relu_bwd_sums(_lib.ptr(S["y"]), _lib.ptr(da), rows, filters, *args, _lib.ptr(sums), _lib.ptr(G[q + "gamma"]),
+                                                 _lib.ptr(G[q + "beta"]), sh), "ocr_bn_relu_bwd_sums")
+                if self.sync_bn:
+                    self._allreduce(sums)
+                dy = da
+                self._c(lib.ocr_bn_relu_bwd_apply(_lib.ptr(S["y"]), _lib.ptr(da), rows, S["n_stat"], filters, *args, _lib.ptr(sums), _lib.ptr(dy), sh),
+                        "ocr_bn_relu_bwd_apply")
+                self._c(lib.ocr_colsum(_lib.ptr(dy), rows, filters, filters, _lib.ptr(G["convnet/%s/bias" % name]), scr, sh), "ocr_colsum")
+            else:
+                dy = da
+                self._c(lib.ocr_relu_bwd_bias(_lib.ptr(S["out"]), _lib.ptr(da), rows, filters, _lib.ptr(dy), _lib.ptr(G["convnet/%s/bias" % name]), scr, sh),
+                        "ocr_relu_bwd_bias")
+            self._conv_wgrad(xin, dy, name)
+            _, wd = self.conv_w[name]
+            dxin = self._conv(dy, wd, self.zero_bias, xin.shape[3], relu=False)
+            if "pool" in S:
+                ph, pw, s_h, s_w = S["pool"]
+                pin = S["pool_in"]
+                da = self._new(*pin.shape)
+                Bp, Hp_, Wp_, Cp = pin.shape
+                self._c(lib.ocr_maxpool_bwd(_lib.ptr(pin), _lib.ptr(dxin), Bp, Hp_, Wp_, Cp, ph, pw, s_h, s_w, _lib.ptr(da), sh), "ocr_maxpool_bwd")
+            else:
+                da = dxin
+            S.clear()
+        a1 = saved["conv1"]["out"]
+        rows = a1.numel() // a1.shape[3]
+        self._c(lib.ocr_relu_bwd_bias(_lib.ptr(a1), _lib.ptr(da), rows, a1.shape[3], _lib.ptr(da), _lib.ptr(G["convnet/conv1/bias"]), scr, sh), "ocr_relu_bwd_bias")
+        self._c(lib.ocr_conv1_wgrad(_lib.ptr(x), int(is_u8), B, Hh, Ww, _lib.ptr(da), a1.shape[3], _lib.ptr(G["convnet/conv1/kernel"]), scr, sh), "ocr_conv1_wgrad")
+        if self.world > 1:
+            works.append(self._allreduce(self.grad[self.n_rnn_floats:], async_op=True))
+            for w in works:
+                w.wait()
+        return losses
+
+    def apply_gradients(self):
+        """AdamOptimizer.apply_gradients with the decayed learning rate of the CURRENT global step, then global_step += 1."""
+        lr = learning_rate(self.global_step, **self.hp)
+        t = self.global_step + 1
+        lr_t = lr * math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1 ** t)
+        self._c(self.lib.ocr_adam_step(_lib.ptr(self.theta), _lib.ptr(self.grad), _lib.ptr(self.adam_m), _lib.ptr(self.adam_v), self.n_floats,
+                                       lr_t, self.beta1, self.beta2, self.epsilon, 1.0 / self.world, self._sh()), "ocr_adam_step")
+        self.global_step += 1
+        self.derive_layouts()
+
+    def train_step(self, image, width, label):
+        """[step_loss, step] = sess.run([train_op, global_step])  (train.py:196): returns the mean CTC loss (device scalar)."""
+        losses = self.forward_backward(image, width, label)
+        self.apply_gradients()
+        return losses.mean()

@@ -156,6 +156,91 @@ int ocr_birnn_layer(int cell, const float* x, int T, int B, int I, int H, const 
                     const float* wh, const float* wh2, const float* bias, float* out, void* workspace,
                     size_t workspace_bytes, ocr_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training step (src/weinman/train.py:101-141 _get_training; model.py with mode=TRAIN).  TensorFlow derives the
+ * backward graph from the registered gradients of the ops model.py uses; each entry point below is one of those
+ * gradients (or a forward op in its training form), so that the Python host layer (cnn_lstm_ctc_ocr_b200/train.py)
+ * can replay train.py's step.  `scratch` arguments are caller-owned device memory of at least
+ * 16 * max(channels, 9 * Cout) bytes unless stated otherwise.
+ *
+ * ocr_transpose            out[c, r] = in[r + src_shift, c] (zero outside [0, rows)); in [rows, cols] with row pitch ld_in,
+ *                          out row pitch ld_out (elements).  src_shift = -+B gives the previous-frame hidden state of a
+ *                          time-major [T*B, H] output.
+ * ocr_nhwc_to_planar_pad   in [B,H,W,C] NHWC -> out [C, B*(H+2)*Wp] (row pitch ld_out), Wp = ocr_planar_pad_pitch(W) =
+ *                          W+2 rounded up to a multiple of 4: channel-planar copy with a zero ring around every image,
+ *                          the operand layout of the filter-gradient contraction.  ncopies = 3 writes three copies,
+ *                          copy_stride elements apart, shifted by -1, 0, +1 pixels (copy k holds pixel r + k - 1 at r).
+ * ocr_gemm_tf32_wgrad      D[batch] (M x N, row pitch ldd, batch_stride apart) =
+ *                              sum_r At[a_row[batch] + m, r + a_shift[batch]] * Wt[n, r]:
+ *                          the weight gradients d kernel = activations^T * d outputs of tf.layers.conv2d (model.py:97),
+ *                          the RNN cells (model_bu.py:173-180) and tf.layers.dense (model.py:216) with the long pixel /
+ *                          frame dimension R contiguous in both operands; split over R across the SMs (tcgen05, TF32),
+ *                          partial tiles reduced in a fixed order.  a_shift / a_row are HOST arrays of nbatch (<= 9) ints
+ *                          (NULL = zeros), At has a_rows rows in total (0 = M): the 3x3 taps are row-shifted views
+ *                          (a_shift = +-Wp, a multiple of 4 as TMA requires) of the three pixel-shifted planar copies
+ *                          (a_row = copy * C).  Reads outside [0, R) give zero.
+ */
+int ocr_transpose(const float* in, long long rows, int cols, int ld_in, float* out, long long ld_out, long long src_shift,
+                  ocr_stream_t stream);
+int ocr_planar_pad_pitch(int W);
+int ocr_nhwc_to_planar_pad(const float* in, int B, int H, int W, int C, float* out, long long ld_out, int ncopies,
+                           long long copy_stride, ocr_stream_t stream);
+int ocr_gemm_wgrad_scratch_bytes(int M, int N, long long R, int nbatch, size_t* bytes);
+int ocr_gemm_tf32_wgrad(const float* At, long long lda, const float* Wt, long long ldw, float* D, int ldd, long long batch_stride,
+                        int M, int N, long long R, int nbatch, const int32_t* a_shift_host, const int32_t* a_row_host,
+                        long long a_rows, void* scratch, size_t scratch_bytes, ocr_stream_t stream);
+/* tf.layers.batch_normalization(training=True) (model.py:118-123) over y [rows, C] (rows = B*H*W of this replica):
+ *   ocr_bn_batch_sums      sums [2][C] DOUBLES: per-channel sum and sum of squares (a data-parallel job may all-reduce them)
+ *   ocr_bn_finalize        n = rows behind `sums` -> batch mean and 1/sqrt(biased variance + eps); moving_mean / moving_var
+ *                          (both or neither NULL) updated in place with `momentum` (the UPDATE_OPS train.py:116-118 runs;
+ *                          the moving variance takes the unbiased batch variance, as TensorFlow's fused kernel does)
+ *   ocr_bn_relu_apply      out = relu(gamma * (y - mean) * inv_std + beta)       (model.py:108 norm_layer + relu)
+ *   ocr_bn_relu_bwd_sums   dout = gradient w.r.t. that output -> sums [2][C] doubles (sum dz, sum dz*xhat), dgamma, dbeta [C]
+ *   ocr_bn_relu_bwd_apply  dy [rows, C] = gamma*inv_std*(dz - sums[0]/n - xhat*sums[1]/n)
+ *   ocr_copy_2d            strided device copy (weight-layout plumbing) */
+int ocr_bn_batch_sums(const float* y, long long rows, int C, void* sums, ocr_stream_t stream);
+int ocr_bn_finalize(const void* sums, long long n, int C, float eps, float momentum, float* mean, float* inv_std,
+                    float* moving_mean, float* moving_var, ocr_stream_t stream);
+int ocr_bn_relu_apply(const float* y, long long rows, int C, const float* mean, const float* inv_std, const float* gamma,
+                      const float* beta, float* out, ocr_stream_t stream);
+int ocr_bn_relu_bwd_sums(const float* y, const float* dout, long long rows, int C, const float* mean, const float* inv_std,
+                         const float* gamma, const float* beta, void* sums, float* dgamma, float* dbeta, ocr_stream_t stream);
+int ocr_bn_relu_bwd_apply(const float* y, const float* dout, long long rows, long long n, int C, const float* mean,
+                          const float* inv_std, const float* gamma, const float* beta, const void* sums, float* dy,
+                          ocr_stream_t stream);
+int ocr_copy_2d(const float* src, long long ld_src, float* dst, long long ld_dst, long long rows, long long cols, ocr_stream_t stream);
+/* ReLU + bias-add gradients: dy = dout * (out > 0) (dy may alias dout), dbias[c] = sum_rows dy;  ocr_colsum: plain column
+ * sums of x [rows, C] (row pitch ldx);  ocr_relu_bwd: dz = g * (z > 0) elementwise. */
+int ocr_relu_bwd_bias(const float* out, const float* dout, long long rows, int C, float* dy, float* dbias, void* scratch,
+                      ocr_stream_t stream);
+int ocr_colsum(const float* x, long long rows, int C, int ldx, float* out, void* scratch, ocr_stream_t stream);
+int ocr_relu_bwd(const float* z, const float* g, long long n, float* dz, ocr_stream_t stream);
+/* max-pool gradients (model.py:111-116,145-147): the window's gradient goes to its first maximum. */
+int ocr_maxpool_bwd(const float* in, const float* dout, int B, int H, int W, int C, int pool_h, int pool_w, int stride_h, int stride_w,
+                    float* din, ocr_stream_t stream);
+int ocr_rows_max_to_seq_bwd(const float* in, const float* dseq, int B, int H, int W, int C, float* din, ocr_stream_t stream);
+/* conv1 filter gradient (one input channel: a reduction over pixels): dw [3,3,1,Cout]. */
+int ocr_conv1_wgrad(const void* in, int in_is_u8, int B, int H, int W, const float* dy, int Cout, float* dw, void* scratch,
+                    ocr_stream_t stream);
+/* kernel-side filter layouts from the master HWIO tensor w [3,3,C,Cout]: w_fwd [Cout, 9*C] for ocr_conv3x3_same, w_dgrad
+ * [C, 9*Cout] = the 180-degree rotated filter, so that d input = ocr_conv3x3_same(dy, w_dgrad).  Either may be NULL. */
+int ocr_conv_filter_layouts(const float* w_hwio, int C, int Cout, float* w_fwd, float* w_dgrad, ocr_stream_t stream);
+/* tf.train.AdamOptimizer.apply_gradients over one flat buffer (train.py:128-137); lr_t = lr*sqrt(1-b2^t)/(1-b1^t) from
+ * the host; grads are multiplied by grad_scale first (1/world_size after a sum all-reduce). */
+int ocr_adam_step(float* params, const float* grads, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
+                  float eps, float grad_scale, ocr_stream_t stream);
+/* Bidirectional LSTM layer in training form (model_bu.py:167-199): like ocr_birnn_layer(cell 0) but keeps, per frame,
+ * the gate activations (gates [T*B, 8H]: fw i, tanh j, f, o | bw ...) and cell states (cstate [T,B,2H]).
+ * ocr_birnn_lstm_bwd: back-propagation through time.  dout [T,B,2H]; gates is overwritten with the gradient of the
+ * gate pre-activations (zero past each example's length), from which d kernel / d bias / d input follow as dense
+ * contractions.  wh_rows [2H, 4H]: rows I.. of the forward cell's TensorFlow kernel, then the backward cell's. */
+int ocr_birnn_lstm_train_workspace_bytes(int T, int B, int H, size_t* bytes);
+int ocr_birnn_lstm_train_fwd(const float* x, int T, int B, int I, int H, const int32_t* seq_len, const float* wx, const float* wh,
+                             const float* bias, float* out, float* gates, float* cstate, void* workspace, size_t workspace_bytes,
+                             ocr_stream_t stream);
+int ocr_birnn_lstm_bwd(const float* dout, int T, int B, int H, const int32_t* seq_len, float* gates, const float* cstate,
+                       const float* wh_rows, void* workspace, size_t workspace_bytes, ocr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
