@@ -24,7 +24,7 @@ constexpr int kGemmThreads = 192;
 
 struct GemmSplit {
     int ksteps_per_split, nbatch;
-    int a_shift[9], a_row[9];
+    int a_shift[9], a_row[9], b_row[9];
     long long split_stride, batch_stride;
 };
 
@@ -60,7 +60,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int nk_all = (K + kGemmBK - 1) / kGemmBK;
     const int k_begin = sp.ksteps_per_split > 0 ? blockIdx.z * sp.ksteps_per_split : 0;
     const int nk = sp.ksteps_per_split > 0 ? min(sp.ksteps_per_split, nk_all - k_begin) : nk_all;
-    const int a_shift = sp.a_shift[batch], a_row = sp.a_row[batch];
+    const int a_shift = sp.a_shift[batch], a_row = sp.a_row[batch], b_row = sp.b_row[batch];
     D += (size_t)batch * sp.batch_stride + (size_t)blockIdx.z * sp.split_stride;
 
     if (threadIdx.x == 0) {
@@ -84,7 +84,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (k >= STAGES) g_mbar_wait(bar_empty + s * 8, ((k / STAGES) - 1) & 1);
                 g_mbar_expect_tx(bar_full + s * 8, (unsigned)S::kStage);
                 tma_load_2d(s_base + s * S::kStage, &tmA, (k_begin + k) * kGemmBK + a_shift, m0 + a_row, bar_full + s * 8);
-                tma_load_2d(s_base + s * S::kStage + S::kA, &tmB, (k_begin + k) * kGemmBK, n0, bar_full + s * 8);
+                tma_load_2d(s_base + s * S::kStage + S::kA, &tmB, (k_begin + k) * kGemmBK, n0 + b_row, bar_full + s * 8);
             }
         }
     } else if (warp == 1) {
@@ -170,7 +170,7 @@ static int launch_planned(const GemmPlan& p, cudaStream_t st)
     GemmSplit sp;
     sp.ksteps_per_split = p.splits > 1 ? p.ksteps_per_split : 0;
     sp.nbatch = p.nbatch;
-    for (int i = 0; i < 9; ++i) { sp.a_shift[i] = p.a_shift[i]; sp.a_row[i] = p.a_row[i]; }
+    for (int i = 0; i < 9; ++i) { sp.a_shift[i] = p.a_shift[i]; sp.a_row[i] = p.a_row[i]; sp.b_row[i] = p.b_row[i]; }
     sp.split_stride = p.split_stride;
     sp.batch_stride = p.batch_stride;
     gemm_tf32_kernel<BN, STAGES><<<grid, kGemmThreads, S::kTotal, st>>>(p.tmA, p.tmB, p.bias, p.D, p.M, p.N, p.K, p.ldd, p.relu, sp);
@@ -198,6 +198,26 @@ int gemm_plan(GemmPlan* p, const float* A, int lda, const float* W, int ldw, con
     int rc = tma_map_2d(&p->tmA, A, M, K, lda, kGemmBM);
     if (rc != OCR_OK) return rc;
     return tma_map_2d(&p->tmB, W, N, K, ldw, bn);
+}
+
+// The two directions of a recurrent layer as ONE launch: batch d multiplies rows [d*M, (d+1)*M) of A with rows
+// [d*N, (d+1)*N) of W; outputs are dense [M, N] tiles batch_stride apart; optional split over K (partials split_stride apart).
+int gemm_plan_dirs(GemmPlan* p, const float* A, int lda, const float* W, int ldw, float* D, int M, int N, int K, int ndir, int splits, int bn)
+{
+    OCR_CHECK_ARG(M >= 1 && N >= 1 && K >= 1 && ndir >= 1 && ndir <= 9 && splits >= 1, "gemm_plan_dirs: bad shape");
+    OCR_CHECK_ARG((lda % 4) == 0 && (ldw % 4) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "gemm_plan_dirs: operands need 16-byte aligned rows");
+    const int nk = (K + kGemmBK - 1) / kGemmBK;
+    if (splits > nk) splits = nk;
+    const int kps = (nk + splits - 1) / splits;
+    splits = (nk + kps - 1) / kps;
+    p->bn = bn; p->bias = nullptr; p->D = D; p->M = M; p->N = N; p->K = K; p->ldd = N; p->relu = 0;
+    p->splits = splits; p->ksteps_per_split = splits > 1 ? kps : 0; p->nbatch = ndir;
+    for (int d = 0; d < ndir; ++d) { p->a_shift[d] = 0; p->a_row[d] = d * M; p->b_row[d] = d * N; }
+    p->split_stride = (long long)M * N;
+    p->batch_stride = (long long)splits * M * N;
+    int rc = tma_map_2d(&p->tmA, A, (long long)ndir * M, K, lda, kGemmBM);
+    if (rc != OCR_OK) return rc;
+    return tma_map_2d(&p->tmB, W, (long long)ndir * N, K, ldw, bn);
 }
 
 int gemm_run(const GemmPlan& p, cudaStream_t st)

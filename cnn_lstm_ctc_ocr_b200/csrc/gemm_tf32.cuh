@@ -15,7 +15,7 @@ struct GemmPlan {
     // split-K / shifted-operand form used by the weight-gradient contractions (gemm_plan_wgrad):
     //   D[batch][split] (M x N) = sum over the split's k range of A[m, k + a_shift[batch]] * W[n, k]
     int splits = 1, ksteps_per_split = 0, nbatch = 1;
-    int a_shift[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, a_row[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int a_shift[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, a_row[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, b_row[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long split_stride = 0, batch_stride = 0;   // elements between the partial outputs of consecutive splits / batches
 };
 
@@ -23,6 +23,8 @@ struct GemmPlan {
 int gemm_plan(GemmPlan* p, const float* A, int lda, const float* W, int ldw, const float* bias, float* D, int ldd, int M, int N,
               int K, int relu);
 int gemm_run(const GemmPlan& p, cudaStream_t st);
+// ndir independent products in one launch: D[d][split] (M x N dense) = A[d*M.., :] * W[d*N.., :]^T over the split's k range
+int gemm_plan_dirs(GemmPlan* p, const float* A, int lda, const float* W, int ldw, float* D, int M, int N, int K, int ndir, int splits, int bn);
 // Weight-gradient contraction over a long row dimension R (both operands R-contiguous, i.e. transposed activations):
 //   D[batch] (M x N, row pitch ldd, batches batch_stride apart) = sum_r A[a_row[batch] + m, r + a_shift[batch]] * W[n, r]
 // (A has a_rows rows in total; a_shift must be a multiple of 4: TMA box origins are 16-byte aligned)

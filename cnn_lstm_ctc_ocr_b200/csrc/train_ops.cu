@@ -44,13 +44,11 @@ transpose_kernel(const float* __restrict__ in, long long rows, int cols, int ld_
         const int c = c0 + tx;
         float v = 0.0f;
         if (r >= 0 && r < rows && c < cols) {
-            if (PAD) {
-                const int Hp = H + 2;
-                const int xp = (int)(r % Wp);
-                const long long q = r / Wp;
-                const int yp = (int)(q % Hp);
-                const long long b = q / Hp;
-                if (xp >= 1 && xp <= W && yp >= 1 && yp <= H) v = __ldg(in + (((size_t)b * H + (yp - 1)) * W + (xp - 1)) * ld_in + c);
+            if (PAD) {       // rows < 2^31 (checked by the caller): 32-bit divisions
+                const unsigned Hp = H + 2, ru = (unsigned)r;
+                const unsigned q = ru / (unsigned)Wp, xp = ru - q * Wp;
+                const unsigned b = q / Hp, yp = q - b * Hp;
+                if (xp >= 1 && xp <= (unsigned)W && yp >= 1 && yp <= (unsigned)H) v = __ldg(in + (((size_t)b * H + (yp - 1)) * W + (xp - 1)) * ld_in + c);
             } else {
                 v = __ldg(in + (size_t)r * ld_in + c);
             }
@@ -86,24 +84,38 @@ channel_reduce_kernel(const float* __restrict__ x, const float* __restrict__ g, 
     float mu = 0.f, is = 0.f, ga = 0.f, be = 0.f;
     if (MODE == 2 && ok) { mu = mean[c]; is = inv_std[c]; ga = gamma[c]; be = beta[c]; }
     float s0 = 0.f, s1 = 0.f, k0 = 0.f, k1 = 0.f;   // Kahan-compensated partial sums
-    for (long long r = (long long)blockIdx.x * 8 + warp; r < rows; r += (long long)gridDim.x * 8) {
+    const long long stride = (long long)gridDim.x * 8;
+    for (long long rb = (long long)blockIdx.x * 8 + warp; rb < rows; rb += 4 * stride) {
         if (!ok) continue;
-        const size_t o = (size_t)r * ldx + c;
-        float a0 = 0.f, a1 = 0.f;
-        if (MODE == 0) { const float v = x[o]; a0 = v; a1 = v * v; }
-        if (MODE == 1) { a0 = x[o]; }
-        if (MODE == 2) {
-            const float xh = (x[o] - mu) * is;
-            const float dz = (ga * xh + be > 0.f) ? g[o] : 0.f;
-            a0 = dz; a1 = dz * xh;
+        float xv[4], gv[4];
+        bool live[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {     // four independent rows in flight
+            const long long r = rb + u * stride;
+            live[u] = r < rows;
+            const size_t o = (size_t)(live[u] ? r : rb) * ldx + c;
+            xv[u] = x[o];
+            gv[u] = (MODE == 2 || MODE == 3) ? g[o] : 0.f;
         }
-        if (MODE == 3) {
-            const float dy = x[o] > 0.f ? g[o] : 0.f;
-            out[o] = dy;
-            a0 = dy;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (!live[u]) continue;
+            float a0 = 0.f, a1 = 0.f;
+            if (MODE == 0) { a0 = xv[u]; a1 = xv[u] * xv[u]; }
+            if (MODE == 1) { a0 = xv[u]; }
+            if (MODE == 2) {
+                const float xh = (xv[u] - mu) * is;
+                const float dz = (ga * xh + be > 0.f) ? gv[u] : 0.f;
+                a0 = dz; a1 = dz * xh;
+            }
+            if (MODE == 3) {
+                const float dy = xv[u] > 0.f ? gv[u] : 0.f;
+                out[(size_t)(rb + u * stride) * ldx + c] = dy;
+                a0 = dy;
+            }
+            { const float y = a0 - k0; const float t = s0 + y; k0 = (t - s0) - y; s0 = t; }
+            if (MODE == 0 || MODE == 2) { const float y = a1 - k1; const float t = s1 + y; k1 = (t - s1) - y; s1 = t; }
         }
-        { const float y = a0 - k0; const float t = s0 + y; k0 = (t - s0) - y; s0 = t; }
-        if (MODE == 0 || MODE == 2) { const float y = a1 - k1; const float t = s1 + y; k1 = (t - s1) - y; s1 = t; }
     }
     red[0][warp][lane] = s0;
     red[1][warp][lane] = s1;
@@ -170,15 +182,25 @@ bn_relu_bwd_apply_kernel(const float* __restrict__ y, const float* __restrict__ 
                          const float* __restrict__ inv_std, const float* __restrict__ gamma, const float* __restrict__ beta,
                          const double* __restrict__ sums, float* __restrict__ dy)
 {
-    const long long total = rows * C;
+    const int c4n = C >> 2;
+    const long long total = rows * c4n;
     const double inv_n = 1.0 / (double)n;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % C);
-        const float is = inv_std[c], ga = gamma[c];
-        const float xh = (y[idx] - mean[c]) * is;
-        const float dz = (ga * xh + beta[c] > 0.f) ? g[idx] : 0.f;
-        const float db = (float)(sums[c] * inv_n), dg = (float)(sums[C + c] * inv_n);
-        dy[idx] = ga * is * (dz - db - xh * dg);
+        const int c = (int)(idx % c4n) * 4;
+        const float4 yv = reinterpret_cast<const float4*>(y)[idx], gv = reinterpret_cast<const float4*>(g)[idx];
+        const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(inv_std + c);
+        const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+        float4 o;
+#define OCR_BNB(f, k)                                                                    \
+        {                                                                                \
+            const float xh = (yv.f - mu.f) * is.f;                                       \
+            const float dz = (ga.f * xh + be.f > 0.f) ? gv.f : 0.f;                      \
+            const float db = (float)(sums[c + k] * inv_n), dg = (float)(sums[C + c + k] * inv_n); \
+            o.f = ga.f * is.f * (dz - db - xh * dg);                                     \
+        }
+        OCR_BNB(x, 0) OCR_BNB(y, 1) OCR_BNB(z, 2) OCR_BNB(w, 3)
+#undef OCR_BNB
+        reinterpret_cast<float4*>(dy)[idx] = o;
     }
 }
 
@@ -189,34 +211,44 @@ __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const float* __restrict__ in, const float* __restrict__ dout, int B, int H, int W, int C, int ph, int pw, int sh, int sw,
                    int Hp, int Wp, float* __restrict__ din)
 {
-    const long long total = (long long)B * H * W * C;
+    const int c4n = C >> 2;
+    const long long total = (long long)B * H * W * c4n;
+    const float4* in4 = reinterpret_cast<const float4*>(in);
+    const float4* dout4 = reinterpret_cast<const float4*>(dout);
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % C);
-        long long p = idx / C;
-        const int x = (int)(p % W); p /= W;
-        const int y = (int)(p % H);
-        const int b = (int)(p / H);
-        const float v = in[idx];
-        float acc = 0.f;
-        // windows (oy, ox) with oy*sh <= y < oy*sh + ph
+        const unsigned c4 = (unsigned)(idx % c4n);
+        unsigned p = (unsigned)(idx / c4n);                 // pixel index < 2^31 (checked by the caller)
+        const int x = (int)(p % (unsigned)W); p /= (unsigned)W;
+        const int y = (int)(p % (unsigned)H);
+        const int b = (int)(p / (unsigned)H);
+        const float4 v = in4[idx];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        // windows (oy, ox) that contain (y, x)
         const int oy_lo = max(0, (y - ph + sh) / sh), oy_hi = min(Hp - 1, y / sh);
         const int ox_lo = max(0, (x - pw + sw) / sw), ox_hi = min(Wp - 1, x / sw);
         for (int oy = oy_lo; oy <= oy_hi; ++oy)
             for (int ox = ox_lo; ox <= ox_hi; ++ox) {
                 if (oy * sh + ph <= y || ox * sw + pw <= x) continue;
-                // is (y, x) the first maximum of this window?
-                bool first = true;
-                for (int dy = 0; dy < ph && first; ++dy)
+                // per channel: is (y, x) the first maximum of this window?
+                bool fx = true, fy = true, fz = true, fw = true;
+                for (int dy = 0; dy < ph; ++dy)
                     for (int dx = 0; dx < pw; ++dx) {
                         const int yy = oy * sh + dy, xx = ox * sw + dx;
                         if (yy == y && xx == x) continue;
-                        const float u = __ldg(in + (((size_t)b * H + yy) * W + xx) * C + c);
+                        const float4 u = __ldg(in4 + (((size_t)b * H + yy) * W + xx) * c4n + c4);
                         const bool before = (yy < y) || (yy == y && xx < x);
-                        if (u > v || (before && u == v)) { first = false; break; }
+                        fx = fx && !(u.x > v.x || (before && u.x == v.x));
+                        fy = fy && !(u.y > v.y || (before && u.y == v.y));
+                        fz = fz && !(u.z > v.z || (before && u.z == v.z));
+                        fw = fw && !(u.w > v.w || (before && u.w == v.w));
                     }
-                if (first) acc += __ldg(dout + (((size_t)b * Hp + oy) * Wp + ox) * C + c);
+                const float4 g = __ldg(dout4 + (((size_t)b * Hp + oy) * Wp + ox) * c4n + c4);
+                if (fx) acc.x += g.x;
+                if (fy) acc.y += g.y;
+                if (fz) acc.z += g.z;
+                if (fw) acc.w += g.w;
             }
-        din[idx] = acc;
+        reinterpret_cast<float4*>(din)[idx] = acc;
     }
 }
 
@@ -257,7 +289,7 @@ lstm_cell_train_kernel(const float* __restrict__ gh, float* __restrict__ xp, con
         const int len = min(seq_len[b], T);
         if (s >= len) continue;
         const int t = dir ? len - 1 - s : s;
-        const float* g = gh + (size_t)r * 8 * H + dir * 4 * H;
+        const float* g = gh + (size_t)r * 4 * H;          // [2][B][4H]: this direction's own product only
         float* x = xp + ((size_t)t * B + b) * 8 * H + dir * 4 * H;
         const float gi = sigm(g[j] + x[j]), gj = tanhf(g[H + j] + x[H + j]);
         const float gf = sigm(g[2 * H + j] + x[2 * H + j] + 1.0f), go = sigm(g[3 * H + j] + x[3 * H + j]);
@@ -272,14 +304,14 @@ lstm_cell_train_kernel(const float* __restrict__ gh, float* __restrict__ xp, con
     }
 }
 
-// One BPTT frame.  act [T*B, 8H]: gate activations in, gate PRE-activation gradients out (in place).  dh_rec [2B, 2H]
-// is the product dG_step * W_h of the step processed just before (columns dir*H.. of row r); dh, dc [2B,H] carry the
+// One BPTT frame.  act [T*B, 8H]: gate activations in, gate PRE-activation gradients out (in place).  dh_rec
+// [2][splits][B][H] holds the split-K partial products dG_step * W_h of the step processed just before; dh, dc [2B,H] carry the
 // state gradients; dgs [2B, 4H] receives this step's gate gradients as the A operand of the next recurrent product
 // (zero rows for examples that are past their length).
 __global__ void __launch_bounds__(256)
 lstm_cell_bwd_kernel(float* __restrict__ act, const float* __restrict__ cs, const float* __restrict__ dout, const float* __restrict__ dh_rec,
-                     const int32_t* __restrict__ seq_len, int s, int last, int T, int B, int H, float* __restrict__ dh, float* __restrict__ dc,
-                     float* __restrict__ dgs)
+                     const int32_t* __restrict__ seq_len, int s, int last, int T, int B, int H, int splits, float* __restrict__ dh,
+                     float* __restrict__ dc, float* __restrict__ dgs)
 {
     const int total = 2 * B * H;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -290,7 +322,11 @@ lstm_cell_bwd_kernel(float* __restrict__ act, const float* __restrict__ cs, cons
         float* gs = dgs + (size_t)r * 4 * H;
         // gradient flowing into h_s from step s+1 (only if that step was live for this example)
         float dhv = 0.f, dcv = 0.f;
-        if (!last && s + 1 < len) { dhv = dh_rec[(size_t)r * 2 * H + dir * H + j]; dcv = dc[idx]; }
+        if (!last && s + 1 < len) {
+            const float* pr = dh_rec + ((size_t)dir * splits * B + b) * H + j;     // [2][splits][B][H] split-K partials
+            for (int z = 0; z < splits; ++z) dhv += pr[(size_t)z * B * H];
+            dcv = dc[idx];
+        }
         if (s >= len) { gs[j] = 0.f; gs[H + j] = 0.f; gs[2 * H + j] = 0.f; gs[3 * H + j] = 0.f; continue; }
         const int t = dir ? len - 1 - s : s;
         const size_t o = ((size_t)t * B + b) * 2 * H + dir * H + j;
@@ -340,22 +376,31 @@ conv1_wgrad_kernel(const void* __restrict__ in_, int B, int H, int W, const floa
     float acc[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[k] = 0.f;
-    for (long long p = (long long)blockIdx.x * 8 + warp; p < npix; p += (long long)gridDim.x * 8) {
-        const int x = (int)(p % Wo);
-        const long long q = p / Wo;
-        const int y = (int)(q % Ho);
-        const int b = (int)(q / Ho);
-        const float g = co < Co ? dy[(size_t)p * Co + co] : 0.f;
+    const long long stride = (long long)gridDim.x * 8;
+    for (long long pb = (long long)blockIdx.x * 8 + warp; pb < npix; pb += 4 * stride) {
+        float g[4];
+        float v[4][9];
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+        for (int u = 0; u < 4; ++u) {     // four independent pixels in flight
+            const long long p = pb + u * stride;
+            const bool live = p < npix;
+            const unsigned pp = (unsigned)(live ? p : pb);
+            const unsigned q = pp / (unsigned)Wo, x = pp - q * Wo;
+            const unsigned b = q / (unsigned)Ho, y = q - b * Ho;
+            g[u] = (live && co < Co) ? dy[(size_t)pp * Co + co] : 0.f;
 #pragma unroll
-            for (int jx = 0; jx < 3; ++jx) {
-                const size_t o = ((size_t)b * H + (y + i)) * W + (x + jx);
-                float v;
-                if (kU8) v = (float)__ldg(reinterpret_cast<const unsigned char*>(in_) + o) / 255.0f - 0.5f;
-                else v = __ldg(reinterpret_cast<const float*>(in_) + o);
-                acc[i * 3 + jx] = fmaf(g, v, acc[i * 3 + jx]);
-            }
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int jx = 0; jx < 3; ++jx) {
+                    const size_t o = ((size_t)b * H + (y + i)) * W + (x + jx);
+                    if (kU8) v[u][i * 3 + jx] = (float)__ldg(reinterpret_cast<const unsigned char*>(in_) + o) / 255.0f - 0.5f;
+                    else v[u][i * 3 + jx] = __ldg(reinterpret_cast<const float*>(in_) + o);
+                }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc[k] = fmaf(g[u], v[u][k], acc[k]);
     }
 #pragma unroll
     for (int k = 0; k < 9; ++k) red[warp][k][lane] = acc[k];
@@ -452,6 +497,7 @@ extern "C" int ocr_nhwc_to_planar_pad(const float* in, int B, int H, int W, int 
 {
     const int Wp = ocr_planar_pad_pitch(W);
     const long long rows = (long long)B * (H + 2) * Wp;
+    OCR_CHECK_ARG(rows < 0x7fffffffLL, "ocr_nhwc_to_planar_pad: too many pixels");
     OCR_CHECK_ARG(B >= 0 && H >= 1 && W >= 1 && C >= 1 && ld_out >= rows && (ncopies == 1 || ncopies == 3) && (ncopies == 1 || copy_stride >= (long long)C * ld_out),
                   "ocr_nhwc_to_planar_pad: bad shape B=%d H=%d W=%d C=%d ld=%lld ncopies=%d", B, H, W, C, ld_out, ncopies);
     if (B == 0) return OCR_OK;
@@ -549,7 +595,8 @@ extern "C" int ocr_bn_relu_bwd_apply(const float* y, const float* dout, long lon
                                      ocr_stream_t stream)
 {
     OCR_CHECK_ARG(rows >= 1 && n >= rows && C >= 1 && y && dout && mean && inv_std && gamma && beta && sums && dy, "ocr_bn_relu_bwd_apply: bad argument");
-    bn_relu_bwd_apply_kernel<<<grid_cap(rows * C), 256, 0, ST(stream)>>>(y, dout, rows, n, C, mean, inv_std, gamma, beta, reinterpret_cast<const double*>(sums), dy);
+    OCR_CHECK_ARG((C % 4) == 0, "ocr_bn_relu_bwd_apply: C must be a multiple of 4");
+    bn_relu_bwd_apply_kernel<<<grid_cap(rows * (C / 4)), 256, 0, ST(stream)>>>(y, dout, rows, n, C, mean, inv_std, gamma, beta, reinterpret_cast<const double*>(sums), dy);
     OCR_CHECK_LAUNCH();
     return OCR_OK;
 }
@@ -600,8 +647,9 @@ extern "C" int ocr_maxpool_bwd(const float* in, const float* dout, int B, int H,
 {
     OCR_CHECK_ARG(B >= 1 && C >= 1 && pool_h >= 1 && pool_w >= 1 && stride_h >= 1 && stride_w >= 1 && H >= pool_h && W >= pool_w && in && dout && din,
                   "ocr_maxpool_bwd: bad argument");
+    OCR_CHECK_ARG((C % 4) == 0 && (long long)B * H * W < 0x7fffffffLL, "ocr_maxpool_bwd: C must be a multiple of 4");
     const int Hp = (H - pool_h) / stride_h + 1, Wp = (W - pool_w) / stride_w + 1;
-    maxpool_bwd_kernel<<<grid_cap((long long)B * H * W * C), 256, 0, ST(stream)>>>(in, dout, B, H, W, C, pool_h, pool_w, stride_h, stride_w, Hp, Wp, din);
+    maxpool_bwd_kernel<<<grid_cap((long long)B * H * W * (C / 4)), 256, 0, ST(stream)>>>(in, dout, B, H, W, C, pool_h, pool_w, stride_h, stride_w, Hp, Wp, din);
     OCR_CHECK_LAUNCH();
     return OCR_OK;
 }
@@ -652,13 +700,23 @@ extern "C" int ocr_adam_step(float* params, const float* grads, float* m, float*
     return OCR_OK;
 }
 
+// tile width of the per-frame recurrent products: enough CTAs for the 148 SMs, as wide as that allows
+static int recurrent_bn(int M, int N, int splits) {
+    const long long mt = (M + kGemmBM - 1) / kGemmBM;
+    int bn = 32;
+    if (N > 32) bn = 64;
+    if (N > 64 && 2 * mt * ((N + 127) / 128) * splits >= 120) bn = 128;
+    if (N > 128 && 2 * mt * ((N + 255) / 256) * splits >= 120) bn = 256;
+    return bn;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // bidirectional LSTM layer, training form (frame by frame; keeps gate activations and cell states)
 extern "C" int ocr_birnn_lstm_train_workspace_bytes(int T, int B, int H, size_t* bytes)
 {
     OCR_CHECK_ARG(bytes && T >= 0 && B >= 0 && H >= 1, "ocr_birnn_lstm_train_workspace_bytes: bad argument");
-    // gh [2B, 8H] + h, c [2B,H] + dgs [2B,4H] + dh_rec [2B,2H] + dh, dc
-    *bytes = sizeof(float) * ((size_t)2 * B * 8 * H + (size_t)2 * B * H * 4 + (size_t)2 * B * 4 * H + (size_t)2 * B * 2 * H) + 256;
+    // gh [2B, 8H] (backward: split-K partials of dh_rec, at most 8 x [2B, H]) + h, c, dh, dc [2B,H] + dgs [2B,4H]
+    *bytes = sizeof(float) * ((size_t)2 * B * 8 * H + (size_t)2 * B * H * 4 + (size_t)2 * B * 4 * H) + 256;
     return OCR_OK;
 }
 
@@ -683,7 +741,8 @@ extern "C" int ocr_birnn_lstm_train_fwd(const float* x, int T, int B, int I, int
     OCR_CHECK_CUDA(cudaMemsetAsync(cstate, 0, sizeof(float) * (size_t)T * B * 2 * H, st));
     OCR_CHECK_CUDA(cudaMemsetAsync(gh, 0, sizeof(float) * (size_t)2 * B * 8 * H, st));
     GemmPlan p1;
-    rc = gemm_plan(&p1, h, H, wh, H, nullptr, gh, 8 * H, 2 * B, 8 * H, H, 0);
+    // both directions in one launch: gh[d] [B, 4H] = h[d] [B, H] * wh[d] [4H, H]^T
+    rc = gemm_plan_dirs(&p1, h, H, wh, H, gh, B, 4 * H, H, 2, 1, recurrent_bn(B, 4 * H, 1));
     if (rc != OCR_OK) return rc;
     const int cg = grid_cap((long long)2 * B * H);
     for (int s = 0; s < T; ++s) {
@@ -706,21 +765,25 @@ extern "C" int ocr_birnn_lstm_bwd(const float* dout, int T, int B, int H, const 
     if (workspace == nullptr || workspace_bytes < need) { set_error("ocr_birnn_lstm_bwd: workspace too small"); return OCR_EWORKSPACE; }
     cudaStream_t st = ST(stream);
     float* ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
-    float* gh = ws;
-    float* dh = gh + (size_t)2 * B * 8 * H;
+    float* dh_rec = ws;                               // [2][splits][B][H], splits <= 8
+    float* dh = dh_rec + (size_t)2 * B * 8 * H;
     float* dc = dh + (size_t)2 * B * H;
     float* dgs = dc + (size_t)2 * B * H * 3;          // [2B, 4H]
-    float* dh_rec = dgs + (size_t)2 * B * 4 * H;      // [2B, 2H]
     OCR_CHECK_CUDA(cudaMemsetAsync(dh, 0, sizeof(float) * (size_t)2 * B * H * 2, st));
     zero_past_len_kernel<<<grid_cap((long long)T * B * 2 * H), 256, 0, st>>>(gates, seq_len, T, B, 2 * H);
     OCR_CHECK_LAUNCH();
     GemmPlan p1;
-    // dh_rec[r, n] = sum_g dgs[r, g] * wh_rows[n, g]
-    int rc = gemm_plan(&p1, dgs, 4 * H, wh_rows, 4 * H, nullptr, dh_rec, 2 * H, 2 * B, 2 * H, 4 * H, 0);
+    // dh_rec[d][b, n] = sum_g dgs[d*B + b, g] * wh_rows[d*H + n, g]: K = 4H is long and the tile count small, so the
+    // contraction is split over K across the SMs; the cell kernel of the next step adds the partials up
+    int want = (148 + 2 * ((B + 127) / 128) * ((H + 63) / 64) - 1) / (2 * ((B + 127) / 128) * ((H + 63) / 64));
+    if (want > 8) want = 8;
+    if (want < 1) want = 1;
+    int rc = gemm_plan_dirs(&p1, dgs, 4 * H, wh_rows, 4 * H, dh_rec, B, H, 4 * H, 2, want, H > 32 ? 64 : 32);
     if (rc != OCR_OK) return rc;
+    const int splits = p1.splits;
     const int cg = grid_cap((long long)2 * B * H);
     for (int s = T - 1; s >= 0; --s) {
-        lstm_cell_bwd_kernel<<<cg, 256, 0, st>>>(gates, cstate, dout, dh_rec, seq_len, s, s == T - 1 ? 1 : 0, T, B, H, dh, dc, dgs);
+        lstm_cell_bwd_kernel<<<cg, 256, 0, st>>>(gates, cstate, dout, dh_rec, seq_len, s, s == T - 1 ? 1 : 0, T, B, H, splits, dh, dc, dgs);
         OCR_CHECK_LAUNCH();
         if (s > 0) { rc = gemm_run(p1, st); if (rc != OCR_OK) return rc; }
     }
