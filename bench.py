@@ -330,6 +330,12 @@ def run_ours(args, cfg):
         infer = None
         if not args.skip_infer:
             infer = inference_block(dev, world, windows, with_cpu=(rank == 0 and world == 1))
+        training = None
+        if not args.skip_train:
+            try:
+                training = training_block(dev, rank, world, windows, steps=args.train_steps, with_cpu=(rank == 0 and world == 1))
+            except torch.cuda.OutOfMemoryError:
+                training = {"error": "out of memory"}
 
     sampler.stop()
     peak, peak_src = _peaks()
@@ -351,6 +357,7 @@ def run_ours(args, cfg):
                          "note": "one step = ctc_loss_fast_kernel + the redo gate; cfg2 (8.3 MB, L2 resident, 64 CTAs of 2x24 dependent lattice frames) is latency-bound, see roofline_bw_regime"},
             "roofline_bw_regime": bw,
             "inference": infer,
+            "training": training,
             "clocks": sampler.summary(windows),
             "parity_status_ok": ok_status,
         }
@@ -455,6 +462,110 @@ def inference_block(dev, world, windows, B=32, W=128, cell="lstm", steps=20, wit
     return out
 
 
+# --------------------------------------------------------------------------- training step (BASELINE configs[2])
+TRAIN_FLOP_PER_CROP = 3 * 3793.1e6   # W=256, LSTM 512/512: 3 x forward
+
+
+def make_train_batch(seed, B, W, num_labels=95, max_label=24):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (B, 32, W, 1)).astype(np.uint8)
+    T = (W - 2) // 2 - 2
+    labels = []
+    for _ in range(B):
+        n = int(rng.integers(1, max_label + 1))
+        l = rng.integers(0, num_labels, n)
+        for i in range(1, n):
+            if rng.random() < 0.15:
+                l[i] = l[i - 1]
+        labels.append([int(v) for v in l])
+    return img, np.full(B, W), labels
+
+
+def training_block(dev, rank, world, windows, global_batch=256, W=256, steps=10, with_cpu=True):
+    """configs[2]: full training step (conv + BiLSTM + CTC forward/backward + Adam), global batch 256 of 32x256 crops,
+    data parallel over `world` GPUs (per-GPU batch 256/world) with the NCCL gradient all-reduce in two buckets, the
+    first overlapped with the conv backward.  value: CUDA-graph replay with the crops resident in HBM;
+    e2e: Trainer.train_step_captured from pinned host uint8 crops + labels to the host loss."""
+    import numpy as np
+    import torch
+    from cnn_lstm_ctc_ocr_b200 import _lib, train
+    from oracle import model_oracle as mo   # parameter initialiser only
+    B = global_batch // world
+    params = mo.init_params(0, "lstm", (512, 512), 95, np.float32)
+    tr = train.Trainer(params, device=dev, process_group=(True if world > 1 else None))
+    batches = [make_train_batch(shard_seed(rank, i), B, W) for i in range(3)]
+    dimg = [torch.from_numpy(b[0]).to(dev) for b in batches]
+    himg = [torch.from_numpy(b[0]).pin_memory() for b in batches]
+    n0 = _lib.launch_count()
+    tr.capture(B, W, max_label_len=24)
+    launches = (_lib.launch_count() - n0) // 2     # warm-up pass + capture pass
+    for i in range(3):
+        tr.train_step_captured(dimg[i % 3], batches[i % 3][1], batches[i % 3][2])
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_a = time.time()
+    e0.record()
+    for i in range(steps):
+        losses = tr.train_step_captured(dimg[i % 3], batches[i % 3][1], batches[i % 3][2])
+    e1.record()
+    torch.cuda.synchronize()
+    windows.append((t_a, time.time()))
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / steps
+    loss_dev = float(losses.mean().item())
+    # end to end: pinned host crops + labels in, host loss out, every step
+    hloss = torch.empty(1, dtype=torch.float32).pin_memory()
+    if world > 1:
+        torch.distributed.barrier()
+    t_a = time.time()
+    e0.record()
+    for i in range(steps):
+        losses = tr.train_step_captured(himg[i % 3], batches[i % 3][1], batches[i % 3][2])
+        hloss.copy_(losses.mean().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    torch.cuda.synchronize()
+    windows.append((t_a, time.time()))
+    ms_e = max_over_ranks(e0.elapsed_time(e1), world, dev) / steps
+    peaks = {}
+    pth = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pth):
+        with open(pth) as fjs:
+            peaks = json.load(fjs)
+    tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
+    ach = TRAIN_FLOP_PER_CROP * global_batch / (ms * 1e-3) / 1e12 / world
+    out = {"workload": "BASELINE configs[2]: full training step (conv+BiLSTM+CTC fwd/bwd + Adam), global batch %d of 32x%d crops, "
+                       "LSTM 512/512, 96 logits, data-parallel over %d GPU(s)" % (global_batch, W, world),
+           "value": global_batch / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "n_gpus": world, "per_gpu_batch": B, "scaling": "strong",
+           "gpu_launches_per_step": launches, "steps": steps, "loss": loss_dev, "finite": bool(np.isfinite(loss_dev)),
+           "timed_region": "CUDA-graph replay of the step (%s), crops resident in HBM" %
+                           ("one graph" if world == 1 else "three graphs, two NCCL bucket all-reduces between them, the first overlapped with the conv backward"),
+           "dtype": "tf32 products, fp32 accumulate/storage/optimizer",
+           "e2e": {"value": global_batch / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(himg[0].numel() + B * 4 + B * 24 * 4 + (B + 1) * 4 + 4),
+                   "d2h_bytes_per_step": 4, "api": "cnn_lstm_ctc_ocr_b200.train.Trainer.train_step_captured (pinned uint8 crops + labels -> loss)"},
+           "allreduce_bytes_per_step": int(tr.n_floats * 4) if world > 1 else 0,
+           "roofline": {"bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s per GPU", "frac": ach / tf32_peak, "traffic": None,
+                        "peak_source": "half of the measured sustained bf16 GEMM peak (TF32 runs at half the bf16 rate)",
+                        "algorithmic_flop_per_step": TRAIN_FLOP_PER_CROP * global_batch}}
+    if with_cpu:
+        from oracle import train_oracle as to
+        nb = 8
+        img, widths, labels = make_train_batch(7, nb, W)
+        p64 = {k: v.astype(np.float64) for k, v in params.items()}
+        t0 = time.perf_counter()
+        to.train_step_reference(p64, img, widths, labels, step=0, cell_type="lstm", sizes=(512, 512))
+        dt = time.perf_counter() - t0
+        import torch as _t
+        out["cpu_baseline"] = {"value": nb / dt, "unit": UNIT, "cores": _t.get_num_threads(), "kind": "port",
+                               "sample": "one training step on %d crops through oracle/train_oracle.py (torch CPU autograd, float64), %.1f s wall "
+                                         "(TensorFlow itself cannot run in this image)" % (nb, dt)}
+    del tr
+    torch.cuda.empty_cache()
+    return out
+
+
 def bandwidth_regime(lib, _lib, dev, T, C, B, windows):
     import torch
     peak, peak_src = _peaks()
@@ -511,6 +622,8 @@ def main():
     ap.add_argument("--skip-bw", action="store_true", help="skip the bandwidth-regime measurement")
     ap.add_argument("--bw-batch", type=int, default=65536)
     ap.add_argument("--skip-infer", action="store_true", help="skip the recognizer-inference block (BASELINE configs[0])")
+    ap.add_argument("--skip-train", action="store_true", help="skip the training-step block (BASELINE configs[2])")
+    ap.add_argument("--train-steps", type=int, default=10)
     args = ap.parse_args()
     cfg = {"T": 64, "B": 256, "C": 63,
            "config": {"workload": "BASELINE configs[1]: CTC loss + gradient only, batch 256, T=64 frames, 63-class alphabet "

@@ -198,9 +198,11 @@ extern "C" int ocr_conv3x3_same(const float* in, int B, int H, int W, int C, con
     if (Cout > 64 && mt * ((Cout + 127) / 128) >= 120) bn = 128;
     if (Cout > 128 && mt * ((Cout + 255) / 256) >= 120) bn = 256;
     switch (bn) {
-        case 32: return launch_conv<32, 8>(in, B, H, W, C, w, bias, Cout, relu, out, st);
-        case 64: return launch_conv<64, 6>(in, B, H, W, C, w, bias, Cout, relu, out, st);
-        case 128: return launch_conv<128, 5>(in, B, H, W, C, w, bias, Cout, relu, out, st);
+        // few stages per CTA, several CTAs per SM (3, 3, 2, 1): a tile is short (9..72 k-steps), so the prologue /
+        // epilogue of one CTA hides behind the main loop of its neighbours
+        case 32: return launch_conv<32, 3>(in, B, H, W, C, w, bias, Cout, relu, out, st);
+        case 64: return launch_conv<64, 3>(in, B, H, W, C, w, bias, Cout, relu, out, st);
+        case 128: return launch_conv<128, 3>(in, B, H, W, C, w, bias, Cout, relu, out, st);
         default: return launch_conv<256, 4>(in, B, H, W, C, w, bias, Cout, relu, out, st);
     }
 }

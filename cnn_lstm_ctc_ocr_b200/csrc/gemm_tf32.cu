@@ -25,6 +25,7 @@ constexpr int kGemmThreads = 192;
 struct GemmSplit {
     int ksteps_per_split, nbatch;
     int a_shift[9], a_row[9], b_row[9];
+    int a_box_bytes;   // bytes one A box delivers (boxes shorter than 128 rows when M < 128: no over-fetch of foreign rows)
     long long split_stride, batch_stride;
 };
 
@@ -82,7 +83,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int k = 0; k < nk; ++k) {
                 const int s = k % STAGES;
                 if (k >= STAGES) g_mbar_wait(bar_empty + s * 8, ((k / STAGES) - 1) & 1);
-                g_mbar_expect_tx(bar_full + s * 8, (unsigned)S::kStage);
+                g_mbar_expect_tx(bar_full + s * 8, (unsigned)(sp.a_box_bytes + S::kB));
                 tma_load_2d(s_base + s * S::kStage, &tmA, (k_begin + k) * kGemmBK + a_shift, m0 + a_row, bar_full + s * 8);
                 tma_load_2d(s_base + s * S::kStage + S::kA, &tmB, (k_begin + k) * kGemmBK, n0 + b_row, bar_full + s * 8);
             }
@@ -172,6 +173,7 @@ static int launch_planned(const GemmPlan& p, cudaStream_t st)
     sp.nbatch = p.nbatch;
     for (int i = 0; i < 9; ++i) { sp.a_shift[i] = p.a_shift[i]; sp.a_row[i] = p.a_row[i]; sp.b_row[i] = p.b_row[i]; }
     sp.split_stride = p.split_stride;
+    sp.a_box_bytes = p.a_box_rows * kGemmBK * 4;
     sp.batch_stride = p.batch_stride;
     gemm_tf32_kernel<BN, STAGES><<<grid, kGemmThreads, S::kTotal, st>>>(p.tmA, p.tmB, p.bias, p.D, p.M, p.N, p.K, p.ldd, p.relu, sp);
     OCR_CHECK_LAUNCH();
@@ -281,7 +283,8 @@ int gemm_wgrad(const float* A, long long lda, const float* W, long long ldw, flo
     p.D = partials; p.ldd = N;
     p.split_stride = (long long)M * N;
     p.batch_stride = (long long)p.splits * M * N;
-    int rc = tma_map_2d(&p.tmA, A, a_rows, R, lda, kGemmBM);
+    p.a_box_rows = M >= kGemmBM ? kGemmBM : (M + 7) / 8 * 8;   // rows past M belong to other views: do not fetch them
+    int rc = tma_map_2d(&p.tmA, A, a_rows, R, lda, p.a_box_rows);
     if (rc != OCR_OK) return rc;
     rc = tma_map_2d(&p.tmB, W, N, R, ldw, p.bn);
     if (rc != OCR_OK) return rc;

@@ -436,8 +436,9 @@ conv_filter_layouts_kernel(const float* __restrict__ w, int C, int Co, float* __
 // lr_t = lr sqrt(1-b2^t) / (1-b1^t) computed by the host.  float4, grid-stride.
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, float lr_t,
-            float b1, float b2, float eps, float gscale)
+            const float* __restrict__ lr_t_dev, float b1, float b2, float eps, float gscale)
 {
+    if (lr_t_dev != nullptr) lr_t = *lr_t_dev;    // a captured CUDA graph replays with a fresh step size
     const long long n4 = n >> 2;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
@@ -688,14 +689,14 @@ extern "C" int ocr_conv_filter_layouts(const float* w_hwio, int C, int Cout, flo
     return OCR_OK;
 }
 
-extern "C" int ocr_adam_step(float* params, const float* grads, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
-                             float eps, float grad_scale, ocr_stream_t stream)
+extern "C" int ocr_adam_step(float* params, const float* grads, float* m, float* v, long long n, float lr_t, const float* lr_t_device,
+                             float beta1, float beta2, float eps, float grad_scale, ocr_stream_t stream)
 {
     OCR_CHECK_ARG(n >= 0 && (n == 0 || (params && grads && m && v)), "ocr_adam_step: bad argument");
     OCR_CHECK_ARG(((uintptr_t)params % 16) == 0 && ((uintptr_t)grads % 16) == 0 && ((uintptr_t)m % 16) == 0 && ((uintptr_t)v % 16) == 0,
                   "ocr_adam_step: buffers must be 16-byte aligned");
     if (n == 0) return OCR_OK;
-    adam_kernel<<<grid_cap((n + 3) / 4, 256, 8), 256, 0, ST(stream)>>>(params, grads, m, v, n, lr_t, beta1, beta2, eps, grad_scale);
+    adam_kernel<<<grid_cap((n + 3) / 4, 256, 8), 256, 0, ST(stream)>>>(params, grads, m, v, n, lr_t, lr_t_device, beta1, beta2, eps, grad_scale);
     OCR_CHECK_LAUNCH();
     return OCR_OK;
 }

@@ -231,18 +231,56 @@ class Trainer:
         return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=None if self.pg is True else self.pg, async_op=async_op)
 
     # ------------------------------------------------------------------ the step
-    def forward_backward(self, image, width, label):
-        """Forward in TRAIN mode + backward; fills self.grad (gradient of the MEAN CTC loss over this replica's batch).
-        Returns the per-example losses [B] (device)."""
-        lib, sh = self.lib, self._sh()
+    def _host_inputs(self, image, width, label):
+        """Host side of a step: argument checks with TensorFlow's messages, sequence lengths (model.py:152-163), flat labels."""
         _lib.require_cuda(image)
         B, Hh, Ww, one = image.shape
         if one != 1:
             raise ValueError("image must be [B, H, W, 1]")
         x = image.contiguous()
-        is_u8 = x.dtype == torch.uint8
-        if not is_u8:
+        if x.dtype != torch.uint8:
             x = x.float()
+        if torch.is_tensor(width) and width.is_cuda:
+            seq_len_host = (torch.div(width.to(torch.int32) - 2, 2, rounding_mode="floor") - 2).tolist()
+        else:
+            seq_len_host = ((np.asarray(width, dtype=np.int64).reshape(-1) - 2) // 2 - 2).tolist()
+        if len(seq_len_host) != B:
+            raise ValueError("width must have one entry per image")
+        T = (Ww - 2) // 2 - 2
+        C = self.logits_w.shape[0]
+        if isinstance(label, (list, tuple)) and len(label) and isinstance(label[0], (list, tuple, np.ndarray)) and not torch.is_tensor(label[0]):
+            lengths = [len(l) for l in label]
+            flat_host = torch.tensor([int(v) for l in label for v in l], dtype=torch.int32)
+        else:
+            _, _, lengths, flat_host = ctc._labels_to_flat(label, B, "cpu")
+        ctc._validate_ctc(flat_host, lengths, seq_len_host, T, C, False)
+        off = np.zeros(B + 1, np.int32)
+        np.cumsum(lengths, out=off[1:])
+        return x, seq_len_host, flat_host, off, (max(lengths) if lengths else 0)
+
+    def forward_backward(self, image, width, label):
+        """Forward in TRAIN mode + backward; fills self.grad (gradient of the MEAN CTC loss over this replica's batch).
+        Returns the per-example losses [B] (device)."""
+        x, seq_len_host, flat_host, off, max_len = self._host_inputs(image, width, label)
+        dev = self.device
+        seq_len = torch.tensor(seq_len_host, dtype=torch.int32).to(dev, non_blocking=True)
+        flat = flat_host.to(dev) if flat_host.numel() else torch.zeros(1, dtype=torch.int32, device=dev)
+        offsets = torch.from_numpy(off).to(dev)
+        losses = self._backward_rnn(*self._forward(x, seq_len, flat, offsets, max_len))
+        works = []
+        if self.world > 1:   # the RNN + logits bucket is complete: its all-reduce runs behind the conv backward
+            works.append(self._allreduce(self.grad[:self.n_rnn_floats], async_op=True))
+        self._backward_conv()
+        if self.world > 1:
+            works.append(self._allreduce(self.grad[self.n_rnn_floats:], async_op=True))
+            for w in works:
+                w.wait()
+        return losses
+
+    def _forward(self, x, seq_len, flat, offsets, max_len):
+        lib, sh = self.lib, self._sh()
+        B, Hh, Ww, one = x.shape
+        is_u8 = x.dtype == torch.uint8
         P, G = self.params, self.grads
         scr = _lib.ptr(self.scratch)
         saved = {}
@@ -285,14 +323,6 @@ class Trainer:
         seq = self._new(Wn, Bn, Cn)
         self._c(lib.ocr_rows_max_to_seq(_lib.ptr(a), Bn, Hn, Wn, Cn, _lib.ptr(seq), sh), "ocr_rows_max_to_seq")
         T = Wn
-        if torch.is_tensor(width) and width.is_cuda:
-            seq_len = (torch.div(width.to(torch.int32) - 2, 2, rounding_mode="floor") - 2).to(torch.int32).contiguous()
-            seq_len_host = seq_len.tolist()
-        else:   # host widths (the usual case): no device round trip for the label validation
-            seq_len_host = ((np.asarray(width, dtype=np.int64).reshape(-1) - 2) // 2 - 2).tolist()          # model.py:152-163
-            seq_len = torch.tensor(seq_len_host, dtype=torch.int32).to(self.device, non_blocking=True)
-        if len(seq_len_host) != B:
-            raise ValueError("width must have one entry per image")
         # ---------------- forward: rnn_layers
         need = ctypes.c_size_t(0)
         Hmax = max(self.rnn_sizes)
@@ -315,10 +345,17 @@ class Trainer:
         logits = self._new(T, B, C)
         self._c(lib.ocr_gemm_tf32(_lib.ptr(xin), F, _lib.ptr(self.logits_w), F, _lib.ptr(P["rnn/logits/bias"]), _lib.ptr(logits), C, R, C, F, 1, sh), "ocr_gemm_tf32")
         # ---------------- ctc_loss_layer: mean over the batch (model.py:224-229); the kernel returns d mean / d logits
-        flat, offsets, lengths, flat_host = ctc._labels_to_flat(label, B, self.device)
-        ctc._validate_ctc(flat_host, lengths, seq_len_host, T, C, False)
-        losses, dlog, _ = ctc.ctc_loss_raw(logits, flat, offsets, seq_len, max(lengths) if lengths else 0, want_grad=True, grad_scale=1.0 / B)
+        losses, dlog, _ = ctc.ctc_loss_raw(logits, flat, offsets, seq_len, max_len, want_grad=True, grad_scale=1.0 / B)
         self.last_logits, self.last_seq_len = logits, seq_len
+        return losses, logits, dlog, rnn_saved, saved, seq_len, ws, need, x
+
+    def _backward_rnn(self, losses, logits, dlog, rnn_saved, saved, seq_len, ws, need, x):
+        lib, sh = self.lib, self._sh()
+        P, G = self.params, self.grads
+        scr = _lib.ptr(self.scratch)
+        T, B, C = logits.shape
+        R = T * B
+        F = rnn_saved[-1]["out"].shape[2]
         # ---------------- backward: logits layer (dense + ReLU, model.py:216-220)
         self._c(lib.ocr_relu_bwd(_lib.ptr(logits), _lib.ptr(dlog), dlog.numel(), _lib.ptr(dlog), sh), "ocr_relu_bwd")
         dz = dlog.view(R, C)
@@ -359,13 +396,20 @@ class Trainer:
             outT, ldo = xT, ldx          # the input of layer 2 is the output of layer 1
             del dGT
             S.clear()
-        # the RNN + logits bucket of the flat gradient is complete: start its all-reduce behind the conv backward
-        works = []
-        if self.world > 1:
-            works.append(self._allreduce(self.grad[:self.n_rnn_floats], async_op=True))
-        # ---------------- backward: convolutional stack
+        self._conv_state = (saved, dout, x)
+        return losses
+
+    def _backward_conv(self):
+        lib, sh = self.lib, self._sh()
+        P, G = self.params, self.grads
+        scr = _lib.ptr(self.scratch)
+        saved, dout, x = self._conv_state
+        self._conv_state = None
+        is_u8 = x.dtype == torch.uint8
+        B, Hh, Ww, _ = x.shape
         S = saved["conv8"]
         a8 = S["out"]
+        Bn, Hn, Wn, Cn = a8.shape
         da = self._new(*a8.shape)
         self._c(lib.ocr_rows_max_to_seq_bwd(_lib.ptr(a8), _lib.ptr(dout), Bn, Hn, Wn, Cn, _lib.ptr(da), sh), "ocr_rows_max_to_seq_bwd")
         for (filters, k, padding, name, bn) in reversed(LAYER_PARAMS[1:]):
@@ -404,19 +448,16 @@ class Trainer:
         rows = a1.numel() // a1.shape[3]
         self._c(lib.ocr_relu_bwd_bias(_lib.ptr(a1), _lib.ptr(da), rows, a1.shape[3], _lib.ptr(da), _lib.ptr(G["convnet/conv1/bias"]), scr, sh), "ocr_relu_bwd_bias")
         self._c(lib.ocr_conv1_wgrad(_lib.ptr(x), int(is_u8), B, Hh, Ww, _lib.ptr(da), a1.shape[3], _lib.ptr(G["convnet/conv1/kernel"]), scr, sh), "ocr_conv1_wgrad")
-        if self.world > 1:
-            works.append(self._allreduce(self.grad[self.n_rnn_floats:], async_op=True))
-            for w in works:
-                w.wait()
-        return losses
 
-    def apply_gradients(self):
-        """AdamOptimizer.apply_gradients with the decayed learning rate of the CURRENT global step, then global_step += 1."""
+    def _lr_t(self):
         lr = learning_rate(self.global_step, **self.hp)
         t = self.global_step + 1
-        lr_t = lr * math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1 ** t)
+        return lr * math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1 ** t)
+
+    def apply_gradients(self, lr_t_device=None):
+        """AdamOptimizer.apply_gradients with the decayed learning rate of the CURRENT global step, then global_step += 1."""
         self._c(self.lib.ocr_adam_step(_lib.ptr(self.theta), _lib.ptr(self.grad), _lib.ptr(self.adam_m), _lib.ptr(self.adam_v), self.n_floats,
-                                       lr_t, self.beta1, self.beta2, self.epsilon, 1.0 / self.world, self._sh()), "ocr_adam_step")
+                                       self._lr_t(), _lib.ptr(lr_t_device), self.beta1, self.beta2, self.epsilon, 1.0 / self.world, self._sh()), "ocr_adam_step")
         self.global_step += 1
         self.derive_layouts()
 
@@ -425,3 +466,105 @@ class Trainer:
         losses = self.forward_backward(image, width, label)
         self.apply_gradients()
         return losses.mean()
+
+    # ------------------------------------------------------------------ the step as CUDA graphs
+    def capture(self, batch_size, width, height=32, max_label_len=None):
+        """Record the step for a fixed input shape [batch_size, height, width, 1] uint8 as CUDA graphs (the ~1100 launches of
+        a step otherwise cost more host time than device time at small per-GPU batches).  One replica: one graph.  Data
+        parallel: three graphs (forward + recurrent backward | conv backward | Adam) with the two NCCL bucket all-reduces
+        issued between them, so the first overlaps the conv backward.  Use train_step_captured afterwards."""
+        dev = self.device
+        T = (width - 2) // 2 - 2
+        Lmax = int(max_label_len) if max_label_len else min(T, 127)
+        g = dict(B=batch_size, W=width, H=height, Lmax=Lmax)
+        g["image"] = torch.zeros((batch_size, height, width, 1), dtype=torch.uint8, device=dev)
+        g["seq_len"] = torch.full((batch_size,), T, dtype=torch.int32, device=dev)
+        g["flat"] = torch.zeros(batch_size * Lmax, dtype=torch.int32, device=dev)
+        g["offsets"] = torch.arange(batch_size + 1, dtype=torch.int32, device=dev)
+        g["lr_t"] = torch.zeros(1, dtype=torch.float32, device=dev)
+        # pinned staging for the small per-step host values
+        g["h_seq_len"] = torch.zeros(batch_size, dtype=torch.int32).pin_memory()
+        g["h_flat"] = torch.zeros(batch_size * Lmax, dtype=torch.int32).pin_memory()
+        g["h_offsets"] = torch.zeros(batch_size + 1, dtype=torch.int32).pin_memory()
+        g["h_lr_t"] = torch.zeros(1, dtype=torch.float32).pin_memory()
+        # warm-up on a side stream (lazy scratch allocations, cudaFuncSetAttribute calls) with a feasible dummy batch
+        g["flat"][:batch_size] = 0
+        step0 = self.global_step
+        backup = [t.clone() for t in (self.theta, self.adam_m, self.adam_v)] + [v.clone() for v in self.stats.values()]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self._backward_rnn(*self._forward(g["image"], g["seq_len"], g["flat"], g["offsets"], Lmax))
+            self._backward_conv()
+            self.apply_gradients(g["lr_t"])
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        pool = torch.cuda.graph_pool_handle()
+        graphs = []
+
+        def rec(fn):
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, pool=pool):
+                out = fn()
+            graphs.append(gr)
+            return out
+
+        if self.world == 1:
+            def whole():
+                losses = self._backward_rnn(*self._forward(g["image"], g["seq_len"], g["flat"], g["offsets"], Lmax))
+                self._backward_conv()
+                self.apply_gradients(g["lr_t"])
+                return losses
+            g["losses"] = rec(whole)
+        else:
+            g["losses"] = rec(lambda: self._backward_rnn(*self._forward(g["image"], g["seq_len"], g["flat"], g["offsets"], Lmax)))
+            rec(self._backward_conv)
+            rec(lambda: self.apply_gradients(g["lr_t"]))
+        # undo the warm-up / capture side effects on the variables (captures do not execute, the warm-up did)
+        for dst, src in zip([self.theta, self.adam_m, self.adam_v] + list(self.stats.values()), backup):
+            dst.copy_(src)
+        self.global_step = step0
+        self.derive_layouts()
+        g["graphs"] = graphs
+        self._graph = g
+        return self
+
+    def train_step_captured(self, image, width, label):
+        """train_step through the captured graphs.  image: uint8 [B,H,W,1] (host pinned or device); returns the per-example
+        losses tensor (device, overwritten by the next step)."""
+        g = self._graph
+        if tuple(image.shape) != (g["B"], g["H"], g["W"], 1) or image.dtype != torch.uint8:
+            raise ValueError("captured for uint8 images of shape %s" % ((g["B"], g["H"], g["W"], 1),))
+        T = (g["W"] - 2) // 2 - 2
+        C = self.logits_w.shape[0]
+        seq_len_host = ((np.asarray(width, dtype=np.int64).reshape(-1) - 2) // 2 - 2)
+        lengths = [len(l) for l in label]
+        if len(lengths) != g["B"] or len(seq_len_host) != g["B"]:
+            raise ValueError("width / label must have one entry per image")
+        if max(lengths, default=0) > g["Lmax"]:
+            raise ValueError("label longer than the captured maximum %d" % g["Lmax"])
+        flat_host = torch.tensor([int(v) for l in label for v in l], dtype=torch.int32)
+        ctc._validate_ctc(flat_host, lengths, seq_len_host.tolist(), T, C, False)
+        g["h_seq_len"].copy_(torch.from_numpy(seq_len_host.astype(np.int32)))
+        g["h_flat"][:flat_host.numel()] = flat_host
+        g["h_offsets"][0] = 0
+        g["h_offsets"][1:] = torch.from_numpy(np.cumsum(lengths).astype(np.int32))
+        g["h_lr_t"][0] = self._lr_t()
+        g["image"].copy_(image, non_blocking=True)
+        g["seq_len"].copy_(g["h_seq_len"], non_blocking=True)
+        g["flat"].copy_(g["h_flat"], non_blocking=True)
+        g["offsets"].copy_(g["h_offsets"], non_blocking=True)
+        g["lr_t"].copy_(g["h_lr_t"], non_blocking=True)
+        gr = g["graphs"]
+        if self.world == 1:
+            gr[0].replay()
+        else:
+            gr[0].replay()
+            w1 = self._allreduce(self.grad[:self.n_rnn_floats], async_op=True)
+            gr[1].replay()
+            w2 = self._allreduce(self.grad[self.n_rnn_floats:], async_op=True)
+            w1.wait()
+            w2.wait()
+            gr[2].replay()
+        self.global_step += 1
+        return g["losses"]

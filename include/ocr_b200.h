@@ -226,9 +226,10 @@ int ocr_conv1_wgrad(const void* in, int in_is_u8, int B, int H, int W, const flo
  * [C, 9*Cout] = the 180-degree rotated filter, so that d input = ocr_conv3x3_same(dy, w_dgrad).  Either may be NULL. */
 int ocr_conv_filter_layouts(const float* w_hwio, int C, int Cout, float* w_fwd, float* w_dgrad, ocr_stream_t stream);
 /* tf.train.AdamOptimizer.apply_gradients over one flat buffer (train.py:128-137); lr_t = lr*sqrt(1-b2^t)/(1-b1^t) from
- * the host; grads are multiplied by grad_scale first (1/world_size after a sum all-reduce). */
-int ocr_adam_step(float* params, const float* grads, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
-                  float eps, float grad_scale, ocr_stream_t stream);
+ * the host, or read from lr_t_device (one float, device) when that is not NULL (a captured CUDA graph replays the
+ * launch with a fresh step size); grads are multiplied by grad_scale first (1/world_size after a sum all-reduce). */
+int ocr_adam_step(float* params, const float* grads, float* m, float* v, long long n, float lr_t, const float* lr_t_device,
+                  float beta1, float beta2, float eps, float grad_scale, ocr_stream_t stream);
 /* Bidirectional LSTM layer in training form (model_bu.py:167-199): like ocr_birnn_layer(cell 0) but keeps, per frame,
  * the gate activations (gates [T*B, 8H]: fw i, tanh j, f, o | bw ...) and cell states (cstate [T,B,2H]).
  * ocr_birnn_lstm_bwd: back-propagation through time.  dout [T,B,2H]; gates is overwritten with the gradient of the

@@ -148,5 +148,5 @@ def train_step_reference(params_np, images_u8, widths, labels, step, cell_type="
             new_params[k], new_adam[k] = pnew, (m, vv)
         else:
             new_params[k] = new_stats[k].numpy()
-    return dict(loss=float(loss), losses=losses.detach().numpy(), logits=logits.detach().numpy(), grads=grads, new_params=new_params,
+    return dict(loss=float(loss.detach()), losses=losses.detach().numpy(), logits=logits.detach().numpy(), grads=grads, new_params=new_params,
                 adam_state=new_adam, lr=lr, seq_len=seq_len)

@@ -227,7 +227,7 @@ def test_adam_matches_oracle():
     pr, mr, vr = to.adam_step(p.astype(np.float64), g.astype(np.float64) * 0.5, m.astype(np.float64), v.astype(np.float64), t, lr)
     dp, dg, dm, dv = _t(p), _t(g), _t(m), _t(v)
     lr_t = lr * np.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
-    L.check(lib.ocr_adam_step(L.ptr(dp), L.ptr(dg), L.ptr(dm), L.ptr(dv), n, lr_t, 0.9, 0.999, 1e-8, 0.5, sh), "adam")
+    L.check(lib.ocr_adam_step(L.ptr(dp), L.ptr(dg), L.ptr(dm), L.ptr(dv), n, lr_t, None, 0.9, 0.999, 1e-8, 0.5, sh), "adam")
     assert np.abs(dp.cpu().numpy() - pr).max() < 2.5e-7     # one float32 ulp of |p| ~ 1-2
     _close(dm.cpu().numpy(), mr, 1e-6, "m")
     _close(dv.cpu().numpy(), vr, 1e-6, "v")
@@ -343,3 +343,23 @@ def test_train_step_vs_oracle(B):
     assert np.isfinite(last) and last < loss
     m = tr.to_model()
     assert len(m.recognize(torch.tensor(img, device=DEV), torch.tensor(widths))) == len(labels)
+
+
+def test_captured_step_matches_eager_step():
+    """The CUDA-graph form of the step (Trainer.capture / train_step_captured) replays the same kernels: same losses,
+    same updated variables as the eager step, step after step (the learning rate reaches Adam through device memory)."""
+    from cnn_lstm_ctc_ocr_b200 import train
+    params, img, widths, labels = _small_problem(B=4)
+    a = train.Trainer(params, rnn_sizes=(32, 32))
+    b = train.Trainer(params, rnn_sizes=(32, 32))
+    b.capture(4, img.shape[2], max_label_len=8)
+    dimg = torch.tensor(img, device=DEV)
+    for step in range(3):
+        la = a.forward_backward(dimg, widths, labels)
+        a.apply_gradients()
+        lb = b.train_step_captured(dimg, widths, labels)
+        _close(lb.cpu().numpy(), la.cpu().numpy(), 1e-5, "losses step %d" % step)
+    assert a.global_step == b.global_step == 3
+    _close(b.theta.cpu().numpy(), a.theta.cpu().numpy(), 1e-5, "variables")
+    for k in a.stats:
+        _close(b.stats[k].cpu().numpy(), a.stats[k].cpu().numpy(), 1e-5, k)
