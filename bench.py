@@ -29,6 +29,7 @@ if ROOT not in sys.path:
 METRIC = "line-crops/sec"
 UNIT = "crops/s"
 L2_BYTES = 126 * 1024 * 1024
+_emit = print
 
 
 def _peaks():
@@ -169,7 +170,7 @@ def run_reference(args, cfg):
                                        "itself cannot run in this image), %d threads" % (B, T, C, cores)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(json.dumps(line))
 
 
 # --------------------------------------------------------------------------- N > 1 plumbing (also exercised on CPU/gloo)
@@ -362,7 +363,7 @@ def run_ours(args, cfg):
             "parity_status_ok": ok_status,
         }
         line["cpu_baseline"] = cpu_baseline_ctc(T, B, C) if world == 1 else None
-        print(json.dumps(line))
+        _emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -630,6 +631,18 @@ def main():
                                   "(blank=62), seq_len U{32..64}, label length U{1..16}, fp32 logits ~N(0,1)",
                       "T": 64, "C": 63, "global_batch": 256 * max(1, int(os.environ.get("WORLD_SIZE", "1"))),
                       "parallelism": "batch-sharded, no collective (weak scaling)"}}
+    # libraries (NCCL's version banner, for one) write to stdout: keep fd 1 clean for the ONE JSON line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+
+    def _emit(text):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(text)
+        sys.stdout.flush()
+        os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, cfg)
     else:

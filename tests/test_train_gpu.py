@@ -363,3 +363,14 @@ def test_captured_step_matches_eager_step():
     _close(b.theta.cpu().numpy(), a.theta.cpu().numpy(), 1e-5, "variables")
     for k in a.stats:
         _close(b.stats[k].cpu().numpy(), a.stats[k].cpu().numpy(), 1e-5, k)
+
+
+def test_data_parallel_step():
+    """2 GPUs: batch-sharded step with the NCCL gradient all-reduce == single-replica step (tests/ddp_train_check.py)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", os.path.join(root, "tests", "ddp_train_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DDP_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
