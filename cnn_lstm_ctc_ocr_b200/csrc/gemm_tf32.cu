@@ -252,7 +252,7 @@ static int wgrad_splits(int M, int N, long long R, int nbatch, int* ksteps_per_s
     const long long nk = (R + kGemmBK - 1) / kGemmBK;
     const int bn = N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
     const long long tiles = (long long)((M + kGemmBM - 1) / kGemmBM) * ((N + bn - 1) / bn) * nbatch;
-    long long want = (2 * 148 + tiles - 1) / tiles;            // about two waves of CTAs
+    long long want = 148 / tiles;                               // one full wave of CTAs (one CTA per SM): no ragged last wave
     if (want > nk / 8) want = nk / 8;                           // at least 8 k-steps per split
     if (want < 1) want = 1;
     const long long kps = (nk + want - 1) / want;

@@ -64,6 +64,54 @@ transpose_kernel(const float* __restrict__ in, long long rows, int cols, int ld_
     }
 }
 
+// Zero-ringed channel-planar copies, the fast path of ocr_nhwc_to_planar_pad: one CTA = 128 padded pixels x 32 channels.
+// The tile (with a one-pixel halo on both sides) is read ONCE with float4 loads along the channels and written NCOPY
+// times (pixel shifts -1, 0, +1, or just 0) as 512-byte runs along the pixels.
+template <int NCOPY>
+__global__ void __launch_bounds__(256)
+planar_pad_kernel(const float* __restrict__ in, unsigned rows, int C, float* __restrict__ out, long long ld, int H, int W, int Wp,
+                  long long copy_stride)
+{
+    constexpr int TP = 128, PITCH = 133;   // odd pitch: the channel-major writes below hit distinct banks
+    __shared__ float tile[32][PITCH];
+    const unsigned r0 = blockIdx.x * TP;
+    const int c0 = blockIdx.y * 32;
+    const int q = threadIdx.x & 7;          // channel quad
+    const int pl = threadIdx.x >> 3;        // pixel lane 0..31
+    const unsigned Hp = H + 2;
+    // tile column j holds padded pixel r0 - 1 + j, j = 0 .. TP + 1
+    for (int j = pl; j < TP + 2; j += 32) {
+        const long long r = (long long)r0 - 1 + j;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c = c0 + 4 * q;
+        if (r >= 0 && r < (long long)rows && c < C) {
+            const unsigned ru = (unsigned)r;
+            const unsigned qq = ru / (unsigned)Wp, xp = ru - qq * Wp;
+            const unsigned b = qq / Hp, yp = qq - b * Hp;
+            if (xp >= 1 && xp <= (unsigned)W && yp >= 1 && yp <= (unsigned)H)
+                v = __ldg(reinterpret_cast<const float4*>(in + (((size_t)b * H + (yp - 1)) * W + (xp - 1)) * C + c));
+        }
+        tile[4 * q + 0][j] = v.x; tile[4 * q + 1][j] = v.y; tile[4 * q + 2][j] = v.z; tile[4 * q + 3][j] = v.w;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NCOPY; ++k) {
+        const int sh = (NCOPY == 3) ? k : 1;     // copy k holds pixel r + k - 1 at r  -> tile column (r - r0) + k
+        float* o = out + (size_t)k * copy_stride;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = warp + 8 * i;
+            if (c0 + c >= C) continue;
+#pragma unroll
+            for (int j = 0; j < TP / 32; ++j) {
+                const unsigned r = r0 + j * 32 + lane;
+                if (r < rows) o[(size_t)(c0 + c) * ld + r] = tile[c][j * 32 + lane + sh];
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // per-channel reductions over the rows of x [rows, C].  One CTA = 8 warps x 32 channels (blockIdx.y = channel group);
 // warp w walks rows w, w + 8*gridDim.x, ...; lane = channel.  MODE selects what is summed:
@@ -503,8 +551,14 @@ extern "C" int ocr_nhwc_to_planar_pad(const float* in, int B, int H, int W, int 
                   "ocr_nhwc_to_planar_pad: bad shape B=%d H=%d W=%d C=%d ld=%lld ncopies=%d", B, H, W, C, ld_out, ncopies);
     if (B == 0) return OCR_OK;
     OCR_CHECK_ARG(in && out, "ocr_nhwc_to_planar_pad: NULL argument");
-    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)ncopies);
-    transpose_kernel<true><<<grid, 256, 0, ST(stream)>>>(in, rows, C, C, out, ld_out, H, W, Wp, ncopies == 3 ? -1 : 0, copy_stride);
+    if ((C % 4) == 0 && ((uintptr_t)in % 16) == 0) {
+        dim3 grid((unsigned)((rows + 127) / 128), (unsigned)((C + 31) / 32));
+        if (ncopies == 3) planar_pad_kernel<3><<<grid, 256, 0, ST(stream)>>>(in, (unsigned)rows, C, out, ld_out, H, W, Wp, copy_stride);
+        else planar_pad_kernel<1><<<grid, 256, 0, ST(stream)>>>(in, (unsigned)rows, C, out, ld_out, H, W, Wp, copy_stride);
+    } else {
+        dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)ncopies);
+        transpose_kernel<true><<<grid, 256, 0, ST(stream)>>>(in, rows, C, C, out, ld_out, H, W, Wp, ncopies == 3 ? -1 : 0, copy_stride);
+    }
     OCR_CHECK_LAUNCH();
     return OCR_OK;
 }
