@@ -14,6 +14,7 @@ torch CUDA tensors.  All arithmetic runs in the hand-written sm_100a kernels of 
 import collections
 import ctypes
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -24,50 +25,61 @@ SparseTensor = collections.namedtuple("SparseTensor", ["indices", "values", "den
 # ----------------------------------------------------------------------------- label handling
 def _labels_to_flat(labels, batch_size, device):
     """Accepts a SparseTensor-like triple, (values, lengths), or a list of int sequences.
-    Returns (flat int32 [N] on device, offsets int32 [B+1] on device, lengths list, host flat list)."""
+    Returns (flat int32 [N] on device, offsets int32 [B+1] on device, lengths list, host flat tensor).
+    All host work is vectorised (numpy): this sits on the end-to-end path of every step."""
     if isinstance(labels, (list, tuple)) and len(labels) == 3 and torch.is_tensor(labels[0]) and labels[0].dim() == 2:
         indices, values, _ = labels
-        rows = indices[:, 0].to("cpu", torch.int64)
-        if rows.numel() > 1 and bool((rows[1:] < rows[:-1]).any()):
+        rows = indices[:, 0].to("cpu", torch.int64).numpy()
+        if rows.size > 1 and bool((rows[1:] < rows[:-1]).any()):
             raise ValueError("labels.indices must be ordered by batch (row-major), as tf.nn.ctc_loss requires")
-        lengths = torch.bincount(rows, minlength=batch_size).tolist() if rows.numel() else [0] * batch_size
-        flat_host = values.to("cpu", torch.int32)
+        lengths = np.bincount(rows, minlength=batch_size) if rows.size else np.zeros(batch_size, np.int64)
+        flat_np = values.to("cpu", torch.int32).numpy()
     elif isinstance(labels, (list, tuple)) and len(labels) == 2 and torch.is_tensor(labels[0]) and torch.is_tensor(labels[1]):
-        flat_host = labels[0].to("cpu", torch.int32)
-        lengths = labels[1].to("cpu").tolist()
+        flat_np = labels[0].to("cpu", torch.int32).numpy()
+        lengths = labels[1].to("cpu", torch.int64).numpy()
     else:
-        lengths = [len(l) for l in labels]
-        flat_host = torch.tensor([int(v) for l in labels for v in l], dtype=torch.int32)
+        lengths = np.fromiter((len(l) for l in labels), dtype=np.int64, count=len(labels))
+        flat_np = np.fromiter((v for l in labels for v in l), dtype=np.int32, count=int(lengths.sum()))
     if len(lengths) != batch_size:
         raise ValueError("labels describe %d examples but logits have batch %d" % (len(lengths), batch_size))
-    off = [0]
-    for n in lengths:
-        off.append(off[-1] + int(n))
-    if flat_host.numel() != off[-1]:
+    off = np.zeros(batch_size + 1, np.int32)
+    np.cumsum(lengths, out=off[1:])
+    if flat_np.size != int(off[-1]):
         raise ValueError("label values/lengths mismatch")
-    offsets = torch.tensor(off, dtype=torch.int32, device=device)
-    flat = flat_host.to(device) if flat_host.numel() else torch.zeros(1, dtype=torch.int32, device=device)
-    return flat, offsets, lengths, flat_host
+    flat_host = torch.from_numpy(np.ascontiguousarray(flat_np))
+    if str(device) == "cpu":
+        return flat_host, torch.from_numpy(off), lengths.tolist(), flat_host
+    offsets = torch.from_numpy(off).to(device, non_blocking=True)
+    flat = flat_host.to(device, non_blocking=True) if flat_np.size else torch.zeros(1, dtype=torch.int32, device=device)
+    return flat, offsets, lengths.tolist(), flat_host
 
 
 def _validate_ctc(flat_host, lengths, seq_len_host, T, C, ignore_longer_outputs_than_inputs):
-    """Host-side argument validation with TensorFlow's error texts."""
-    if any(s > T or s < 0 for s in seq_len_host):
+    """Host-side argument validation with TensorFlow's error texts; vectorised."""
+    sl = np.asarray(seq_len_host, dtype=np.int64).reshape(-1)
+    if sl.size and (int(sl.max()) > T or int(sl.min()) < 0):
         raise ValueError("sequence_length(b) <= %d required (max_time)" % T)
-    if flat_host.numel() and (int(flat_host.max()) >= C - 1 or int(flat_host.min()) < 0):
+    flat = np.asarray(flat_host, dtype=np.int64).reshape(-1)
+    if flat.size and (int(flat.max()) >= C - 1 or int(flat.min()) < 0):
         raise ValueError("Saw a non-null label (index >= num_classes - 1) following a null label, or a label "
                          "outside [0, %d): labels must be < num_classes - 1 = %d" % (C - 1, C - 1))
-    if ignore_longer_outputs_than_inputs:
+    if ignore_longer_outputs_than_inputs or not flat.size:
         return
-    vals = flat_host.tolist()
-    o = 0
-    for b, n in enumerate(lengths):
-        need = n + sum(1 for i in range(1, n) if vals[o + i] == vals[o + i - 1])
-        if seq_len_host[b] > 0 and need > seq_len_host[b]:
-            raise ValueError("Not enough time for target transition sequence (required: %d, available: %d)%d"
-                             "You can turn this error into a warning by using the flag "
-                             "ignore_longer_outputs_than_inputs" % (need, seq_len_host[b], b))
-        o += n
+    ln = np.asarray(lengths, dtype=np.int64).reshape(-1)
+    off = np.zeros(ln.size + 1, np.int64)
+    np.cumsum(ln, out=off[1:])
+    rep = np.zeros(flat.size + 1, np.int64)           # rep[i+1] = repeats among flat[:i+1] that are not example starts
+    eq = np.zeros(flat.size, np.int64)
+    eq[1:] = flat[1:] == flat[:-1]
+    eq[off[:-1][ln > 0]] = 0
+    np.cumsum(eq, out=rep[1:])
+    need = ln + rep[off[1:]] - rep[off[:-1]]
+    bad = np.nonzero((sl > 0) & (need > sl))[0]
+    if bad.size:
+        b = int(bad[0])
+        raise ValueError("Not enough time for target transition sequence (required: %d, available: %d)%d"
+                         "You can turn this error into a warning by using the flag "
+                         "ignore_longer_outputs_than_inputs" % (int(need[b]), int(sl[b]), b))
 
 
 def ctc_loss_raw(logits, flat, offsets, seq_len, max_label_len, want_grad=True, grad_scale=1.0):
@@ -115,8 +127,9 @@ def ctc_loss(labels, inputs, sequence_length, preprocess_collapse_repeated=False
     _lib.require_cuda(inputs)
     T, B, C = inputs.shape
     flat, offsets, lengths, flat_host = _labels_to_flat(labels, B, inputs.device)
-    seq_len = sequence_length.to(device=inputs.device, dtype=torch.int32).contiguous()
-    _validate_ctc(flat_host, lengths, seq_len.tolist(), T, C, ignore_longer_outputs_than_inputs)
+    sl_host = sequence_length if not sequence_length.is_cuda else sequence_length.cpu()   # host lengths: no device round trip
+    seq_len = sequence_length.to(device=inputs.device, dtype=torch.int32, non_blocking=True).contiguous()
+    _validate_ctc(flat_host, lengths, sl_host.numpy(), T, C, ignore_longer_outputs_than_inputs)
     return _CtcLossFn.apply(inputs.contiguous().float(), flat, offsets, seq_len, max(lengths) if lengths else 0)
 
 
