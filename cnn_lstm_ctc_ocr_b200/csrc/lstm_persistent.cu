@@ -42,13 +42,14 @@ __device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned targe
     __trap();
 }
 
-template <int HS>  // hidden units per CTA; N = 4*HS gate columns
+template <int HS, bool TRAIN>  // hidden units per CTA; N = 4*HS gate columns.  TRAIN: keep gate activations + cell states
 __global__ void __launch_bounds__(kRnnThreads, 1)
 lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH00,
                        const __grid_constant__ CUtensorMap tmH01, const __grid_constant__ CUtensorMap tmH10,
                        const __grid_constant__ CUtensorMap tmH11, const float* __restrict__ xp, const int32_t* __restrict__ seq_len,
                        float* __restrict__ hbuf /*[2 parity][2 dir][B][H]*/, float* __restrict__ out /*[T,B,2H]*/,
-                       unsigned* __restrict__ counters /*[2]*/, int T, int B, int H, int NS, int a_rows, int n_stages)
+                       unsigned* __restrict__ counters /*[2]*/, int T, int B, int H, int NS, int a_rows, int n_stages, int MT,
+                       float* gates_out /*[T*B, 8H], may alias xp*/, float* __restrict__ cs_out /*[T,B,2H]*/)
 {
     constexpr int N = 4 * HS;
     const int nk = H / kGemmBK;
@@ -66,7 +67,9 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + (s_bar - s_base) + (2 * kRnnMaxStages + 2) * 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int d = blockIdx.x / NS, j = blockIdx.x % NS;  // direction, hidden slice
+    // direction, hidden slice, batch tile (rows [mt*128, +128) of the batch)
+    const int mt = blockIdx.x % MT, j = (blockIdx.x / MT) % NS, d = blockIdx.x / (MT * NS);
+    const int m0 = mt * kGemmBM;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < n_stages; ++s) { g_mbar_init(bar_full + s * 8, 1); g_mbar_init(bar_empty + s * 8, 1); }
@@ -91,7 +94,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
             int it = 0;
             for (int s = 0; s < T; ++s) {
                 if (s > 0) {
-                    wait_counter(counters + d, (unsigned)NS * (unsigned)s);   // every slice of this direction wrote h_s
+                    wait_counter(counters + d, (unsigned)(NS * MT) * (unsigned)s);   // every slice / batch tile of this direction wrote h_s
                     asm volatile("fence.proxy.async;" ::: "memory");          // generic-proxy writes -> async-proxy (TMA) reads
                 }
                 const CUtensorMap* tm = (s & 1) ? (d ? &tmH11 : &tmH10) : (d ? &tmH01 : &tmH00);
@@ -99,7 +102,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
                     const int st = it % n_stages;
                     if (it >= n_stages) g_mbar_wait(bar_empty + st * 8, ((it / n_stages) - 1) & 1);
                     g_mbar_expect_tx(bar_full + st * 8, a_bytes);
-                    tma_load_2d(s_a + st * a_bytes, tm, k * kGemmBK, 0, bar_full + st * 8);
+                    tma_load_2d(s_a + st * a_bytes, tm, k * kGemmBK, m0, bar_full + st * 8);
                 }
             }
         }
@@ -126,7 +129,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
         }
     } else {
         const int q = warp & 3;
-        const int r = q * 32 + lane;           // batch row = TMEM lane
+        const int r = m0 + q * 32 + lane;      // batch row (TMEM lane q*32 + lane of this batch tile)
         const bool live_row = r < B;
         const int len = live_row ? min(max(seq_len[r], 0), T) : 0;
         float c[HS], h[HS];
@@ -140,11 +143,11 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
             if (upd) {
                 const float* x = xp + ((size_t)t * B + r) * 8 * H + (size_t)d * 4 * H + j * HS;
 #pragma unroll
-                for (int u = 0; u < HS; u += 4) {
-                    *reinterpret_cast<float4*>(xi + u) = __ldg(reinterpret_cast<const float4*>(x + u));
-                    *reinterpret_cast<float4*>(xj + u) = __ldg(reinterpret_cast<const float4*>(x + H + u));
-                    *reinterpret_cast<float4*>(xf + u) = __ldg(reinterpret_cast<const float4*>(x + 2 * H + u));
-                    *reinterpret_cast<float4*>(xo + u) = __ldg(reinterpret_cast<const float4*>(x + 3 * H + u));
+                for (int u = 0; u < HS; u += 4) {   // plain loads: in TRAIN mode the same thread overwrites these slots below
+                    *reinterpret_cast<float4*>(xi + u) = *reinterpret_cast<const float4*>(x + u);
+                    *reinterpret_cast<float4*>(xj + u) = *reinterpret_cast<const float4*>(x + H + u);
+                    *reinterpret_cast<float4*>(xf + u) = *reinterpret_cast<const float4*>(x + 2 * H + u);
+                    *reinterpret_cast<float4*>(xo + u) = *reinterpret_cast<const float4*>(x + 3 * H + u);
                 }
             }
             g_mbar_wait(bar_acc, s & 1);
@@ -170,12 +173,26 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
                         const float zj = __uint_as_float(g[HS + u]) + xj[u];
                         const float zf = __uint_as_float(g[2 * HS + u]) + xf[u];
                         const float zo = __uint_as_float(g[3 * HS + u]) + xo[u];
-                        c[u] = sigm(zf + 1.0f) * c[u] + sigm(zi) * tanh_fast(zj);
-                        h[u] = sigm(zo) * tanh_fast(c[u]);
+                        const float gi = sigm(zi), gj = tanh_fast(zj), gf = sigm(zf + 1.0f), go = sigm(zo);
+                        c[u] = gf * c[u] + gi * gj;
+                        h[u] = go * tanh_fast(c[u]);
+                        if (TRAIN) { xi[u] = gi; xj[u] = gj; xf[u] = gf; xo[u] = go; }
                     }
                     float* o = out + ((size_t)t * B + r) * 2 * H + (size_t)d * H + j * HS;
 #pragma unroll
                     for (int u = 0; u < HS; u += 4) *reinterpret_cast<float4*>(o + u) = make_float4(h[u], h[u + 1], h[u + 2], h[u + 3]);
+                    if (TRAIN) {   // what back-propagation through time needs: gate activations (in place of the pre-activations) and c_t
+                        float* ga = gates_out + ((size_t)t * B + r) * 8 * H + (size_t)d * 4 * H + j * HS;
+                        float* cso = cs_out + ((size_t)t * B + r) * 2 * H + (size_t)d * H + j * HS;
+#pragma unroll
+                        for (int u = 0; u < HS; u += 4) {
+                            *reinterpret_cast<float4*>(ga + u) = *reinterpret_cast<float4*>(xi + u);
+                            *reinterpret_cast<float4*>(ga + H + u) = *reinterpret_cast<float4*>(xj + u);
+                            *reinterpret_cast<float4*>(ga + 2 * H + u) = *reinterpret_cast<float4*>(xf + u);
+                            *reinterpret_cast<float4*>(ga + 3 * H + u) = *reinterpret_cast<float4*>(xo + u);
+                            *reinterpret_cast<float4*>(cso + u) = make_float4(c[u], c[u + 1], c[u + 2], c[u + 3]);
+                        }
+                    }
                 }
                 // carried or updated, the state is the next frame's operand
 #pragma unroll
@@ -219,12 +236,12 @@ constexpr int kHS = 16;
 namespace ocr {
 
 bool lstm_persistent_supported(int T, int B, int H) {
-    if (B > kGemmBM || (H % kGemmBK) != 0 || (H % kHS) != 0) return false;
-    const int NS = H / kHS;
-    if (2 * NS > 148) return false;   // one CTA per SM, all co-resident
+    if ((H % kGemmBK) != 0 || (H % kHS) != 0 || B < 1) return false;
+    const int NS = H / kHS, MT = (B + kGemmBM - 1) / kGemmBM;
+    if (2 * NS * MT > 148) return false;   // one CTA per SM, all co-resident
     if (H / kGemmBK > kRnnMaxStages) return false;
     const size_t w = (size_t)H / kGemmBK * (4 * kHS) * kGemmBK * 4;
-    const size_t a = (size_t)((B + 7) / 8 * 8) * kGemmBK * 4;
+    const size_t a = (size_t)(B >= kGemmBM ? kGemmBM : (B + 7) / 8 * 8) * kGemmBK * 4;
     // weights + at least 2 stages of h + the slack tile + barriers + alignment
     return w + 2 * a + kGemmBM * kGemmBK * 4 + 1024 + 1024 <= (size_t)kMaxDynSmem && T >= 1;
 }
@@ -246,9 +263,10 @@ int lstm_permute_wh(const float* wh, int H, float* whp, cudaStream_t st)
 
 // wh_perm: gate-major permuted recurrent weights from lstm_permute_wh, or NULL to permute wh into the workspace now
 int lstm_persistent_run(const float* xp, const float* wh, const float* wh_perm, const int32_t* seq_len, int T, int B, int H,
-                        float* out, float* ws, cudaStream_t st)
+                        float* out, float* ws, cudaStream_t st, float* gates_out, float* cs_out)
 {
-    const int NS = H / kHS;
+    const int NS = H / kHS, MT = (B + kGemmBM - 1) / kGemmBM;
+    const bool train = gates_out != nullptr;
     float* whp_ws = ws;
     float* hbuf = whp_ws + (size_t)8 * H * H;
     unsigned* counters = reinterpret_cast<unsigned*>(hbuf + (size_t)4 * B * H);
@@ -261,7 +279,7 @@ int lstm_persistent_run(const float* xp, const float* wh, const float* wh_perm, 
     OCR_CHECK_CUDA(cudaMemsetAsync(hbuf, 0, sizeof(float) * ((size_t)4 * B * H + 64), st));
     OCR_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)T * B * 2 * H, st));
     const int nk = H / kGemmBK;
-    const int a_rows = (B + 7) / 8 * 8;
+    const int a_rows = B >= kGemmBM ? kGemmBM : (B + 7) / 8 * 8;
     const size_t w_bytes = (size_t)nk * (4 * kHS) * kGemmBK * 4, a_bytes = (size_t)a_rows * kGemmBK * 4;
     const size_t fixed = w_bytes + kGemmBM * kGemmBK * 4 + 1024 + 1024;
     int n_stages = (int)(((size_t)kMaxDynSmem - fixed) / a_bytes);
@@ -279,11 +297,12 @@ int lstm_persistent_run(const float* xp, const float* wh, const float* wh_perm, 
     int dev = 0;
     OCR_CHECK_CUDA(cudaGetDevice(&dev));
     if (configured != dev) {
-        OCR_CHECK_CUDA(cudaFuncSetAttribute(lstm_persistent_kernel<kHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        OCR_CHECK_CUDA(cudaFuncSetAttribute(lstm_persistent_kernel<kHS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        OCR_CHECK_CUDA(cudaFuncSetAttribute(lstm_persistent_kernel<kHS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
         configured = dev;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * NS);
+    cfg.gridDim = dim3(2 * NS * MT);
     cfg.blockDim = dim3(kRnnThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -292,8 +311,12 @@ int lstm_persistent_run(const float* xp, const float* wh, const float* wh_perm, 
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_persistent_kernel<kHS>, tmW, tmH[0][0], tmH[0][1], tmH[1][0], tmH[1][1], xp, seq_len, hbuf, out,
-                                      counters, T, B, H, NS, a_rows, n_stages));
+    if (train)
+        OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_persistent_kernel<kHS, true>, tmW, tmH[0][0], tmH[0][1], tmH[1][0], tmH[1][1], xp, seq_len, hbuf,
+                                          out, counters, T, B, H, NS, a_rows, n_stages, MT, gates_out, cs_out));
+    else
+        OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_persistent_kernel<kHS, false>, tmW, tmH[0][0], tmH[0][1], tmH[1][0], tmH[1][1], xp, seq_len, hbuf,
+                                          out, counters, T, B, H, NS, a_rows, n_stages, MT, (float*)nullptr, (float*)nullptr));
     count_launch();
     return OCR_OK;
 }

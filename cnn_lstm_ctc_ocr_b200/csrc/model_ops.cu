@@ -177,7 +177,7 @@ bool lstm_persistent_supported(int T, int B, int H);
 size_t lstm_persistent_workspace_floats(int B, int H);
 int lstm_permute_wh(const float* wh, int H, float* whp, cudaStream_t st);
 int lstm_persistent_run(const float* xp, const float* wh, const float* wh_perm, const int32_t* seq_len, int T, int B, int H,
-                        float* out, float* ws, cudaStream_t st);
+                        float* out, float* ws, cudaStream_t st, float* gates_out = nullptr, float* cs_out = nullptr);
 
 static inline int grid_for(long long total, int threads = 256) {
     long long g = (total + threads - 1) / threads;
@@ -228,7 +228,7 @@ extern "C" int ocr_rows_max_to_seq(const float* in, int B, int H, int W, int C, 
 }
 
 // 0 = automatic (persistent LSTM kernel when the shape allows), 1 = frame-by-frame launches only
-static int g_birnn_path = 0;
+namespace ocr { int g_birnn_path = 0; }
 extern "C" int ocr_birnn_set_path(int path) {
     OCR_CHECK_ARG(path == 0 || path == 1, "ocr_birnn_set_path: path=%d outside [0,1]", path);
     g_birnn_path = path;

@@ -755,6 +755,14 @@ extern "C" int ocr_adam_step(float* params, const float* grads, float* m, float*
     return OCR_OK;
 }
 
+namespace ocr {  // lstm_persistent.cu / model_ops.cu
+bool lstm_persistent_supported(int T, int B, int H);
+size_t lstm_persistent_workspace_floats(int B, int H);
+int lstm_persistent_run(const float* xp, const float* wh, const float* wh_perm, const int32_t* seq_len, int T, int B, int H,
+                        float* out, float* ws, cudaStream_t st, float* gates_out, float* cs_out);
+extern int g_birnn_path;
+}
+
 // tile width of the per-frame recurrent products: enough CTAs for the 148 SMs, as wide as that allows
 static int recurrent_bn(int M, int N, int splits) {
     const long long mt = (M + kGemmBM - 1) / kGemmBM;
@@ -771,7 +779,9 @@ extern "C" int ocr_birnn_lstm_train_workspace_bytes(int T, int B, int H, size_t*
 {
     OCR_CHECK_ARG(bytes && T >= 0 && B >= 0 && H >= 1, "ocr_birnn_lstm_train_workspace_bytes: bad argument");
     // gh [2B, 8H] (backward: split-K partials of dh_rec, at most 8 x [2B, H]) + h, c, dh, dc [2B,H] + dgs [2B,4H]
-    *bytes = sizeof(float) * ((size_t)2 * B * 8 * H + (size_t)2 * B * H * 4 + (size_t)2 * B * 4 * H) + 256;
+    size_t fl = (size_t)2 * B * 8 * H + (size_t)2 * B * H * 4 + (size_t)2 * B * 4 * H;
+    if (T >= 1 && B >= 1 && lstm_persistent_supported(T, B, H) && lstm_persistent_workspace_floats(B, H) > fl) fl = lstm_persistent_workspace_floats(B, H);
+    *bytes = sizeof(float) * fl + 256;
     return OCR_OK;
 }
 
@@ -791,6 +801,11 @@ extern "C" int ocr_birnn_lstm_train_fwd(const float* x, int T, int B, int I, int
     float* c = h + (size_t)2 * B * H;
     int rc = ocr_gemm_tf32(x, I, wx, I, bias, gates, 8 * H, T * B, 8 * H, I, 0, stream);
     if (rc != OCR_OK) return rc;
+    if (g_birnn_path == 0 && lstm_persistent_supported(T, B, H)) {
+        // all T frames of both directions in ONE cooperative launch, W_h resident in shared memory (lstm_persistent.cu)
+        OCR_CHECK_CUDA(cudaMemsetAsync(cstate, 0, sizeof(float) * (size_t)T * B * 2 * H, st));
+        return lstm_persistent_run(gates, wh, nullptr, seq_len, T, B, H, out, ws, st, gates, cstate);
+    }
     OCR_CHECK_CUDA(cudaMemsetAsync(h, 0, sizeof(float) * (size_t)2 * B * H * 2, st));
     OCR_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)T * B * 2 * H, st));
     OCR_CHECK_CUDA(cudaMemsetAsync(cstate, 0, sizeof(float) * (size_t)T * B * 2 * H, st));

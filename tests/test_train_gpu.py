@@ -249,13 +249,16 @@ def _small_problem(seed=0, B=4, W=44, sizes=(32, 32), classes=19):
     return params, img, widths, labels
 
 
-def test_lstm_layer_train_forward_backward():
-    """ocr_birnn_lstm_train_fwd / _bwd against autograd through the oracle's bidirectional_dynamic_rnn restatement."""
+@pytest.mark.parametrize("H,path", [(16, 0), (32, 0), (32, 1)])
+def test_lstm_layer_train_forward_backward(H, path):
+    """ocr_birnn_lstm_train_fwd / _bwd against autograd through the oracle's bidirectional_dynamic_rnn restatement.
+    H = 32, path 0: the frames run in the persistent cooperative kernel; path 1 / H = 16: one launch pair per frame."""
     from oracle import train_oracle as to
     L, lib, sh = _lib()
     rng = np.random.default_rng(6)
-    T, B, I, H = 9, 5, 24, 16
+    T, B, I = 9, 5, 24
     sl = np.array([9, 4, 7, 1, 9], np.int32)
+    L.check(lib.ocr_birnn_set_path(path), "path")
     x = rng.standard_normal((T, B, I))
     ks = {d: rng.standard_normal((I + H, 4 * H)) * 0.3 for d in ("fw", "bw")}
     bs = {d: rng.standard_normal(4 * H) * 0.1 for d in ("fw", "bw")}
@@ -288,6 +291,7 @@ def test_lstm_layer_train_forward_backward():
         _close(X.T @ dGd, tp["p/%s/lstm_cell/kernel" % dn].grad.numpy()[:I], 1e-2, "dWx " + dn)
     dx = dG[:, :4 * H] @ ks["fw"][:I].T + dG[:, 4 * H:] @ ks["bw"][:I].T
     _close(dx.reshape(T, B, I), xt.grad.numpy(), 1e-2, "dx")
+    L.check(lib.ocr_birnn_set_path(0), "path")
 
 
 @pytest.mark.parametrize("B", [4, 3])
