@@ -224,11 +224,24 @@ int gemm_plan_dirs(GemmPlan* p, const float* A, int lda, const float* W, int ldw
 
 int gemm_run(const GemmPlan& p, cudaStream_t st)
 {
+    // Two shapes of pipeline.  Grids that put at most one CTA on an SM (split-K contractions, the small per-frame
+    // products) get a deep TMA ring: the k loop is all there is.  Grids of many short tiles get a shallow ring so that
+    // 2-3 CTAs share an SM (shared memory and the 512 TMEM columns allow it) and the epilogue of one tile -- one thread per
+    // row draining TMEM to global memory, which is what bounds the K <= 1024 projections -- overlaps the main loop of another.
+    const long long ctas = (long long)((p.M + kGemmBM - 1) / kGemmBM) * p.nbatch * ((p.N + p.bn - 1) / p.bn) * p.splits;
+    if (ctas <= 148) {
+        switch (p.bn) {
+            case 32: return launch_planned<32, 8>(p, st);
+            case 64: return launch_planned<64, 6>(p, st);
+            case 128: return launch_planned<128, 5>(p, st);
+            default: return launch_planned<256, 4>(p, st);
+        }
+    }
     switch (p.bn) {
-        case 32: return launch_planned<32, 8>(p, st);
-        case 64: return launch_planned<64, 6>(p, st);
-        case 128: return launch_planned<128, 5>(p, st);
-        default: return launch_planned<256, 4>(p, st);
+        case 32: return launch_planned<32, 3>(p, st);     // 60 KB  -> 3 CTAs / SM
+        case 64: return launch_planned<64, 3>(p, st);     // 72 KB  -> 3
+        case 128: return launch_planned<128, 3>(p, st);   // 96 KB  -> 2
+        default: return launch_planned<256, 2>(p, st);    // 96 KB  -> 2 (2 x 256 TMEM columns)
     }
 }
 

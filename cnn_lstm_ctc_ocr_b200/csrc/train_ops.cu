@@ -845,7 +845,7 @@ extern "C" int ocr_birnn_lstm_bwd(const float* dout, int T, int B, int H, const 
     GemmPlan p1;
     // dh_rec[d][b, n] = sum_g dgs[d*B + b, g] * wh_rows[d*H + n, g]: K = 4H is long and the tile count small, so the
     // contraction is split over K across the SMs; the cell kernel of the next step adds the partials up
-    int want = (148 + 2 * ((B + 127) / 128) * ((H + 63) / 64) - 1) / (2 * ((B + 127) / 128) * ((H + 63) / 64));
+    int want = 148 / (2 * ((B + 127) / 128) * ((H + 63) / 64));     // one full wave of CTAs, no ragged second wave
     if (want > 8) want = 8;
     if (want < 1) want = 1;
     int rc = gemm_plan_dirs(&p1, dgs, 4 * H, wh_rows, 4 * H, dh_rec, B, H, 4 * H, 2, want, H > 32 ? 64 : 32);
