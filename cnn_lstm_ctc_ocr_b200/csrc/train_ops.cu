@@ -416,6 +416,10 @@ template <bool kU8>
 __global__ void __launch_bounds__(256)
 conv1_wgrad_kernel(const void* __restrict__ in_, int B, int H, int W, const float* __restrict__ dy, int Co, double* __restrict__ sums /*[9][Co]*/)
 {
+    // per iteration the CTA stages the 3x3 neighbourhoods of 256 consecutive output pixels in shared memory (one pixel
+    // per thread, coalesced byte loads), then every warp sweeps 32 of them: lane = filter, dy row coalesced (128 B),
+    // image taps broadcast from shared memory
+    __shared__ float taps[9][256 + 1];
     __shared__ float red[8][9][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int co = blockIdx.y * 32 + lane;
@@ -424,31 +428,51 @@ conv1_wgrad_kernel(const void* __restrict__ in_, int B, int H, int W, const floa
     float acc[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[k] = 0.f;
-    const long long stride = (long long)gridDim.x * 8;
-    for (long long pb = (long long)blockIdx.x * 8 + warp; pb < npix; pb += 4 * stride) {
-        float g[4];
-        float v[4][9];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {     // four independent pixels in flight
-            const long long p = pb + u * stride;
-            const bool live = p < npix;
-            const unsigned pp = (unsigned)(live ? p : pb);
+    for (long long p0 = (long long)blockIdx.x * 256; p0 < npix; p0 += (long long)gridDim.x * 256) {
+        const long long p = p0 + threadIdx.x;
+        if (p < npix) {
+            const unsigned pp = (unsigned)p;
             const unsigned q = pp / (unsigned)Wo, x = pp - q * Wo;
             const unsigned b = q / (unsigned)Ho, y = q - b * Ho;
-            g[u] = (live && co < Co) ? dy[(size_t)pp * Co + co] : 0.f;
 #pragma unroll
             for (int i = 0; i < 3; ++i)
 #pragma unroll
                 for (int jx = 0; jx < 3; ++jx) {
                     const size_t o = ((size_t)b * H + (y + i)) * W + (x + jx);
-                    if (kU8) v[u][i * 3 + jx] = (float)__ldg(reinterpret_cast<const unsigned char*>(in_) + o) / 255.0f - 0.5f;
-                    else v[u][i * 3 + jx] = __ldg(reinterpret_cast<const float*>(in_) + o);
+                    float v;
+                    if (kU8) v = (float)__ldg(reinterpret_cast<const unsigned char*>(in_) + o) / 255.0f - 0.5f;
+                    else v = __ldg(reinterpret_cast<const float*>(in_) + o);
+                    taps[i * 3 + jx][threadIdx.x] = v;
                 }
         }
+        __syncthreads();
+        const int n = (int)min((long long)256, npix - p0);
+        float g[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 8; ++u) {    // eight dy rows in flight per warp
+            const int pl = warp * 32 + u;
+            g[u] = (pl < n && co < Co) ? dy[(size_t)(p0 + pl) * Co + co] : 0.f;
+        }
 #pragma unroll
-            for (int k = 0; k < 9; ++k) acc[k] = fmaf(g[u], v[u][k], acc[k]);
+        for (int u0 = 0; u0 < 32; u0 += 8) {
+            float gn[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int pl = warp * 32 + u0 + 8 + u;
+                gn[u] = (u0 + 8 < 32 && pl < n && co < Co) ? dy[(size_t)(p0 + pl) * Co + co] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int pl = warp * 32 + u0 + u;
+                if (pl < n) {
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) acc[k] = fmaf(g[u], taps[k][pl], acc[k]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) g[u] = gn[u];
+        }
+        __syncthreads();
     }
 #pragma unroll
     for (int k = 0; k < 9; ++k) red[warp][k][lane] = acc[k];
@@ -725,8 +749,9 @@ extern "C" int ocr_conv1_wgrad(const void* in, int in_is_u8, int B, int H, int W
     OCR_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * 9 * Cout, ST(stream)));
     const int gy = (Cout + 31) / 32;
     const long long npix = (long long)B * (H - 2) * (W - 2);
-    long long gx = (npix + 7) / 8;
-    if (gx > 148 * 8) gx = 148 * 8;
+    long long gx = (npix + 255) / 256;
+    if (gx > 148 * 6) gx = 148 * 6;
+    OCR_CHECK_ARG(npix < 0x7fffffffLL, "ocr_conv1_wgrad: too many pixels");
     if (in_is_u8) conv1_wgrad_kernel<true><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, ST(stream)>>>(in, B, H, W, dy, Cout, sums);
     else conv1_wgrad_kernel<false><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, ST(stream)>>>(in, B, H, W, dy, Cout, sums);
     OCR_CHECK_LAUNCH();
