@@ -331,6 +331,9 @@ def run_ours(args, cfg):
         infer = None
         if not args.skip_infer:
             infer = inference_block(dev, world, windows, with_cpu=(rank == 0 and world == 1))
+        extra = None
+        if not args.skip_extra:
+            extra = {"beam_search": beam_block(dev, rank, world, windows), "sweep": sweep_block(dev, rank, world, windows)}
         training = None
         if not args.skip_train:
             try:
@@ -359,6 +362,8 @@ def run_ours(args, cfg):
             "roofline_bw_regime": bw,
             "inference": infer,
             "training": training,
+            "beam_search": extra["beam_search"] if extra else None,
+            "sweep": extra["sweep"] if extra else None,
             "clocks": sampler.summary(windows),
             "parity_status_ok": ok_status,
         }
@@ -461,6 +466,72 @@ def inference_block(dev, world, windows, B=32, W=128, cell="lstm", steps=20, wit
                                "sample": "one batch of %d crops through oracle/model_oracle.py (numpy float32, BLAS threads) + "
                                          "the C greedy decoder, %.1f s wall (TensorFlow itself cannot run in this image)" % (B, dt)}
     return out
+
+
+# --------------------------------------------------------------------------- beam search (configs[3]) and width sweep (configs[4])
+def beam_block(dev, rank, world, windows, batch=1024, T=64, C=63, beam=128, reps=3):
+    """configs[3]: CTC beam-search decode (beam width 128, top path) over batch 1024 logits, sharded by crop across the
+    GPUs (no collective).  Latency/dependency bound: T frames x up to 128 sequential expansions per sequence."""
+    import numpy as np
+    import torch
+    from cnn_lstm_ctc_ocr_b200 import ctc
+    B = batch // world
+    rng = np.random.default_rng(shard_seed(rank, 2))
+    x = torch.from_numpy((rng.standard_normal((T, B, C)) * 3).astype(np.float32)).to(dev)
+    sl = torch.from_numpy(rng.integers(T // 2, T + 1, B).astype(np.int32)).to(dev)
+    for _ in range(2):
+        dec, ln, lp = ctc.ctc_beam_search_raw(x, sl, beam, 1, True, True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_a = time.time()
+    e0.record()
+    for _ in range(reps):
+        dec, ln, lp = ctc.ctc_beam_search_raw(x, sl, beam, 1, True, True)
+    e1.record()
+    torch.cuda.synchronize()
+    windows.append((t_a, time.time()))
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev) / reps
+    return {"workload": "BASELINE configs[3]: CTC beam search, beam width %d, top path, merge_repeated, batch %d logits [T=%d, C=%d] ~3*N(0,1), "
+                        "sharded by crop over %d GPU(s)" % (beam, batch, T, C, world),
+            "value": batch / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "per_gpu_batch": B, "scaling": "strong",
+            "mean_decoded_len": float(ln.float().mean().item()), "bound": "latency (sequential beam expansion), not HBM"}
+
+
+def sweep_block(dev, rank, world, windows, n_crops=10000, bucket_size=32):
+    """configs[4]: receipt-line recognition sweep, 10k synthetic variable-width crops (32x64 .. 32x1024), bucketed by
+    width exactly as the reference's LocalServer does (32-px buckets, zero right-padding, fixed batch with filler crops),
+    inference + greedy decode to strings; crops are dealt round-robin to the GPUs, no collective.  End to end: host
+    uint8 crops in, host strings out."""
+    import numpy as np
+    import torch
+    from cnn_lstm_ctc_ocr_b200 import model, server
+    from oracle import model_oracle as mo   # parameter initialiser only
+    params = mo.init_params(0, "lstm", (512, 512), 95, np.float32)
+    m = model.Model(params, cell_type="lstm", rnn_sizes=(512, 512), device=dev)
+    rng = np.random.default_rng(3)
+    widths = rng.integers(64, 1025, n_crops)
+    mine = widths[rank::world]
+    crops = [rng.integers(0, 256, (32, int(w)), dtype=np.uint8) for w in mine]
+    srv = server.LocalServer(m, bucket_size=bucket_size, device=dev)
+    pred = server.BatchLinePredictor(srv)
+    pred.predict_batch("warm", crops[:64])
+    srv.padded_pixels = srv.real_pixels = 0
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_a = time.time()
+    e0.record()
+    texts = pred.predict_batch("sweep", crops)
+    e1.record()
+    torch.cuda.synchronize()
+    windows.append((t_a, time.time()))
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    return {"workload": "BASELINE configs[4]: %d synthetic crops, widths U{64..1024}, bucketed per server.py (32-px buckets, batch %d), "
+                        "CNN-BiLSTM inference + greedy decode to strings, %d GPU(s)" % (n_crops, bucket_size, world),
+            "e2e": {"value": n_crops / (ms * 1e-3), "unit": UNIT, "api": "server.BatchLinePredictor.predict_batch (host uint8 crops -> strings)"},
+            "ms_total": ms, "strings": len(texts), "scaling": "strong",
+            "padded_pixel_overhead": (srv.padded_pixels / max(srv.real_pixels, 1)) - 1.0}
 
 
 # --------------------------------------------------------------------------- training step (BASELINE configs[2])
@@ -623,6 +694,7 @@ def main():
     ap.add_argument("--skip-bw", action="store_true", help="skip the bandwidth-regime measurement")
     ap.add_argument("--bw-batch", type=int, default=65536)
     ap.add_argument("--skip-infer", action="store_true", help="skip the recognizer-inference block (BASELINE configs[0])")
+    ap.add_argument("--skip-extra", action="store_true", help="skip the beam-search (configs[3]) and width-sweep (configs[4]) blocks")
     ap.add_argument("--skip-train", action="store_true", help="skip the training-step block (BASELINE configs[2])")
     ap.add_argument("--train-steps", type=int, default=10)
     args = ap.parse_args()

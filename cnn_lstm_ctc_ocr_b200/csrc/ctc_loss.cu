@@ -291,6 +291,12 @@ extern "C" int ocr_debug_ctc_timeline(long long* device_buffer) {
 }
 
 struct FastPlan { int G, NP, CR, bulk, smem; };
+static int g_ctc_group = 0;   // tuning override of the group size (0 = automatic)
+extern "C" int ocr_debug_ctc_group(int G) {
+    OCR_CHECK_ARG(G == 0 || G == 1 || G == 2 || G == 4 || G == 8, "ocr_debug_ctc_group: G=%d", G);
+    g_ctc_group = G;
+    return OCR_OK;
+}
 
 // Chooses the group size G of the fast kernel: the shared-memory footprint is ~G*(T*C + 2*T*(Lmax+1))*4
 // bytes; prefer TMA-eligible groups (G*C*4 a multiple of 16 bytes, 16-byte aligned tensors) and as many
@@ -304,6 +310,7 @@ static bool plan_fast(const void* logits, const void* grad, int T, int B, int C,
                         ((long long)B * C) % 4 == 0 && g_ctc_path != 2;  // path 2: LSU loads/stores
     int best = -1, best_score = -1, best_smem = 0, best_bulk = 0;
     for (int G = 1; G <= maxG; G *= 2) {
+        if (g_ctc_group != 0 && G != g_ctc_group) continue;
         const FastLayout lay = fast_layout(T, C, Lmax, G);
         if (lay.total > kMaxDynSmem) break;
         const int bulk = ptr_ok && (G * C) % 4 == 0;

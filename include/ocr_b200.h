@@ -70,6 +70,8 @@ int ocr_ctc_loss_set_path(int path);
 /* Tuning aid: per-warp clock64() stamps at the fast kernel's phase boundaries (12 int64 per warp, CTA-major);
  * pass NULL to switch it off.  Not part of the product path. */
 int ocr_debug_ctc_timeline(long long* device_buffer);
+/* Tuning aid: force the number of sequences per CTA of the fast kernel (1, 2, 4, 8; 0 = automatic). */
+int ocr_debug_ctc_group(int G);
 
 /* ---------------------------------------------------------------------------------------------
  * CTC greedy decoder.  Replaces tf.nn.ctc_greedy_decoder(merge_repeated=True) at
