@@ -60,6 +60,9 @@ SIGNATURES = {
     "ocr_birnn_lstm_train_workspace_bytes": (_i, [_i, _i, _i, _c.POINTER(_sz)]),
     "ocr_birnn_lstm_train_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ocr_birnn_lstm_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ocr_birnn_gru_train_workspace_bytes": (_i, [_i, _i, _i, _c.POINTER(_sz)]),
+    "ocr_birnn_gru_train_fwd": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ocr_birnn_gru_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None

@@ -397,6 +397,113 @@ lstm_cell_bwd_kernel(float* __restrict__ act, const float* __restrict__ cs, cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// GRU frames for training (tf.contrib.rnn.GRUCell, model.py:173-180): r,u = sigmoid([x,h] Wg + bg);
+// c = tanh([x, r*h] Wc + bc); h' = u*h + (1-u)*c.  act [T*B, 6H] (per direction r | u | c) holds the input projections
+// on entry and the activations afterwards; rh_all [T,B,2H] keeps r*h_{prev} (the operand of the candidate kernel's gradient).
+__global__ void __launch_bounds__(256)
+gru_gates_train_kernel(const float* __restrict__ gh /*[2][B][2H]*/, float* __restrict__ act, const int32_t* __restrict__ seq_len, int s, int T,
+                       int B, int H, const float* __restrict__ h, float* __restrict__ rh /*[2B,H]*/, float* __restrict__ rh_all)
+{
+    const int total = 2 * B * H;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int j = idx % H;
+        const int r = idx / H;
+        const int dir = r >= B, b = dir ? r - B : r;
+        const int len = min(seq_len[b], T);
+        if (s >= len) { rh[idx] = 0.0f; continue; }
+        const int t = dir ? len - 1 - s : s;
+        const float* g = gh + (size_t)r * 2 * H;
+        float* a = act + ((size_t)t * B + b) * 6 * H + dir * 3 * H;
+        const float rr = sigm(g[j] + a[j]), uu = sigm(g[H + j] + a[H + j]);
+        a[j] = rr; a[H + j] = uu;
+        const float v = rr * h[idx];
+        rh[idx] = v;
+        rh_all[((size_t)t * B + b) * 2 * H + dir * H + j] = v;
+    }
+}
+__global__ void __launch_bounds__(256)
+gru_cell_train_kernel(const float* __restrict__ ch /*[2][B][H]*/, float* __restrict__ act, const int32_t* __restrict__ seq_len, int s, int T,
+                      int B, int H, float* __restrict__ h, float* __restrict__ out)
+{
+    const int total = 2 * B * H;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int j = idx % H;
+        const int r = idx / H;
+        const int dir = r >= B, b = dir ? r - B : r;
+        const int len = min(seq_len[b], T);
+        if (s >= len) continue;
+        const int t = dir ? len - 1 - s : s;
+        float* a = act + ((size_t)t * B + b) * 6 * H + dir * 3 * H;
+        const float cand = tanhf(ch[idx] + a[2 * H + j]);
+        a[2 * H + j] = cand;
+        const float uu = a[H + j];
+        const float hn = uu * h[idx] + (1.0f - uu) * cand;
+        h[idx] = hn;
+        out[((size_t)t * B + b) * 2 * H + dir * H + j] = hn;
+    }
+}
+// BPTT, first half of a frame: gradients of u and the candidate.  carry = d loss / d h_s from step s+1:
+// dhd (through u*h) + dhr (through r*h) + the split-K partials of [dzr,dzu] * Wg_h.
+__global__ void __launch_bounds__(256)
+gru_bwd1_kernel(float* __restrict__ act, const float* __restrict__ out, const float* __restrict__ dout, const int32_t* __restrict__ seq_len, int s,
+                int last, int T, int B, int H, float* __restrict__ dhd, const float* __restrict__ dhr, const float* __restrict__ dhg, int splits,
+                float* __restrict__ dzc_step /*[2B,H]*/, float* __restrict__ dzg_step /*[2B,2H]*/, float* __restrict__ dht /*[2B,H]*/)
+{
+    const int total = 2 * B * H;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int j = idx % H;
+        const int r = idx / H;
+        const int dir = r >= B, b = dir ? r - B : r;
+        const int len = min(seq_len[b], T);
+        float carry = 0.f;
+        if (!last && s + 1 < len) {
+            carry = dhd[idx] + dhr[idx];
+            const float* pr = dhg + ((size_t)dir * splits * B + b) * H + j;
+            for (int z = 0; z < splits; ++z) carry += pr[(size_t)z * B * H];
+        }
+        if (s >= len) { dzc_step[idx] = 0.f; dzg_step[(size_t)r * 2 * H + H + j] = 0.f; dht[idx] = 0.f; continue; }
+        const int t = dir ? len - 1 - s : s;
+        const size_t o = ((size_t)t * B + b) * 2 * H + dir * H + j;
+        float* a = act + ((size_t)t * B + b) * 6 * H + dir * 3 * H;
+        const float uu = a[H + j], cand = a[2 * H + j];
+        float hprev = 0.f;
+        if (s > 0) { const int tp = dir ? t + 1 : t - 1; hprev = out[((size_t)tp * B + b) * 2 * H + dir * H + j]; }
+        const float d = dout[o] + carry;
+        const float dzc = d * (1.f - uu) * (1.f - cand * cand);
+        const float dzu = d * (hprev - cand) * uu * (1.f - uu);
+        a[H + j] = dzu; a[2 * H + j] = dzc;
+        dzc_step[idx] = dzc;
+        dzg_step[(size_t)r * 2 * H + H + j] = dzu;
+        dhd[idx] = d * uu;
+        dht[idx] = hprev;      // kept for the second half
+    }
+}
+// second half: through r*h.  drh [2][splits][B][H] = split-K partials of dzc * Wc_h
+__global__ void __launch_bounds__(256)
+gru_bwd2_kernel(float* __restrict__ act, const float* __restrict__ drh, int splits, const int32_t* __restrict__ seq_len, int s, int T, int B, int H,
+                const float* __restrict__ hprev, float* __restrict__ dhr, float* __restrict__ dzg_step)
+{
+    const int total = 2 * B * H;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int j = idx % H;
+        const int r = idx / H;
+        const int dir = r >= B, b = dir ? r - B : r;
+        const int len = min(seq_len[b], T);
+        if (s >= len) { dzg_step[(size_t)r * 2 * H + j] = 0.f; continue; }
+        const int t = dir ? len - 1 - s : s;
+        float* a = act + ((size_t)t * B + b) * 6 * H + dir * 3 * H;
+        float d = 0.f;
+        const float* pr = drh + ((size_t)dir * splits * B + b) * H + j;
+        for (int z = 0; z < splits; ++z) d += pr[(size_t)z * B * H];
+        const float rr = a[j];
+        const float dzr = d * hprev[idx] * rr * (1.f - rr);
+        a[j] = dzr;
+        dzg_step[(size_t)r * 2 * H + j] = dzr;
+        dhr[idx] = d * rr;
+    }
+}
+
 // rows (t, b) with t >= len_b were never visited: their slots still hold input-projection values; their gradient is 0
 __global__ void __launch_bounds__(256)
 zero_past_len_kernel(float* __restrict__ a, const int32_t* __restrict__ seq_len, int T, int B, int cols4)
@@ -881,6 +988,103 @@ extern "C" int ocr_birnn_lstm_bwd(const float* dout, int T, int B, int H, const 
         lstm_cell_bwd_kernel<<<cg, 256, 0, st>>>(gates, cstate, dout, dh_rec, seq_len, s, s == T - 1 ? 1 : 0, T, B, H, splits, dh, dc, dgs);
         OCR_CHECK_LAUNCH();
         if (s > 0) { rc = gemm_run(p1, st); if (rc != OCR_OK) return rc; }
+    }
+    return OCR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// bidirectional GRU layer, training form (model.py:167-199) and its back-propagation through time
+static int gru_splits(int B, int H, int K) {
+    int want = 148 / (2 * ((B + 127) / 128) * ((H + 63) / 64));
+    if (want > 8) want = 8;
+    if (want > K / 64) want = K / 64;     // at least two k-steps of work per split
+    return want < 1 ? 1 : want;
+}
+
+extern "C" int ocr_birnn_gru_train_workspace_bytes(int T, int B, int H, size_t* bytes)
+{
+    OCR_CHECK_ARG(bytes && T >= 0 && B >= 0 && H >= 1, "ocr_birnn_gru_train_workspace_bytes: bad argument");
+    // gh [2B,2H], ch, h, rh, dzc, dhd, dhr, hprev [2B,H] each, dzg [2B,2H], two partial buffers of <= 8 x [2B,H]
+    *bytes = sizeof(float) * (size_t)2 * B * H * (2 + 7 + 2 + 16) + 256;
+    return OCR_OK;
+}
+
+extern "C" int ocr_birnn_gru_train_fwd(const float* x, int T, int B, int I, int H, const int32_t* seq_len, const float* wx, const float* whg,
+                                       const float* whc, const float* bias, float* out, float* act, float* rh_all, void* workspace,
+                                       size_t workspace_bytes, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(T >= 1 && B >= 1 && I >= 4 && (I % 4) == 0 && H >= 4 && (H % 4) == 0, "ocr_birnn_gru_train_fwd: bad shape T=%d B=%d I=%d H=%d", T, B, I, H);
+    OCR_CHECK_ARG(x && seq_len && wx && whg && whc && bias && out && act && rh_all, "ocr_birnn_gru_train_fwd: NULL argument");
+    size_t need = 0;
+    ocr_birnn_gru_train_workspace_bytes(T, B, H, &need);
+    if (workspace == nullptr || workspace_bytes < need) { set_error("ocr_birnn_gru_train_fwd: workspace too small"); return OCR_EWORKSPACE; }
+    cudaStream_t st = ST(stream);
+    float* ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    const size_t n = (size_t)2 * B * H;
+    float* gh = ws;            // [2][B][2H]
+    float* ch = gh + 2 * n;    // [2][B][H]
+    float* h = ch + n;
+    float* rh = h + n;
+    int rc = ocr_gemm_tf32(x, I, wx, I, bias, act, 6 * H, T * B, 6 * H, I, 0, stream);
+    if (rc != OCR_OK) return rc;
+    OCR_CHECK_CUDA(cudaMemsetAsync(gh, 0, sizeof(float) * 5 * n, st));
+    OCR_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)T * B * 2 * H, st));
+    OCR_CHECK_CUDA(cudaMemsetAsync(rh_all, 0, sizeof(float) * (size_t)T * B * 2 * H, st));
+    GemmPlan p1, p2;
+    rc = gemm_plan_dirs(&p1, h, H, whg, H, gh, B, 2 * H, H, 2, 1, recurrent_bn(B, 2 * H, 1));
+    if (rc != OCR_OK) return rc;
+    rc = gemm_plan_dirs(&p2, rh, H, whc, H, ch, B, H, H, 2, 1, recurrent_bn(B, H, 1));
+    if (rc != OCR_OK) return rc;
+    const int cg = grid_cap((long long)n);
+    for (int s = 0; s < T; ++s) {
+        if (s > 0) { rc = gemm_run(p1, st); if (rc != OCR_OK) return rc; }
+        gru_gates_train_kernel<<<cg, 256, 0, st>>>(gh, act, seq_len, s, T, B, H, h, rh, rh_all);
+        OCR_CHECK_LAUNCH();
+        if (s > 0) { rc = gemm_run(p2, st); if (rc != OCR_OK) return rc; }
+        gru_cell_train_kernel<<<cg, 256, 0, st>>>(ch, act, seq_len, s, T, B, H, h, out);
+        OCR_CHECK_LAUNCH();
+    }
+    return OCR_OK;
+}
+
+// wg_rows [2H, 2H]: rows I.. of the forward cell's gates kernel (TensorFlow layout [H, 2H]) then the backward cell's;
+// wc_rows [2H, H]: the same for the candidate kernels.  act: activations in, gradients of the pre-activations out.
+extern "C" int ocr_birnn_gru_bwd(const float* dout, int T, int B, int H, const int32_t* seq_len, float* act, const float* out,
+                                 const float* wg_rows, const float* wc_rows, void* workspace, size_t workspace_bytes, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(T >= 1 && B >= 1 && H >= 4 && (H % 4) == 0, "ocr_birnn_gru_bwd: bad shape T=%d B=%d H=%d", T, B, H);
+    OCR_CHECK_ARG(dout && seq_len && act && out && wg_rows && wc_rows, "ocr_birnn_gru_bwd: NULL argument");
+    size_t need = 0;
+    ocr_birnn_gru_train_workspace_bytes(T, B, H, &need);
+    if (workspace == nullptr || workspace_bytes < need) { set_error("ocr_birnn_gru_bwd: workspace too small"); return OCR_EWORKSPACE; }
+    cudaStream_t st = ST(stream);
+    float* ws = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    const size_t n = (size_t)2 * B * H;
+    float* dzg = ws;               // [2B, 2H]
+    float* dzc = dzg + 2 * n;      // [2B, H]
+    float* dhd = dzc + n;
+    float* dhr = dhd + n;
+    float* hprev = dhr + n;
+    float* drh = hprev + n + 2 * n;   // <= 8 partials [2][B][H]
+    float* dhg = drh + 8 * n;         // <= 8 partials
+    OCR_CHECK_CUDA(cudaMemsetAsync(dhd, 0, sizeof(float) * 2 * n, st));
+    zero_past_len_kernel<<<grid_cap((long long)T * B * 6 * H / 4), 256, 0, st>>>(act, seq_len, T, B, 6 * H / 4);
+    OCR_CHECK_LAUNCH();
+    GemmPlan pa, pb;
+    // drh[d][b, n] = sum_k dzc[d*B + b, k] * wc_rows[d*H + n, k];  dhg[d][b, n] = sum_k dzg[d*B + b, k] * wg_rows[d*H + n, k]
+    int rc = gemm_plan_dirs(&pa, dzc, H, wc_rows, H, drh, B, H, H, 2, gru_splits(B, H, H), H > 32 ? 64 : 32);
+    if (rc != OCR_OK) return rc;
+    rc = gemm_plan_dirs(&pb, dzg, 2 * H, wg_rows, 2 * H, dhg, B, H, 2 * H, 2, gru_splits(B, H, 2 * H), H > 32 ? 64 : 32);
+    if (rc != OCR_OK) return rc;
+    const int cg = grid_cap((long long)n);
+    for (int s = T - 1; s >= 0; --s) {
+        gru_bwd1_kernel<<<cg, 256, 0, st>>>(act, out, dout, seq_len, s, s == T - 1 ? 1 : 0, T, B, H, dhd, dhr, dhg, pb.splits, dzc, dzg, hprev);
+        OCR_CHECK_LAUNCH();
+        rc = gemm_run(pa, st);
+        if (rc != OCR_OK) return rc;
+        gru_bwd2_kernel<<<cg, 256, 0, st>>>(act, drh, pa.splits, seq_len, s, T, B, H, hprev, dhr, dzg);
+        OCR_CHECK_LAUNCH();
+        if (s > 0) { rc = gemm_run(pb, st); if (rc != OCR_OK) return rc; }
     }
     return OCR_OK;
 }

@@ -44,8 +44,12 @@ def _is_trainable(name):
 def _param_order(cell_type):
     names = ["rnn/logits/kernel", "rnn/logits/bias"]
     for scope in ("bdrnn2", "bdrnn1"):
-        names += ["rnn/%s/fw/lstm_cell/kernel" % scope, "rnn/%s/bw/lstm_cell/kernel" % scope,
-                  "rnn/%s/fw/lstm_cell/bias" % scope, "rnn/%s/bw/lstm_cell/bias" % scope]
+        if cell_type == "lstm":
+            names += ["rnn/%s/fw/lstm_cell/kernel" % scope, "rnn/%s/bw/lstm_cell/kernel" % scope,
+                      "rnn/%s/fw/lstm_cell/bias" % scope, "rnn/%s/bw/lstm_cell/bias" % scope]
+        else:
+            for d in ("fw", "bw"):
+                names += ["rnn/%s/%s/gru_cell/%s" % (scope, d, v) for v in ("gates/kernel", "gates/bias", "candidate/kernel", "candidate/bias")]
     n_rnn = len(names)
     for (filters, k, padding, name, bn) in reversed(LAYER_PARAMS):
         names += ["convnet/%s/kernel" % name, "convnet/%s/bias" % name]
@@ -58,8 +62,8 @@ class Trainer:
     def __init__(self, params, cell_type="lstm", rnn_sizes=(512, 512), device="cuda", learning_rate=1e-4, momentum=0.9,
                  decay_rate=0.9, decay_steps=2 ** 16, decay_staircase=False, beta2=0.999, epsilon=1e-8,
                  process_group=None, sync_bn=False, global_step=0):
-        if cell_type != "lstm":
-            raise NotImplementedError("the training step is built for the LSTM model (model_bu.py); GRU training is not built")
+        if cell_type not in ("lstm", "gru"):
+            raise ValueError("cell_type must be 'lstm' (model_bu.py) or 'gru' (model.py)")
         self.cell_type = cell_type
         self.rnn_sizes = tuple(rnn_sizes)
         self.device = torch.device(device)
@@ -143,7 +147,11 @@ class Trainer:
         self.rnn_w = []
         I = 256
         for H in self.rnn_sizes:
-            self.rnn_w.append(dict(I=I, H=H, wx=self._new(8 * H, I), wh=self._new(8 * H, H), wxcat=self._new(I, 8 * H), wh_rows=self._new(2 * H, 4 * H)))
+            if self.cell_type == "lstm":
+                self.rnn_w.append(dict(I=I, H=H, wx=self._new(8 * H, I), wh=self._new(8 * H, H), wxcat=self._new(I, 8 * H), wh_rows=self._new(2 * H, 4 * H)))
+            else:
+                self.rnn_w.append(dict(I=I, H=H, wx=self._new(6 * H, I), whg=self._new(4 * H, H), whc=self._new(2 * H, H), bias=self._new(6 * H),
+                                       wxcat=self._new(I, 6 * H), wg_rows=self._new(2 * H, 2 * H), wc_rows=self._new(2 * H, H)))
             I = 2 * H
         C = self.shapes["rnn/logits/kernel"][1]
         self.logits_w = self._new(C, I)
@@ -160,6 +168,9 @@ class Trainer:
             cin = filters
         for scope, L in zip(("bdrnn1", "bdrnn2"), self.rnn_w):
             I, H = L["I"], L["H"]
+            if self.cell_type == "gru":
+                self._derive_gru(scope, L)
+                continue
             for d, dn in enumerate(("fw", "bw")):
                 kern = self.params["rnn/%s/%s/lstm_cell/kernel" % (scope, dn)]      # [I+H, 4H]
                 kp = kern.data_ptr()
@@ -170,6 +181,29 @@ class Trainer:
                 self._c(lib.ocr_copy_2d(ctypes.c_void_p(kp + I * 4 * H * 4), 4 * H, ctypes.c_void_p(L["wh_rows"].data_ptr() + d * H * 4 * H * 4), 4 * H, H, 4 * H, sh), "ocr_copy_2d")
         kl = self.params["rnn/logits/kernel"]                                        # [2H, C]
         self._c(lib.ocr_transpose(_lib.ptr(kl), kl.shape[0], kl.shape[1], kl.shape[1], _lib.ptr(self.logits_w), kl.shape[0], 0, sh), "ocr_transpose")
+
+    def _derive_gru(self, scope, L):
+        """GRUCell variables (gates/kernel [I+H,2H], candidate/kernel [I+H,H] + biases, per direction) -> kernel operands."""
+        lib, sh = self.lib, self._sh()
+        I, H = L["I"], L["H"]
+        vp = ctypes.c_void_p
+        for d, dn in enumerate(("fw", "bw")):
+            q = "rnn/%s/%s/gru_cell/" % (scope, dn)
+            gk, ck = self.params[q + "gates/kernel"].data_ptr(), self.params[q + "candidate/kernel"].data_ptr()
+            gb, cb = self.params[q + "gates/bias"].data_ptr(), self.params[q + "candidate/bias"].data_ptr()
+            f = 4  # bytes
+            # forward operands: wx rows d*3H.. = [gates x-part^T (2H) ; candidate x-part^T (H)], whg rows d*2H.., whc rows d*H..
+            self._c(lib.ocr_transpose(vp(gk), I, 2 * H, 2 * H, vp(L["wx"].data_ptr() + d * 3 * H * I * f), I, 0, sh), "ocr_transpose")
+            self._c(lib.ocr_transpose(vp(ck), I, H, H, vp(L["wx"].data_ptr() + (d * 3 * H + 2 * H) * I * f), I, 0, sh), "ocr_transpose")
+            self._c(lib.ocr_transpose(vp(gk + I * 2 * H * f), H, 2 * H, 2 * H, vp(L["whg"].data_ptr() + d * 2 * H * H * f), H, 0, sh), "ocr_transpose")
+            self._c(lib.ocr_transpose(vp(ck + I * H * f), H, H, H, vp(L["whc"].data_ptr() + d * H * H * f), H, 0, sh), "ocr_transpose")
+            self._c(lib.ocr_copy_2d(vp(gb), 2 * H, vp(L["bias"].data_ptr() + d * 3 * H * f), 2 * H, 1, 2 * H, sh), "ocr_copy_2d")
+            self._c(lib.ocr_copy_2d(vp(cb), H, vp(L["bias"].data_ptr() + (d * 3 * H + 2 * H) * f), H, 1, H, sh), "ocr_copy_2d")
+            # backward operands: wxcat [I, 6H] columns d*3H.. = [gates x-part | candidate x-part]; h-part rows as they are
+            self._c(lib.ocr_copy_2d(vp(gk), 2 * H, vp(L["wxcat"].data_ptr() + d * 3 * H * f), 6 * H, I, 2 * H, sh), "ocr_copy_2d")
+            self._c(lib.ocr_copy_2d(vp(ck), H, vp(L["wxcat"].data_ptr() + (d * 3 * H + 2 * H) * f), 6 * H, I, H, sh), "ocr_copy_2d")
+            self._c(lib.ocr_copy_2d(vp(gk + I * 2 * H * f), 2 * H, vp(L["wg_rows"].data_ptr() + d * H * 2 * H * f), 2 * H, H, 2 * H, sh), "ocr_copy_2d")
+            self._c(lib.ocr_copy_2d(vp(ck + I * H * f), H, vp(L["wc_rows"].data_ptr() + d * H * H * f), H, H, H, sh), "ocr_copy_2d")
 
     # ------------------------------------------------------------------ building blocks
     def _conv(self, x, w, bias, cout, relu):
@@ -326,12 +360,23 @@ class Trainer:
         # ---------------- forward: rnn_layers
         need = ctypes.c_size_t(0)
         Hmax = max(self.rnn_sizes)
-        self._c(lib.ocr_birnn_lstm_train_workspace_bytes(T, B, Hmax, ctypes.byref(need)), "ocr_birnn_lstm_train_workspace_bytes")
+        if self.cell_type == "lstm":
+            self._c(lib.ocr_birnn_lstm_train_workspace_bytes(T, B, Hmax, ctypes.byref(need)), "ocr_birnn_lstm_train_workspace_bytes")
+        else:
+            self._c(lib.ocr_birnn_gru_train_workspace_bytes(T, B, Hmax, ctypes.byref(need)), "ocr_birnn_gru_train_workspace_bytes")
         ws = torch.empty(need.value, dtype=torch.uint8, device=self.device)
         rnn_saved = []
         xin = seq
         for scope, L in zip(("bdrnn1", "bdrnn2"), self.rnn_w):
             I, H = L["I"], L["H"]
+            if self.cell_type == "gru":
+                out, act, rh = self._new(T, B, 2 * H), self._new(T * B, 6 * H), self._new(T, B, 2 * H)
+                self._c(lib.ocr_birnn_gru_train_fwd(_lib.ptr(xin), T, B, I, H, _lib.ptr(seq_len), _lib.ptr(L["wx"]), _lib.ptr(L["whg"]), _lib.ptr(L["whc"]),
+                                                    _lib.ptr(L["bias"]), _lib.ptr(out), _lib.ptr(act), _lib.ptr(rh), _lib.ptr(ws), need.value, sh),
+                        "ocr_birnn_gru_train_fwd")
+                rnn_saved.append(dict(x=xin, out=out, gates=act, rh=rh))
+                xin = out
+                continue
             out, gates, cs = self._new(T, B, 2 * H), self._new(T * B, 8 * H), self._new(T, B, 2 * H)
             o = self.offsets["rnn/%s/fw/lstm_cell/bias" % scope]
             bias8 = self.theta[o:o + 8 * H]     # fw | bw biases are adjacent in the flat buffer
@@ -371,6 +416,9 @@ class Trainer:
             scope = ("bdrnn1", "bdrnn2")[li]
             L, S = self.rnn_w[li], rnn_saved[li]
             I, H = L["I"], L["H"]
+            if self.cell_type == "gru":
+                dout, outT, ldo = self._backward_gru_layer(scope, L, S, dout, outT, ldo, T, B, seq_len, ws, need)
+                continue
             self._c(lib.ocr_birnn_lstm_bwd(_lib.ptr(dout), T, B, H, _lib.ptr(seq_len), _lib.ptr(S["gates"]), _lib.ptr(S["cs"]), _lib.ptr(L["wh_rows"]),
                                            _lib.ptr(ws), need.value, sh), "ocr_birnn_lstm_bwd")
             dG = S["gates"]                                   # [R, 8H] gradient of the gate pre-activations
@@ -398,6 +446,42 @@ class Trainer:
             S.clear()
         self._conv_state = (saved, dout, x)
         return losses
+
+    def _backward_gru_layer(self, scope, L, S, dout, outT, ldo, T, B, seq_len, ws, need):
+        """BPTT of one bidirectional GRU layer, then d kernel / d bias / d input as contractions.  Returns (d input, input^T, ld)."""
+        lib, sh, G = self.lib, self._sh(), self.grads
+        scr = _lib.ptr(self.scratch)
+        I, H = L["I"], L["H"]
+        R = T * B
+        vp = ctypes.c_void_p
+        self._c(lib.ocr_birnn_gru_bwd(_lib.ptr(dout), T, B, H, _lib.ptr(seq_len), _lib.ptr(S["gates"]), _lib.ptr(S["out"]), _lib.ptr(L["wg_rows"]),
+                                      _lib.ptr(L["wc_rows"]), _lib.ptr(ws), need.value, sh), "ocr_birnn_gru_bwd")
+        dA = S["gates"]                                      # [R, 6H]: per direction d z_r | d z_u | d z_c
+        dAT, lda_ = self._transposed(dA)
+        xT, ldx = self._transposed(S["x"].reshape(R, I))
+        rhT, ldr = self._transposed(S["rh"].view(R, 2 * H))
+        for d, dn in enumerate(("fw", "bw")):
+            q = "rnn/%s/%s/gru_cell/" % (scope, dn)
+            gk, ck = G[q + "gates/kernel"], G[q + "candidate/kernel"]
+            col = d * 3 * H
+            self._c(lib.ocr_colsum(vp(dA.data_ptr() + col * 4), R, 2 * H, 6 * H, _lib.ptr(G[q + "gates/bias"]), scr, sh), "ocr_colsum")
+            self._c(lib.ocr_colsum(vp(dA.data_ptr() + (col + 2 * H) * 4), R, H, 6 * H, _lib.ptr(G[q + "candidate/bias"]), scr, sh), "ocr_colsum")
+            Wg = vp(dAT.data_ptr() + col * lda_ * 4)                 # rows d z_r, d z_u of this direction
+            Wc = vp(dAT.data_ptr() + (col + 2 * H) * lda_ * 4)       # rows d z_c
+            self._wgrad(_lib.ptr(xT), ldx, Wg, lda_, _lib.ptr(gk), 2 * H, 0, I, 2 * H, R, [0])
+            self._wgrad(_lib.ptr(xT), ldx, Wc, lda_, _lib.ptr(ck), H, 0, I, H, R, [0])
+            shift = -B if d == 0 else B                              # h_prev = the layer's output one frame earlier / later
+            if B % 4 == 0:
+                At, lda, shifts = vp(outT.data_ptr() + d * H * ldo * 4), ldo, [shift]
+            else:
+                hprevT, lda = self._transposed(S["out"].view(R, 2 * H)[:, d * H:(d + 1) * H], shift)
+                At, shifts = _lib.ptr(hprevT), [0]
+            self._wgrad(At, lda, Wg, lda_, vp(gk.data_ptr() + I * 2 * H * 4), 2 * H, 0, H, 2 * H, R, shifts)
+            self._wgrad(vp(rhT.data_ptr() + d * H * ldr * 4), ldr, Wc, lda_, vp(ck.data_ptr() + I * H * 4), H, 0, H, H, R, [0])
+        dx = self._new(T, B, I)
+        self._c(lib.ocr_gemm_tf32(_lib.ptr(dA), 6 * H, _lib.ptr(L["wxcat"]), 6 * H, None, _lib.ptr(dx), I, R, I, 6 * H, 0, sh), "ocr_gemm_tf32")
+        S.clear()
+        return dx, xT, ldx
 
     def _backward_conv(self):
         lib, sh = self.lib, self._sh()

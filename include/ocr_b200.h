@@ -244,6 +244,20 @@ int ocr_birnn_lstm_train_fwd(const float* x, int T, int B, int I, int H, const i
 int ocr_birnn_lstm_bwd(const float* dout, int T, int B, int H, const int32_t* seq_len, float* gates, const float* cstate,
                        const float* wh_rows, void* workspace, size_t workspace_bytes, ocr_stream_t stream);
 
+/* Bidirectional GRU layer in training form (model.py:167-199, tf.contrib.rnn.GRUCell: the reset gate multiplies h BEFORE the
+ * candidate product) and its back-propagation through time.
+ *   wx [6H, I] (rows per direction r, u, candidate), whg [4H, H] (r, u per direction), whc [2H, H], bias [6H] as ocr_birnn_layer;
+ *   act [T*B, 6H] out: activations r | u | c per direction;  rh_all [T,B,2H] out: r * h_prev (operand of d candidate kernel).
+ * ocr_birnn_gru_bwd: dout [T,B,2H]; act is overwritten with the gradients of the pre-activations (zero past each length);
+ *   out = the layer's forward output; wg_rows [2H, 2H] / wc_rows [2H, H]: rows I.. of the gates / candidate kernels
+ *   (TensorFlow layout), forward direction's H rows then the backward direction's. */
+int ocr_birnn_gru_train_workspace_bytes(int T, int B, int H, size_t* bytes);
+int ocr_birnn_gru_train_fwd(const float* x, int T, int B, int I, int H, const int32_t* seq_len, const float* wx, const float* whg,
+                            const float* whc, const float* bias, float* out, float* act, float* rh_all, void* workspace,
+                            size_t workspace_bytes, ocr_stream_t stream);
+int ocr_birnn_gru_bwd(const float* dout, int T, int B, int H, const int32_t* seq_len, float* act, const float* out,
+                      const float* wg_rows, const float* wc_rows, void* workspace, size_t workspace_bytes, ocr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -233,13 +233,13 @@ def test_adam_matches_oracle():
     _close(dv.cpu().numpy(), vr, 1e-6, "v")
 
 
-def _small_problem(seed=0, B=4, W=44, sizes=(32, 32), classes=19):
+def _small_problem(seed=0, B=4, W=44, sizes=(32, 32), classes=19, cell="lstm"):
     """B = 4: frame shifts of the transposed outputs are aligned TMA offsets; B = 3 takes the shifted-copy path."""
     from oracle import model_oracle as mo
     rng = np.random.default_rng(seed)
-    params = mo.init_params(seed, "lstm", sizes, classes, np.float64, randomize_bn=True)
+    params = mo.init_params(seed, cell, sizes, classes, np.float64, randomize_bn=True)
     for k in list(params):       # make the recurrence and the biases matter
-        if "lstm_cell/kernel" in k:
+        if "_cell/" in k and k.endswith("kernel"):
             params[k] = params[k] * 8
         if k.endswith("bias"):
             params[k] = params[k] + rng.normal(0, 0.05, params[k].shape)
@@ -294,14 +294,15 @@ def test_lstm_layer_train_forward_backward(H, path):
     L.check(lib.ocr_birnn_set_path(0), "path")
 
 
-@pytest.mark.parametrize("B", [4, 3])
-def test_train_step_vs_oracle(B):
-    """One full step of train.py's graph: loss, every gradient, moving statistics and the Adam update."""
+@pytest.mark.parametrize("B,cell,sizes", [(4, "lstm", (32, 32)), (3, "lstm", (32, 32)), (4, "gru", (32, 16)), (3, "gru", (32, 16))])
+def test_train_step_vs_oracle(B, cell, sizes):
+    """One full step of train.py's graph: loss, every gradient, moving statistics and the Adam update
+    (LSTM model of model_bu.py and GRU model of model.py)."""
     from cnn_lstm_ctc_ocr_b200 import train
     from oracle import train_oracle as to
-    params, img, widths, labels = _small_problem(B=B)
-    ref = to.train_step_reference(params, img, widths, labels, step=0, cell_type="lstm", sizes=(32, 32))
-    tr = train.Trainer(params, rnn_sizes=(32, 32))
+    params, img, widths, labels = _small_problem(B=B, cell=cell, sizes=sizes)
+    ref = to.train_step_reference(params, img, widths, labels, step=0, cell_type=cell, sizes=sizes)
+    tr = train.Trainer(params, cell_type=cell, rnn_sizes=sizes)
     losses = tr.forward_backward(torch.tensor(img, device=DEV), widths, labels)
     _close(losses.cpu().numpy(), ref["losses"], 5e-3, "losses")
     _close(tr.last_logits.cpu().numpy(), ref["logits"], 1e-2, "logits")
