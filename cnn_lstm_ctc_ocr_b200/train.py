@@ -17,6 +17,7 @@ remaining backward pass is still running.  Per-replica batch-norm statistics by 
 sync_bn=True all-reduces the per-channel sums so that N replicas reproduce the single-GPU step exactly.
 PyTorch supplies device memory, streams and torch.distributed only.  There is no CPU path.
 """
+import contextlib
 import ctypes
 import math
 
@@ -61,7 +62,7 @@ def _param_order(cell_type):
 class Trainer:
     def __init__(self, params, cell_type="lstm", rnn_sizes=(512, 512), device="cuda", learning_rate=1e-4, momentum=0.9,
                  decay_rate=0.9, decay_steps=2 ** 16, decay_staircase=False, beta2=0.999, epsilon=1e-8,
-                 process_group=None, sync_bn=False, global_step=0):
+                 process_group=None, sync_bn=False, global_step=0, overlap_weight_gradients=True):
         if cell_type not in ("lstm", "gru"):
             raise ValueError("cell_type must be 'lstm' (model_bu.py) or 'gru' (model.py)")
         self.cell_type = cell_type
@@ -108,6 +109,13 @@ class Trainer:
         self.stats = {n: torch.as_tensor(np.asarray(v), dtype=torch.float32).to(dev).contiguous() for n, v in params.items() if not _is_trainable(n)}
         self.scratch = torch.zeros(16 * 9 * 4096, dtype=torch.uint8, device=dev)   # double sums: up to 8H = 4096 columns x 2
         self.zero_bias = torch.zeros(1024, dtype=torch.float32, device=dev)
+        # Weight gradients are off the critical path of the backward pass (nothing downstream reads them before the
+        # all-reduce / Adam), while the chain of input gradients -- above all the frame-by-frame BPTT loops -- leaves most
+        # SMs idle: the transposes and split-K contractions of every layer's weight gradient run on a side stream.
+        self.overlap = bool(overlap_weight_gradients)
+        self.side = torch.cuda.Stream(device=dev) if self.overlap else None
+        self.scratch_side = torch.zeros_like(self.scratch)
+        self._side_keep = []
         self.wscratch = None
         self._alloc_derived()
         self.derive_layouts()
@@ -121,6 +129,23 @@ class Trainer:
 
     def _new(self, *shape):
         return torch.empty(shape, dtype=torch.float32, device=self.device)
+
+    @contextlib.contextmanager
+    def _on_side(self, *keep):
+        """Enqueue the enclosed work on the side stream, after everything issued so far on the current stream.  `keep`:
+        tensors the side work reads; they stay referenced until _join_side."""
+        if not self.overlap:
+            yield
+            return
+        self.side.wait_stream(torch.cuda.current_stream(self.device))
+        self._side_keep.extend(keep)
+        with torch.cuda.stream(self.side):
+            yield
+
+    def _join_side(self):
+        if self.overlap:
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
+        self._side_keep.clear()
 
     def all_params(self):
         """name -> tensor in TensorFlow variable naming (trainable variables + batch-norm moving statistics)."""
@@ -404,13 +429,15 @@ class Trainer:
         # ---------------- backward: logits layer (dense + ReLU, model.py:216-220)
         self._c(lib.ocr_relu_bwd(_lib.ptr(logits), _lib.ptr(dlog), dlog.numel(), _lib.ptr(dlog), sh), "ocr_relu_bwd")
         dz = dlog.view(R, C)
-        self._c(lib.ocr_colsum(_lib.ptr(dz), R, C, C, _lib.ptr(G["rnn/logits/bias"]), scr, sh), "ocr_colsum")
-        dzT, ldz = self._transposed(dz)
-        outT, ldo = self._transposed(rnn_saved[-1]["out"].view(R, F))
-        self._wgrad(_lib.ptr(outT), ldo, _lib.ptr(dzT), ldz, _lib.ptr(G["rnn/logits/kernel"]), C, 0, F, C, R, [0])
+        scr_s = _lib.ptr(self.scratch_side)
+        with self._on_side(dz, rnn_saved[-1]["out"]):
+            self._c(lib.ocr_colsum(_lib.ptr(dz), R, C, C, _lib.ptr(G["rnn/logits/bias"]), scr_s, self._sh()), "ocr_colsum")
+            dzT, ldz = self._transposed(dz)
+            outT, ldo = self._transposed(rnn_saved[-1]["out"].view(R, F))
+            self._wgrad(_lib.ptr(outT), ldo, _lib.ptr(dzT), ldz, _lib.ptr(G["rnn/logits/kernel"]), C, 0, F, C, R, [0])
+            del dzT
         dout = self._new(T, B, F)
         self._c(lib.ocr_gemm_tf32(_lib.ptr(dz), C, _lib.ptr(P["rnn/logits/kernel"]), C, None, _lib.ptr(dout), F, R, F, C, 0, sh), "ocr_gemm_tf32")
-        del dzT
         # ---------------- backward: recurrent layers (BPTT), last layer first
         for li in (1, 0):
             scope = ("bdrnn1", "bdrnn2")[li]
@@ -422,28 +449,31 @@ class Trainer:
             self._c(lib.ocr_birnn_lstm_bwd(_lib.ptr(dout), T, B, H, _lib.ptr(seq_len), _lib.ptr(S["gates"]), _lib.ptr(S["cs"]), _lib.ptr(L["wh_rows"]),
                                            _lib.ptr(ws), need.value, sh), "ocr_birnn_lstm_bwd")
             dG = S["gates"]                                   # [R, 8H] gradient of the gate pre-activations
-            o = self.offsets["rnn/%s/fw/lstm_cell/bias" % scope]
-            self._c(lib.ocr_colsum(_lib.ptr(dG), R, 8 * H, 8 * H, _lib.ptr(self.grad[o:o + 8 * H]), scr, sh), "ocr_colsum")
-            dGT, ldg = self._transposed(dG)
-            xT, ldx = self._transposed(S["x"].reshape(R, I))
-            for d, dn in enumerate(("fw", "bw")):
-                gk = G["rnn/%s/%s/lstm_cell/kernel" % (scope, dn)]                 # [I+H, 4H]
-                Wt = ctypes.c_void_p(dGT.data_ptr() + d * 4 * H * ldg * 4)
-                self._wgrad(_lib.ptr(xT), ldx, Wt, ldg, _lib.ptr(gk), 4 * H, 0, I, 4 * H, R, [0])
-                # h_{prev}: the layer's own output one frame earlier (forward) / later (backward direction)
-                shift = -B if d == 0 else B
-                if B % 4 == 0:      # a frame shift of the transposed output is an aligned TMA coordinate offset
-                    At, lda, shifts = ctypes.c_void_p(outT.data_ptr() + d * H * ldo * 4), ldo, [shift]
-                else:
-                    hprevT, lda = self._transposed(S["out"].view(R, 2 * H)[:, d * H:(d + 1) * H], shift)
-                    At, shifts = _lib.ptr(hprevT), [0]
-                self._wgrad(At, lda, Wt, ldg, ctypes.c_void_p(gk.data_ptr() + I * 4 * H * 4), 4 * H, 0, H, 4 * H, R, shifts)
+            with self._on_side(dG, S["x"], S["out"]):
+                o = self.offsets["rnn/%s/fw/lstm_cell/bias" % scope]
+                self._c(lib.ocr_colsum(_lib.ptr(dG), R, 8 * H, 8 * H, _lib.ptr(self.grad[o:o + 8 * H]), scr_s, self._sh()), "ocr_colsum")
+                dGT, ldg = self._transposed(dG)
+                xT, ldx = self._transposed(S["x"].reshape(R, I))
+                for d, dn in enumerate(("fw", "bw")):
+                    gk = G["rnn/%s/%s/lstm_cell/kernel" % (scope, dn)]                 # [I+H, 4H]
+                    Wt = ctypes.c_void_p(dGT.data_ptr() + d * 4 * H * ldg * 4)
+                    self._wgrad(_lib.ptr(xT), ldx, Wt, ldg, _lib.ptr(gk), 4 * H, 0, I, 4 * H, R, [0])
+                    # h_{prev}: the layer's own output one frame earlier (forward) / later (backward direction)
+                    shift = -B if d == 0 else B
+                    if B % 4 == 0:      # a frame shift of the transposed output is an aligned TMA coordinate offset
+                        At, lda, shifts = ctypes.c_void_p(outT.data_ptr() + d * H * ldo * 4), ldo, [shift]
+                    else:
+                        hprevT, lda = self._transposed(S["out"].view(R, 2 * H)[:, d * H:(d + 1) * H], shift)
+                        At, shifts = _lib.ptr(hprevT), [0]
+                    self._wgrad(At, lda, Wt, ldg, ctypes.c_void_p(gk.data_ptr() + I * 4 * H * 4), 4 * H, 0, H, 4 * H, R, shifts)
+                outT, ldo = xT, ldx          # the input of layer 2 is the output of layer 1
+                del dGT
             dx = self._new(T, B, I)
             self._c(lib.ocr_gemm_tf32(_lib.ptr(dG), 8 * H, _lib.ptr(L["wxcat"]), 8 * H, None, _lib.ptr(dx), I, R, I, 8 * H, 0, sh), "ocr_gemm_tf32")
             dout = dx
-            outT, ldo = xT, ldx          # the input of layer 2 is the output of layer 1
-            del dGT
             S.clear()
+        del outT
+        self._join_side()     # the RNN + logits bucket of the flat gradient is complete on the current stream
         self._conv_state = (saved, dout, x)
         return losses
 
@@ -457,6 +487,12 @@ class Trainer:
         self._c(lib.ocr_birnn_gru_bwd(_lib.ptr(dout), T, B, H, _lib.ptr(seq_len), _lib.ptr(S["gates"]), _lib.ptr(S["out"]), _lib.ptr(L["wg_rows"]),
                                       _lib.ptr(L["wc_rows"]), _lib.ptr(ws), need.value, sh), "ocr_birnn_gru_bwd")
         dA = S["gates"]                                      # [R, 6H]: per direction d z_r | d z_u | d z_c
+        dx = self._new(T, B, I)
+        self._c(lib.ocr_gemm_tf32(_lib.ptr(dA), 6 * H, _lib.ptr(L["wxcat"]), 6 * H, None, _lib.ptr(dx), I, R, I, 6 * H, 0, sh), "ocr_gemm_tf32")
+        ctx = self._on_side(dA, S["x"], S["out"], S["rh"])
+        ctx.__enter__()
+        scr = _lib.ptr(self.scratch_side)
+        sh = self._sh()
         dAT, lda_ = self._transposed(dA)
         xT, ldx = self._transposed(S["x"].reshape(R, I))
         rhT, ldr = self._transposed(S["rh"].view(R, 2 * H))
@@ -478,8 +514,7 @@ class Trainer:
                 At, shifts = _lib.ptr(hprevT), [0]
             self._wgrad(At, lda, Wg, lda_, vp(gk.data_ptr() + I * 2 * H * 4), 2 * H, 0, H, 2 * H, R, shifts)
             self._wgrad(vp(rhT.data_ptr() + d * H * ldr * 4), ldr, Wc, lda_, vp(ck.data_ptr() + I * H * 4), H, 0, H, H, R, [0])
-        dx = self._new(T, B, I)
-        self._c(lib.ocr_gemm_tf32(_lib.ptr(dA), 6 * H, _lib.ptr(L["wxcat"]), 6 * H, None, _lib.ptr(dx), I, R, I, 6 * H, 0, sh), "ocr_gemm_tf32")
+        ctx.__exit__(None, None, None)
         S.clear()
         return dx, xT, ldx
 
@@ -516,7 +551,8 @@ class Trainer:
                 dy = da
                 self._c(lib.ocr_relu_bwd_bias(_lib.ptr(S["out"]), _lib.ptr(da), rows, filters, _lib.ptr(dy), _lib.ptr(G["convnet/%s/bias" % name]), scr, sh),
                         "ocr_relu_bwd_bias")
-            self._conv_wgrad(xin, dy, name)
+            with self._on_side(xin, dy):
+                self._conv_wgrad(xin, dy, name)
             _, wd = self.conv_w[name]
             dxin = self._conv(dy, wd, self.zero_bias, xin.shape[3], relu=False)
             if "pool" in S:
@@ -532,6 +568,7 @@ class Trainer:
         rows = a1.numel() // a1.shape[3]
         self._c(lib.ocr_relu_bwd_bias(_lib.ptr(a1), _lib.ptr(da), rows, a1.shape[3], _lib.ptr(da), _lib.ptr(G["convnet/conv1/bias"]), scr, sh), "ocr_relu_bwd_bias")
         self._c(lib.ocr_conv1_wgrad(_lib.ptr(x), int(is_u8), B, Hh, Ww, _lib.ptr(da), a1.shape[3], _lib.ptr(G["convnet/conv1/kernel"]), scr, sh), "ocr_conv1_wgrad")
+        self._join_side()
 
     def _lr_t(self):
         lr = learning_rate(self.global_step, **self.hp)
