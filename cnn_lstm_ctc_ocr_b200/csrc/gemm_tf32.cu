@@ -229,7 +229,7 @@ int gemm_run(const GemmPlan& p, cudaStream_t st)
     // 2-3 CTAs share an SM (shared memory and the 512 TMEM columns allow it) and the epilogue of one tile -- one thread per
     // row draining TMEM to global memory, which is what bounds the K <= 1024 projections -- overlaps the main loop of another.
     const long long ctas = (long long)((p.M + kGemmBM - 1) / kGemmBM) * p.nbatch * ((p.N + p.bn - 1) / p.bn) * p.splits;
-    if (ctas <= 148) {
+    if (ctas <= 148 && !p.shallow) {
         switch (p.bn) {
             case 32: return launch_planned<32, 8>(p, st);
             case 64: return launch_planned<64, 6>(p, st);
