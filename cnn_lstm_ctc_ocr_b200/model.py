@@ -233,10 +233,54 @@ class Model:
         predictions, _ = ctc.ctc_greedy_decoder(rnn_logits, sequence_length, merge_repeated=True)
         return [ctc.sparse_tensor_to_dense(predictions[0], default_value=-1)]
 
-    def recognize(self, images, widths):
+    def recognize(self, images, widths, use_graph=True):
         """images [B,32,W,1] uint8 or float -> list of strings: the graph LocalServer.run builds (server.py:80-89)
-        plus its post-processing (server.py:134-138)."""
-        features, sl = self.convnet_layers(images, widths, ModeKeys.INFER)
-        logits = self.rnn_layers(features, sl)
-        dense = self.get_output(logits, sl)[0].cpu().numpy()
-        return [get_string([c for c in row if c >= 0]) for row in dense]
+        plus its post-processing (server.py:134-138).
+
+        uint8 batches (what the server feeds, server.py:71-78) replay a CUDA graph recorded per batch shape -- the
+        reference builds its TensorFlow graph once per process for the same reason: the ~20 launches of a batch cost more
+        host time than device time.  All recorded shapes share one memory pool (they never run concurrently)."""
+        if not (use_graph and images.dtype == torch.uint8 and self.device.type == "cuda"):
+            features, sl = self.convnet_layers(images.to(self.device), widths, ModeKeys.INFER)
+            logits = self.rnn_layers(features, sl)
+            dense = self.get_output(logits, sl)[0].cpu().numpy()
+            return [get_string([c for c in row if c >= 0]) for row in dense]
+        key = tuple(images.shape)
+        cache = self.__dict__.setdefault("_graphs", {})
+        g = cache.get(key)
+        if g is None:
+            g = self._record(key)
+            cache[key] = g
+        g["img"].copy_(images, non_blocking=True)
+        g["widths"].copy_(torch.as_tensor(widths).to(torch.int32), non_blocking=True)
+        g["graph"].replay()
+        g["host"].copy_(g["dec"], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        dense = g["host"].numpy()
+        chars = self.__dict__.setdefault("_charset_arr", np.array(list(out_charset)))
+        return ["".join(chars[row[row >= 0]]) for row in dense]
+
+    def _record(self, shape):
+        from . import ctc as _ctc
+        dev = self.device
+        g = dict(img=torch.zeros(shape, dtype=torch.uint8, device=dev), widths=torch.full((shape[0],), shape[2], dtype=torch.int32, device=dev))
+
+        def run():
+            features, sl = self.convnet_layers(g["img"], g["widths"], ModeKeys.INFER)
+            logits = self.rnn_layers(features, sl)
+            dec, ln, ns = _ctc.ctc_greedy_decode_raw(logits, sl)
+            return dec
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            run()                                   # warm-up outside the capture (lazy one-time initialisation)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        if "_graph_pool" not in self.__dict__:
+            self._graph_pool = torch.cuda.graph_pool_handle()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, pool=self._graph_pool):
+            g["dec"] = run()
+        g["graph"] = gr
+        g["host"] = torch.empty(tuple(g["dec"].shape), dtype=torch.int64).pin_memory()
+        return g

@@ -92,7 +92,7 @@ class LocalServer(object):
             infos = infos + [("-1", "0")] * (self.bucket_size - n)
         self.padded_pixels += int(batch.shape[0] * batch.shape[2])
         self.real_pixels += int(widths[:n].sum())
-        texts = self.model.recognize(torch.from_numpy(batch).to(self.device), torch.from_numpy(widths))
+        texts = self.model.recognize(torch.from_numpy(batch), torch.from_numpy(widths))   # host crops: copied into the recorded graph's input
         for (clientid, imgid), txt in zip(infos, texts):
             if clientid == "-1":
                 continue

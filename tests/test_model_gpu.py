@@ -122,3 +122,19 @@ def test_get_testing_metrics():
     assert abs(float(loss) - l64.mean()) < 1e-4 * l64.mean()
     assert abs(float(le) - d.sum() / sum(len(l) for l in labels)) < 1e-6
     assert abs(float(se) - np.count_nonzero(d) / 24.0) < 1e-6
+
+
+def test_recognize_graph_equals_eager():
+    """Model.recognize replays a CUDA graph recorded per batch shape: same strings as the eager path, for device and
+    host (pinned or pageable) uint8 batches, across shapes and repeated calls."""
+    from cnn_lstm_ctc_ocr_b200 import model
+    params = mo.init_params(seed=3, cell_type="lstm", sizes=(512, 512), num_classes=95, dtype=np.float32)
+    m = model.Model(params)
+    for (B, W) in ((4, 128), (3, 96), (4, 128)):
+        img, widths = _inputs(B, W, 7 + W)
+        widths[0] = W - 9
+        eager = m.recognize(torch.tensor(img, device="cuda:0"), torch.tensor(widths), use_graph=False)
+        assert m.recognize(torch.tensor(img, device="cuda:0"), torch.tensor(widths)) == eager
+        assert m.recognize(torch.tensor(img), torch.tensor(widths)) == eager
+        assert m.recognize(torch.tensor(img).pin_memory(), torch.tensor(widths)) == eager
+    assert len(m._graphs) == 2
