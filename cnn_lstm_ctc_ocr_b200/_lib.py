@@ -34,6 +34,7 @@ SIGNATURES = {
     "ocr_maxpool": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "ocr_birnn_workspace_bytes": (_i, [_i, _i, _i, _i, _c.POINTER(_sz)]),
     "ocr_birnn_set_path": (_i, [_i]),
+    "ocr_debug_lstm_timeline": (_i, [_vp]),
     "ocr_lstm_prepare_wh": (_i, [_vp, _i, _vp, _vp]),
     "ocr_birnn_layer": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ocr_edit_distance": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),

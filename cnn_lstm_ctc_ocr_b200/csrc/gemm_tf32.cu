@@ -156,6 +156,24 @@ int tma_map_2d(CUtensorMap* tm, const float* base, long long rows, long long K, 
 }
 }  // namespace ocr
 
+// 3-D view of a [rows, K] fp32 matrix as [K/32 chunks][rows][32 floats]: ONE request fetches `box_chunks` consecutive
+// 128-byte-swizzled k-chunk tiles of `box_rows` rows (each tile laid out exactly as tma_map_2d's boxes)
+namespace ocr {
+int tma_map_chunks(CUtensorMap* tm, const float* base, long long rows, long long K, long long ld, int box_rows, int box_chunks) {
+    EncodeTiledFn enc = get_encode();
+    if (enc == nullptr) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return OCR_ECUDA; }
+    cuuint64_t dims[3] = {(cuuint64_t)kGemmBK, (cuuint64_t)rows, (cuuint64_t)(K / kGemmBK)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)kGemmBK * 4};
+    cuuint32_t box[3] = {(cuuint32_t)kGemmBK, (cuuint32_t)box_rows, (cuuint32_t)box_chunks};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (3-D) failed (%d) rows=%lld K=%lld ld=%lld", (int)r, rows, K, ld); return OCR_ECUDA; }
+    return OCR_OK;
+}
+}  // namespace ocr
+
 template <int BN, int STAGES>
 static int launch_planned(const GemmPlan& p, cudaStream_t st)
 {

@@ -41,6 +41,9 @@ constexpr int kGemmBK = 32;  // fp32 elements = one 128-byte swizzle row
 // 2-D fp32 tensor [rows, K] row-major with row pitch ld elements; box = [box_rows, 32 floats], 128-byte swizzle
 int tma_map_2d(CUtensorMap* tm, const float* base, long long rows, long long K, long long ld, int box_rows);
 
+// 3-D view [K/32][rows][32]: one request loads box_chunks consecutive swizzled k-chunk tiles of box_rows rows
+int tma_map_chunks(CUtensorMap* tm, const float* base, long long rows, long long K, long long ld, int box_rows, int box_chunks);
+
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned g_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -66,6 +69,10 @@ __device__ __forceinline__ void g_mbar_wait(unsigned bar, unsigned parity) {
 __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* tm, int c0, int c1, unsigned bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* tm, int c0, int c1, int c2, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 // shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows of 128 bytes, 8-row atoms 1024 bytes apart
 __device__ __forceinline__ unsigned long long umma_desc_k128(unsigned smem_addr) {

@@ -31,6 +31,15 @@ __device__ __forceinline__ float tanh_fast(float x) {
 }
 __device__ __forceinline__ float sigm(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
+// Optional phase timeline for tuning (ocr_debug_lstm_timeline): CTA 0 stamps globaltimer-free clock64() values, 8 per frame:
+// [0] producer past the grid barrier, [1] last h tile requested, [2] first h tile landed (MMA lane), [3] last MMA issued,
+// [4] accumulator complete (epilogue), [5] TMEM read, [6] cell update + stores done, [7] slice published.
+__device__ long long* g_lstm_timeline = nullptr;
+__device__ __forceinline__ void lstm_mark(int s, int slot) {
+    long long* tl = g_lstm_timeline;
+    if (tl != nullptr && blockIdx.x == 0) tl[s * 8 + slot] = clock64();
+}
+
 // bounded spin on a global counter (acquire)
 __device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned target) {
     for (unsigned it = 0; it < (1u << 27); ++it) {
@@ -48,7 +57,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
                        const __grid_constant__ CUtensorMap tmH01, const __grid_constant__ CUtensorMap tmH10,
                        const __grid_constant__ CUtensorMap tmH11, const float* __restrict__ xp, const int32_t* __restrict__ seq_len,
                        float* __restrict__ hbuf /*[2 parity][2 dir][B][H]*/, float* __restrict__ out /*[T,B,2H]*/,
-                       unsigned* __restrict__ counters /*[2]*/, int T, int B, int H, int NS, int a_rows, int n_stages, int MT,
+                       unsigned* __restrict__ counters /*[2]*/, int T, int B, int H, int NS, int a_rows, int n_stages, int gc, int MT,
                        float* gates_out /*[T*B, 8H], may alias xp*/, float* __restrict__ cs_out /*[T,B,2H]*/)
 {
     constexpr int N = 4 * HS;
@@ -61,8 +70,12 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
     // rows, the rest is whatever follows in shared memory and lands in TMEM lanes no thread looks at
     const unsigned a_bytes = (unsigned)a_rows * kGemmBK * 4;
     const unsigned s_w = s_base;                                 // nk resident weight tiles
-    const unsigned s_a = s_w + (unsigned)nk * w_bytes;           // ring of kRnnStages h tiles
-    const unsigned s_bar = s_a + (unsigned)n_stages * a_bytes + kGemmBM * kGemmBK * 4;  // + one full tile of slack for the 128-row read
+    // ring of n_stages groups of gc k-chunk tiles of h; ONE 3-D TMA request per group (issuing sixteen 4 KB requests one by
+    // one cost the producer lane ~450 cycles each: measured with ocr_debug_lstm_timeline)
+    const unsigned s_a = s_w + (unsigned)nk * w_bytes;
+    const unsigned g_bytes = (unsigned)gc * a_bytes;
+    const int ng = nk / gc;                                      // groups per frame
+    const unsigned s_bar = s_a + (unsigned)n_stages * g_bytes + kGemmBM * kGemmBK * 4;  // + one full tile of slack for the 128-row read
     const unsigned bar_full = s_bar, bar_empty = s_bar + kRnnMaxStages * 8, bar_w = bar_empty + kRnnMaxStages * 8, bar_acc = bar_w + 8;
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + (s_bar - s_base) + (2 * kRnnMaxStages + 2) * 8);
 
@@ -98,12 +111,14 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
                     asm volatile("fence.proxy.async;" ::: "memory");          // generic-proxy writes -> async-proxy (TMA) reads
                 }
                 const CUtensorMap* tm = (s & 1) ? (d ? &tmH11 : &tmH10) : (d ? &tmH01 : &tmH00);
-                for (int k = 0; k < nk; ++k, ++it) {
+                lstm_mark(s, 0);
+                for (int gi = 0; gi < ng; ++gi, ++it) {
                     const int st = it % n_stages;
                     if (it >= n_stages) g_mbar_wait(bar_empty + st * 8, ((it / n_stages) - 1) & 1);
-                    g_mbar_expect_tx(bar_full + st * 8, a_bytes);
-                    tma_load_2d(s_a + st * a_bytes, tm, k * kGemmBK, m0, bar_full + st * 8);
+                    g_mbar_expect_tx(bar_full + st * 8, g_bytes);
+                    tma_load_3d(s_a + st * g_bytes, tm, 0, m0, gi * gc, bar_full + st * 8);
                 }
+                lstm_mark(s, 1);
             }
         }
     } else if (warp == 1) {
@@ -112,17 +127,22 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
             g_mbar_wait(bar_w, 0);
             int it = 0;
             for (int s = 0; s < T; ++s) {
-                for (int k = 0; k < nk; ++k, ++it) {
+                for (int gi = 0; gi < ng; ++gi, ++it) {
                     const int st = it % n_stages;
                     g_mbar_wait(bar_full + st * 8, (it / n_stages) & 1);
+                    if (gi == 0) lstm_mark(s, 2);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const unsigned long long da = umma_desc_k128(s_a + st * a_bytes), db = umma_desc_k128(s_w + k * w_bytes);
+                    for (int c = 0; c < gc; ++c) {
+                        const int k = gi * gc + c;
+                        const unsigned long long da = umma_desc_k128(s_a + st * g_bytes + c * a_bytes), db = umma_desc_k128(s_w + k * w_bytes);
 #pragma unroll
-                    for (int kk = 0; kk < kGemmBK / 8; ++kk)
-                        umma_tf32(tmem_d, da + (unsigned long long)(kk * 2), db + (unsigned long long)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+                        for (int kk = 0; kk < kGemmBK / 8; ++kk)
+                            umma_tf32(tmem_d, da + (unsigned long long)(kk * 2), db + (unsigned long long)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+                    }
                     umma_commit(bar_empty + st * 8);
                 }
                 umma_commit(bar_acc);   // gate pre-activations of frame step s are in TMEM
+                lstm_mark(s, 3);
                 // the next frame's first MMA overwrites TMEM; it cannot start before the epilogue has read this frame:
                 // its operand h_{s+1} only exists after every CTA (this one included) passed the grid barrier
             }
@@ -151,6 +171,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
                 }
             }
             g_mbar_wait(bar_acc, s & 1);
+            if (threadIdx.x == 64) lstm_mark(s, 4);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             unsigned g[N];
 #pragma unroll
@@ -164,6 +185,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
                     : "r"(taddr) : "memory");
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (threadIdx.x == 64) lstm_mark(s, 5);
             if (live_row) {
                 float* hn = hbuf + (((size_t)((s + 1) & 1) * 2 + d) * B + r) * H + j * HS;
                 if (upd) {
@@ -198,10 +220,13 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
 #pragma unroll
                 for (int u = 0; u < HS; u += 4) *reinterpret_cast<float4*>(hn + u) = make_float4(h[u], h[u + 1], h[u + 2], h[u + 3]);
             }
+            if (threadIdx.x == 64) lstm_mark(s, 6);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps: their h stores are ordered before...
-            if (warp == 2 && lane == 0)                      // ...this gpu-scope release (cumulative) that publishes the slice
+            if (warp == 2 && lane == 0) {                    // ...this gpu-scope release (cumulative) that publishes the slice
                 asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counters + d) : "memory");
+                lstm_mark(s, 7);
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -234,6 +259,11 @@ using namespace ocr;
 constexpr int kHS = 16;
 
 namespace ocr {
+
+int lstm_set_timeline(long long* buf) {
+    OCR_CHECK_CUDA(cudaMemcpyToSymbol(g_lstm_timeline, &buf, sizeof(buf)));
+    return OCR_OK;
+}
 
 bool lstm_persistent_supported(int T, int B, int H) {
     if ((H % kGemmBK) != 0 || (H % kHS) != 0 || B < 1) return false;
@@ -282,17 +312,27 @@ int lstm_persistent_run(const float* xp, const float* wh, const float* wh_perm, 
     const int a_rows = B >= kGemmBM ? kGemmBM : (B + 7) / 8 * 8;
     const size_t w_bytes = (size_t)nk * (4 * kHS) * kGemmBK * 4, a_bytes = (size_t)a_rows * kGemmBK * 4;
     const size_t fixed = w_bytes + kGemmBM * kGemmBK * 4 + 1024 + 1024;
-    int n_stages = (int)(((size_t)kMaxDynSmem - fixed) / a_bytes);
-    n_stages = n_stages > nk ? nk : n_stages;   // the whole h row block in flight when it fits
+    // h streams in groups of gc k-chunk tiles, one TMA request each: the whole row block as one group when it fits,
+    // else two ring stages of the largest group (a divisor of nk) that fits twice
+    const int fit = (int)(((size_t)kMaxDynSmem - fixed) / a_bytes);     // chunk tiles that fit beside the weights
+    int gc = nk, n_stages = 1;
+    if (fit < nk) {
+        gc = 1;
+        for (int c = 1; c <= nk; ++c)
+            if (nk % c == 0 && 2 * c <= fit) gc = c;
+        n_stages = fit / gc;
+        if (n_stages > nk / gc) n_stages = nk / gc;
+        if (n_stages > kRnnMaxStages) n_stages = kRnnMaxStages;
+    }
     CUtensorMap tmW, tmH[2][2];
     int rc = tma_map_2d(&tmW, whp, (long long)8 * H, H, H, 4 * kHS);
     if (rc != OCR_OK) return rc;
     for (int p = 0; p < 2; ++p)
         for (int d = 0; d < 2; ++d) {
-            rc = tma_map_2d(&tmH[p][d], hbuf + ((size_t)p * 2 + d) * B * H, B, H, H, a_rows);
+            rc = tma_map_chunks(&tmH[p][d], hbuf + ((size_t)p * 2 + d) * B * H, B, H, H, a_rows, gc);
             if (rc != OCR_OK) return rc;
         }
-    const size_t smem = fixed + (size_t)n_stages * a_bytes;
+    const size_t smem = fixed + (size_t)n_stages * gc * a_bytes;
     static int configured = -1;
     int dev = 0;
     OCR_CHECK_CUDA(cudaGetDevice(&dev));
@@ -313,10 +353,10 @@ int lstm_persistent_run(const float* xp, const float* wh, const float* wh_perm, 
     cfg.numAttrs = 1;
     if (train)
         OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_persistent_kernel<kHS, true>, tmW, tmH[0][0], tmH[0][1], tmH[1][0], tmH[1][1], xp, seq_len, hbuf,
-                                          out, counters, T, B, H, NS, a_rows, n_stages, MT, gates_out, cs_out));
+                                          out, counters, T, B, H, NS, a_rows, n_stages, gc, MT, gates_out, cs_out));
     else
         OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_persistent_kernel<kHS, false>, tmW, tmH[0][0], tmH[0][1], tmH[1][0], tmH[1][1], xp, seq_len, hbuf,
-                                          out, counters, T, B, H, NS, a_rows, n_stages, MT, (float*)nullptr, (float*)nullptr));
+                                          out, counters, T, B, H, NS, a_rows, n_stages, gc, MT, (float*)nullptr, (float*)nullptr));
     count_launch();
     return OCR_OK;
 }

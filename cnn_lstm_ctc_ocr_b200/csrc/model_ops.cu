@@ -179,6 +179,8 @@ int lstm_permute_wh(const float* wh, int H, float* whp, cudaStream_t st);
 int lstm_persistent_run(const float* xp, const float* wh, const float* wh_perm, const int32_t* seq_len, int T, int B, int H,
                         float* out, float* ws, cudaStream_t st, float* gates_out = nullptr, float* cs_out = nullptr);
 
+int lstm_set_timeline(long long* buf);
+
 static inline int grid_for(long long total, int threads = 256) {
     long long g = (total + threads - 1) / threads;
     const long long cap = 148LL * 16;
@@ -234,6 +236,9 @@ extern "C" int ocr_birnn_set_path(int path) {
     g_birnn_path = path;
     return OCR_OK;
 }
+
+// Tuning aid: per-frame clock64() stamps of CTA 0 of the persistent LSTM kernel (8 int64 per frame; NULL = off).
+extern "C" int ocr_debug_lstm_timeline(long long* device_buffer) { return lstm_set_timeline(device_buffer); }
 
 extern "C" int ocr_birnn_workspace_bytes(int cell, int T, int B, int H, size_t* bytes)
 {

@@ -154,6 +154,10 @@ int ocr_lstm_prepare_wh(const float* wh, int H, float* wh_perm, ocr_stream_t str
 /* Kernel-path override for tests: 0 = automatic (LSTM layers with B <= 128, H <= 512 run as ONE persistent
  * tcgen05 kernel for all frames), 1 = one recurrent GEMM + one cell kernel per frame. */
 int ocr_birnn_set_path(int path);
+/* Tuning aid: per-frame clock64() stamps of CTA 0 of the persistent LSTM kernel (8 int64 per frame: producer past the grid
+ * barrier, last h tile requested, first tile landed, last MMA issued, accumulator complete, TMEM read, cell update + stores
+ * done, slice published); NULL switches it off.  Not part of the product path. */
+int ocr_debug_lstm_timeline(long long* device_buffer);
 int ocr_birnn_layer(int cell, const float* x, int T, int B, int I, int H, const int32_t* seq_len, const float* wx,
                     const float* wh, const float* wh2, const float* bias, float* out, void* workspace,
                     size_t workspace_bytes, ocr_stream_t stream);
