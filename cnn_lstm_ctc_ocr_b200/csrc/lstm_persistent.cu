@@ -75,7 +75,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
     const unsigned s_a = s_w + (unsigned)nk * w_bytes;
     const unsigned g_bytes = (unsigned)gc * a_bytes;
     const int ng = nk / gc;                                      // groups per frame
-    const unsigned s_bar = s_a + (unsigned)n_stages * g_bytes + kGemmBM * kGemmBK * 4;  // + one full tile of slack for the 128-row read
+    const unsigned s_bar = s_a + (unsigned)n_stages * g_bytes + (a_rows < kGemmBM ? kGemmBM * kGemmBK * 4 : 0);  // + one tile of slack for the 128-row read of a short tile
     const unsigned bar_full = s_bar, bar_empty = s_bar + kRnnMaxStages * 8, bar_w = bar_empty + kRnnMaxStages * 8, bar_acc = bar_w + 8;
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + (s_bar - s_base) + (2 * kRnnMaxStages + 2) * 8);
 
@@ -311,7 +311,7 @@ int lstm_persistent_run(const float* xp, const float* wh, const float* wh_perm, 
     const int nk = H / kGemmBK;
     const int a_rows = B >= kGemmBM ? kGemmBM : (B + 7) / 8 * 8;
     const size_t w_bytes = (size_t)nk * (4 * kHS) * kGemmBK * 4, a_bytes = (size_t)a_rows * kGemmBK * 4;
-    const size_t fixed = w_bytes + kGemmBM * kGemmBK * 4 + 1024 + 1024;
+    const size_t fixed = w_bytes + (a_rows < kGemmBM ? kGemmBM * kGemmBK * 4 : 0) + 1024 + 1024;
     // h streams in groups of gc k-chunk tiles, one TMA request each: the whole row block as one group when it fits,
     // else two ring stages of the largest group (a divisor of nk) that fits twice
     const int fit = (int)(((size_t)kMaxDynSmem - fixed) / a_bytes);     // chunk tiles that fit beside the weights
