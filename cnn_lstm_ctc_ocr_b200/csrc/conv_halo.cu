@@ -1,0 +1,224 @@
+// 3x3 'same' convolution for the wide, shallow layers (conv2..conv4 of /root/reference/src/weinman/model.py:47-54,84-109 and
+// their input gradients): implicit GEMM on tcgen05 with NO gather at all.
+//
+// conv_igemm.cu builds every tap's patch tile with per-pixel cp.async copies: each input element crosses L2 -> SM nine
+// times, and for C = 32 / 64 channels that traffic, not the tensor pipe, is the limit (ncu: L2 66 %, tensor pipe 5 % on
+// conv2).  Here a CTA owns a 16 x 8 patch of output pixels and TMA loads the 18 x 16-pixel input halo of each 32-channel
+// chunk ONCE (4-D tensor map over NHWC, out-of-image pixels zero-filled = the 'same' padding) as a 128B-swizzled tile with
+// one 128-byte row per pixel.  Row group ty of the A operand of tap (dy, dx) -- the 8 pixels (y0+ty+dy-1, x0+dx-1 .. +7) --
+// is 8 consecutive rows of that tile, and consecutive groups are one halo row (16 pixels = 2048 bytes) apart: every tap's
+// patch matrix IS a view of the halo tile, described to the MMA by a shared-memory descriptor with stride-byte-offset
+// 2048 whose start address sits dx rows into a 1024-byte swizzle atom.  (Measured: the MMA un-swizzles by the ABSOLUTE
+// shared-memory address bits [7:9], exactly as TMA swizzled on the way in, so the view needs matrix-base-offset 0; a
+// base offset of dx is subtracted from those bits and scrambles the 16-byte channel groups.)  Nine taps x C/32 chunks x 4
+// MMAs read the same staged bytes; nothing is copied, no thread touches the input.
+//   warp 0 / one lane : TMA: halo tiles (once), then the filter tiles of each k-step (tap-major, chunk inner: the same
+//                       k order as conv_igemm.cu, so both kernels produce bit-identical sums) through a small ring
+//   warp 1 / one lane : tcgen05.mma.kind::tf32, accumulator in TMEM
+//   warps 2..5        : epilogue, TMEM lane m = ty*8 + tx -> out[b, y0+ty, x0+tx, :] (+ bias, ReLU)
+#include "gemm_tf32.cuh"
+
+namespace ocr {
+
+constexpr int kHaloTY = 16, kHaloTX = 8;                       // output patch
+constexpr int kHaloRows = kHaloTY + 2, kHaloCols = 16;         // staged pixels: 18 rows x 16 columns (10 used)
+constexpr int kHaloBytes = kHaloRows * kHaloCols * 128;        // per 32-channel chunk: 36 KB
+constexpr int kHaloThreads = 192;
+
+__device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// K-major, 128-byte swizzle, 8-row groups `sbo` bytes apart; base_off = matrix-base-offset field (0 for TMA-written tiles)
+__device__ __forceinline__ unsigned long long umma_desc_view(unsigned smem_addr, unsigned sbo, unsigned base_off) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((smem_addr >> 4) & 0x3FFF);
+    d |= (unsigned long long)1 << 16;
+    d |= (unsigned long long)(sbo >> 4) << 32;
+    d |= (unsigned long long)1 << 46;
+    d |= (unsigned long long)(base_off & 7) << 49;
+    d |= (unsigned long long)2 << 61;
+    return d;
+}
+
+template <int BN, int WSTAGES>
+__global__ void __launch_bounds__(kHaloThreads)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW, int B, int H, int W, int C,
+                    const float* __restrict__ bias, float* __restrict__ out, int Cout, int relu, int tiles_x, int tiles_y)
+{
+    constexpr int kWB = BN * kGemmBK * 4;                       // one filter tile
+    extern __shared__ unsigned char halo_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(halo_smem_raw) + 1023) & ~(uintptr_t)1023);
+    const unsigned s_base = g_smem_u32(smem);
+    const int cpt = C / kGemmBK;                                // channel chunks
+    const unsigned s_halo = s_base;                             // cpt halo tiles
+    const unsigned s_w = s_halo + (unsigned)cpt * kHaloBytes;   // filter ring
+    const unsigned s_bar = s_w + WSTAGES * kWB;
+    const unsigned bar_full = s_bar, bar_empty = s_bar + WSTAGES * 8, bar_halo = bar_empty + WSTAGES * 8, bar_acc = bar_halo + 8;
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + (s_bar - s_base) + (2 * WSTAGES + 2) * 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int tile = blockIdx.x;
+    const int tx_i = tile % tiles_x; tile /= tiles_x;
+    const int ty_i = tile % tiles_y;
+    const int b = tile / tiles_y;
+    const int x0 = tx_i * kHaloTX, y0 = ty_i * kHaloTY;
+    const int n0 = blockIdx.y * BN;
+    const int nk = 9 * cpt;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < WSTAGES; ++s) { g_mbar_init(bar_full + s * 8, 1); g_mbar_init(bar_empty + s * 8, 1); }
+        g_mbar_init(bar_halo, 1);
+        g_mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)), "r"((unsigned)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_d = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // halo of every channel chunk: box {32 ch, 16 x, 18 y, 1 image} at (c, x0-1, y0-1, b); outside the image -> 0
+            g_mbar_expect_tx(bar_halo, (unsigned)cpt * kHaloBytes);
+            for (int c = 0; c < cpt; ++c) tma_load_4d(s_halo + c * kHaloBytes, &tmIn, c * kGemmBK, x0 - 1, y0 - 1, b, bar_halo);
+            for (int k = 0; k < nk; ++k) {
+                const int s = k % WSTAGES;
+                if (k >= WSTAGES) g_mbar_wait(bar_empty + s * 8, ((k / WSTAGES) - 1) & 1);
+                g_mbar_expect_tx(bar_full + s * 8, (unsigned)kWB);
+                tma_load_2d(s_w + s * kWB, &tmW, k * kGemmBK, n0, bar_full + s * 8);     // filter columns (tap, chunk) = k-step k
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(kGemmBM >> 4) << 24);
+            g_mbar_wait(bar_halo, 0);
+            for (int k = 0; k < nk; ++k) {
+                const int s = k % WSTAGES;
+                g_mbar_wait(bar_full + s * 8, (k / WSTAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int tap = k / cpt, c = k - tap * cpt;
+                const int dy = tap / 3, dx = tap % 3;                       // halo row / column of the patch's first pixel
+                const unsigned a_addr = s_halo + c * kHaloBytes + (unsigned)(dy * kHaloCols + dx) * 128u;
+                const unsigned long long da = umma_desc_view(a_addr, kHaloCols * 128u, 0u);
+                const unsigned long long db = umma_desc_k128(s_w + s * kWB);
+#pragma unroll
+                for (int kk = 0; kk < kGemmBK / 8; ++kk)
+                    umma_tf32(tmem_d, da + (unsigned long long)(kk * 2), db + (unsigned long long)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+                umma_commit(bar_empty + s * 8);
+            }
+            umma_commit(bar_acc);
+        }
+    } else {
+        const int q = warp & 3;
+        const int m = q * 32 + lane;                    // TMEM lane = patch pixel ty*8 + tx
+        const int y = y0 + (m >> 3), x = x0 + (m & 7);
+        const bool live = y < H && x < W;
+        g_mbar_wait(bar_acc, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float* drow = out + (((size_t)b * H + y) * W + x) * Cout + n0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            unsigned r[32];
+            const unsigned taddr = tmem_d + ((unsigned)(q * 32) << 16) + (unsigned)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (n0 + c0 + j < Cout) {            // Cout % 4 == 0
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
+                        float4 v = make_float4(__uint_as_float(r[j]) + bb.x, __uint_as_float(r[j + 1]) + bb.y,
+                                               __uint_as_float(r[j + 2]) + bb.z, __uint_as_float(r[j + 3]) + bb.w);
+                        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        *reinterpret_cast<float4*>(drow + c0 + j) = v;
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((unsigned)BN) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn4)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// NHWC activation as a 4-D tensor {C, W, H, B}; box {32 channels, 16 x, 18 y, 1}, 128-byte swizzle, zero fill outside
+static int tma_map_nhwc_halo(CUtensorMap* tm, const float* base, int B, int H, int W, int C) {
+    static EncodeTiledFn4 enc = nullptr;
+    if (enc == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            enc = reinterpret_cast<EncodeTiledFn4>(p);
+    }
+    if (enc == nullptr) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return OCR_ECUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    cuuint32_t box[4] = {(cuuint32_t)kGemmBK, (cuuint32_t)kHaloCols, (cuuint32_t)kHaloRows, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (NHWC halo) failed (%d) B=%d H=%d W=%d C=%d", (int)r, B, H, W, C); return OCR_ECUDA; }
+    return OCR_OK;
+}
+
+template <int BN, int WSTAGES>
+static int launch_halo(const float* in, int B, int H, int W, int C, const float* w, const float* bias, int Cout, int relu, float* out,
+                       cudaStream_t st)
+{
+    CUtensorMap tmIn, tmW;
+    int rc = tma_map_nhwc_halo(&tmIn, in, B, H, W, C);
+    if (rc != OCR_OK) return rc;
+    rc = tma_map_2d(&tmW, w, Cout, 9 * C, 9 * C, BN);
+    if (rc != OCR_OK) return rc;
+    const int cpt = C / kGemmBK;
+    const size_t smem = (size_t)cpt * kHaloBytes + (size_t)WSTAGES * BN * kGemmBK * 4 + (2 * WSTAGES + 2) * 8 + 16 + 1024;
+    static int configured = -1;
+    int dev = 0;
+    OCR_CHECK_CUDA(cudaGetDevice(&dev));
+    if (configured != dev) {
+        OCR_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<BN, WSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        configured = dev;
+    }
+    const int tiles_x = (W + kHaloTX - 1) / kHaloTX, tiles_y = (H + kHaloTY - 1) / kHaloTY;
+    dim3 grid((unsigned)((long long)tiles_x * tiles_y * B), (unsigned)((Cout + BN - 1) / BN));
+    conv3x3_halo_kernel<BN, WSTAGES><<<grid, kHaloThreads, smem, st>>>(tmIn, tmW, B, H, W, C, bias, out, Cout, relu, tiles_x, tiles_y);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+// Is the halo kernel the better choice for this layer?  Shallow inputs (the gather of conv_igemm.cu is L2-bound), enough rows
+// to fill the 16-row patch, channel counts whose halo tiles fit beside two more CTAs.
+bool conv_halo_supported(int B, int H, int W, int C, int Cout) {
+    if (C != 32 && C != 64) return false;
+    if ((Cout % 4) != 0 || H < 12 || W < 8) return false;
+    const long long tiles = (long long)((W + kHaloTX - 1) / kHaloTX) * ((H + kHaloTY - 1) / kHaloTY) * B;
+    return tiles < 0x7fffffffLL;
+}
+
+int conv_halo_run(const float* in, int B, int H, int W, int C, const float* w, const float* bias, int Cout, int relu, float* out, cudaStream_t st) {
+    if (Cout <= 32) return launch_halo<32, 4>(in, B, H, W, C, w, bias, Cout, relu, out, st);
+    return launch_halo<64, 4>(in, B, H, W, C, w, bias, Cout, relu, out, st);
+}
+
+}  // namespace ocr

@@ -183,6 +183,18 @@ static int launch_conv(const float* in, int B, int H, int W, int C, const float*
     return OCR_OK;
 }
 
+namespace ocr {   // conv_halo.cu
+bool conv_halo_supported(int B, int H, int W, int C, int Cout);
+int conv_halo_run(const float* in, int B, int H, int W, int C, const float* w, const float* bias, int Cout, int relu, float* out, cudaStream_t st);
+}
+// 0 = automatic (halo-tile kernel for the wide shallow layers, gather kernel otherwise), 1 = gather kernel only, 2 = halo kernel only
+static int g_conv_path = 0;
+extern "C" int ocr_conv_set_path(int path) {
+    OCR_CHECK_ARG(path >= 0 && path <= 2, "ocr_conv_set_path: path=%d outside [0,2]", path);
+    g_conv_path = path;
+    return OCR_OK;
+}
+
 extern "C" int ocr_conv3x3_same(const float* in, int B, int H, int W, int C, const float* w, const float* bias, int Cout, int relu,
                                 float* out, ocr_stream_t stream)
 {
@@ -192,6 +204,8 @@ extern "C" int ocr_conv3x3_same(const float* in, int B, int H, int W, int C, con
     OCR_CHECK_ARG(((uintptr_t)in % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)out % 16) == 0, "ocr_conv3x3_same: pointers must be 16-byte aligned");
     OCR_CHECK_ARG((long long)B * H * W < 0x7fffffffLL, "ocr_conv3x3_same: too many output pixels");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (g_conv_path != 1 && conv_halo_supported(B, H, W, C, Cout)) return conv_halo_run(in, B, H, W, C, w, bias, Cout, relu, out, st);
+    OCR_CHECK_ARG(g_conv_path != 2, "ocr_conv3x3_same: the halo-tile kernel does not take this shape (B=%d H=%d W=%d C=%d Cout=%d)", B, H, W, C, Cout);
     const long long mt = ((long long)B * H * W + kGemmBM - 1) / kGemmBM;
     int bn = 32;
     if (Cout > 32) bn = 64;

@@ -149,6 +149,10 @@ int ocr_conv3x3_same(const float* in, int B, int H, int W, int C, const float* w
                      float* out, ocr_stream_t stream);
 int ocr_maxpool(const float* in, int B, int H, int W, int C, int pool_h, int pool_w, int stride_h, int stride_w, float* out,
                 ocr_stream_t stream);
+/* Kernel-path override of ocr_conv3x3_same for tests: 0 = automatic (the wide shallow layers, C = 32 / 64 and H >= 12, run a
+ * kernel that TMA-loads the input halo of a 16x8 pixel patch once and feeds all nine taps from it as shifted views; other
+ * shapes gather each tap's patch rows with cp.async), 1 = gather kernel only, 2 = halo kernel only.  Same sums, bit for bit. */
+int ocr_conv_set_path(int path);
 int ocr_birnn_workspace_bytes(int cell, int T, int B, int H, size_t* bytes);
 int ocr_lstm_prepare_wh(const float* wh, int H, float* wh_perm, ocr_stream_t stream);
 /* Kernel-path override for tests: 0 = automatic (LSTM layers with B <= 128, H <= 512 run as ONE persistent

@@ -138,3 +138,32 @@ def test_recognize_graph_equals_eager():
         assert m.recognize(torch.tensor(img), torch.tensor(widths)) == eager
         assert m.recognize(torch.tensor(img).pin_memory(), torch.tensor(widths)) == eager
     assert len(m._graphs) == 2
+
+
+@pytest.mark.parametrize("B,H,W,C,Co,relu", [(2, 30, 37, 32, 32, 1), (3, 15, 21, 32, 64, 0), (2, 15, 40, 64, 64, 1), (1, 12, 8, 64, 32, 0),
+                                              (2, 30, 254, 32, 32, 1)])
+def test_conv_halo_kernel_equals_gather_kernel(B, H, W, C, Co, relu):
+    """The halo-tile convolution (TMA-loaded input halo, nine taps as shifted descriptor views) and the gather kernel run the
+    same MMAs in the same k order: identical bits, and both within TF32 tolerance of a float64 convolution."""
+    import torch.nn.functional as F
+    from cnn_lstm_ctc_ocr_b200 import _lib as L
+    lib = L.load()
+    rng = np.random.default_rng(B * 1000 + W)
+    x = rng.standard_normal((B, H, W, C)).astype(np.float32)
+    w = (rng.standard_normal((3, 3, C, Co)) * 0.1).astype(np.float32)
+    bias = rng.standard_normal(Co).astype(np.float32)
+    dx, dbias = torch.tensor(x, device="cuda:0"), torch.tensor(bias, device="cuda:0")
+    dw = torch.tensor(np.ascontiguousarray(w.reshape(9 * C, Co).T), device="cuda:0")     # [Co, 9C] K-major
+    outs = []
+    for path in (1, 2):
+        L.check(lib.ocr_conv_set_path(path), "path")
+        out = torch.full((B, H, W, Co), 7.0, device="cuda:0")
+        L.check(lib.ocr_conv3x3_same(L.ptr(dx), B, H, W, C, L.ptr(dw), L.ptr(dbias), Co, relu, L.ptr(out), L.stream_handle()), "conv")
+        outs.append(out.cpu().numpy())
+    L.check(lib.ocr_conv_set_path(0), "path")
+    ref = F.conv2d(torch.tensor(x, dtype=torch.float64).permute(0, 3, 1, 2), torch.tensor(w, dtype=torch.float64).permute(3, 2, 0, 1),
+                   torch.tensor(bias, dtype=torch.float64), padding=1).permute(0, 2, 3, 1).numpy()
+    if relu:
+        ref = np.maximum(ref, 0)
+    assert np.abs(outs[1] - ref).max() <= 3e-3 * np.abs(ref).max()
+    assert (outs[0] == outs[1]).all()
