@@ -278,7 +278,7 @@ static size_t ctc_ws_floats_per_seq(int T, int Lmax) {
 // path selection: 0 auto, 1 general kernel only, 2 fast kernel with LSU loads/stores (no TMA bulk copies)
 static int g_ctc_path = 0;
 extern "C" int ocr_ctc_loss_set_path(int path) {
-    OCR_CHECK_ARG(path >= 0 && path <= 3, "ocr_ctc_loss_set_path: path=%d outside [0,3]", path);
+    OCR_CHECK_ARG(path >= 0 && path <= 6, "ocr_ctc_loss_set_path: path=%d outside [0,4]", path);
     g_ctc_path = path;
     return OCR_OK;
 }
@@ -312,7 +312,7 @@ static bool plan_fast(const void* logits, const void* grad, int T, int B, int C,
     for (int G = 1; G <= maxG; G *= 2) {
         if (g_ctc_group != 0 && G != g_ctc_group) continue;
         const FastLayout lay = fast_layout(T, C, Lmax, G);
-        if (lay.total > kMaxDynSmem) break;
+        if (lay.total + 128 > kMaxDynSmem) break;
         const int bulk = ptr_ok && (G * C) % 4 == 0;
         int per_sm = (227 * 1024) / (lay.total + 1024);
         per_sm = per_sm < 1 ? 1 : per_sm;
@@ -344,11 +344,43 @@ extern "C" int ocr_ctc_loss_workspace_bytes(int T, int B, int C, int max_label_l
     return OCR_OK;
 }
 
+// [T, B*C] fp32 tensor, box {G*C floats, 16 frames}, no swizzle: the staging layout of the fast kernel when its row pitch
+// is dense (RS == G*C)
+static int ctc_tensor_map(CUtensorMap* tm, const float* base, int T, int B, int C, int G) {
+    typedef CUresult (*Enc)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                            const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static Enc enc = nullptr;
+    if (enc == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            enc = reinterpret_cast<Enc>(p);
+    }
+    if (enc == nullptr) return OCR_ECUDA;
+    cuuint64_t dims[2] = {(cuuint64_t)B * C, (cuuint64_t)T};
+    cuuint64_t strides[1] = {(cuuint64_t)B * C * 4};
+    cuuint32_t box[2] = {(cuuint32_t)(G * C), (cuuint32_t)kTmRows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? OCR_OK : OCR_ECUDA;
+}
+
 template <int NP, int CR>
 static int launch_fast(const FastPlan& fp, const float* logits, int T, int B, int C, const int32_t* labels,
                        const int32_t* label_offsets, const int32_t* seq_len, int Lmax, float* loss, float* grad,
                        int32_t* status, float grad_scale, cudaStream_t st)
 {
+    // tensor-map transfers (one request per 16 frames) when the staging rows are dense, a box fits the TMA limits and
+    // whole boxes stay inside the tensor (T a multiple of 16: a partial last box would be clipped and deliver fewer bytes)
+    CUtensorMap tmIn, tmOut;
+    memset(&tmIn, 0, sizeof(tmIn));
+    memset(&tmOut, 0, sizeof(tmOut));
+    int bulk = fp.bulk;
+    const FastLayout lay = fast_layout(T, C, Lmax, fp.G);
+    if (bulk && g_ctc_path != 4 && lay.RS == fp.G * C && fp.G * C <= 256 && (T % kTmRows) == 0 && (B % fp.G) == 0 && grad != nullptr &&
+        ctc_tensor_map(&tmIn, logits, T, B, C, fp.G) == OCR_OK && ctc_tensor_map(&tmOut, grad, T, B, C, fp.G) == OCR_OK)
+        bulk = (g_ctc_path == 5 || g_ctc_path == 6) ? g_ctc_path : 2;
     static int configured = -1;
     int dev = 0;
     OCR_CHECK_CUDA(cudaGetDevice(&dev));
@@ -357,8 +389,8 @@ static int launch_fast(const FastPlan& fp, const float* logits, int T, int B, in
         configured = dev;
     }
     const int grid = (B + fp.G - 1) / fp.G;
-    ctc_loss_fast_kernel<NP, CR><<<grid, 64 * fp.G, fp.smem, st>>>(logits, T, B, C, labels, label_offsets, seq_len, Lmax, fp.G,
-                                                             fp.bulk, loss, grad, status, grad_scale);
+    ctc_loss_fast_kernel<NP, CR><<<grid, 64 * fp.G, fp.smem + 128, st>>>(logits, T, B, C, labels, label_offsets, seq_len, Lmax, fp.G,
+                                                             bulk, loss, grad, status, grad_scale, tmIn, tmOut);
     OCR_CHECK_LAUNCH();
     return OCR_OK;
 }

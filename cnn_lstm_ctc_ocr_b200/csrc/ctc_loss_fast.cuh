@@ -33,6 +33,7 @@
 // Numerics: float32; loss rel. error ~1e-6, gradient abs. error ~1e-6 against the float64
 // recursion (an order of magnitude tighter than the float32 log-domain recursion TF itself runs).
 #pragma once
+#include <cuda.h>
 #include <type_traits>
 
 #include "common.cuh"
@@ -71,7 +72,7 @@ __host__ __device__ inline FastLayout fast_layout(int T, int C, int Lmax, int G)
     f.HI = 2 * Lmax + 2;
     f.EX = 2 * Lmax + 4;
     f.lat_seq = T * f.LS;
-    int o = f.RS * 4;  // one pad row: the beta chain prefetches e_{t-1} unconditionally
+    int o = (f.RS * 4 + 127) & ~127;  // one pad row (the beta chain prefetches e_{t-1} unconditionally), staging block 128-byte aligned
     f.stage = o; o += T * f.RS * 4;
     f.lat = o;   o += (G * f.lat_seq + f.LS) * 4;  // + one row: the alpha warp's look-ahead read past the last frame
     f.lab = o;   o += G * (Lmax + 1) * 4;
@@ -106,6 +107,15 @@ __device__ __forceinline__ void bulk_load(unsigned dst, const void* src, unsigne
 }
 __device__ __forceinline__ void bulk_store(void* dst, unsigned src, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+// tensor-map forms (one request per kTmRows frames instead of one per frame)
+constexpr int kTmRows = 16;
+__device__ __forceinline__ void tm_load_2d(unsigned dst, const CUtensorMap* tm, int c0, int c1, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tm_store_2d(const CUtensorMap* tm, int c0, int c1, unsigned src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ float fast_ex2(float x) {
     float y;
@@ -231,10 +241,11 @@ __global__ void __launch_bounds__(CR > 64 ? 64 * 4 : 64 * kFastMaxG)
 ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, const int32_t* __restrict__ labels,
                      const int32_t* __restrict__ label_offsets, const int32_t* __restrict__ seq_len, int Lmax, int G,
                      int use_bulk, float* __restrict__ loss, float* __restrict__ grad, int32_t* __restrict__ status,
-                     float grad_scale)
+                     float grad_scale, const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut)
 {
     extern __shared__ __align__(128) unsigned char smem_f[];
-    unsigned char* smem = smem_f;
+    // tensor-map TMA wants 128-byte aligned shared-memory boxes: align by hand (the launch adds 128 bytes)
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_f) + 127) & ~(uintptr_t)127);
     const FastLayout lay = fast_layout(T, C, Lmax, G);
     float* stage = reinterpret_cast<float*>(smem + lay.stage);
     float* s_info = reinterpret_cast<float*>(smem + lay.info);
@@ -269,13 +280,24 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
             if (lane == 0) {
                 mbar_init(bar, 1);
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-                if (tm > 0) mbar_expect_tx(bar, row_bytes * (unsigned)tm);
+                // tensor-map requests deliver whole boxes of kTmRows frames: expect the rows of the last box past tm too
+                const bool tmap = use_bulk == 2 || use_bulk == 5;
+                if (tm > 0) mbar_expect_tx(bar, row_bytes * (unsigned)(tmap ? (tm + kTmRows - 1) / kTmRows * kTmRows : tm));
             }
             __syncwarp();
             const float* src = logits + (size_t)b0 * C;
             const unsigned dst = smem_u32(stage);
-            for (int t = lane; t < tm; t += 32)
-                bulk_load(dst + (unsigned)t * RS * 4, src + (size_t)t * B * C, row_bytes, bar);
+            if (use_bulk == 2 || use_bulk == 5) {
+                // use_bulk 2: the logits as a 2-D tensor [T, B*C]; one request per 16 frames (box G*C floats x 16 rows lands
+                // in the dense [T][G*C] staging layout).
+                if (lane == 0 && tm > 0) {
+                    const int nreq = (tm + kTmRows - 1) / kTmRows;
+                    for (int q = 0; q < nreq; ++q) tm_load_2d(dst + (unsigned)(q * kTmRows) * RS * 4, &tmIn, b0 * C, q * kTmRows, bar);
+                }
+            } else {
+                for (int t = lane; t < tm; t += 32)
+                    bulk_load(dst + (unsigned)t * RS * 4, src + (size_t)t * B * C, row_bytes, bar);
+            }
         }
     }
 
@@ -731,7 +753,12 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
             const unsigned row_bytes = (unsigned)(G * C * 4);
             float* dst = grad + (size_t)b0 * C;
             const unsigned src = smem_u32(stage);
-            for (int t = lane; t < T; t += 32) bulk_store(dst + (size_t)t * B * C, src + (unsigned)t * RS * 4, row_bytes);
+            if (use_bulk == 2 || use_bulk == 6) {
+                if (lane == 0)
+                    for (int q = 0; q * kTmRows < T; ++q) tm_store_2d(&tmOut, b0 * C, q * kTmRows, src + (unsigned)(q * kTmRows) * RS * 4);
+            } else {
+                for (int t = lane; t < T; t += 32) bulk_store(dst + (size_t)t * B * C, src + (unsigned)t * RS * 4, row_bytes);
+            }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }

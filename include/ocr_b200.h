@@ -63,7 +63,8 @@ int ocr_ctc_loss(const float* logits, int T, int B, int C, const int32_t* labels
                  ocr_stream_t stream);
 /* Kernel-path override for tests and profiling: 0 = automatic (default), 1 = general kernel only
  * (one CTA per sequence, log-domain lattice), 2 = fast kernel with LSU loads/stores instead of TMA
- * bulk copies, 3 = fast kernel only (sequences it flags for the exact kernel keep status 100; diagnostics).
+ * bulk copies, 3 = fast kernel only (sequences it flags for the exact kernel keep status 100; diagnostics), 4 = fast kernel
+ * with one TMA bulk copy per frame instead of one tensor-map request per 16 frames.
  * The automatic choice uses the fast kernel whenever its staging block fits in
  * shared memory and falls back to the general kernel for very long sequences. */
 int ocr_ctc_loss_set_path(int path);
