@@ -232,7 +232,7 @@ extern "C" int ocr_rows_max_to_seq(const float* in, int B, int H, int W, int C, 
 // 0 = automatic (persistent LSTM kernel when the shape allows), 1 = frame-by-frame launches only
 namespace ocr { int g_birnn_path = 0; }
 extern "C" int ocr_birnn_set_path(int path) {
-    OCR_CHECK_ARG(path == 0 || path == 1, "ocr_birnn_set_path: path=%d outside [0,1]", path);
+    OCR_CHECK_ARG(path >= 0 && path <= 3, "ocr_birnn_set_path: path=%d outside [0,3]", path);
     g_birnn_path = path;
     return OCR_OK;
 }

@@ -893,6 +893,11 @@ size_t lstm_persistent_workspace_floats(int B, int H);
 int lstm_persistent_run(const float* xp, const float* wh, const float* wh_perm, const int32_t* seq_len, int T, int B, int H,
                         float* out, float* ws, cudaStream_t st, float* gates_out, float* cs_out);
 extern int g_birnn_path;
+// lstm_bptt_persistent.cu
+bool lstm_bptt_supported(int T, int B, int H);
+size_t lstm_bptt_workspace_floats(int B, int H);
+int lstm_bptt_run(const float* dout, int T, int B, int H, const int32_t* seq_len, float* act, const float* cstate, const float* wh_rows,
+                  float* ws, cudaStream_t st);
 }
 
 // tile width of the per-frame recurrent products: enough CTAs for the 148 SMs, as wide as that allows
@@ -913,6 +918,7 @@ extern "C" int ocr_birnn_lstm_train_workspace_bytes(int T, int B, int H, size_t*
     // gh [2B, 8H] (backward: split-K partials of dh_rec, at most 8 x [2B, H]) + h, c, dh, dc [2B,H] + dgs [2B,4H]
     size_t fl = (size_t)2 * B * 8 * H + (size_t)2 * B * H * 4 + (size_t)2 * B * 4 * H;
     if (T >= 1 && B >= 1 && lstm_persistent_supported(T, B, H) && lstm_persistent_workspace_floats(B, H) > fl) fl = lstm_persistent_workspace_floats(B, H);
+    if (T >= 1 && B >= 1 && lstm_bptt_supported(T, B, H) && lstm_bptt_workspace_floats(B, H) > fl) fl = lstm_bptt_workspace_floats(B, H);
     *bytes = sizeof(float) * fl + 256;
     return OCR_OK;
 }
@@ -933,7 +939,7 @@ extern "C" int ocr_birnn_lstm_train_fwd(const float* x, int T, int B, int I, int
     float* c = h + (size_t)2 * B * H;
     int rc = ocr_gemm_tf32(x, I, wx, I, bias, gates, 8 * H, T * B, 8 * H, I, 0, stream);
     if (rc != OCR_OK) return rc;
-    if (g_birnn_path == 0 && lstm_persistent_supported(T, B, H)) {
+    if ((g_birnn_path == 0 || g_birnn_path == 2) && lstm_persistent_supported(T, B, H)) {
         // all T frames of both directions in ONE cooperative launch, W_h resident in shared memory (lstm_persistent.cu)
         OCR_CHECK_CUDA(cudaMemsetAsync(cstate, 0, sizeof(float) * (size_t)T * B * 2 * H, st));
         return lstm_persistent_run(gates, wh, nullptr, seq_len, T, B, H, out, ws, st, gates, cstate);
@@ -974,6 +980,10 @@ extern "C" int ocr_birnn_lstm_bwd(const float* dout, int T, int B, int H, const 
     OCR_CHECK_CUDA(cudaMemsetAsync(dh, 0, sizeof(float) * (size_t)2 * B * H * 2, st));
     zero_past_len_kernel<<<grid_cap((long long)T * B * 2 * H), 256, 0, st>>>(gates, seq_len, T, B, 2 * H);
     OCR_CHECK_LAUNCH();
+    // all frames in one cooperative launch, W_h slices resident on chip.  Its partial-sum exchange grows with the batch
+    // (512 KB per CTA per frame at 128 rows): measured faster than the per-frame launches up to B = 64 (12-16 % of the step)
+    if (((g_birnn_path == 0 && B <= 64) || g_birnn_path == 3) && lstm_bptt_supported(T, B, H))
+        return lstm_bptt_run(dout, T, B, H, seq_len, gates, cstate, wh_rows, ws, st);
     GemmPlan p1;
     // dh_rec[d][b, n] = sum_g dgs[d*B + b, g] * wh_rows[d*H + n, g]: K = 4H is long and the tile count small, so the
     // contraction is split over K across the SMs; the cell kernel of the next step adds the partials up

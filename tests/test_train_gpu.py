@@ -249,10 +249,11 @@ def _small_problem(seed=0, B=4, W=44, sizes=(32, 32), classes=19, cell="lstm"):
     return params, img, widths, labels
 
 
-@pytest.mark.parametrize("H,path", [(16, 0), (32, 0), (32, 1)])
+@pytest.mark.parametrize("H,path", [(16, 0), (32, 0), (32, 1), (32, 2), (64, 3)])
 def test_lstm_layer_train_forward_backward(H, path):
     """ocr_birnn_lstm_train_fwd / _bwd against autograd through the oracle's bidirectional_dynamic_rnn restatement.
-    H = 32, path 0: the frames run in the persistent cooperative kernel; path 1 / H = 16: one launch pair per frame."""
+    H = 32, path 0: forward and BPTT frames run in the persistent cooperative kernels; path 1 / H = 16: one launch pair per
+    frame; path 2: persistent forward only; path 3: persistent BPTT forced."""
     from oracle import train_oracle as to
     L, lib, sh = _lib()
     rng = np.random.default_rng(6)
