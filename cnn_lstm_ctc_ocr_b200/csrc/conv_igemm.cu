@@ -207,10 +207,17 @@ extern "C" int ocr_conv3x3_same(const float* in, int B, int H, int W, int C, con
     if (g_conv_path != 1 && conv_halo_supported(B, H, W, C, Cout)) return conv_halo_run(in, B, H, W, C, w, bias, Cout, relu, out, st);
     OCR_CHECK_ARG(g_conv_path != 2, "ocr_conv3x3_same: the halo-tile kernel does not take this shape (B=%d H=%d W=%d C=%d Cout=%d)", B, H, W, C, Cout);
     const long long mt = ((long long)B * H * W + kGemmBM - 1) / kGemmBM;
+    // The main loop is bound by the bytes an SM pulls in per k-step (patch tile 16 KB + filter tile BN * 128 B at ~35 B/clk),
+    // so the tile width that minimises (waves of CTAs over the 148 SMs) x (bytes per k-step) wins: wide tiles when there are
+    // many pixel tiles, but also when there are so few that narrow tiles would only add a second wave.
     int bn = 32;
-    if (Cout > 32) bn = 64;
-    if (Cout > 64 && mt * ((Cout + 127) / 128) >= 120) bn = 128;
-    if (Cout > 128 && mt * ((Cout + 255) / 256) >= 120) bn = 256;
+    long long best = -1;
+    for (int cand = 32; cand <= 256; cand *= 2) {
+        if (cand > 32 && cand / 2 >= Cout) break;                       // no point in tiles wider than the layer
+        const long long tiles = mt * ((Cout + cand - 1) / cand);
+        const long long cost = ((tiles + 147) / 148) * (128 + cand);
+        if (best < 0 || cost < best) { best = cost; bn = cand; }
+    }
     switch (bn) {
         // few stages per CTA, several CTAs per SM (3, 3, 2, 1): a tile is short (9..72 k-steps), so the prologue /
         // epilogue of one CTA hides behind the main loop of its neighbours

@@ -209,11 +209,16 @@ int gemm_plan(GemmPlan* p, const float* A, int lda, const float* W, int ldw, con
     OCR_CHECK_ARG((lda % 4) == 0 && (ldw % 4) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0,
                   "gemm: A and W need 16-byte aligned rows (pointer and leading dimension * 4 bytes)");
     const long long mt = (M + kGemmBM - 1) / kGemmBM;
-    // widest tile that still gives the 148 SMs something to do
+    // tile width: the main loop is bound by the bytes an SM pulls in per k-step (16 KB of A + BN * 128 B of W), so minimise
+    // (waves of CTAs over the 148 SMs) x (bytes per k-step); see conv_igemm.cu
     int bn = 32;
-    if (N > 32) bn = 64;
-    if (N > 64 && mt * ((N + 127) / 128) >= 120) bn = 128;
-    if (N > 128 && mt * ((N + 255) / 256) >= 120) bn = 256;
+    long long best = -1;
+    for (int cand = 32; cand <= 256; cand *= 2) {
+        if (cand > 32 && cand / 2 >= N) break;
+        const long long tiles = mt * ((N + cand - 1) / cand);
+        const long long cost = ((tiles + 147) / 148) * (128 + cand);
+        if (best < 0 || cost < best) { best = cost; bn = cand; }
+    }
     p->bn = bn; p->bias = bias; p->D = D; p->M = M; p->N = N; p->K = K; p->ldd = ldd; p->relu = relu;
     int rc = tma_map_2d(&p->tmA, A, M, K, lda, kGemmBM);
     if (rc != OCR_OK) return rc;
