@@ -83,15 +83,21 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
     // direction, hidden slice, batch tile (rows [mt*128, +128) of the batch)
     const int mt = blockIdx.x % MT, j = (blockIdx.x / MT) % NS, d = blockIdx.x / (MT * NS);
     const int m0 = mt * kGemmBM;
+    // Two issuing threads when the whole h block is one resident group (small batches): a frame's 4*nk MMAs issue at ~70
+    // cycles each from one thread although the tensor pipe needs ~34 (measured: 4560 of 10600 cycles per frame at B = 32).
+    // The producer lane, idle once its TMA request is out, issues the odd k-chunks into a SECOND accumulator (TMEM columns
+    // N..2N); the epilogue adds the two.
+    const bool dual = n_stages == 1 && gc == nk && nk >= 2;
+    const unsigned tmem_cols = (unsigned)(2 * N < 32 ? 32 : 2 * N);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < n_stages; ++s) { g_mbar_init(bar_full + s * 8, 1); g_mbar_init(bar_empty + s * 8, 1); }
+        for (int s = 0; s < n_stages; ++s) { g_mbar_init(bar_full + s * 8, 1); g_mbar_init(bar_empty + s * 8, dual ? 2 : 1); }
         g_mbar_init(bar_w, 1);
-        g_mbar_init(bar_acc, 1);
+        g_mbar_init(bar_acc, dual ? 2 : 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)), "r"((unsigned)(N < 32 ? 32 : N)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(g_smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -119,6 +125,20 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
                     tma_load_3d(s_a + st * g_bytes, tm, 0, m0, gi * gc, bar_full + st * 8);
                 }
                 lstm_mark(s, 1);
+                if (dual) {   // second MMA issuer: odd k-chunks -> accumulator 1
+                    const unsigned idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(kGemmBM >> 4) << 24);
+                    if (s == 0) g_mbar_wait(bar_w, 0);
+                    g_mbar_wait(bar_full, s & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    for (int k = 1; k < nk; k += 2) {
+                        const unsigned long long da = umma_desc_k128(s_a + k * a_bytes), db = umma_desc_k128(s_w + k * w_bytes);
+#pragma unroll
+                        for (int kk = 0; kk < kGemmBK / 8; ++kk)
+                            umma_tf32(tmem_d + (unsigned)N, da + (unsigned long long)(kk * 2), db + (unsigned long long)(kk * 2), idesc2, (k > 1 || kk) ? 1u : 0u);
+                    }
+                    umma_commit(bar_empty);
+                    umma_commit(bar_acc);
+                }
             }
         }
     } else if (warp == 1) {
@@ -132,7 +152,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
                     g_mbar_wait(bar_full + st * 8, (it / n_stages) & 1);
                     if (gi == 0) lstm_mark(s, 2);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    for (int c = 0; c < gc; ++c) {
+                    for (int c = 0; c < gc; c += (dual ? 2 : 1)) {   // dual: even chunks here, odd chunks on the producer lane
                         const int k = gi * gc + c;
                         const unsigned long long da = umma_desc_k128(s_a + st * g_bytes + c * a_bytes), db = umma_desc_k128(s_w + k * w_bytes);
 #pragma unroll
@@ -185,6 +205,21 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
                     : "r"(taddr) : "memory");
             }
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (dual) {   // add the second accumulator (odd k-chunks)
+#pragma unroll
+                for (int c0 = 0; c0 < N; c0 += 16) {
+                    unsigned g2[16];
+                    const unsigned taddr = tmem_d + ((unsigned)(q * 32) << 16) + (unsigned)(N + c0);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                        : "=r"(g2[0]), "=r"(g2[1]), "=r"(g2[2]), "=r"(g2[3]), "=r"(g2[4]), "=r"(g2[5]), "=r"(g2[6]), "=r"(g2[7]), "=r"(g2[8]),
+                          "=r"(g2[9]), "=r"(g2[10]), "=r"(g2[11]), "=r"(g2[12]), "=r"(g2[13]), "=r"(g2[14]), "=r"(g2[15])
+                        : "r"(taddr) : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) g[c0 + i] = __float_as_uint(__uint_as_float(g[c0 + i]) + __uint_as_float(g2[i]));
+                }
+            }
             if (threadIdx.x == 64) lstm_mark(s, 5);
             if (live_row) {
                 float* hn = hbuf + (((size_t)((s + 1) & 1) * 2 + d) * B + r) * H + j * HS;
@@ -233,7 +268,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((unsigned)(N < 32 ? 32 : N)) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
     }
 }
 
