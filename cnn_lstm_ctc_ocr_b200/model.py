@@ -149,7 +149,7 @@ class Model:
         """inputs [B,32,W,1] float32 NHWC (preprocessed) or uint8 (preprocessing fused), widths [B] int32
         -> (features [B,T,256], sequence_length [B] int32).   model.py:126-165"""
         if mode == ModeKeys.TRAIN:
-            raise NotImplementedError("TRAIN mode (batch statistics, backward) is not built yet; see DESIGN.md section 0")
+            raise NotImplementedError("Model is the inference graph; TRAIN mode (batch statistics + backward pass) lives in cnn_lstm_ctc_ocr_b200.train.Trainer")
         _lib.require_cuda(inputs)
         lib = _lib.load()
         sh = _lib.stream_handle()

@@ -97,7 +97,7 @@ def test_conv_paths_agree():
     assert torch.equal(f1, f2)
 
 
-def test_train_mode_not_built_yet():
+def test_train_mode_is_the_trainers_job():
     from cnn_lstm_ctc_ocr_b200 import model
     m = model.Model(mo.init_params(0, dtype=np.float32))
     with pytest.raises(NotImplementedError):
