@@ -46,6 +46,51 @@ _POOL_BEFORE = {"conv2": (1, 1, 1, 1), "conv3": (2, 2, 2, 2), "conv4": (1, 1, 1,
 BN_EPS = 1e-3
 
 
+def _truncated_normal(rng, shape, std):
+    x = rng.standard_normal(shape)
+    bad = np.abs(x) > 2
+    while bad.any():           # tf.truncated_normal: resample beyond two standard deviations
+        x[bad] = rng.standard_normal(int(bad.sum()))
+        bad = np.abs(x) > 2
+    return x * std
+
+
+def init_params(seed=0, cell_type="lstm", rnn_sizes=(512, 512), num_classes=None, dtype=np.float32):
+    """Fresh variables with the reference's initialisers, keyed by TensorFlow variable names: what
+    tf.global_variables_initializer() gives train.py's graph.  Convolutions / logits: variance_scaling_initializer
+    (factor 2, FAN_IN, truncated normal; model.py:94,207), zero biases (model.py:95,208); RNN cell kernels
+    truncated_normal(stddev 0.01) (model.py:170), LSTM biases zero, GRU biases truncated normal; batch-norm gamma 1, beta 0,
+    moving mean 0, moving variance 1."""
+    n_out = (len(out_charset) if num_classes is None else num_classes) + 1
+    rng = np.random.default_rng(seed)
+    p = {}
+    cin = 1
+    for (filters, k, padding, name, bn) in LAYER_PARAMS:
+        p["convnet/%s/kernel" % name] = _truncated_normal(rng, (k, k, cin, filters), np.sqrt(1.3 * 2.0 / (k * k * cin)))
+        p["convnet/%s/bias" % name] = np.zeros(filters)
+        if bn:
+            q = "convnet/%s/batch_norm/" % name
+            p[q + "gamma"], p[q + "beta"] = np.ones(filters), np.zeros(filters)
+            p[q + "moving_mean"], p[q + "moving_variance"] = np.zeros(filters), np.ones(filters)
+        cin = filters
+    I = 256
+    for scope, H in (("bdrnn1", rnn_sizes[0]), ("bdrnn2", rnn_sizes[1])):
+        for d in ("fw", "bw"):
+            q = "rnn/%s/%s/" % (scope, d)
+            if cell_type == "lstm":
+                p[q + "lstm_cell/kernel"] = _truncated_normal(rng, (I + H, 4 * H), 0.01)
+                p[q + "lstm_cell/bias"] = np.zeros(4 * H)
+            else:
+                p[q + "gru_cell/gates/kernel"] = _truncated_normal(rng, (I + H, 2 * H), 0.01)
+                p[q + "gru_cell/gates/bias"] = _truncated_normal(rng, (2 * H,), 0.01)
+                p[q + "gru_cell/candidate/kernel"] = _truncated_normal(rng, (I + H, H), 0.01)
+                p[q + "gru_cell/candidate/bias"] = _truncated_normal(rng, (H,), 0.01)
+        I = 2 * H
+    p["rnn/logits/kernel"] = _truncated_normal(rng, (I, n_out), np.sqrt(1.3 * 2.0 / I))
+    p["rnn/logits/bias"] = np.zeros(n_out)
+    return {k: v.astype(dtype) for k, v in p.items()}
+
+
 def preprocess_image(image):
     """validate._preprocess_image: uint8 -> float32 in [-0.5, 0.5].  (Model.convnet_layers also accepts the uint8
     tensor directly and fuses this into conv1.)"""

@@ -92,3 +92,15 @@ def test_full_graph_shapes_and_relu_logits():
     logits = mo.rnn_layers(feats, sl, p, "gru", (512, 256))
     assert logits.shape == (17, 2, 96) and (logits >= 0).all()
     assert sl.tolist() == [17, 15]
+
+
+def test_product_initialiser_matches_the_oracles():
+    """cnn_lstm_ctc_ocr_b200.model.init_params (what bench.py and a training run start from) draws the same variables as the
+    oracle's restatement of the reference's initialisers, for both cells, under TensorFlow's variable names."""
+    from cnn_lstm_ctc_ocr_b200 import model
+    for cell, sizes in (("lstm", (512, 512)), ("gru", (512, 256))):
+        a = model.init_params(3, cell, sizes)
+        b = mo.init_params(3, cell, sizes, 95, np.float32)
+        assert sorted(a) == sorted(b)
+        assert all(np.array_equal(a[k], b[k]) for k in a)
+    assert model.init_params(0, num_classes=62)["rnn/logits/bias"].shape == (63,)

@@ -5,12 +5,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 from cnn_lstm_ctc_ocr_b200 import model, _lib
-from oracle import model_oracle as mo   # parameter initialiser only (tool, not product)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 W = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 cell = sys.argv[3] if len(sys.argv) > 3 else "lstm"
 sizes = (512, 512) if cell == "lstm" else (512, 256)
-m = model.Model(mo.init_params(0, cell, sizes), cell_type=cell, rnn_sizes=sizes)
+m = model.Model(model.init_params(0, cell, sizes), cell_type=cell, rnn_sizes=sizes)
 dev = torch.device("cuda:0")
 img = torch.randint(0, 256, (B, 32, W, 1), dtype=torch.uint8, device=dev)
 widths = torch.full((B,), W, dtype=torch.int32, device=dev)

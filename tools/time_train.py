@@ -3,7 +3,7 @@ import sys, time
 sys.path.insert(0, ".")
 import numpy as np, torch
 from cnn_lstm_ctc_ocr_b200 import train, _lib
-from oracle import model_oracle as mo
+from cnn_lstm_ctc_ocr_b200 import model as _model
 sys.path.insert(0, "tests")
 from util import make_labels
 
@@ -11,7 +11,7 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 W = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 rng = np.random.default_rng(0)
-params = mo.init_params(0, "lstm", (512, 512), 95, np.float32)
+params = _model.init_params(0, "lstm", (512, 512))
 tr = train.Trainer(params)
 img = torch.tensor(rng.integers(0, 256, (B, 32, W, 1)).astype(np.uint8), device="cuda")
 widths = np.full(B, W)
