@@ -38,6 +38,29 @@ def learning_rate(step, learning_rate=1e-4, decay_steps=2 ** 16, decay_rate=0.9,
     return learning_rate * decay_rate ** e
 
 
+def flat_layout(shapes, cell_type="lstm"):
+    """Offsets of the trainable variables in the flat parameter / gradient / Adam buffers and the boundary between the two
+    all-reduce buckets.  shapes: name -> shape.  Returns (names in buffer order, offsets, floats in bucket 1 (logits + RNN),
+    total floats).  Host logic only (shared by Trainer and the CPU tests of the data-parallel exchange)."""
+    names, n_rnn = _param_order(cell_type)
+    offsets, off, first = {}, 0, 0
+    for i, n in enumerate(names):
+        if i == n_rnn:
+            first = off
+        offsets[n] = off
+        off += (int(np.prod(shapes[n])) + 63) // 64 * 64     # 256-byte aligned slots (TMA operands, float4)
+    return names, offsets, first, off
+
+
+def allreduce_buckets(flat_grad, n_first, world, all_reduce, async_first=True):
+    """The data-parallel exchange of a step: SUM all-reduce of bucket 1 (issued when the recurrent layers' gradients are
+    complete) and bucket 2 (the convolutional stack), then the 1/world scale the optimiser applies.  `all_reduce(tensor)` is
+    the collective (NCCL on GPU; gloo in the CPU tests).  Returns the scale to apply."""
+    all_reduce(flat_grad[:n_first])
+    all_reduce(flat_grad[n_first:])
+    return 1.0 / world
+
+
 def _is_trainable(name):
     return "moving_mean" not in name and "moving_variance" not in name
 
@@ -87,13 +110,7 @@ class Trainer:
             raise KeyError("parameters missing: %s" % missing[:3])
         self.names = names
         self.shapes = {n: tuple(np.asarray(params[n]).shape) for n in names}
-        self.offsets = {}
-        off = 0
-        for i, n in enumerate(names):
-            if i == n_rnn:
-                self.n_rnn_floats = off
-            self.offsets[n] = off
-            off += (int(np.prod(self.shapes[n])) + 63) // 64 * 64     # 256-byte aligned slots (TMA operands, float4)
+        _, self.offsets, self.n_rnn_floats, off = flat_layout(self.shapes, cell_type)
         self.n_floats = off
         dev = self.device
         self.theta = torch.zeros(off, dtype=torch.float32, device=dev)

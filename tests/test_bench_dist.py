@@ -52,3 +52,33 @@ def test_reference_arm_rank0_only():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["gpu_launches"] == 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
+
+
+def _ddp_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    from cnn_lstm_ctc_ocr_b200 import model, train
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shapes = {k: v.shape for k, v in model.init_params(0, "lstm", (32, 32), num_classes=19).items()}
+    names, offsets, n_first, n_total = train.flat_layout(shapes, "lstm")
+    # every replica holds the gradient of ITS half batch's mean loss; after the exchange all hold the global-batch mean
+    g = torch.arange(n_total, dtype=torch.float32) * (rank + 1)
+    scale = train.allreduce_buckets(g, n_first, world, lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM))
+    g *= scale
+    if rank == 0:
+        json.dump({"ok": bool(torch.allclose(g, torch.arange(n_total, dtype=torch.float32) * 1.5)), "n_first": n_first, "n_total": n_total,
+                   "first_is_rnn": all(n.startswith("rnn/") for n in names if offsets[n] < n_first),
+                   "rest_is_conv": all(n.startswith("convnet/") for n in names if offsets[n] >= n_first),
+                   "aligned": all(o % 64 == 0 for o in offsets.values())}, open(out, "w"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_bucket_exchange_gloo(tmp_path):
+    """The training step's one exchange: two contiguous buckets of the flat gradient buffer (logits + RNN, then
+    the convolutional stack), SUM all-reduced and scaled by 1/world = the gradient of the global-batch mean loss."""
+    out = str(tmp_path / "g.json")
+    mp.spawn(_ddp_worker, args=(2, 29517, out), nprocs=2, join=True)
+    r = json.load(open(out))
+    assert r["ok"] and r["first_is_rnn"] and r["rest_is_conv"] and r["aligned"] and 0 < r["n_first"] < r["n_total"]
