@@ -122,6 +122,21 @@ def get_testing(rnn_logits, sequence_length, label, label_length):
     return loss, label_error, sequence_error
 
 
+class _Pending:
+    """A batch in flight (Model.recognize_async)."""
+
+    def __init__(self, model, g, host, event):
+        self.model, self.g, self.host, self.event = model, g, host, event
+
+    def result(self):
+        self.event.synchronize()
+        dense = self.host.numpy()
+        chars = self.model.__dict__.setdefault("_charset_arr", np.array(list(out_charset)))
+        texts = ["".join(chars[row[row >= 0]]) for row in dense]
+        self.g["free"].append(self.host)
+        return texts
+
+
 class Model:
     """Weights of the recognizer + the reference's graph-building functions as methods."""
 
@@ -290,6 +305,11 @@ class Model:
             logits = self.rnn_layers(features, sl)
             dense = self.get_output(logits, sl)[0].cpu().numpy()
             return [get_string([c for c in row if c >= 0]) for row in dense]
+        return self.recognize_async(images, widths).result()
+
+    def recognize_async(self, images, widths):
+        """Enqueue one uint8 batch (copy in, graph replay, copy out) and return a handle; handle.result() waits for it and
+        gives the strings.  Lets a caller prepare the next batch on the host while this one runs (server.LocalServer.flush)."""
         key = tuple(images.shape)
         cache = self.__dict__.setdefault("_graphs", {})
         g = cache.get(key)
@@ -299,11 +319,11 @@ class Model:
         g["img"].copy_(images, non_blocking=True)
         g["widths"].copy_(torch.as_tensor(widths).to(torch.int32), non_blocking=True)
         g["graph"].replay()
-        g["host"].copy_(g["dec"], non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        dense = g["host"].numpy()
-        chars = self.__dict__.setdefault("_charset_arr", np.array(list(out_charset)))
-        return ["".join(chars[row[row >= 0]]) for row in dense]
+        host = g["free"].pop() if g["free"] else torch.empty(tuple(g["dec"].shape), dtype=torch.int64).pin_memory()
+        host.copy_(g["dec"], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return _Pending(self, g, host, ev)
 
     def _record(self, shape):
         from . import ctc as _ctc
@@ -327,5 +347,5 @@ class Model:
         with torch.cuda.graph(gr, pool=self._graph_pool):
             g["dec"] = run()
         g["graph"] = gr
-        g["host"] = torch.empty(tuple(g["dec"].shape), dtype=torch.int64).pin_memory()
+        g["free"] = []          # pinned result buffers, recycled by _Pending.result
         return g

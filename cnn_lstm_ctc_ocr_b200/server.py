@@ -73,6 +73,7 @@ class LocalServer(object):
         self.device = torch.device(device)
         self.buckets = [Bucket(bucket_max_time, bucket_size, (w, w + 32)) for w in range(32, 1000, 32)]  # server.py:64-65
         self.results = {}
+        self._pending = []
         self.padded_pixels = 0
         self.real_pixels = 0
 
@@ -92,11 +93,28 @@ class LocalServer(object):
             infos = infos + [("-1", "0")] * (self.bucket_size - n)
         self.padded_pixels += int(batch.shape[0] * batch.shape[2])
         self.real_pixels += int(widths[:n].sum())
-        texts = self.model.recognize(torch.from_numpy(batch), torch.from_numpy(widths))   # host crops: copied into the recorded graph's input
+        if hasattr(self.model, "recognize_async"):
+            # host crops are copied into the recorded graph's input; the strings are collected one batch later, so the
+            # host assembles the next batch while this one runs on the GPU
+            self._pending.append((infos, self.model.recognize_async(torch.from_numpy(batch), torch.from_numpy(widths))))
+            while len(self._pending) > 1:
+                self._collect()
+        else:
+            self._store(infos, self.model.recognize(torch.from_numpy(batch), torch.from_numpy(widths)))
+
+    def _collect(self):
+        infos, handle = self._pending.pop(0)
+        self._store(infos, handle.result())
+
+    def _store(self, infos, texts):
         for (clientid, imgid), txt in zip(infos, texts):
             if clientid == "-1":
                 continue
             self.results.setdefault(clientid, {})[imgid] = txt
+
+    def _drain(self):
+        while self._pending:
+            self._collect()
 
     def poll(self):
         """One pass of the reference's loop body over the buckets (server.py:120-140)."""
@@ -104,6 +122,7 @@ class LocalServer(object):
             b = bucket.getBatch()
             if b is not None:
                 self._run_batch(*b)
+        self._drain()
 
     def flush(self):
         """Release every bucket regardless of fill level or age."""
@@ -113,6 +132,7 @@ class LocalServer(object):
                 if b is None:
                     break
                 self._run_batch(*b)
+        self._drain()
 
     def take(self, clientid):
         return self.results.pop(clientid, {})
