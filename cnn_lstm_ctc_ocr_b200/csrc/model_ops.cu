@@ -180,6 +180,7 @@ int lstm_persistent_run(const float* xp, const float* wh, const float* wh_perm, 
                         float* out, float* ws, cudaStream_t st, float* gates_out = nullptr, float* cs_out = nullptr);
 
 int lstm_set_timeline(long long* buf);
+int lstm_bptt_set_timeline(long long* buf);
 
 static inline int grid_for(long long total, int threads = 256) {
     long long g = (total + threads - 1) / threads;
@@ -238,7 +239,10 @@ extern "C" int ocr_birnn_set_path(int path) {
 }
 
 // Tuning aid: per-frame clock64() stamps of CTA 0 of the persistent LSTM kernel (8 int64 per frame; NULL = off).
-extern "C" int ocr_debug_lstm_timeline(long long* device_buffer) { return lstm_set_timeline(device_buffer); }
+extern "C" int ocr_debug_lstm_timeline(long long* device_buffer) {
+    const int rc = lstm_set_timeline(device_buffer);
+    return rc != OCR_OK ? rc : lstm_bptt_set_timeline(device_buffer);     // the persistent BPTT kernel stamps the same buffer
+}
 
 extern "C" int ocr_birnn_workspace_bytes(int cell, int T, int B, int H, size_t* bytes)
 {
