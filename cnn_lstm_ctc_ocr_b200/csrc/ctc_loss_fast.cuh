@@ -117,6 +117,13 @@ __device__ __forceinline__ void tm_load_2d(unsigned dst, const CUtensorMap* tm, 
 __device__ __forceinline__ void tm_store_2d(const CUtensorMap* tm, int c0, int c1, unsigned src) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
+// L2 prefetch of a tensor-map box / of a contiguous run: no shared-memory destination, no completion to wait for
+__device__ __forceinline__ void tm_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch(const void* src, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ float fast_ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -182,23 +189,16 @@ __device__ __forceinline__ int prod_exponent(const float (&a0)[NP], const float 
     k = __reduce_max_sync(kFullMask, k);
     return k <= -100000 ? 0 : k;
 }
-// product (a * w) * 2^k without leaving the float32 range on the way: one factor while |k| <= 100 (the usual
-// case, a warp-uniform branch), two half factors up to |k| = 240.  Beyond that the row sum misses p(z|x) and
-// the sequence goes to the exact kernel.
+// product (a * w) * 2^k without leaving the float32 range on the way: the factor is always applied as two halves
+// (a * 2^(k/2)) * (w * 2^(k - k/2)), exact for |k| <= 240 -- no branch on the size of k inside the chain loops.
+// Beyond that the row sum misses p(z|x) and the sequence goes to the exact kernel.
 struct Boost {
     float f1, f2;
-    bool split;
     __device__ __forceinline__ explicit Boost(int k) {
-        split = (k > 100) || (k < -100);
-        if (split) {
-            k = max(-240, min(240, k));
-            const int k1 = k >> 1;
-            f1 = __uint_as_float((unsigned)(127 + k1) << 23);
-            f2 = __uint_as_float((unsigned)(127 + k - k1) << 23);
-        } else {
-            f1 = __uint_as_float((unsigned)(127 + k) << 23);
-            f2 = 1.0f;
-        }
+        k = max(-240, min(240, k));
+        const int k1 = k >> 1;
+        f1 = __uint_as_float((unsigned)(127 + k1) << 23);
+        f2 = __uint_as_float((unsigned)(127 + k - k1) << 23);
     }
 };
 // "lane per frame" sweeps over one staged row of C floats, skewed by r columns (r < 4) against bank conflicts
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(CR > 64 ? 64 * 4 : 64 * kFastMaxG)
 ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, const int32_t* __restrict__ labels,
                      const int32_t* __restrict__ label_offsets, const int32_t* __restrict__ seq_len, int Lmax, int G,
                      int use_bulk, float* __restrict__ loss, float* __restrict__ grad, int32_t* __restrict__ status,
-                     float grad_scale, const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut)
+                     float grad_scale, const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut, int pf_stride)
 {
     extern __shared__ __align__(128) unsigned char smem_f[];
     // tensor-map TMA wants 128-byte aligned shared-memory boxes: align by hand (the launch adds 128 bytes)
@@ -263,6 +263,17 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
     const int blank = C - 1;
     const int b = b0 + s;
     const bool have_seq = s < nb;
+
+    // The group that will take a finished CTA's place on this SM (pf_stride CTAs further down the grid: CTAs start in
+    // index order) should find its logits, lengths and labels in L2.  Its label range is read now and used after this
+    // CTA's own loads have landed.
+    const long long pf_b0 = ((long long)blockIdx.x + pf_stride) * G;
+    const bool pf = pf_stride > 0 && bulk && warp == 1 && pf_b0 + G <= B;
+    int pf_lab0 = 0, pf_lab1 = 0;
+    if (pf && lane == 31) {
+        pf_lab0 = __ldg(label_offsets + pf_b0);
+        pf_lab1 = __ldg(label_offsets + pf_b0 + G);
+    }
 
     // ---- group frame count, TMA loads (warp 0: one bulk copy per frame, spread over the lanes)
     __shared__ int s_tmax;
@@ -335,6 +346,19 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
         mbar_wait(bar, 0);
     }
     ctc_mark(tl, 1);
+    // L2 prefetch for the successor group: its load phase becomes an L2 hit instead of a DRAM round trip under load, and
+    // DRAM sees requests while this CTA computes.  Issued after this CTA's own loads landed, so never queued ahead of them.
+    if (pf) {
+        if (use_bulk == 2 || use_bulk == 5) {
+            if (lane < (T + kTmRows - 1) / kTmRows) tm_prefetch_2d(&tmIn, (int)pf_b0 * C, lane * kTmRows);
+        } else {
+            for (int t = lane; t < T; t += 32) bulk_prefetch(logits + ((size_t)t * B + pf_b0) * C, (unsigned)(G * C * 4));
+        }
+        if (lane == 31) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(seq_len + pf_b0));
+            for (int o = pf_lab0; o < pf_lab1; o += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(labels + o));
+        }
+    }
 
     float* st_s = stage + s * C;  // this sequence's column block
     float* lat = reinterpret_cast<float*>(smem + lay.lat) + s * lay.lat_seq;
@@ -501,13 +525,13 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
             pair_barrier(1 + s);  // partner has stored beta_t (and its exponents) for t >= mid
             ctc_mark(tl, 5);
             int Pt = 0;
-            bool first_consume = true;
             // the partner's beta_t for the frame about to be consumed is fetched one frame ahead
             float wb_n[NP], wl_n[NP];
 #pragma unroll
             for (int j = 0; j < NP; ++j) { wb_n[j] = lds(pl[j]); wl_n[j] = lds4(pl[j]); }
             int ex_n = ldsi(pex);
-            auto consume = [&]() {
+            // `first`: the frame where the chains meet fixes Pt (peeled out of the loops: no flag inside them)
+            auto consume = [&](auto first) {
                 float wb[NP], wl[NP];
 #pragma unroll
                 for (int j = 0; j < NP; ++j) { wb[j] = wb_n[j]; wl[j] = wl_n[j]; }
@@ -515,27 +539,23 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
 #pragma unroll
                 for (int j = 0; j < NP; ++j) { wb_n[j] = lds(pl[j] + LSB); wl_n[j] = lds4(pl[j] + LSB); }
                 ex_n = ldsi(pex + LSB);  // one row past the sequence on the last frame: inside the CTA's shared memory
-                if (first_consume) { Pt = Es + prod_exponent<NP>(ab, al, wb, wl); first_consume = false; }
+                if constexpr (decltype(first)::value) Pt = Es + prod_exponent<NP>(ab, al, wb, wl);
                 const Boost bo(Es - Pt);
-                if (bo.split) {
 #pragma unroll
-                    for (int j = 0; j < NP; ++j) {
-                        sts(pl[j], (ab[j] * bo.f1) * (wb[j] * bo.f2));
-                        sts4(pl[j], (al[j] * bo.f1) * (wl[j] * bo.f2));
-                        pl[j] += LSB;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < NP; ++j) {
-                        sts(pl[j], (ab[j] * bo.f1) * wb[j]);
-                        sts4(pl[j], (al[j] * bo.f1) * wl[j]);
-                        pl[j] += LSB;
-                    }
+                for (int j = 0; j < NP; ++j) {
+                    sts(pl[j], (ab[j] * bo.f1) * (wb[j] * bo.f2));
+                    sts4(pl[j], (al[j] * bo.f1) * (wl[j] * bo.f2));
+                    pl[j] += LSB;
                 }
                 pex += LSB;
             };
-            for (; t < min(Tb, tm0); ++t) { step(t, std::false_type()); consume(); }
-            for (; t < Tb; ++t) { step(t, std::true_type()); consume(); }
+            if (t < Tb) {
+                if (t < tm0) step(t, std::false_type()); else step(t, std::true_type());
+                consume(std::true_type());
+                ++t;
+            }
+            for (; t < min(Tb, tm0); ++t) { step(t, std::false_type()); consume(std::false_type()); }
+            for (; t < Tb; ++t) { step(t, std::true_type()); consume(std::false_type()); }
             // p(z|x) in e-units: alpha(2L) + alpha(2L-1) at the last frame
             float up = __shfl_up_sync(kFullMask, al[NP - 1], 1);
             if (lane == 0) up = 0.0f;
@@ -635,7 +655,6 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
             }
             rs.next(1.0f);
             int Pt = 0;
-            bool first_consume = true;
             float vl_n[NP], vb_n[NP];
             int ex_n = 0;
             auto consume_prefetch = [&]() {  // the partner's alpha_t of the first frame to be consumed
@@ -643,7 +662,7 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 for (int j = 0; j < NP; ++j) { vl_n[j] = lds(pl[j]); vb_n[j] = lds4(pl[j]); }
                 ex_n = ldsi(pex);
             };
-            auto consume = [&]() {
+            auto consume = [&](auto first) {
                 float vl[NP], vb[NP];
 #pragma unroll
                 for (int j = 0; j < NP; ++j) { vl[j] = vl_n[j]; vb[j] = vb_n[j]; }
@@ -651,22 +670,13 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
 #pragma unroll
                 for (int j = 0; j < NP; ++j) { vl_n[j] = lds(pl[j] - LSB); vb_n[j] = lds4(pl[j] - LSB); }
                 ex_n = ldsi(pex - LSB);  // one row before the sequence on the last frame: inside the CTA's shared memory
-                if (first_consume) { Pt = Es + prod_exponent<NP>(bb, bl, vb, vl); first_consume = false; }
+                if constexpr (decltype(first)::value) Pt = Es + prod_exponent<NP>(bb, bl, vb, vl);
                 const Boost bo(Es - Pt);
-                if (bo.split) {
 #pragma unroll
-                    for (int j = 0; j < NP; ++j) {
-                        sts(pl[j], (bl[j] * bo.f1) * (vl[j] * bo.f2));
-                        sts4(pl[j], (bb[j] * bo.f1) * (vb[j] * bo.f2));
-                        pl[j] -= LSB;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < NP; ++j) {
-                        sts(pl[j], (bl[j] * bo.f1) * vl[j]);
-                        sts4(pl[j], (bb[j] * bo.f1) * vb[j]);
-                        pl[j] -= LSB;
-                    }
+                for (int j = 0; j < NP; ++j) {
+                    sts(pl[j], (bl[j] * bo.f1) * (vl[j] * bo.f2));
+                    sts4(pl[j], (bb[j] * bo.f1) * (vb[j] * bo.f2));
+                    pl[j] -= LSB;
                 }
                 pex -= LSB;
             };
@@ -680,14 +690,18 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 pair_barrier(1 + s);  // partner has stored alpha_t (and its exponents) for t < mid
                 ctc_mark(tl, 5);
                 consume_prefetch();
+                // t = mid - 1 >= 0: the frame where the chains meet fixes Pt
+                if (t >= L) step(t, std::false_type()); else step(t, std::true_type());
+                consume(std::true_type());
+                --t;
             } else {
                 pair_barrier(1 + s);  // Tb == 1: the only frame belongs to the partner's half
                 consume_prefetch();
-                consume();
+                consume(std::true_type());
                 --t;
             }
-            for (; t >= L; --t) { step(t, std::false_type()); consume(); }
-            for (; t >= 0; --t) { step(t, std::true_type()); consume(); }
+            for (; t >= L; --t) { step(t, std::false_type()); consume(std::false_type()); }
+            for (; t >= 0; --t) { step(t, std::true_type()); consume(std::false_type()); }
             if (lane == 0) infoi[6] = Pt;
             ctc_mark(tl, 6);
             pair_barrier(1 + s);

@@ -73,6 +73,8 @@ int ocr_ctc_loss_set_path(int path);
 int ocr_debug_ctc_timeline(long long* device_buffer);
 /* Tuning aid: force the number of sequences per CTA of the fast kernel (1, 2, 4, 8; 0 = automatic). */
 int ocr_debug_ctc_group(int G);
+/* Tuning aid: L2 prefetch distance of the fast kernel in CTAs (-1 = automatic: half the resident CTAs of the grid, 0 = off). */
+int ocr_debug_ctc_prefetch(int stride);
 
 /* ---------------------------------------------------------------------------------------------
  * CTC greedy decoder.  Replaces tf.nn.ctc_greedy_decoder(merge_repeated=True) at
