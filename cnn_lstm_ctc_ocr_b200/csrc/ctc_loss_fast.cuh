@@ -53,7 +53,7 @@ __device__ __forceinline__ void ctc_mark(long long* tl, int slot) {
 
 struct FastLayout {
     int RS;        // floats between consecutive frames in the staging block (4 * odd)
-    int LS;        // floats per lattice row: [trash][state 0 .. 2*Lmax][pad][trash pair][exponent]  (2 * odd)
+    int LS;        // floats per lattice row: [trash][state 0 .. 2*Lmax][pad][trash pair][exponent]  (odd)
     int EX;        // index of the exponent slot inside a lattice row
     int HI;        // index of the high trash pair
     int stage, lat, lab, info, zero, mbar, total;  // byte offsets
@@ -66,9 +66,7 @@ __host__ __device__ inline FastLayout fast_layout(int T, int C, int Lmax, int G)
     if (!(rs4 & 1)) rs4 += 1;
     f.RS = rs4 * 4;
     // positions: 0 low trash, 1+u state u (u <= 2*Lmax), HI,HI+1 high trash, EX exponent
-    int ls2 = Lmax + 3;  // (2*Lmax + 6) / 2
-    if (!(ls2 & 1)) ls2 += 1;
-    f.LS = ls2 * 2;
+    f.LS = 2 * Lmax + 5;  // odd: pass 3 reads the lattice lane-per-frame (stride LS words) without bank conflicts
     f.HI = 2 * Lmax + 2;
     f.EX = 2 * Lmax + 4;
     f.lat_seq = T * f.LS;
@@ -145,6 +143,18 @@ __device__ __forceinline__ float lds4(unsigned a) {
 __device__ __forceinline__ int ldsi(unsigned a) {
     int v;
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+// loads of data that no thread writes during the phase that reads it (lattice products and labels in pass 3): not
+// volatile, no memory clobber, so the compiler may hoist them over the read-modify-writes of the staged rows
+__device__ __forceinline__ float lds_pure(unsigned a) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int ldsi_pure(unsigned a) {
+    int v;
+    asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
 __device__ __forceinline__ void sts(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v)); }
@@ -236,6 +246,45 @@ __device__ __forceinline__ void for_row(int n, F&& f) {
     }
 }
 
+// fb(kb) for every whole step of eight classes [kb, kb+8) below n, fp(k) for the classes of the last, partial step;
+// kb and k are compile-time constants after unrolling
+template <int CR, typename FB, typename FP>
+__device__ __forceinline__ void for_blocks(int n, FB&& fb, FP&& fp) {
+#pragma unroll
+    for (int kb = 0; kb < CR; kb += 8) {
+        if (kb + 8 <= n) {
+            fb(kb);
+        } else if (kb < n) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (kb + q < n) fp(kb + q);
+        }
+    }
+}
+
+// two float32 per 64-bit register pair: sm_100 issues FFMA2 / FADD2 / FMUL2 on them (IEEE results per half)
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void up2(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 template <int NP, int CR>
 __global__ void __launch_bounds__(CR > 64 ? 64 * 4 : 64 * kFastMaxG)
 ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, const int32_t* __restrict__ labels,
@@ -245,7 +294,8 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
 {
     extern __shared__ __align__(128) unsigned char smem_f[];
     // tensor-map TMA wants 128-byte aligned shared-memory boxes: align by hand (the launch adds 128 bytes)
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_f) + 127) & ~(uintptr_t)127);
+    // (pointer arithmetic, not an integer round trip: the compiler keeps the shared address space and emits LDS/STS, not generic LD/ST)
+    unsigned char* smem = smem_f + ((128u - (smem_u32(smem_f) & 127u)) & 127u);
     const FastLayout lay = fast_layout(T, C, Lmax, G);
     float* stage = reinterpret_cast<float*>(smem + lay.stage);
     float* s_info = reinterpret_cast<float*>(smem + lay.info);
@@ -383,25 +433,67 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                     int kt[3];
 #pragma unroll
                     for (int q = 0; q < 3; ++q) { int k = skew + n + q; kt[q] = (k >= C) ? k - C : k; }
+                    // Three passes over the register-resident row, eight classes per step; the arithmetic of whole steps is
+                    // packed two floats per instruction (FFMA2 / FADD2 / FMUL2: same IEEE results, half the issue slots).
                     float x[CR], xt[3];
-                    for_row<CR>(n, [&](int k) { x[k] = p[k]; });
+                    float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                    for_blocks<CR>(n,
+                        [&](int kb) {
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) xt[q] = (q < tail) ? row[kt[q]] : -INFINITY;
-                    float m[4] = {xt[0], xt[1], xt[2], -INFINITY};
-                    for_row<CR>(n, [&](int k) { m[k & 3] = fmaxf(m[k & 3], x[k]); });
-                    const float ml = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])) * 1.4426950408889634f;
-                    float z[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                    for_row<CR>(n, [&](int k) {
-                        x[k] = fast_ex2(fmaf(x[k], 1.4426950408889634f, -ml));
-                        z[k & 3] += x[k];
-                    });
+                            for (int q = 0; q < 8; ++q) x[kb + q] = p[kb + q];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) m[q] = fmaxf(m[q], fmaxf(x[kb + q], x[kb + 4 + q]));   // FMNMX3
+                        },
+                        [&](int k) { x[k] = p[k]; m[k & 3] = fmaxf(m[k & 3], x[k]); });
 #pragma unroll
                     for (int q = 0; q < 3; ++q) {
-                        xt[q] = (q < tail) ? fast_ex2(fmaf(xt[q], 1.4426950408889634f, -ml)) : 0.0f;
+                        xt[q] = (q < tail) ? row[kt[q]] : -INFINITY;
+                        m[q] = fmaxf(m[q], xt[q]);
+                    }
+                    const float l2e = 1.4426950408889634f;
+                    const float ml = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])) * l2e;
+                    const unsigned long long l2e2 = pk2(l2e, l2e), nml2 = pk2(-ml, -ml);
+                    unsigned long long z01 = pk2(0.0f, 0.0f), z23 = z01;   // (z0, z1), (z2, z3): class k adds into z[k & 3]
+                    float zs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                    for_blocks<CR>(n,
+                        [&](int kb) {
+#pragma unroll
+                            for (int q = 0; q < 8; q += 2) {
+                                float a0, a1;
+                                up2(ffma2(pk2(x[kb + q], x[kb + q + 1]), l2e2, nml2), a0, a1);
+                                x[kb + q] = fast_ex2(a0);
+                                x[kb + q + 1] = fast_ex2(a1);
+                                if (q & 2) z23 = fadd2(z23, pk2(x[kb + q], x[kb + q + 1]));
+                                else z01 = fadd2(z01, pk2(x[kb + q], x[kb + q + 1]));
+                            }
+                        },
+                        [&](int k) {
+                            x[k] = fast_ex2(fmaf(x[k], l2e, -ml));
+                            zs[k & 3] += x[k];
+                        });
+                    float z[4];
+                    up2(z01, z[0], z[1]);
+                    up2(z23, z[2], z[3]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) z[q] += zs[q];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        xt[q] = (q < tail) ? fast_ex2(fmaf(xt[q], l2e, -ml)) : 0.0f;
                         z[q] += xt[q];
                     }
                     const float gz = grad_scale / ((z[0] + z[1]) + (z[2] + z[3]));
-                    for_row<CR>(n, [&](int k) { p[k] = x[k] * gz; });
+                    const unsigned long long gz2 = pk2(gz, gz);
+                    for_blocks<CR>(n,
+                        [&](int kb) {
+#pragma unroll
+                            for (int q = 0; q < 8; q += 2) {
+                                float a0, a1;
+                                up2(fmul2(pk2(x[kb + q], x[kb + q + 1]), gz2), a0, a1);
+                                p[kb + q] = a0;
+                                p[kb + q + 1] = a1;
+                            }
+                        },
+                        [&](int k) { p[k] = x[k] * gz; });
 #pragma unroll
                     for (int q = 0; q < 3; ++q)
                         if (q < tail) row[kt[q]] = xt[q] * gz;
@@ -730,19 +822,23 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
             if (t < r_hi) {
                 float* row = st_s + t * RS;
                 if (!novalid) {
-                    const float* rp = lat + (size_t)t * LS + 1;  // rp[u] = product at state u
+                    const unsigned rp = smem_u32(lat + (size_t)t * LS + 1);  // rp + 4u: product at state u
+                    const unsigned lb = smem_u32(s_lab);
                     float S = 0.0f, Bs = 0.0f;
+#pragma unroll 4
                     for (int i = 0; i < L; ++i) {
-                        Bs += rp[2 * i];
-                        S += rp[2 * i + 1];
+                        Bs += lds_pure(rp + 8u * i);
+                        S += lds_pure(rp + 8u * i + 4u);
                     }
-                    Bs += rp[2 * L];
+                    Bs += lds_pure(rp + 8u * L);
                     S += Bs;
                     lost = lost || !(fabsf(log2f(S) - l2pe + dexp) < thr);
                     if (grad) {
                         const float r = (S > 0.0f) ? grad_scale / S : 0.0f;
                         row[blank] -= Bs * r;
-                        for (int i = 0; i < L; ++i) row[s_lab[i]] -= rp[2 * i + 1] * r;
+                        // in label order: a class that occurs twice is updated twice, one after the other
+#pragma unroll 4
+                        for (int i = 0; i < L; ++i) row[ldsi_pure(lb + 4u * i)] -= lds_pure(rp + 8u * i + 4u) * r;
                     }
                 }
             }
@@ -755,8 +851,17 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
         // frames past the sequence end: zero gradient (both warps, lane per class: conflict-free)
         const int Tr = run ? Tb : 0;
         float* p = st_s + (size_t)(Tr + role) * RS + lane;
-        for (int t = Tr + role; t < T; t += 2, p += 2 * RS)
-            for (int k = 0; k + lane < C; k += 32) p[k] = 0.0f;
+        if (CR > 0) {
+#pragma unroll 4
+            for (int t = Tr + role; t < T; t += 2, p += 2 * RS) {
+#pragma unroll
+                for (int k = 0; k < CR; k += 32)
+                    if (k + lane < C) p[k] = 0.0f;
+            }
+        } else {
+            for (int t = Tr + role; t < T; t += 2, p += 2 * RS)
+                for (int k = 0; k + lane < C; k += 32) p[k] = 0.0f;
+        }
     }
     ctc_mark(tl, 9);
     if (bulk) {
