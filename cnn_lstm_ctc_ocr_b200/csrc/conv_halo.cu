@@ -48,7 +48,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
 {
     constexpr int kWB = BN * kGemmBK * 4;                       // one filter tile
     extern __shared__ unsigned char halo_smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(halo_smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem = halo_smem_raw + ((1024u - (g_smem_u32(halo_smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     const unsigned s_base = g_smem_u32(smem);
     const int cpt = C / kGemmBK;                                // channel chunks
     const unsigned s_halo = s_base;                             // cpt halo tiles

@@ -45,7 +45,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const float* __res
 {
     using S = ConvSmem<BN, STAGES>;
     extern __shared__ unsigned char conv_smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(conv_smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem = conv_smem_raw + ((1024u - (g_smem_u32(conv_smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     const unsigned s_base = g_smem_u32(smem);
     const unsigned bar_full = s_base + S::kBars;
     const unsigned bar_empty = bar_full + STAGES * 8;

@@ -47,7 +47,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     using S = GemmSmem<BN, STAGES>;
     extern __shared__ unsigned char gemm_smem_raw[];
     // 128-byte swizzle wants 1024-byte aligned tiles
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem = gemm_smem_raw + ((1024u - (g_smem_u32(gemm_smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     const unsigned s_base = g_smem_u32(smem);
     const unsigned bar_full = s_base + S::kBars;
     const unsigned bar_empty = bar_full + STAGES * 8;

@@ -50,7 +50,7 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW, float* act /*[T*B, 8H]
     const int NH = H > 256 ? H / 2 : H;                 // columns per MMA (N), halves = H / NH
     const int halves = H / NH;
     extern __shared__ unsigned char bp_smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(bp_smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem = bp_smem_raw + ((1024u - (g_smem_u32(bp_smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     const unsigned s_base = g_smem_u32(smem);
     const unsigned w_chunk = (unsigned)H * 128u;        // one 32-wide k-chunk of the weight slice: [H rows][128 B]
     const unsigned s_w = s_base;                        // 2 chunks

@@ -63,7 +63,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
     constexpr int N = 4 * HS;
     const int nk = H / kGemmBK;
     extern __shared__ unsigned char rnn_smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(rnn_smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem = rnn_smem_raw + ((1024u - (g_smem_u32(rnn_smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     const unsigned s_base = g_smem_u32(smem);
     const unsigned w_bytes = (unsigned)N * kGemmBK * 4;          // one k-chunk of the weight slice
     // one k-chunk of h: only the a_rows (>= B, multiple of 8) real batch rows are fetched; the MMA still reads 128
