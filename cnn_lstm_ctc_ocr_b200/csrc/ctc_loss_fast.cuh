@@ -292,6 +292,9 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                      int use_bulk, float* __restrict__ loss, float* __restrict__ grad, int32_t* __restrict__ status,
                      float grad_scale, const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut, int pf_stride)
 {
+    // programmatic dependent launch (launch_pdl): this grid may have been scheduled while its predecessor was still running;
+    // nothing here touches global memory before the predecessor's results are visible
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     extern __shared__ __align__(128) unsigned char smem_f[];
     // tensor-map TMA wants 128-byte aligned shared-memory boxes: align by hand (the launch adds 128 bytes)
     // (pointer arithmetic, not an integer round trip: the compiler keeps the shared address space and emits LDS/STS, not generic LD/ST)

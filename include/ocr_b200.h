@@ -75,6 +75,8 @@ int ocr_debug_ctc_timeline(long long* device_buffer);
 int ocr_debug_ctc_group(int G);
 /* Tuning aid: L2 prefetch distance of the fast kernel in CTAs (-1 = automatic: half the resident CTAs of the grid, 0 = off). */
 int ocr_debug_ctc_prefetch(int stride);
+/* Tuning aid: programmatic dependent launch of the CTC kernels on (1, default) / off (0). */
+int ocr_debug_ctc_pdl(int on);
 
 /* ---------------------------------------------------------------------------------------------
  * CTC greedy decoder.  Replaces tf.nn.ctc_greedy_decoder(merge_repeated=True) at
