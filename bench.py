@@ -291,26 +291,40 @@ def run_ours(args, cfg):
         hx = [torch.from_numpy(h[0]).pin_memory() for h in host]
         hlab = [(torch.from_numpy(h[1]).pin_memory(), torch.from_numpy(h[4]).pin_memory()) for h in host]
         hsl = [torch.from_numpy(h[3]).pin_memory() for h in host]
-        hloss = torch.empty(B, dtype=torch.float32).pin_memory()
+        hloss = [torch.empty(B, dtype=torch.float32).pin_memory() for _ in range(2)]
         dx = torch.empty((T, B, C), device=dev)
         dx.requires_grad_(True)
 
-        def e2e_step(i):
+        def e2e_enqueue(i):
+            """Step i: H2D of its logits/labels/lengths, loss + gradient, D2H of its losses -- all queued on the stream."""
             j = i % len(host)
             with torch.no_grad():
                 dx.copy_(hx[j], non_blocking=True)
             loss = ctc.ctc_loss(hlab[j], dx, hsl[j])  # labels/seq_len are host tensors: copied inside
-            hloss.copy_(loss.detach(), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return loss
-        for i in range(3):
-            e2e_step(i)
+            hloss[i % 2].copy_(loss.detach(), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            return ev
+
+        def e2e_run(n):
+            """n steps with one step in flight: step i+1 is queued before step i's losses are read on the host, so the
+            host-side label packing and launch overhead overlap the copies; every step's copies are inside the region."""
+            acc, prev = 0.0, None
+            for i in range(n):
+                ev = e2e_enqueue(i)
+                if prev is not None:
+                    prev.synchronize()
+                    acc += float(hloss[(i - 1) % 2][0])
+                prev = ev
+            prev.synchronize()
+            acc += float(hloss[(n - 1) % 2][0])
+            return acc
+        e2e_run(3)
         KE = max(5, min(K, 200))
         barrier()
         t_a = time.time()
         e0.record(stream)
-        for i in range(KE):
-            e2e_step(i)
+        e2e_run(KE)
         e1.record(stream)
         barrier()
         windows.append((t_a, time.time()))
@@ -319,7 +333,8 @@ def run_ours(args, cfg):
         e2e = {"value": whole_job_value(B, KE, ms_e, world), "unit": UNIT,
                "h2d_bytes_per_step": int(h[0].nbytes + h[1].nbytes + h[2].nbytes + h[3].nbytes),
                "d2h_bytes_per_step": int(B * 4), "steps": KE,
-               "api": "cnn_lstm_ctc_ocr_b200.ctc.ctc_loss (loss + gradient), pinned host logits/labels in, losses out"}
+               "api": "cnn_lstm_ctc_ocr_b200.ctc.ctc_loss (loss + gradient), pinned host logits/labels in, losses out; one step in flight "
+                      "(step i+1 is queued before step i's losses are read)"}
 
         # ---- bandwidth regime of the same kernel (inputs >> L2): where the >=60%-of-HBM target applies
         bw = None
