@@ -61,7 +61,15 @@ __device__ __forceinline__ float lse3(float a, float b, float c) {
     return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
 }
 
-template <bool kLatticeInSmem>
+// CTA barrier of the general routine: the whole CTA in its own kernel, the first 128 threads (named barrier 9; the fast
+// kernel's pair barriers use 1..8) when it runs as the tail of the fast kernel
+template <bool kInFast>
+__device__ __forceinline__ void gen_sync() {
+    if constexpr (kInFast) asm volatile("bar.sync 9, 128;" ::: "memory");
+    else __syncthreads();
+}
+
+template <bool kLatticeInSmem, bool kInFast>
 __device__ __forceinline__ void
 ctc_general_one(unsigned char* smem, const int b, const float* __restrict__ logits, int T, int B, int C,
                 const int32_t* __restrict__ labels, const int32_t* __restrict__ label_offsets,
@@ -90,7 +98,7 @@ ctc_general_one(unsigned char* smem, const int b, const float* __restrict__ logi
     }
     __shared__ float s_logp;
     __shared__ int s_bad;
-    __syncthreads();  // previous sequence of this persistent CTA is done with shared memory
+    gen_sync<kInFast>();  // previous sequence of this persistent CTA is done with shared memory
 
     const int off = label_offsets[b];
     const int L = label_offsets[b + 1] - off;
@@ -105,7 +113,7 @@ ctc_general_one(unsigned char* smem, const int b, const float* __restrict__ logi
     if (tid == 0) s_bad = 0;
     for (int k = tid; k < C; k += kCtcThreads) s_head[k] = -1;
     for (int s = tid; s < L; s += kCtcThreads) s_lab[s] = labels[off + s];
-    __syncthreads();
+    gen_sync<kInFast>();
     if (tid == 0) {
         int need = L, bad = 0;
         for (int s = L - 1; s >= 0; --s) {
@@ -123,7 +131,7 @@ ctc_general_one(unsigned char* smem, const int b, const float* __restrict__ logi
         // state u (odd = label (u>>1)) may be entered from u-2 iff it is a label differing from the previous label
         s_skip[u] = (u & 1) && (u >= 3) && (labels[off + (u >> 1)] != labels[off + (u >> 1) - 1]);
     }
-    __syncthreads();
+    gen_sync<kInFast>();
     const int bad = s_bad;
     if (bad || Tb == 0) {
         // TF: zero-length sequence -> loss 0, grad 0.  Infeasible / invalid -> flagged, zero outputs.
@@ -157,7 +165,7 @@ ctc_general_one(unsigned char* smem, const int b, const float* __restrict__ logi
         if (lane == 0) lpl[t * Lp1 + L] = s_stage[blank] - lse;
         __syncwarp();
     }
-    __syncthreads();
+    gen_sync<kInFast>();
 
     // ---- phase 2: alpha (warp 0, forward) and beta (warp 1, backward) chains, concurrently
     if (warp == 0) {
@@ -195,7 +203,7 @@ ctc_general_one(unsigned char* smem, const int b, const float* __restrict__ logi
             __syncwarp();
         }
     }
-    __syncthreads();
+    gen_sync<kInFast>();
 
     // ---- log p(z|x) = LSE_u(alpha(u,0) + beta(u,0))   (CalculateLoss)
     if (warp == 0) {
@@ -213,7 +221,7 @@ ctc_general_one(unsigned char* smem, const int b, const float* __restrict__ logi
             if (status) status[b] = (lp == -INFINITY) ? 1 : 0;
         }
     }
-    __syncthreads();
+    gen_sync<kInFast>();
     if (!gb) return;
     const float logp = s_logp;
     const bool novalid = (logp == -INFINITY);
@@ -268,7 +276,7 @@ ctc_loss_kernel(const float* __restrict__ logits, int T, int B, int C, const int
     asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         if (only_flagged && status[b] != kCtcRedo) continue;
-        ctc_general_one<kLatticeInSmem>(smem, b, logits, T, B, C, labels, label_offsets, seq_len, Lmax, loss, grad,
+        ctc_general_one<kLatticeInSmem, false>(smem, b, logits, T, B, C, labels, label_offsets, seq_len, Lmax, loss, grad,
                                         status, grad_scale, workspace);
     }
 }
@@ -312,7 +320,7 @@ extern "C" int ocr_debug_ctc_group(int G) {
 // (16.0 us with the release at its start, 15.6 us with the release before its gradient store).
 static int g_ctc_pdl = 1;
 extern "C" int ocr_debug_ctc_pdl(int on) {
-    g_ctc_pdl = on ? 1 : 0;
+    g_ctc_pdl = on;   // 2: single-wave fast grids also release their successor at once (tuning)
     return OCR_OK;
 }
 template <typename... KArgs, typename... Args>
@@ -328,6 +336,12 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_
     cfg.attrs = attr;
     cfg.numAttrs = g_ctc_pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+static int g_ctc_inline_redo = 1;   // flagged sequences are redone in the fast kernel's tail when the exact routine fits there (0: always the gate launch)
+extern "C" int ocr_debug_ctc_inline_redo(int on) {
+    g_ctc_inline_redo = on ? 1 : 0;
+    return OCR_OK;
 }
 
 static int g_ctc_prefetch = -1;   // L2 prefetch distance of the fast kernel in CTAs (-1 = half the resident CTAs of the grid, 0 = off)
@@ -417,7 +431,7 @@ static int sms_of(int dev) {
 template <int NP, int CR>
 static int launch_fast(const FastPlan& fp, const float* logits, int T, int B, int C, const int32_t* labels,
                        const int32_t* label_offsets, const int32_t* seq_len, int Lmax, float* loss, float* grad,
-                       int32_t* status, float grad_scale, cudaStream_t st)
+                       int32_t* status, float grad_scale, cudaStream_t st, int* redo_inlined)
 {
     // tensor-map transfers (one request per 16 frames) when the staging rows are dense, a box fits the TMA limits and
     // whole boxes stay inside the tensor (T a multiple of 16: a partial last box would be clipped and deliver fewer bytes)
@@ -452,8 +466,12 @@ static int launch_fast(const FastPlan& fp, const float* logits, int T, int B, in
         pf = resident / 2;
     }
     if (grid <= (resident > 0 ? resident : pf)) pf = 0;   // one wave: nobody comes after
+    // flagged sequences (lattice outside the float32 range: rare) are redone by the flagging CTA itself when the exact
+    // routine's 128 threads and shared-memory layout fit it; otherwise (and on path 3) the caller launches the redo gate
+    const int inl = (g_ctc_inline_redo && g_ctc_path != 3 && 64 * fp.G >= kCtcThreads && ctc_layout(T, C, Lmax, true).total <= fp.smem) ? 1 : 0;
+    *redo_inlined = inl;
     OCR_CHECK_CUDA(launch_pdl(ctc_loss_fast_kernel<NP, CR>, grid, 64 * fp.G, (size_t)fp.smem + 128, st, logits, T, B, C, labels, label_offsets,
-                              seq_len, Lmax, fp.G, bulk, loss, grad, status, grad_scale, tmIn, tmOut, pf));
+                              seq_len, Lmax, fp.G, bulk, loss, grad, status, grad_scale, tmIn, tmOut, pf, inl | ((g_ctc_pdl == 2 && grid * 2 <= sms_of(dev)) ? 2 : 0)));
     count_launch();
     return OCR_OK;
 }
@@ -510,12 +528,13 @@ extern "C" int ocr_ctc_loss(const float* logits, int T, int B, int C, const int3
     // the fast kernel stages y * grad_scale and runs its lattice on it: it needs a positive scale
     if (g_ctc_path != 1 && grad_scale > 0.0f && plan_fast(logits, grad, T, B, C, max_label_len, &fp)) {
         int rc;
-#define OCR_FAST(NP_, CR_) rc = launch_fast<NP_, CR_>(fp, logits, T, B, C, labels, label_offsets, seq_len, max_label_len, loss, grad, st_buf, grad_scale, st)
+        int inlined = 0;
+#define OCR_FAST(NP_, CR_) rc = launch_fast<NP_, CR_>(fp, logits, T, B, C, labels, label_offsets, seq_len, max_label_len, loss, grad, st_buf, grad_scale, st, &inlined)
         if (fp.CR == 64) { if (fp.NP == 1) OCR_FAST(1, 64); else if (fp.NP == 2) OCR_FAST(2, 64); else OCR_FAST(4, 64); }
         else if (fp.CR == 128) { if (fp.NP == 1) OCR_FAST(1, 128); else if (fp.NP == 2) OCR_FAST(2, 128); else OCR_FAST(4, 128); }
         else { if (fp.NP == 1) OCR_FAST(1, 0); else if (fp.NP == 2) OCR_FAST(2, 0); else OCR_FAST(4, 0); }
 #undef OCR_FAST
-        if (rc != OCR_OK || g_ctc_path == 3) return rc;  // path 3 (diagnostics): leave kCtcRedo flags in status
+        if (rc != OCR_OK || g_ctc_path == 3 || inlined) return rc;  // path 3 (diagnostics): leave kCtcRedo flags in status
         // sequences whose lattice left the float32 range of the fast kernel (status kCtcRedo): exact kernel
         return launch_general(logits, T, B, C, labels, label_offsets, seq_len, max_label_len, loss, grad, st_buf,
                               grad_scale, lattice_ws, 1, st);

@@ -43,6 +43,14 @@ namespace ocr {
 constexpr int kFastMaxG = 8;
 constexpr int kCtcRedo = 100;  // internal status: recompute this sequence with the exact log-domain kernel
 
+// The exact log-domain routine of ctc_loss.cu (one sequence, 128 threads).  kInFast: called from the tail of the fast
+// kernel by its first 128 threads (named barrier instead of __syncthreads) on the CTA's own, by then idle, shared memory.
+template <bool kLatticeInSmem, bool kInFast>
+__device__ void ctc_general_one(unsigned char* smem, const int b, const float* __restrict__ logits, int T, int B, int C,
+                                const int32_t* __restrict__ labels, const int32_t* __restrict__ label_offsets,
+                                const int32_t* __restrict__ seq_len, int Lmax, float* __restrict__ loss, float* __restrict__ grad,
+                                int32_t* __restrict__ status, float grad_scale, float* __restrict__ workspace);
+
 // Optional phase timeline for tuning (ocr_debug_ctc_timeline): per warp, clock64() at up to 12 phase boundaries.
 __device__ long long* g_ctc_timeline = nullptr;
 constexpr int kCtcTimelineSlots = 12;
@@ -290,11 +298,13 @@ __global__ void __launch_bounds__(CR > 64 ? 64 * 4 : 64 * kFastMaxG)
 ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, const int32_t* __restrict__ labels,
                      const int32_t* __restrict__ label_offsets, const int32_t* __restrict__ seq_len, int Lmax, int G,
                      int use_bulk, float* __restrict__ loss, float* __restrict__ grad, int32_t* __restrict__ status,
-                     float grad_scale, const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut, int pf_stride)
+                     float grad_scale, const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut, int pf_stride, int inline_redo)
 {
     // programmatic dependent launch (launch_pdl): this grid may have been scheduled while its predecessor was still running;
     // nothing here touches global memory before the predecessor's results are visible
+    if (inline_redo & 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // tuning knob (ocr_debug_ctc_pdl(2))
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    inline_redo &= 1;
     extern __shared__ __align__(128) unsigned char smem_f[];
     // tensor-map TMA wants 128-byte aligned shared-memory boxes: align by hand (the launch adds 128 bytes)
     // (pointer arithmetic, not an integer round trip: the compiler keeps the shared address space and emits LDS/STS, not generic LD/ST)
@@ -330,6 +340,8 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
 
     // ---- group frame count, TMA loads (warp 0: one bulk copy per frame, spread over the lanes)
     __shared__ int s_tmax;
+    __shared__ int s_redo[kFastMaxG];   // sequences of this CTA whose lattice left the float32 range (redone in the tail)
+    if (tid < kFastMaxG) s_redo[tid] = 0;   // ordered before the first write by the CTA barrier below
     if (warp == 0) {
         int tm = 0;
         for (int i = lane; i < nb; i += 32) tm = max(tm, min(max(seq_len[b0 + i], 0), T));
@@ -669,6 +681,7 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 const float lp = novalid ? -INFINITY : (logf(pev) + (float)rs.E * 0.6931471805599453f);
                 loss[b] = -lp;
                 status[b] = novalid ? kCtcRedo : 0;  // an all-zero lattice may be underflow: the exact kernel decides
+                if (novalid) s_redo[s] = 1;
                 info[2] = novalid ? 1.0f : 0.0f;
                 info[3] = novalid ? 0.0f : log2f(pev);
                 infoi[4] = rs.E;
@@ -846,10 +859,26 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 }
             }
         }
-        if (run && !novalid && __any_sync(kFullMask, lost) && lane == 0) status[b] = kCtcRedo;
+        if (run && !novalid && __any_sync(kFullMask, lost) && lane == 0) { status[b] = kCtcRedo; s_redo[s] = 1; }
     }
     ctc_mark(tl, 8);
-    if (!grad) return;
+    // Tail of a CTA that flagged a sequence (rare): once the CTA's own gradient block has left shared memory, its first
+    // 128 threads recompute the flagged sequences with the exact log-domain routine, in place of a second kernel launch
+    // that would have to visit every sequence's flag (inline_redo: the routine's layout fits this CTA's allocation).
+    auto redo_flagged = [&]() {   // called by every thread, after a CTA barrier that follows pass 3 and the CTA's stores
+        if (tid >= 128) return;
+        for (int i = 0; i < nb; ++i)
+            if (s_redo[i])
+                ctc_general_one<true, true>(smem, b0 + i, logits, T, B, C, labels, label_offsets, seq_len, Lmax, loss, grad, status,
+                                            grad_scale, nullptr);
+    };
+    if (!grad) {
+        if (inline_redo) {
+            __syncthreads();
+            redo_flagged();
+        }
+        return;
+    }
     if (have_seq) {
         // frames past the sequence end: zero gradient (both warps, lane per class: conflict-free)
         const int Tr = run ? Tb : 0;
@@ -871,6 +900,9 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         ctc_mark(tl, 10);
+        bool redo = false;
+        if (inline_redo)
+            for (int i = 0; i < nb; ++i) redo = redo || s_redo[i] != 0;   // CTA-uniform
         if (warp == 0) {
             const unsigned row_bytes = (unsigned)(G * C * 4);
             float* dst = grad + (size_t)b0 * C;
@@ -882,15 +914,24 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 for (int t = lane; t < T; t += 32) bulk_store(dst + (size_t)t * B * C, src + (unsigned)t * RS * 4, row_bytes);
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            if (redo) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the block has reached global memory: the redo overwrites part of it
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
         ctc_mark(tl, 11);
+        if (redo) {
+            __syncthreads();
+            redo_flagged();
+        }
     } else {
         __syncthreads();
         const int n = nb * C;
         for (int t = 0; t < T; ++t) {
             float* dst = grad + ((size_t)t * B + b0) * C;
             for (int j = tid; j < n; j += blockDim.x) st_stream(dst + j, stage[t * RS + j]);
+        }
+        if (inline_redo) {
+            __syncthreads();
+            redo_flagged();
         }
     }
 }

@@ -77,6 +77,8 @@ int ocr_debug_ctc_group(int G);
 int ocr_debug_ctc_prefetch(int stride);
 /* Tuning aid: programmatic dependent launch of the CTC kernels on (1, default) / off (0). */
 int ocr_debug_ctc_pdl(int on);
+/* Tuning aid: sequences the fast kernel flags are redone in its own tail (1, default) or by a second launch (0). */
+int ocr_debug_ctc_inline_redo(int on);
 
 /* ---------------------------------------------------------------------------------------------
  * CTC greedy decoder.  Replaces tf.nn.ctc_greedy_decoder(merge_repeated=True) at

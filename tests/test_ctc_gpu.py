@@ -135,6 +135,35 @@ def test_loss_extreme_dynamic_range(oracle):
     assert np.abs(grad - g64).max() < 1e-3
 
 
+def test_loss_redo_in_kernel_tail_equals_gate_launch(oracle):
+    """Sequences the fast kernel flags (lattice outside the float32 range) are redone by the exact routine either in the
+    fast kernel's own tail (default) or by the separate gate launch: same bits both ways, with and without a gradient."""
+    from cnn_lstm_ctc_ocr_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(78)
+    T, B, C = 64, 64, 63
+    x = (rng.standard_normal((T, B, C)) * 8).astype(np.float32)
+    seq_len = rng.integers(T // 2, T + 1, B).astype(np.int32)
+    labels = make_labels(rng, B, seq_len, max_len=16, num_labels=C - 1)
+    _, _, flags = _gpu_loss(x, labels, seq_len, path=3)          # diagnostics path: flags left in status
+    assert 0 < int((flags == 100).sum()) < B                      # some sequences take the redo, some do not
+    l64, g64, s64 = oracle.ctc_loss(x, labels, seq_len, nthreads=8, f64=True)
+    res = {}
+    try:
+        for inline in (1, 0):
+            _lib.check(lib.ocr_debug_ctc_inline_redo(inline), "inline_redo")
+            res[inline] = _gpu_loss(x, labels, seq_len) + (_gpu_loss(x, labels, seq_len, want_grad=False)[0],)
+    finally:
+        lib.ocr_debug_ctc_inline_redo(1)
+    for inline in (1, 0):
+        loss, grad, st, loss_only = res[inline]
+        assert (st == 0).all()
+        np.testing.assert_allclose(loss, l64, rtol=1e-5)
+        assert np.abs(grad - g64).max() < 1e-3
+        assert np.array_equal(loss, loss_only)
+    assert np.array_equal(res[1][0], res[0][0]) and np.array_equal(res[1][1], res[0][1])
+
+
 def test_loss_edge_cases(oracle):
     rng = np.random.default_rng(3)
     T, C = 6, 5

@@ -28,7 +28,8 @@ def call(r, sh):
                                 _lib.ptr(r["grad"]), _lib.ptr(r["status"]), 1.0 / B, _lib.ptr(ws), need.value, sh), "ctc")
 stream = torch.cuda.Stream(device=dev)
 ref = None
-for pdl in (0, 1, 0, 1):
+for pdl, inl in ((1, 0), (1, 1), (0, 1), (2, 1), (1, 0), (1, 1), (2, 1)):
+    lib.ocr_debug_ctc_inline_redo(inl)
     lib.ocr_debug_ctc_pdl(pdl)
     with torch.cuda.stream(stream):
         sh = _lib.stream_handle()
@@ -47,6 +48,6 @@ for pdl in (0, 1, 0, 1):
     out = (ring[0]["loss"].clone(), ring[0]["grad"].clone(), ring[(K - 1) % ring_n]["grad"].clone())
     if ref is None: ref = out
     same = all(torch.equal(a, b) for a, b in zip(ref, out))
-    print("pdl %d: %.2f us per call (graph of %d), %.1f GB/s algorithmic, outputs identical to the first run: %s, flagged %d"
-          % (pdl, us, K, 2 * T * B * C * 4 / us / 1e3, same, int((ring[0]["status"] == 100).sum())))
-lib.ocr_debug_ctc_pdl(1)
+    print("inline_redo %d pdl %d: %.2f us per call (graph of %d), %.1f GB/s algorithmic, outputs identical to the first run: %s, flagged %d"
+          % (inl, pdl, us, K, 2 * T * B * C * 4 / us / 1e3, same, int((ring[0]["status"] == 100).sum())))
+lib.ocr_debug_ctc_pdl(1); lib.ocr_debug_ctc_inline_redo(1)
