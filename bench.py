@@ -282,7 +282,7 @@ def run_ours(args, cfg):
         windows.append((t_a, t_b))
         ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
         value = whole_job_value(B, K, ms, world)
-        # one step = ctc_loss_fast_kernel (the dominant kernel) + the redo gate (a flag read per sequence);
+        # one step = one launch of ctc_loss_fast_kernel (it redoes the sequences it flags in its own tail);
         # the whole step is charged to the dominant kernel (conservative)
         kernel_us = ms * 1e3 / K
         ok_status = int(ring[0]["status"].sum().item()) == 0
@@ -373,7 +373,7 @@ def run_ours(args, cfg):
             "roofline": {"bound": "hbm", "kernel": "ctc_loss_fast_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": _traffic("ctc_cfg2"), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_us": kernel_us,
-                         "note": "one step = ctc_loss_fast_kernel + the redo gate; cfg2 (8.3 MB, L2 resident, 64 CTAs of 2x24 dependent lattice frames) is latency-bound, see roofline_bw_regime"},
+                         "note": "one step = one launch of ctc_loss_fast_kernel; cfg2 (8.3 MB, 64 CTAs of 2x24 dependent lattice frames on 148 SMs) is latency-bound, see roofline_bw_regime"},
             "roofline_bw_regime": bw,
             "inference": infer,
             "training": training,
