@@ -11,8 +11,8 @@
 //     block; the finished gradient leaves the same block through cp.async.bulk stores, so
 //     the LSU never issues a global access on the aligned path;
 //   * two warps per sequence.  The softmax is computed "lane per frame": each lane pulls one logit
-//     row out of shared memory into registers (the row pitch is 4*odd words and lanes are skewed by
-//     lane/8 columns, so the 32 lanes always hit 32 distinct banks), reduces max and sum(exp) there
+//     row out of shared memory into registers (LDS.128 from the sequence's first 16-byte aligned class on; the
+//     row pitch is 4*odd words, so each quarter-warp phase covers all 32 banks), reduces max and sum(exp) there
 //     and writes y * grad_scale back -- one read and one write of the staged block, which is already
 //     the gradient of every class the label does not contain;
 //   * the lattice runs in the LINEAR domain on y, register resident: lane i holds the state pair
@@ -448,7 +448,7 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
     int* infoi = reinterpret_cast<int*>(info);
     const bool run = have_seq && !bad && Tb > 0;
     const int mid = (Tb + 1) >> 1;
-    const int skew = (C >= 8) ? (lane >> 3) : 0;  // row pitch is 4*odd words: lanes l, l+8, l+16, l+24 share a bank
+    const int skew = (C >= 8) ? (lane >> 3) : 0;  // three-sweep path (CR == 0), scalar accesses: lanes l, l+8, l+16, l+24 share a bank
     bool novalid = false;
 
     if (run) {
@@ -461,18 +461,24 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 if constexpr (CR > 0) {
                     // the whole row lives in registers between the one read and the one write
                     const int tail = C < 3 ? C : 3, n = C - tail;
-                    float* p = row + skew;
+                    // the sweep starts at the first 16-byte aligned class of this sequence's column block (row pitch and
+                    // block base are multiples of 4 words: the offset depends on the sequence only) and moves four classes
+                    // per LDS.128 / STS.128; eight consecutive rows at a pitch of 4*odd words cover all 32 banks, so the
+                    // quarter-warp phases of a 128-bit access are conflict-free without a per-lane skew
+                    const int c0 = (C >= 8) ? ((4 - ((s * C) & 3)) & 3) : 0;
+                    float* p = row + c0;
                     int kt[3];
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) { int k = skew + n + q; kt[q] = (k >= C) ? k - C : k; }
+                    for (int q = 0; q < 3; ++q) { int k = c0 + n + q; kt[q] = (k >= C) ? k - C : k; }
                     // Three passes over the register-resident row, eight classes per step; the arithmetic of whole steps is
                     // packed two floats per instruction (FFMA2 / FADD2 / FMUL2: same IEEE results, half the issue slots).
                     float x[CR], xt[3];
                     float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
                     for_blocks<CR>(n,
                         [&](int kb) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) x[kb + q] = p[kb + q];
+                            const float4 v0 = *reinterpret_cast<const float4*>(p + kb), v1 = *reinterpret_cast<const float4*>(p + kb + 4);
+                            x[kb] = v0.x; x[kb + 1] = v0.y; x[kb + 2] = v0.z; x[kb + 3] = v0.w;
+                            x[kb + 4] = v1.x; x[kb + 5] = v1.y; x[kb + 6] = v1.z; x[kb + 7] = v1.w;
 #pragma unroll
                             for (int q = 0; q < 4; ++q) m[q] = fmaxf(m[q], fmaxf(x[kb + q], x[kb + 4 + q]));   // FMNMX3
                         },
@@ -517,13 +523,11 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                     const unsigned long long gz2 = pk2(gz, gz);
                     for_blocks<CR>(n,
                         [&](int kb) {
+                            float o[8];
 #pragma unroll
-                            for (int q = 0; q < 8; q += 2) {
-                                float a0, a1;
-                                up2(fmul2(pk2(x[kb + q], x[kb + q + 1]), gz2), a0, a1);
-                                p[kb + q] = a0;
-                                p[kb + q + 1] = a1;
-                            }
+                            for (int q = 0; q < 8; q += 2) up2(fmul2(pk2(x[kb + q], x[kb + q + 1]), gz2), o[q], o[q + 1]);
+                            *reinterpret_cast<float4*>(p + kb) = make_float4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<float4*>(p + kb + 4) = make_float4(o[4], o[5], o[6], o[7]);
                         },
                         [&](int k) { p[k] = x[k] * gz; });
 #pragma unroll
@@ -882,75 +886,76 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
     // Tail of a CTA that flagged a sequence (rare): once the CTA's own gradient block has left shared memory, its first
     // 128 threads recompute the flagged sequences with the exact log-domain routine, in place of a second kernel launch
     // that would have to visit every sequence's flag (inline_redo: the routine's layout fits this CTA's allocation).
-    auto redo_flagged = [&]() {   // called by every thread, after a CTA barrier that follows pass 3 and the CTA's stores
-        if (tid >= 128) return;
+    // Called by the whole CTA after a barrier that follows pass 3 and the CTA's own stores.
+    bool do_redo = false;   // CTA-uniform; set after a CTA barrier that follows pass 3 and the CTA's stores
+    if (!grad) {
+        if (inline_redo) {
+            __syncthreads();
+            do_redo = true;
+        }
+    } else {
+        if (have_seq) {
+            // frames past the sequence end: zero gradient (both warps, lane per class: conflict-free)
+            const int Tr = run ? Tb : 0;
+            float* p = st_s + (size_t)(Tr + role) * RS + lane;
+            if (CR > 0) {
+#pragma unroll 4
+                for (int t = Tr + role; t < T; t += 2, p += 2 * RS) {
+#pragma unroll
+                    for (int k = 0; k < CR; k += 32)
+                        if (k + lane < C) p[k] = 0.0f;
+                }
+            } else {
+                for (int t = Tr + role; t < T; t += 2, p += 2 * RS)
+                    for (int k = 0; k + lane < C; k += 32) p[k] = 0.0f;
+            }
+        }
+        ctc_mark(tl, 9);
+        if (bulk) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            ctc_mark(tl, 10);
+            bool redo = false;
+            if (inline_redo)
+                for (int i = 0; i < nb; ++i) redo = redo || s_redo[i] != 0;   // CTA-uniform
+            if (warp == 0) {
+                const unsigned row_bytes = (unsigned)(G * C * 4);
+                float* dst = grad + (size_t)b0 * C;
+                const unsigned src = smem_u32(stage);
+                if (use_bulk == 2 || use_bulk == 6) {
+                    if (lane == 0)
+                        for (int q = 0; q * kTmRows < T; ++q) tm_store_2d(&tmOut, b0 * C, q * kTmRows, src + (unsigned)(q * kTmRows) * RS * 4);
+                } else {
+                    for (int t = lane; t < T; t += 32) bulk_store(dst + (size_t)t * B * C, src + (unsigned)t * RS * 4, row_bytes);
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (redo) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the block has reached global memory: the redo overwrites part of it
+                else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            ctc_mark(tl, 11);
+            if (redo) {
+                __syncthreads();
+                do_redo = true;
+            }
+        } else {
+            __syncthreads();
+            const int n = nb * C;
+            for (int t = 0; t < T; ++t) {
+                float* dst = grad + ((size_t)t * B + b0) * C;
+                for (int j = tid; j < n; j += blockDim.x) st_stream(dst + j, stage[t * RS + j]);
+            }
+            if (inline_redo) {
+                __syncthreads();
+                do_redo = true;
+            }
+        }
+    }
+    // (one call site: the routine is inlined once)
+    if (do_redo && tid < 128)
         for (int i = 0; i < nb; ++i)
             if (s_redo[i])
                 ctc_general_one<true, true>(smem, b0 + i, logits, T, B, C, labels, label_offsets, seq_len, Lmax, loss, grad, status,
                                             grad_scale, nullptr);
-    };
-    if (!grad) {
-        if (inline_redo) {
-            __syncthreads();
-            redo_flagged();
-        }
-        return;
-    }
-    if (have_seq) {
-        // frames past the sequence end: zero gradient (both warps, lane per class: conflict-free)
-        const int Tr = run ? Tb : 0;
-        float* p = st_s + (size_t)(Tr + role) * RS + lane;
-        if (CR > 0) {
-#pragma unroll 4
-            for (int t = Tr + role; t < T; t += 2, p += 2 * RS) {
-#pragma unroll
-                for (int k = 0; k < CR; k += 32)
-                    if (k + lane < C) p[k] = 0.0f;
-            }
-        } else {
-            for (int t = Tr + role; t < T; t += 2, p += 2 * RS)
-                for (int k = 0; k + lane < C; k += 32) p[k] = 0.0f;
-        }
-    }
-    ctc_mark(tl, 9);
-    if (bulk) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        ctc_mark(tl, 10);
-        bool redo = false;
-        if (inline_redo)
-            for (int i = 0; i < nb; ++i) redo = redo || s_redo[i] != 0;   // CTA-uniform
-        if (warp == 0) {
-            const unsigned row_bytes = (unsigned)(G * C * 4);
-            float* dst = grad + (size_t)b0 * C;
-            const unsigned src = smem_u32(stage);
-            if (use_bulk == 2 || use_bulk == 6) {
-                if (lane == 0)
-                    for (int q = 0; q * kTmRows < T; ++q) tm_store_2d(&tmOut, b0 * C, q * kTmRows, src + (unsigned)(q * kTmRows) * RS * 4);
-            } else {
-                for (int t = lane; t < T; t += 32) bulk_store(dst + (size_t)t * B * C, src + (unsigned)t * RS * 4, row_bytes);
-            }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            if (redo) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the block has reached global memory: the redo overwrites part of it
-            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        }
-        ctc_mark(tl, 11);
-        if (redo) {
-            __syncthreads();
-            redo_flagged();
-        }
-    } else {
-        __syncthreads();
-        const int n = nb * C;
-        for (int t = 0; t < T; ++t) {
-            float* dst = grad + ((size_t)t * B + b0) * C;
-            for (int j = tid; j < n; j += blockDim.x) st_stream(dst + j, stage[t * RS + j]);
-        }
-        if (inline_redo) {
-            __syncthreads();
-            redo_flagged();
-        }
-    }
 }
 
 }  // namespace ocr
