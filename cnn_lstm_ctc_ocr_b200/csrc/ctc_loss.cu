@@ -299,8 +299,9 @@ extern "C" int ocr_ctc_loss_set_path(int path) {
 
 // Tuning aid: buffer of clock64() stamps, kCtcTimelineSlots per warp of every CTA of the fast kernel
 // (NULL switches it off).  The caller sizes it for ceil(B/G) CTAs x 2G warps.
+static long long* g_ctc_timeline = nullptr;
 extern "C" int ocr_debug_ctc_timeline(long long* device_buffer) {
-    OCR_CHECK_CUDA(cudaMemcpyToSymbol(g_ctc_timeline, &device_buffer, sizeof(device_buffer)));
+    g_ctc_timeline = device_buffer;
     return OCR_OK;
 }
 
@@ -471,7 +472,7 @@ static int launch_fast(const FastPlan& fp, const float* logits, int T, int B, in
     const int inl = (g_ctc_inline_redo && g_ctc_path != 3 && 64 * fp.G >= kCtcThreads && ctc_layout(T, C, Lmax, true).total <= fp.smem) ? 1 : 0;
     *redo_inlined = inl;
     OCR_CHECK_CUDA(launch_pdl(ctc_loss_fast_kernel<NP, CR>, grid, 64 * fp.G, (size_t)fp.smem + 128, st, logits, T, B, C, labels, label_offsets,
-                              seq_len, Lmax, fp.G, bulk, loss, grad, status, grad_scale, tmIn, tmOut, pf, inl | ((g_ctc_pdl == 2 && grid * 2 <= sms_of(dev)) ? 2 : 0)));
+                              seq_len, Lmax, fp.G, bulk, loss, grad, status, grad_scale, tmIn, tmOut, pf, inl | ((g_ctc_pdl == 2 && grid * 2 <= sms_of(dev)) ? 2 : 0), g_ctc_timeline));
     count_launch();
     return OCR_OK;
 }

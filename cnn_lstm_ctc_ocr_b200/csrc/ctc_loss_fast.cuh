@@ -51,8 +51,9 @@ __device__ void ctc_general_one(unsigned char* smem, const int b, const float* _
                                 const int32_t* __restrict__ seq_len, int Lmax, float* __restrict__ loss, float* __restrict__ grad,
                                 int32_t* __restrict__ status, float grad_scale, float* __restrict__ workspace);
 
-// Optional phase timeline for tuning (ocr_debug_ctc_timeline): per warp, clock64() at up to 12 phase boundaries.
-__device__ long long* g_ctc_timeline = nullptr;
+// Optional phase timeline for tuning (ocr_debug_ctc_timeline): per warp, clock64() at up to 12 phase boundaries.  The
+// buffer pointer is a kernel PARAMETER: as a __device__ global it was a load every warp waited on at its first mark
+// (6 % of the kernel's stall samples, and it delayed the TMA requests of every CTA).
 constexpr int kCtcTimelineSlots = 12;
 __device__ __forceinline__ void ctc_mark(long long* tl, int slot) {
     if (tl != nullptr && (threadIdx.x & 31) == 0)
@@ -298,7 +299,8 @@ __global__ void __launch_bounds__(CR > 64 ? 64 * 4 : 64 * kFastMaxG)
 ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, const int32_t* __restrict__ labels,
                      const int32_t* __restrict__ label_offsets, const int32_t* __restrict__ seq_len, int Lmax, int G,
                      int use_bulk, float* __restrict__ loss, float* __restrict__ grad, int32_t* __restrict__ status,
-                     float grad_scale, const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut, int pf_stride, int inline_redo)
+                     float grad_scale, const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut, int pf_stride, int inline_redo,
+                     long long* const tl)
 {
     // programmatic dependent launch (launch_pdl): this grid may have been scheduled while its predecessor was still running;
     // nothing here touches global memory before the predecessor's results are visible
@@ -318,7 +320,6 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = warp >> 1, role = warp & 1;  // role 0: alpha (forward), 1: beta (backward)
-    long long* const tl = g_ctc_timeline;
     ctc_mark(tl, 0);
     const int b0 = blockIdx.x * G;
     const int nb = min(G, B - b0);

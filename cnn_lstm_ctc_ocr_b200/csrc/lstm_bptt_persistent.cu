@@ -28,9 +28,9 @@ constexpr int kBpK = 4 * kBpHS;           // K-slice: 64 gate columns
 
 // phase timeline of CTA 0 (shared with the forward kernel's hook, ocr_debug_lstm_timeline): 8 stamps per frame
 __device__ long long* g_bptt_timeline = nullptr;
-__device__ __forceinline__ void bp_mark(int f, int slot) {
-    long long* tl = g_bptt_timeline;
-    if (tl != nullptr && blockIdx.x == 0) tl[f * 8 + slot] = clock64();
+// (the pointer is read once per thread at kernel start, not at every mark)
+__device__ __forceinline__ void bp_mark(long long* tl, int f, int slot) {
+    if (tl != nullptr) tl[f * 8 + slot] = clock64();
 }
 
 __device__ __forceinline__ void bp_wait_counter(const unsigned* ctr, unsigned target) {
@@ -47,6 +47,7 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW, float* act /*[T*B, 8H]
                  const float* __restrict__ cs /*[T,B,2H]*/, const float* __restrict__ dout /*[T,B,2H]*/, const int32_t* __restrict__ seq_len,
                  float* part /*[2][2][MT][NS][NS][128][16]*/, unsigned* __restrict__ counters /*[2][MT]*/, int T, int B, int H, int NS, int MT)
 {
+    long long* const tl = blockIdx.x == 0 ? g_bptt_timeline : nullptr;
     const int NH = H > 256 ? H / 2 : H;                 // columns per MMA (N), halves = H / NH
     const int halves = H / NH;
     extern __shared__ unsigned char bp_smem_raw[];
@@ -107,7 +108,7 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW, float* act /*[T*B, 8H]
                         }
                 }
                 umma_commit(bar_acc);
-                bp_mark(f, 3);
+                bp_mark(tl, f, 3);
             }
         }
     } else {
@@ -144,7 +145,7 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW, float* act /*[T*B, 8H]
             if (f > 0) {
                 if (threadIdx.x == 64) bp_wait_counter(counters + d * MT + mt, (unsigned)NS * (unsigned)f);
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (threadIdx.x == 64) bp_mark(f, 0);
+                if (threadIdx.x == 64) bp_mark(tl, f, 0);
                 if (live && s + 1 < len) {
                     const float* src = part + ((size_t)((f - 1) & 1) * 2 + d) * part_pd + (((size_t)mt * NS + j) * NS) * part_tile + (size_t)rl * kBpHS;
                     for (int js = 0; js < NS; ++js) {     // fixed order: deterministic sums
@@ -157,7 +158,7 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW, float* act /*[T*B, 8H]
                     }
                 }
             }
-            if (threadIdx.x == 64) bp_mark(f, 1);
+            if (threadIdx.x == 64) bp_mark(tl, f, 1);
             // ---- cell backward for my units; gate gradients to global memory and into the A tile (k = gate*16 + unit)
             float dg[kBpK];
             if (live) {
@@ -211,12 +212,12 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW, float* act /*[T*B, 8H]
             if (threadIdx.x == 64) {
                 unsigned long long st_;
                 asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st_) : "r"(bar_a) : "memory");
-                bp_mark(f, 2);
+                bp_mark(tl, f, 2);
             }
             if (f == T - 1) break;                        // the last step's product has no consumer (no MMA is issued for it)
             // ---- partial d h_{prev}[row, all H units] over my K-slice: scatter 16 columns to each slice owner
             g_mbar_wait(bar_acc, f & 1);
-            if (threadIdx.x == 64) bp_mark(f, 4);
+            if (threadIdx.x == 64) bp_mark(tl, f, 4);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             {
                 float* dst = part + ((size_t)(f & 1) * 2 + d) * part_pd + ((size_t)mt * NS * NS + j) * part_tile + (size_t)rl * kBpHS;
@@ -245,12 +246,12 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW, float* act /*[T*B, 8H]
                     }
                 }
             }
-            if (threadIdx.x == 64) bp_mark(f, 5);
+            if (threadIdx.x == 64) bp_mark(tl, f, 5);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");   // all partial stores of this CTA are ordered before ...
             if (threadIdx.x == 64) {                          // ... this gpu-scope release that publishes the slice
                 asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counters + d * MT + mt) : "memory");
-                bp_mark(f, 6);
+                bp_mark(tl, f, 6);
             }
         }
     }

@@ -35,9 +35,9 @@ __device__ __forceinline__ float sigm(float x) { return fmaf(0.5f, tanh_fast(0.5
 // [0] producer past the grid barrier, [1] last h tile requested, [2] first h tile landed (MMA lane), [3] last MMA issued,
 // [4] accumulator complete (epilogue), [5] TMEM read, [6] cell update + stores done, [7] slice published.
 __device__ long long* g_lstm_timeline = nullptr;
-__device__ __forceinline__ void lstm_mark(int s, int slot) {
-    long long* tl = g_lstm_timeline;
-    if (tl != nullptr && blockIdx.x == 0) tl[s * 8 + slot] = clock64();
+// (the pointer is read ONCE per thread at kernel start: read at every mark it was a dependent load on the frame's critical path)
+__device__ __forceinline__ void lstm_mark(long long* tl, int s, int slot) {
+    if (tl != nullptr) tl[s * 8 + slot] = clock64();
 }
 
 // bounded spin on a global counter (acquire)
@@ -62,6 +62,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
 {
     constexpr int N = 4 * HS;
     const int nk = H / kGemmBK;
+    long long* const tl = blockIdx.x == 0 ? g_lstm_timeline : nullptr;
     extern __shared__ unsigned char rnn_smem_raw[];
     unsigned char* smem = rnn_smem_raw + ((1024u - (g_smem_u32(rnn_smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     const unsigned s_base = g_smem_u32(smem);
@@ -117,14 +118,14 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
                     asm volatile("fence.proxy.async;" ::: "memory");          // generic-proxy writes -> async-proxy (TMA) reads
                 }
                 const CUtensorMap* tm = (s & 1) ? (d ? &tmH11 : &tmH10) : (d ? &tmH01 : &tmH00);
-                lstm_mark(s, 0);
+                lstm_mark(tl, s, 0);
                 for (int gi = 0; gi < ng; ++gi, ++it) {
                     const int st = it % n_stages;
                     if (it >= n_stages) g_mbar_wait(bar_empty + st * 8, ((it / n_stages) - 1) & 1);
                     g_mbar_expect_tx(bar_full + st * 8, g_bytes);
                     tma_load_3d(s_a + st * g_bytes, tm, 0, m0, gi * gc, bar_full + st * 8);
                 }
-                lstm_mark(s, 1);
+                lstm_mark(tl, s, 1);
                 if (dual) {   // second MMA issuer: odd k-chunks -> accumulator 1
                     const unsigned idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(kGemmBM >> 4) << 24);
                     if (s == 0) g_mbar_wait(bar_w, 0);
@@ -150,7 +151,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
                 for (int gi = 0; gi < ng; ++gi, ++it) {
                     const int st = it % n_stages;
                     g_mbar_wait(bar_full + st * 8, (it / n_stages) & 1);
-                    if (gi == 0) lstm_mark(s, 2);
+                    if (gi == 0) lstm_mark(tl, s, 2);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     for (int c = 0; c < gc; c += (dual ? 2 : 1)) {   // dual: even chunks here, odd chunks on the producer lane
                         const int k = gi * gc + c;
@@ -162,7 +163,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
                     umma_commit(bar_empty + st * 8);
                 }
                 umma_commit(bar_acc);   // gate pre-activations of frame step s are in TMEM
-                lstm_mark(s, 3);
+                lstm_mark(tl, s, 3);
                 // the next frame's first MMA overwrites TMEM; it cannot start before the epilogue has read this frame:
                 // its operand h_{s+1} only exists after every CTA (this one included) passed the grid barrier
             }
@@ -191,7 +192,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
                 }
             }
             g_mbar_wait(bar_acc, s & 1);
-            if (threadIdx.x == 64) lstm_mark(s, 4);
+            if (threadIdx.x == 64) lstm_mark(tl, s, 4);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             unsigned g[N];
 #pragma unroll
@@ -220,7 +221,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
                     for (int i = 0; i < 16; ++i) g[c0 + i] = __float_as_uint(__uint_as_float(g[c0 + i]) + __uint_as_float(g2[i]));
                 }
             }
-            if (threadIdx.x == 64) lstm_mark(s, 5);
+            if (threadIdx.x == 64) lstm_mark(tl, s, 5);
             if (live_row) {
                 float* hn = hbuf + (((size_t)((s + 1) & 1) * 2 + d) * B + r) * H + j * HS;
                 if (upd) {
@@ -255,12 +256,12 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
 #pragma unroll
                 for (int u = 0; u < HS; u += 4) *reinterpret_cast<float4*>(hn + u) = make_float4(h[u], h[u + 1], h[u + 2], h[u + 3]);
             }
-            if (threadIdx.x == 64) lstm_mark(s, 6);
+            if (threadIdx.x == 64) lstm_mark(tl, s, 6);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps: their h stores are ordered before...
             if (warp == 2 && lane == 0) {                    // ...this gpu-scope release (cumulative) that publishes the slice
                 asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counters + d) : "memory");
-                lstm_mark(s, 7);
+                lstm_mark(tl, s, 7);
             }
         }
     }
