@@ -339,6 +339,11 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
+static int g_ctc_speculate = 1;   // tensor-map path: request all boxes of a group before its sequence lengths are known
+extern "C" int ocr_debug_ctc_speculate(int on) {
+    g_ctc_speculate = on ? 1 : 0;
+    return OCR_OK;
+}
 static int g_ctc_inline_redo = 1;   // flagged sequences are redone in the fast kernel's tail when the exact routine fits there (0: always the gate launch)
 extern "C" int ocr_debug_ctc_inline_redo(int on) {
     g_ctc_inline_redo = on ? 1 : 0;
@@ -472,7 +477,8 @@ static int launch_fast(const FastPlan& fp, const float* logits, int T, int B, in
     const int inl = (g_ctc_inline_redo && g_ctc_path != 3 && 64 * fp.G >= kCtcThreads && ctc_layout(T, C, Lmax, true).total <= fp.smem) ? 1 : 0;
     *redo_inlined = inl;
     OCR_CHECK_CUDA(launch_pdl(ctc_loss_fast_kernel<NP, CR>, grid, 64 * fp.G, (size_t)fp.smem + 128, st, logits, T, B, C, labels, label_offsets,
-                              seq_len, Lmax, fp.G, bulk, loss, grad, status, grad_scale, tmIn, tmOut, pf, inl | ((g_ctc_pdl == 2 && grid * 2 <= sms_of(dev)) ? 2 : 0), g_ctc_timeline));
+                              seq_len, Lmax, fp.G, bulk, loss, grad, status, grad_scale, tmIn, tmOut, pf, inl | ((g_ctc_pdl == 2 && grid * 2 <= sms_of(dev)) ? 2 : 0) | (g_ctc_speculate ? 4 : 0),
+                              g_ctc_timeline));
     count_launch();
     return OCR_OK;
 }

@@ -306,6 +306,7 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
     // nothing here touches global memory before the predecessor's results are visible
     if (inline_redo & 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // tuning knob (ocr_debug_ctc_pdl(2))
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    const bool spec_flag = (inline_redo & 4) != 0;   // request every box of the group before its lengths are known
     inline_redo &= 1;
     extern __shared__ __align__(128) unsigned char smem_f[];
     // tensor-map TMA wants 128-byte aligned shared-memory boxes: align by hand (the launch adds 128 bytes)
@@ -343,7 +344,18 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
     __shared__ int s_tmax;
     __shared__ int s_redo[kFastMaxG];   // sequences of this CTA whose lattice left the float32 range (redone in the tail)
     if (tid < kFastMaxG) s_redo[tid] = 0;   // ordered before the first write by the CTA barrier below
+    // Speculative requests (tensor-map path): all T/16 boxes go out at once instead of after the lengths have come back
+    // from global memory (a dependent load of ~800 cycles at the head of every CTA).  The rows past the group's longest
+    // sequence are wasted L2 -> shared-memory traffic only: the predecessor's L2 prefetch fetched them anyway.
+    const bool spec = spec_flag && bulk && (use_bulk == 2 || use_bulk == 5);
     if (warp == 0) {
+        if (spec && lane == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(bar, (unsigned)(G * C * 4) * (unsigned)T);
+            const unsigned dst = smem_u32(stage);
+            for (int q = 0; q * kTmRows < T; ++q) tm_load_2d(dst + (unsigned)(q * kTmRows) * RS * 4, &tmIn, b0 * C, q * kTmRows, bar);
+        }
         int tm = 0;
         for (int i = lane; i < nb; i += 32) tm = max(tm, min(max(seq_len[b0 + i], 0), T));
 #pragma unroll
@@ -352,7 +364,7 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
             s_tmax = tm;
             s_zero[0] = 0.0f;
         }
-        if (bulk) {
+        if (bulk && !spec) {
             const unsigned row_bytes = (unsigned)(G * C * 4);
             if (lane == 0) {
                 mbar_init(bar, 1);
@@ -425,7 +437,7 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
             }
         }
         __syncthreads();
-    } else if (tmax > 0) {
+    } else if (tmax > 0 || spec) {
         mbar_wait(bar, 0);
     }
     ctc_mark(tl, 1);

@@ -79,6 +79,9 @@ int ocr_debug_ctc_prefetch(int stride);
 int ocr_debug_ctc_pdl(int on);
 /* Tuning aid: sequences the fast kernel flags are redone in its own tail (1, default) or by a second launch (0). */
 int ocr_debug_ctc_inline_redo(int on);
+/* Tuning aid: the fast kernel requests every TMA box of a group before its sequence lengths are known (1, default) or only
+ * the boxes up to the group's longest sequence, after reading the lengths (0). */
+int ocr_debug_ctc_speculate(int on);
 
 /* ---------------------------------------------------------------------------------------------
  * CTC greedy decoder.  Replaces tf.nn.ctc_greedy_decoder(merge_repeated=True) at

@@ -66,22 +66,24 @@ def test_loss_cfg2_vs_oracle(oracle, C, ragged, relu, path):
 def test_loss_many_waves_prefetch_and_pdl(oracle):
     """B = 2048 is several waves of the fast kernel (512 CTAs of 4 sequences, 296 resident on a B200): the L2 prefetch of the
     successor group is live.  Parity against the oracle, and the launch-time knobs (prefetch distance, programmatic
-    dependent launch) must not change a single bit."""
+    dependent launch, speculative box requests) must not change a single bit."""
     from cnn_lstm_ctc_ocr_b200 import _lib
     lib = _lib.load()
     x, labels, seq_len = cfg2_inputs(seed=5, T=64, B=2048, C=63, ragged=True)
     l64, g64, _ = oracle.ctc_loss(x, labels, seq_len, nthreads=8, f64=True)
     outs = []
     try:
-        for prefetch, pdl in ((-1, 1), (0, 1), (37, 1), (-1, 0)):
+        for prefetch, pdl, spec in ((-1, 1, 1), (0, 1, 1), (37, 1, 0), (-1, 0, 0)):
             _lib.check(lib.ocr_debug_ctc_prefetch(prefetch), "prefetch")
             _lib.check(lib.ocr_debug_ctc_pdl(pdl), "pdl")
+            _lib.check(lib.ocr_debug_ctc_speculate(spec), "speculate")
             loss, grad, st = _gpu_loss(x, labels, seq_len)
             assert (st == 0).all()
             outs.append((loss, grad))
     finally:
         lib.ocr_debug_ctc_prefetch(-1)
         lib.ocr_debug_ctc_pdl(1)
+        lib.ocr_debug_ctc_speculate(1)
     np.testing.assert_allclose(outs[0][0], l64, rtol=1e-5)
     assert np.abs(outs[0][1] - g64).max() < 1e-5
     for loss, grad in outs[1:]:

@@ -25,6 +25,10 @@ def go():
                                 _lib.ptr(grad), _lib.ptr(status), 1.0 / B, _lib.ptr(ws), need.value, _lib.stream_handle()), "ctc")
 ref = None
 for s in strides:
+    spec = 1
+    if s <= -2:      # -2: automatic distance, speculative box requests off
+        spec, s = 0, -1
+    lib.ocr_debug_ctc_speculate(spec)
     _lib.check(lib.ocr_debug_ctc_prefetch(s), "prefetch")
     go(); go(); torch.cuda.synchronize()
     ts = []
@@ -37,5 +41,5 @@ for s in strides:
     if ref is None:
         ref = (loss.clone(), grad.clone())
     same = torch.equal(ref[0], loss) and torch.equal(ref[1], grad)
-    print("prefetch %4d: %.1f us, %.1f GB/s algorithmic, bit-identical to the first setting: %s" % (s, us, 2 * T * B * C * 4 / us / 1e3, same))
-lib.ocr_debug_ctc_prefetch(-1)
+    print("speculate %d prefetch %4d: %.1f us, %.1f GB/s algorithmic, bit-identical to the first setting: %s" % (spec, s, us, 2 * T * B * C * 4 / us / 1e3, same))
+lib.ocr_debug_ctc_prefetch(-1); lib.ocr_debug_ctc_speculate(1)
