@@ -82,3 +82,23 @@ def test_ctc_fast_kernel_sass_evidence(so_path):
         assert count(pat) > 0, pat
     assert count(r"\bFFMA2\b") >= 16 and count(r"\bFADD2\b") >= 16 and count(r"\bFMUL2\b") >= 16
     assert count(r"LDS\.128") >= 8 and count(r"STS\.128") >= 8
+
+
+def test_tensor_core_kernels_sass_evidence(so_path):
+    """The dense-contraction kernels issue tcgen05 (UTC*MMA), read their accumulators from TMEM (LDTM) and are fed by the TMA
+    engine (UTMALDG): the SASS mnemonics /opt/skills/guides/B200_PROFILING.md names as the proof."""
+    import re, shutil, subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-sass", so_path], capture_output=True, text=True).stdout
+    funcs = {}
+    for p in out.split("Function : ")[1:]:
+        funcs[p.split("\n", 1)[0].strip()] = p
+    for stem in ("gemm_tf32_kernel", "conv3x3_igemm_kernel", "conv3x3_halo_kernel", "lstm_persistent_kernel", "lstm_bptt_kernel"):
+        bodies = [b for n, b in funcs.items() if stem in n]
+        assert bodies, stem
+        for b in bodies:
+            assert re.search(r"\bUTC[A-Z]*MMA\b", b), stem + ": no tcgen05.mma"
+            assert "LDTM" in b, stem + ": no tcgen05.ld"
+            assert "UTMALDG" in b, stem + ": no TMA load"
