@@ -66,6 +66,9 @@ def _validate_ctc(flat_host, lengths, seq_len_host, T, C, ignore_longer_outputs_
     if ignore_longer_outputs_than_inputs or not flat.size:
         return
     ln = np.asarray(lengths, dtype=np.int64).reshape(-1)
+    # a label of length L needs at most 2L - 1 frames (every neighbour repeated): nothing to count when all have that many
+    if bool(((sl >= 2 * ln) | (sl <= 0)).all()):
+        return
     off = np.zeros(ln.size + 1, np.int64)
     np.cumsum(ln, out=off[1:])
     rep = np.zeros(flat.size + 1, np.int64)           # rep[i+1] = repeats among flat[:i+1] that are not example starts
