@@ -31,6 +31,7 @@ SIGNATURES = {
     "ocr_ctc_beam_search_workspace_bytes": (_i, [_i, _i, _i, _i, _c.POINTER(_sz)]),
     "ocr_ctc_beam_search": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ocr_gemm_tf32": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "ocr_preprocess_train": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "ocr_conv1_3x3_valid": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "ocr_im2col3x3_same": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "ocr_rows_max_to_seq": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),

@@ -101,7 +101,11 @@ ctc_general_one(unsigned char* smem, const int b, const float* __restrict__ logi
     gen_sync<kInFast>();  // previous sequence of this persistent CTA is done with shared memory
 
     const int off = label_offsets[b];
-    const int L = label_offsets[b + 1] - off;
+    const int Lraw = label_offsets[b + 1] - off;
+    // the label arrays and the lattice strides are sized for the caller's max_label_len (Lp1 - 1): a label outside
+    // [0, Lmax] is an invalid argument (flagged 3 below), never an overrun
+    const bool bad_len = Lraw < 0 || Lraw > Lp1 - 1;
+    const int L = bad_len ? 0 : Lraw;
     const int U = 2 * L + 1;
     const int Tb = seq_len[b];
     const int blank = C - 1;
@@ -124,7 +128,7 @@ ctc_general_one(unsigned char* smem, const int b, const float* __restrict__ logi
             if (s > 0 && s_lab[s] == s_lab[s - 1]) need++;
         }
         if (!bad && need > Tb && Tb > 0) bad = 2;
-        if (Tb < 0 || Tb > T) bad = 3;
+        if (Tb < 0 || Tb > T || bad_len) bad = 3;
         s_bad = bad;
     }
     for (int u = tid; u < U; u += kCtcThreads) {
@@ -292,7 +296,7 @@ static size_t ctc_ws_floats_per_seq(int T, int Lmax) {
 // path selection: 0 auto, 1 general kernel only, 2 fast kernel with LSU loads/stores (no TMA bulk copies)
 static int g_ctc_path = 0;
 extern "C" int ocr_ctc_loss_set_path(int path) {
-    OCR_CHECK_ARG(path >= 0 && path <= 6, "ocr_ctc_loss_set_path: path=%d outside [0,4]", path);
+    OCR_CHECK_ARG(path >= 0 && path <= 6, "ocr_ctc_loss_set_path: path=%d outside [0,6]", path);
     g_ctc_path = path;
     return OCR_OK;
 }

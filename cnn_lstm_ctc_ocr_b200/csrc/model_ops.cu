@@ -16,7 +16,28 @@
 namespace ocr {
 
 // ---------------------------------------------------------------------------------------------------------------
-// conv1: out[b,y,x,:] = relu(bias + sum_{i,j} w[i,j,:] * in[b,y+i,x+j]),   in = u8/255 - 0.5 or float
+// tf.image.convert_image_dtype(uint8 -> float32) multiplies by the float32 constant 1/255 (scale = 1. / dtype.max)
+__device__ constexpr float kInv255 = (float)(1.0 / 255.0);
+
+// mjsynth._preprocess_image + the zero padding of the batcher (mjsynth.py:185-194, 56, 69): u8 rows -> float32, first row
+// duplicated on top, 0.0 (not -0.5) right of each crop's own width.  One thread = one output pixel.
+__global__ void __launch_bounds__(256)
+preprocess_train_kernel(const unsigned char* __restrict__ in, int B, int Hin, int W, const int32_t* __restrict__ widths, float* __restrict__ out)
+{
+    const long long total = (long long)B * (Hin + 1) * W;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % W);
+        long long p = idx / W;
+        const int r = (int)(p % (Hin + 1));
+        const int b = (int)(p / (Hin + 1));
+        const int src = r > 0 ? r - 1 : 0;
+        float v = 0.0f;
+        if (x < __ldg(widths + b)) v = (float)__ldg(in + ((size_t)b * Hin + src) * W + x) * kInv255 - 0.5f;
+        out[idx] = v;
+    }
+}
+
+// conv1: out[b,y,x,:] = relu(bias + sum_{i,j} w[i,j,:] * in[b,y+i,x+j]),   in = u8 * (1/255) - 0.5 or float
 // one thread = one output pixel x 4 channels
 template <bool kU8>
 __global__ void __launch_bounds__(256)
@@ -38,7 +59,7 @@ conv1_kernel(const void* __restrict__ in_, int B, int H, int W, const float* __r
             for (int j = 0; j < 3; ++j) {
                 const size_t o = ((size_t)b * H + (y + i)) * W + (x + j);
                 float v;
-                if (kU8) v = (float)__ldg(reinterpret_cast<const unsigned char*>(in_) + o) / 255.0f - 0.5f;
+                if (kU8) v = (float)__ldg(reinterpret_cast<const unsigned char*>(in_) + o) * kInv255 - 0.5f;
                 else v = __ldg(reinterpret_cast<const float*>(in_) + o);
                 const float4 ww = __ldg(reinterpret_cast<const float4*>(w + (i * 3 + j) * Co) + c4);
                 acc.x = fmaf(v, ww.x, acc.x); acc.y = fmaf(v, ww.y, acc.y); acc.z = fmaf(v, ww.z, acc.z); acc.w = fmaf(v, ww.w, acc.w);
@@ -202,6 +223,16 @@ extern "C" int ocr_conv1_3x3_valid(const void* in, int in_is_u8, int B, int H, i
     const long long total = (long long)B * (H - 2) * (W - 2) * (Cout / 4);
     if (in_is_u8) conv1_kernel<true><<<grid_for(total), 256, 0, st>>>(in, B, H, W, w, bias, Cout, out);
     else conv1_kernel<false><<<grid_for(total), 256, 0, st>>>(in, B, H, W, w, bias, Cout, out);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+extern "C" int ocr_preprocess_train(const unsigned char* in, int B, int Hin, int W, const int32_t* widths, float* out, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(B >= 0 && Hin >= 1 && W >= 1, "ocr_preprocess_train: bad shape B=%d Hin=%d W=%d", B, Hin, W);
+    if (B == 0) return OCR_OK;
+    OCR_CHECK_ARG(in && widths && out, "ocr_preprocess_train: NULL argument");
+    preprocess_train_kernel<<<grid_for((long long)B * (Hin + 1) * W), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, B, Hin, W, widths, out);
     OCR_CHECK_LAUNCH();
     return OCR_OK;
 }

@@ -547,7 +547,7 @@ conv1_wgrad_kernel(const void* __restrict__ in_, int B, int H, int W, const floa
                 for (int jx = 0; jx < 3; ++jx) {
                     const size_t o = ((size_t)b * H + (y + i)) * W + (x + jx);
                     float v;
-                    if (kU8) v = (float)__ldg(reinterpret_cast<const unsigned char*>(in_) + o) / 255.0f - 0.5f;
+                    if (kU8) v = (float)__ldg(reinterpret_cast<const unsigned char*>(in_) + o) * (float)(1.0 / 255.0) - 0.5f;
                     else v = __ldg(reinterpret_cast<const float*>(in_) + o);
                     taps[i * 3 + jx][threadIdx.x] = v;
                 }

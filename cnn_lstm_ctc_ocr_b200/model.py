@@ -22,7 +22,7 @@ import torch
 from . import _lib, ctc
 
 # mjsynth.py:23-26
-out_charset = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789 `~!@#$%^&*()-=_+[]{};'\\:\"|,./<>?"
+out_charset = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789 `~!@#$%^&*()-=_+[]{};'\\:\"|,./<>?"
 
 
 def num_classes():
@@ -94,7 +94,7 @@ def init_params(seed=0, cell_type="lstm", rnn_sizes=(512, 512), num_classes=None
 def preprocess_image(image):
     """validate._preprocess_image: uint8 -> float32 in [-0.5, 0.5].  (Model.convnet_layers also accepts the uint8
     tensor directly and fuses this into conv1.)"""
-    return image.to(torch.float32) / 255.0 - 0.5
+    return image.to(torch.float32) * float(np.float32(1.0 / 255.0)) - 0.5     # convert_image_dtype multiplies by float32(1/255)
 
 
 def get_string(labels):
@@ -154,8 +154,12 @@ class Model:
     # ------------------------------------------------------------------ weights
     @classmethod
     def load_npz(cls, path, **kw):
+        """Variables from an .npz keyed by TensorFlow variable names (validate._get_init_trained, validate.py:116-124: a
+        Saver over the graph's variables).  Training-only entries of a Trainer checkpoint (Adam slots, beta powers,
+        global_step) are ignored, as a Saver built from the inference graph ignores them."""
+        skip = ("global_step", "beta1_power", "beta2_power")
         with np.load(path) as z:
-            return cls({k: z[k] for k in z.files}, **kw)
+            return cls({k: z[k] for k in z.files if k not in skip and not k.endswith(("/Adam", "/Adam_1"))}, **kw)
 
     def save_npz(self, path):
         np.savez(path, **{k: v.cpu().numpy() for k, v in self.params.items()})

@@ -85,11 +85,15 @@ def _param_order(cell_type):
 class Trainer:
     def __init__(self, params, cell_type="lstm", rnn_sizes=(512, 512), device="cuda", learning_rate=1e-4, momentum=0.9,
                  decay_rate=0.9, decay_steps=2 ** 16, decay_staircase=False, beta2=0.999, epsilon=1e-8,
-                 process_group=None, sync_bn=False, global_step=0, overlap_weight_gradients=True):
+                 process_group=None, sync_bn=False, global_step=0, overlap_weight_gradients=True, tune_scope="", tune_from=None):
         if cell_type not in ("lstm", "gru"):
             raise ValueError("cell_type must be 'lstm' (model_bu.py) or 'gru' (model.py)")
         self.cell_type = cell_type
         self.rnn_sizes = tuple(rnn_sizes)
+        if cell_type == "lstm" and any(h % 16 for h in self.rnn_sizes):
+            # the fw | bw LSTM biases are read (and their gradient written) as ONE [8H] slice of the flat buffer, whose
+            # slots are padded to 64 floats: adjacent only when 4H % 64 == 0
+            raise ValueError("LSTM sizes must be multiples of 16, got %s" % (self.rnn_sizes,))
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.OcrLibraryError("Trainer needs a CUDA device; there is no CPU path")
@@ -134,8 +138,11 @@ class Trainer:
         self.scratch_side = torch.zeros_like(self.scratch)
         self._side_keep = []
         self.wscratch = None
+        self._set_tune_scope(tune_scope)
         self._alloc_derived()
         self.derive_layouts()
+        if tune_from:
+            self.restore(tune_from)
 
     # ------------------------------------------------------------------ helpers
     def _c(self, rc, what):
@@ -175,8 +182,94 @@ class Trainer:
         return Model({k: v.detach().cpu().numpy() for k, v in self.all_params().items()}, cell_type=self.cell_type,
                      rnn_sizes=self.rnn_sizes, device=self.device, **kw)
 
-    def save_npz(self, path):
-        np.savez(path, global_step=np.int64(self.global_step), **{k: v.detach().cpu().numpy() for k, v in self.all_params().items()})
+    def save_npz(self, path, with_optimizer=True):
+        """tf.train.Saver over the training graph (train.py:185-201): the variables, global_step and -- with_optimizer -- the
+        Adam slots under TensorFlow's slot names ("<variable>/Adam" = m, "<variable>/Adam_1" = v).  The beta powers TF also
+        saves (beta1_power, beta2_power) are functions of global_step here (_lr_t) and are written for completeness."""
+        d = {k: v.detach().cpu().numpy() for k, v in self.all_params().items()}
+        d["global_step"] = np.int64(self.global_step)
+        if with_optimizer:
+            m, v = self.adam_m.cpu().numpy(), self.adam_v.cpu().numpy()
+            for n in self.names:
+                o, sz = self.offsets[n], int(np.prod(self.shapes[n]))
+                d[n + "/Adam"] = m[o:o + sz].reshape(self.shapes[n])
+                d[n + "/Adam_1"] = v[o:o + sz].reshape(self.shapes[n])
+            d["beta1_power"] = np.float32(self.beta1 ** (self.global_step + 1))
+            d["beta2_power"] = np.float32(self.beta2 ** (self.global_step + 1))
+        np.savez(path, **d)
+
+    def load_optimizer_state(self, state):
+        """Restore the Adam slots saved by save_npz (name -> array with "<variable>/Adam", "<variable>/Adam_1").  Variables
+        without saved slots keep zeros (what TensorFlow gives freshly created slots)."""
+        for n in self.names:
+            o, sz = self.offsets[n], int(np.prod(self.shapes[n]))
+            for suffix, buf in (("/Adam", self.adam_m), ("/Adam_1", self.adam_v)):
+                if n + suffix in state:
+                    a = np.asarray(state[n + suffix], dtype=np.float32)
+                    if a.shape != self.shapes[n]:
+                        raise ValueError("optimizer slot %s has shape %s, variable has %s" % (n + suffix, a.shape, self.shapes[n]))
+                    buf[o:o + sz].copy_(torch.from_numpy(a.reshape(-1)))
+
+    @classmethod
+    def load_npz(cls, path, **kw):
+        """A Trainer resumed from a checkpoint written by save_npz -- the Supervisor's restore from FLAGS.output
+        (train.py:185-201): variables, batch-norm moving statistics, Adam slots and global_step."""
+        with np.load(path) as z:
+            state = {k: z[k] for k in z.files}
+        variables = {k: v for k, v in state.items() if not k.endswith(("/Adam", "/Adam_1")) and k not in ("beta1_power", "beta2_power", "global_step")}
+        kw.setdefault("global_step", int(state.get("global_step", 0)))
+        t = cls(variables, **kw)
+        t.load_optimizer_state(state)
+        return t
+
+    def restore(self, tune_from):
+        """train._get_init_pretrained (train.py:152-165): `--tune_from` restores a Saver over ALL global variables of the
+        training graph -- the model variables, the batch-norm moving statistics, the Adam slots and global_step -- from a
+        checkpoint (.npz keyed by TensorFlow names as written by save_npz, or a dict).  Like tf.train.Saver.restore, a
+        model variable missing from the checkpoint is an error; a checkpoint without optimizer slots (exported from an
+        inference Model) leaves the slots and global_step as they are."""
+        if isinstance(tune_from, dict):
+            src = tune_from
+        else:
+            with np.load(tune_from) as z:
+                src = {k: z[k] for k in z.files}
+        names = list(self.params) + list(self.stats)
+        missing = [n for n in names if n not in src]
+        if missing:
+            raise KeyError("checkpoint lacks %d variable(s), e.g. %s" % (len(missing), missing[0]))
+        for n in names:
+            dst = self.params[n] if n in self.params else self.stats[n]
+            a = torch.as_tensor(np.asarray(src[n]), dtype=torch.float32)
+            if tuple(a.shape) != tuple(dst.shape):
+                raise ValueError("checkpoint variable %s has shape %s, graph has %s" % (n, tuple(a.shape), tuple(dst.shape)))
+            dst.copy_(a)
+        self.load_optimizer_state(src)
+        if "global_step" in src:
+            self.global_step = int(src["global_step"])
+        self.derive_layouts()
+
+    def _set_tune_scope(self, tune_scope):
+        """`--tune_scope` (train.py:105-111,132-137): only the TRAINABLE variables whose name matches the scope are handed to
+        the optimiser (tf.get_collection(..., scope=s) keeps names for which re.match(s, name) succeeds; default
+        "convnet|rnn" = all of them).  The others keep their values; batch-norm moving averages update regardless
+        (UPDATE_OPS, train.py:116-118).  Stored as contiguous runs of the flat buffer: one Adam launch per run."""
+        import re
+        self.tune_scope = tune_scope or "convnet|rnn"
+        pat = re.compile(self.tune_scope)
+        self.tuned = [n for n in self.names if pat.match(n)]
+        if not self.tuned:
+            raise ValueError("No variables to optimize.")     # tf.contrib.layers.optimize_loss would have nothing to minimise
+        runs = []
+        for n in self.names:
+            if not pat.match(n):
+                continue
+            o = self.offsets[n]
+            e = o + (int(np.prod(self.shapes[n])) + 63) // 64 * 64
+            if runs and runs[-1][1] == o:
+                runs[-1][1] = e
+            else:
+                runs.append([o, e])
+        self.adam_runs = [tuple(r) for r in runs]
 
     # ------------------------------------------------------------------ kernel-side weight layouts
     def _alloc_derived(self):
@@ -342,7 +435,10 @@ class Trainer:
         seq_len = torch.tensor(seq_len_host, dtype=torch.int32).to(dev, non_blocking=True)
         flat = flat_host.to(dev) if flat_host.numel() else torch.zeros(1, dtype=torch.int32, device=dev)
         offsets = torch.from_numpy(off).to(dev)
-        losses = self._backward_rnn(*self._forward(x, seq_len, flat, offsets, max_len))
+        widths_dev = None
+        if x.dtype == torch.uint8 and x.shape[1] == 31:      # raw mjsynth rows: training-side preprocessing on the device
+            widths_dev = torch.as_tensor(np.asarray(width.cpu() if torch.is_tensor(width) else width, dtype=np.int32).reshape(-1)).to(dev, non_blocking=True)
+        losses = self._backward_rnn(*self._forward(x, seq_len, flat, offsets, max_len, widths_dev))
         works = []
         if self.world > 1:   # the RNN + logits bucket is complete: its all-reduce runs behind the conv backward
             works.append(self._allreduce(self.grad[:self.n_rnn_floats], async_op=True))
@@ -353,8 +449,20 @@ class Trainer:
                 w.wait()
         return losses
 
-    def _forward(self, x, seq_len, flat, offsets, max_len):
+    def preprocess_train(self, image_u8, widths):
+        """mjsynth._preprocess_image + the batcher's 0.0 padding (mjsynth.py:185-194,56,69) on the device:
+        uint8 [B,31,W,1] rows + widths [B] int32 (device) -> float32 [B,32,W,1]."""
+        B, Hin, Ww, _ = image_u8.shape
+        out = self._new(B, Hin + 1, Ww, 1)
+        self._c(self.lib.ocr_preprocess_train(_lib.ptr(image_u8), B, Hin, Ww, _lib.ptr(widths), _lib.ptr(out), self._sh()), "ocr_preprocess_train")
+        return out
+
+    def _forward(self, x, seq_len, flat, offsets, max_len, widths=None):
         lib, sh = self.lib, self._sh()
+        if x.dtype == torch.uint8 and x.shape[1] == 31:
+            if widths is None:
+                raise ValueError("31-row uint8 images (raw mjsynth crops) need their widths for the training-side padding")
+            x = self.preprocess_train(x, widths)
         B, Hh, Ww, one = x.shape
         is_u8 = x.dtype == torch.uint8
         P, G = self.params, self.grads
@@ -594,8 +702,11 @@ class Trainer:
 
     def apply_gradients(self, lr_t_device=None):
         """AdamOptimizer.apply_gradients with the decayed learning rate of the CURRENT global step, then global_step += 1."""
-        self._c(self.lib.ocr_adam_step(_lib.ptr(self.theta), _lib.ptr(self.grad), _lib.ptr(self.adam_m), _lib.ptr(self.adam_v), self.n_floats,
-                                       self._lr_t(), _lib.ptr(lr_t_device), self.beta1, self.beta2, self.epsilon, 1.0 / self.world, self._sh()), "ocr_adam_step")
+        vp = ctypes.c_void_p
+        for (o, e) in self.adam_runs:      # one run = the whole buffer unless tune_scope froze some variables
+            self._c(self.lib.ocr_adam_step(vp(self.theta.data_ptr() + 4 * o), vp(self.grad.data_ptr() + 4 * o), vp(self.adam_m.data_ptr() + 4 * o),
+                                           vp(self.adam_v.data_ptr() + 4 * o), e - o, self._lr_t(), _lib.ptr(lr_t_device), self.beta1, self.beta2,
+                                           self.epsilon, 1.0 / self.world, self._sh()), "ocr_adam_step")
         self.global_step += 1
         self.derive_layouts()
 
@@ -620,6 +731,8 @@ class Trainer:
         g["flat"] = torch.zeros(batch_size * Lmax, dtype=torch.int32, device=dev)
         g["offsets"] = torch.arange(batch_size + 1, dtype=torch.int32, device=dev)
         g["lr_t"] = torch.zeros(1, dtype=torch.float32, device=dev)
+        g["widths"] = torch.full((batch_size,), width, dtype=torch.int32, device=dev)
+        g["h_widths"] = torch.zeros(batch_size, dtype=torch.int32).pin_memory()
         # pinned staging for the small per-step host values
         g["h_seq_len"] = torch.zeros(batch_size, dtype=torch.int32).pin_memory()
         g["h_flat"] = torch.zeros(batch_size * Lmax, dtype=torch.int32).pin_memory()
@@ -632,7 +745,7 @@ class Trainer:
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            self._backward_rnn(*self._forward(g["image"], g["seq_len"], g["flat"], g["offsets"], Lmax))
+            self._backward_rnn(*self._forward(g["image"], g["seq_len"], g["flat"], g["offsets"], Lmax, g["widths"]))
             self._backward_conv()
             self.apply_gradients(g["lr_t"])
         torch.cuda.current_stream(dev).wait_stream(side)
@@ -649,13 +762,13 @@ class Trainer:
 
         if self.world == 1:
             def whole():
-                losses = self._backward_rnn(*self._forward(g["image"], g["seq_len"], g["flat"], g["offsets"], Lmax))
+                losses = self._backward_rnn(*self._forward(g["image"], g["seq_len"], g["flat"], g["offsets"], Lmax, g["widths"]))
                 self._backward_conv()
                 self.apply_gradients(g["lr_t"])
                 return losses
             g["losses"] = rec(whole)
         else:
-            g["losses"] = rec(lambda: self._backward_rnn(*self._forward(g["image"], g["seq_len"], g["flat"], g["offsets"], Lmax)))
+            g["losses"] = rec(lambda: self._backward_rnn(*self._forward(g["image"], g["seq_len"], g["flat"], g["offsets"], Lmax, g["widths"])))
             rec(self._backward_conv)
             rec(lambda: self.apply_gradients(g["lr_t"]))
         # undo the warm-up / capture side effects on the variables (captures do not execute, the warm-up did)
@@ -683,16 +796,25 @@ class Trainer:
             raise ValueError("label longer than the captured maximum %d" % g["Lmax"])
         flat_host = torch.tensor([int(v) for l in label for v in l], dtype=torch.int32)
         ctc._validate_ctc(flat_host, lengths, seq_len_host.tolist(), T, C, False)
+        # The pinned staging buffers are rewritten every call: wait until the previous call's host-to-device copies have
+        # executed, or a host running ahead of the GPU would hand step N the labels / lengths / step size of step N+1.
+        if g.get("staged") is not None:
+            g["staged"].synchronize()
         g["h_seq_len"].copy_(torch.from_numpy(seq_len_host.astype(np.int32)))
         g["h_flat"][:flat_host.numel()] = flat_host
         g["h_offsets"][0] = 0
         g["h_offsets"][1:] = torch.from_numpy(np.cumsum(lengths).astype(np.int32))
         g["h_lr_t"][0] = self._lr_t()
+        g["h_widths"].copy_(torch.from_numpy(np.asarray(width, dtype=np.int32).reshape(-1)))
+        g["widths"].copy_(g["h_widths"], non_blocking=True)
         g["image"].copy_(image, non_blocking=True)
         g["seq_len"].copy_(g["h_seq_len"], non_blocking=True)
         g["flat"].copy_(g["h_flat"], non_blocking=True)
         g["offsets"].copy_(g["h_offsets"], non_blocking=True)
         g["lr_t"].copy_(g["h_lr_t"], non_blocking=True)
+        if g.get("staged") is None:
+            g["staged"] = torch.cuda.Event()
+        g["staged"].record(torch.cuda.current_stream(self.device))
         gr = g["graphs"]
         if self.world == 1:
             gr[0].replay()

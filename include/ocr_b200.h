@@ -133,7 +133,8 @@ int ocr_gemm_tf32(const float* A, int lda, const float* W, int ldw, const float*
  * Recognizer layers around the GEMM (INFER mode; batch-norm folded into filters/biases by the caller).
  *
  * ocr_conv1_3x3_valid: conv1 of convnet_layers (model.py:47,134; 3x3 'valid', ONE input channel, ReLU) with
- *   validate._preprocess_image (validate.py:56-68: u8/255 - 0.5) fused in when in_is_u8 != 0.
+ *   validate._preprocess_image (validate.py:56-68: convert_image_dtype = u8 * float32(1/255), then - 0.5) fused in when
+ *   in_is_u8 != 0.
  *   in [B,H,W] u8 or f32;  w [3,3,1,Cout] (HWIO);  out [B,H-2,W-2,Cout] f32 NHWC.  Cout % 4 == 0.
  * ocr_im2col3x3_same: patches of a 3x3 'same' convolution (model.py:97-104) taken from max_pool(in)
  *   (model.py:111-116; window pool_h x pool_w, strides stride_h x stride_w, 'valid'; 1,1,1,1 = no pooling):
@@ -145,6 +146,11 @@ int ocr_gemm_tf32(const float* A, int lda, const float* W, int ldw, const float*
  *   cell 0 = LSTM: wx [8H,I] (rows fw i,j,f,o then bw), wh [8H,H], bias [8H]; forget_bias 1.0; wh2 = NULL or the
  *            [8H,H] output of ocr_lstm_prepare_wh(wh) (weights pre-arranged for the persistent kernel, do it once)
  *   cell 1 = GRU : wx [6H,I] (rows per direction r,u,candidate), wh [4H,H] (r,u per direction), wh2 [2H,H], bias [6H] */
+/* ocr_preprocess_train: the TRAINING-side preprocessing, mjsynth._preprocess_image (mjsynth.py:185-194) plus the zero
+ *   padding the bucketing batcher applies to the PREPROCESSED tensor (mjsynth.py:56,69): in [B,Hin,W] u8 (right-padded
+ *   with anything), widths [B] int32 -> out [B,Hin+1,W] f32 = u8 * float32(1/255) - 0.5 with the first row duplicated on
+ *   top (31 -> 32 rows) and 0.0 at columns >= widths[b]. */
+int ocr_preprocess_train(const unsigned char* in, int B, int Hin, int W, const int32_t* widths, float* out, ocr_stream_t stream);
 int ocr_conv1_3x3_valid(const void* in, int in_is_u8, int B, int H, int W, const float* w, const float* bias, int Cout,
                         float* out, ocr_stream_t stream);
 int ocr_im2col3x3_same(const float* in, int B, int H, int W, int C, int pool_h, int pool_w, int stride_h, int stride_w,

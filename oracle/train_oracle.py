@@ -69,7 +69,10 @@ def forward_train(params, images, widths, cell_type="lstm", sizes=(512, 512), fu
     return logits, seq_len, new_stats
 
 
-def _run_direction(seq, seq_len, params, p, cell_type, H, reverse):
+def _run_direction(seq, seq_len, params, p, cell_type, H, reverse, probe=None):
+    """One direction of tf.nn.bidirectional_dynamic_rnn.  probe (LSTM only): a zero tensor [T,B,4H] with
+    requires_grad, added to the gate pre-activations of the step that visits frame t -- after backward() its .grad is the
+    gradient of the pre-activations frame by frame (what ocr_birnn_lstm_bwd leaves in `gates`)."""
     T, B, _ = seq.shape
     h = torch.zeros((B, H), dtype=seq.dtype)
     c = torch.zeros((B, H), dtype=seq.dtype)
@@ -84,6 +87,8 @@ def _run_direction(seq, seq_len, params, p, cell_type, H, reverse):
         x = seq[t, idx]
         if cell_type == "lstm":
             z = torch.cat([x, h], dim=1) @ params[p + "lstm_cell/kernel"] + params[p + "lstm_cell/bias"]
+            if probe is not None:
+                z = z + probe[t, idx] * live[:, None].to(seq.dtype)
             i, j, f, o = z[:, :H], z[:, H:2 * H], z[:, 2 * H:3 * H], z[:, 3 * H:]
             c_new = torch.sigmoid(f + 1.0) * c + torch.sigmoid(i) * torch.tanh(j)
             h_new = torch.sigmoid(o) * torch.tanh(c_new)

@@ -1,0 +1,27 @@
+"""The label alphabet is part of the interface (mjsynth.py:23-26, used by validate.py:126-129 and server.py:136-138):
+it must equal the reference's constant byte for byte."""
+import importlib.util
+import os
+
+from cnn_lstm_ctc_ocr_b200 import model
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference/src/weinman/mjsynth.py"
+
+
+def _golden():
+    return open(os.path.join(HERE, "golden", "out_charset.txt"), encoding="utf-8").read()
+
+
+def test_out_charset_equals_the_reference_constant():
+    gold = _golden()
+    if os.path.exists(REF):    # this container: read the constant out of the reference file itself
+        spec = importlib.util.spec_from_file_location("make_out_charset", os.path.join(HERE, "golden", "make_out_charset.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        assert mod.read_reference_charset(REF) == gold
+    assert model.out_charset == gold
+    assert model.num_classes() == 95
+    assert model.out_charset.index("A") == 0 and model.out_charset.index("a") == 26 and model.out_charset.index("0") == 52
+    assert model.get_string([0, 26, 52]) == "Aa0"
+    assert model.get_string(range(95)) == gold
