@@ -27,6 +27,7 @@ SIGNATURES = {
     "ocr_debug_ctc_pdl": (_i, [_i]),
     "ocr_debug_ctc_inline_redo": (_i, [_i]),
     "ocr_debug_ctc_speculate": (_i, [_i]),
+    "ocr_debug_ctc_stream_nbuf": (_i, [_i]),
     "ocr_ctc_greedy_decode": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "ocr_ctc_beam_search_workspace_bytes": (_i, [_i, _i, _i, _i, _c.POINTER(_sz)]),
     "ocr_ctc_beam_search": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),

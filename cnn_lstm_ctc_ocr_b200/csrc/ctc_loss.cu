@@ -19,6 +19,7 @@
 #include <algorithm>
 #include "common.cuh"
 #include "ctc_loss_fast.cuh"
+#include "ctc_loss_stream.cuh"
 
 namespace ocr {
 
@@ -293,10 +294,12 @@ static size_t ctc_ws_floats_per_seq(int T, int Lmax) {
     return (size_t)T * ((size_t)(Lmax + 1) + 2 * (size_t)(2 * Lmax + 1));
 }
 
-// path selection: 0 auto, 1 general kernel only, 2 fast kernel with LSU loads/stores (no TMA bulk copies)
+// path selection: 0 auto (streaming kernel where eligible, else the fast kernel, else the general one), 1 general kernel
+// only, 2 fast kernel with LSU loads/stores (no TMA bulk copies), 3 fast kernel leaving its redo flags (diagnostics),
+// 4 per-frame bulk copies, 5/6 tensor-map loads / stores only, 7 fast kernel as on path 0 but never the streaming kernel
 static int g_ctc_path = 0;
 extern "C" int ocr_ctc_loss_set_path(int path) {
-    OCR_CHECK_ARG(path >= 0 && path <= 6, "ocr_ctc_loss_set_path: path=%d outside [0,6]", path);
+    OCR_CHECK_ARG(path >= 0 && path <= 8, "ocr_ctc_loss_set_path: path=%d outside [0,8]", path);
     g_ctc_path = path;
     return OCR_OK;
 }
@@ -487,6 +490,78 @@ static int launch_fast(const FastPlan& fp, const float* logits, int T, int B, in
     return OCR_OK;
 }
 
+struct StreamPlan { int G, nbuf, smem; };
+static int g_ctc_stream_nbuf = 0;   // tuning override of the ring depth (0 = automatic)
+extern "C" int ocr_debug_ctc_stream_nbuf(int n) {
+    OCR_CHECK_ARG(n >= 0 && n <= kStreamMaxBuf, "ocr_debug_ctc_stream_nbuf: n=%d", n);
+    g_ctc_stream_nbuf = n;
+    return OCR_OK;
+}
+
+// The streaming kernel takes TMA-eligible tensors (16-byte aligned, G*C*4 a multiple of 16 bytes, whole groups), labels up
+// to 31 (one state pair per lane) and up to 67 classes (a row passes through 2 x 32 registers).  Per sequence it holds T*(Lmax+1) + T*(2*Lmax+5) floats.
+static bool plan_stream(const void* logits, const void* grad, int T, int B, int C, int Lmax, int dev, StreamPlan* out) {
+    if (g_ctc_path != 8 || Lmax + 1 > 32 || C > 67 || T < kTmRows) return false;   // two lanes x 8 float4 per row (+ up to 3 scalars)
+    if (((uintptr_t)logits % 16) != 0 || (grad != nullptr && ((uintptr_t)grad % 16) != 0) || ((long long)B * C) % 4 != 0) return false;
+    const int NC = (T + kTmRows - 1) / kTmRows;
+    static const int order[3] = {4, 2, 8};
+    for (int k = 0; k < 3; ++k) {
+        const int G = order[k];
+        if (g_ctc_group != 0 && G != g_ctc_group) continue;
+        if ((G * C) % 4 != 0 || G * C > 256 || B % G != 0) continue;
+        const int grid = B / G;
+        // one wave: the whole sequence block in flight at once (nothing else competes for the SM's shared memory)
+        int nbuf = g_ctc_stream_nbuf ? g_ctc_stream_nbuf : (grid <= sms_of(dev) ? NC : 2);
+        nbuf = nbuf > kStreamMaxBuf ? kStreamMaxBuf : nbuf;
+        nbuf = nbuf > NC ? NC : nbuf;
+        if (nbuf < NC && nbuf > 3) nbuf = 3;   // a reused slot must stay with one front warp group (at most three of them work)
+        for (; nbuf >= 1; --nbuf) {
+            const StreamLayout lay = stream_layout(T, C, Lmax, G, nbuf);
+            if (lay.total + 128 <= kMaxDynSmem) {
+                out->G = G; out->nbuf = nbuf; out->smem = lay.total + 128;
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
+template <int G>
+static int launch_stream(const StreamPlan& sp, const float* logits, int T, int B, int C, const int32_t* labels,
+                         const int32_t* label_offsets, const int32_t* seq_len, int Lmax, float* loss, float* grad,
+                         int32_t* status, float grad_scale, cudaStream_t st, int dev, int* redo_inlined, bool* launched)
+{
+    *launched = false;
+    CUtensorMap tmIn, tmOut;
+    memset(&tmIn, 0, sizeof(tmIn));
+    memset(&tmOut, 0, sizeof(tmOut));
+    if (ctc_tensor_map(&tmIn, logits, T, B, C, G) != OCR_OK || (grad != nullptr && ctc_tensor_map(&tmOut, grad, T, B, C, G) != OCR_OK)) return OCR_OK;
+    static int configured = -1;
+    if (configured != dev) {
+        OCR_CHECK_CUDA(cudaFuncSetAttribute(ctc_loss_stream_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        configured = dev;
+    }
+    const int grid = B / G, threads = 64 * G;
+    int pf = g_ctc_prefetch, resident = 0;
+    if (pf < 0) {
+        static int key_smem = -1, per_sm = 0;
+        if (key_smem != sp.smem) {
+            OCR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctc_loss_stream_kernel<G>, threads, sp.smem));
+            key_smem = sp.smem;
+        }
+        resident = per_sm * sms_of(dev);
+        pf = resident / 2;
+    }
+    if (grid <= (resident > 0 ? resident : pf)) pf = 0;   // one wave: nobody comes after
+    const int inl = (g_ctc_inline_redo && 64 * G >= kCtcThreads && ctc_layout(T, C, Lmax, true).total <= sp.smem - 128) ? 1 : 0;
+    *redo_inlined = inl;
+    OCR_CHECK_CUDA(launch_pdl(ctc_loss_stream_kernel<G>, grid, threads, (size_t)sp.smem, st, logits, T, B, C, labels, label_offsets,
+                              seq_len, Lmax, sp.nbuf, loss, grad, status, grad_scale, tmIn, tmOut, pf, inl, g_ctc_timeline, stream_layout(T, C, Lmax, G, sp.nbuf)));
+    count_launch();
+    *launched = true;
+    return OCR_OK;
+}
+
 static int launch_general(const float* logits, int T, int B, int C, const int32_t* labels, const int32_t* label_offsets,
                           const int32_t* seq_len, int Lmax, float* loss, float* grad, int32_t* status, float grad_scale,
                           float* lattice_ws, int only_flagged, cudaStream_t st)
@@ -536,6 +611,23 @@ extern "C" int ocr_ctc_loss(const float* logits, int T, int B, int C, const int3
     int32_t* st_buf = status ? status : static_cast<int32_t*>(workspace);
     float* lattice_ws = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + ws_status_bytes(B));
     FastPlan fp;
+    StreamPlan sp;
+    int dev = 0;
+    OCR_CHECK_CUDA(cudaGetDevice(&dev));
+    if (grad_scale > 0.0f && plan_stream(logits, grad, T, B, C, max_label_len, dev, &sp)) {
+        int rc = OCR_OK, inlined = 0;
+        bool launched = false;
+#define OCR_STREAM(G_) rc = launch_stream<G_>(sp, logits, T, B, C, labels, label_offsets, seq_len, max_label_len, loss, grad, st_buf, grad_scale, st, dev, &inlined, &launched)
+        if (sp.G == 2) OCR_STREAM(2); else if (sp.G == 4) OCR_STREAM(4); else OCR_STREAM(8);
+#undef OCR_STREAM
+        if (rc != OCR_OK) return rc;
+        if (launched) {
+            if (inlined) return OCR_OK;
+            return launch_general(logits, T, B, C, labels, label_offsets, seq_len, max_label_len, loss, grad, st_buf,
+                                  grad_scale, lattice_ws, 1, st);
+        }
+        // no tensor map for this tensor: the fast kernel below takes it
+    }
     // the fast kernel stages y * grad_scale and runs its lattice on it: it needs a positive scale
     if (g_ctc_path != 1 && grad_scale > 0.0f && plan_fast(logits, grad, T, B, C, max_label_len, &fp)) {
         int rc;

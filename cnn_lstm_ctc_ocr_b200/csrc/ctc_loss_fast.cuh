@@ -108,6 +108,18 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
+// waits that may last thousands of cycles: a nanosleep between polls keeps the waiting threads out of the issue slots
+// (ncu: the spinning form cost 7.5 % of all executed instructions, and so did try_wait with a suspend-time hint)
+__device__ __forceinline__ void mbar_wait_sleep(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "nanosleep.u32 %2;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(128u) : "memory");
+}
 __device__ __forceinline__ void bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -438,7 +450,7 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
         }
         __syncthreads();
     } else if (tmax > 0 || spec) {
-        mbar_wait(bar, 0);
+        mbar_wait_sleep(bar, 0);
     }
     ctc_mark(tl, 1);
     // L2 prefetch for the successor group: its load phase becomes an L2 hit instead of a DRAM round trip under load, and
@@ -578,7 +590,6 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
             // pair i = lane*NP + j : (ab = alpha(blank before label i), al = alpha(label i))
             float ab[NP], al[NP], skp[NP];
             unsigned pe[NP], pes[NP], pl[NP];  // e_t(label i) address / stride (0: constant zero), lattice slot
-            int tdl[NP];
             const float first = lane == 0 ? 0.0f : 1.0f;  // lane 0 has no left neighbour
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
@@ -588,7 +599,6 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 pe[j] = hasl ? a_st + 4u * li : a_zero;
                 pes[j] = hasl ? RSB : 0u;
                 skp[j] = (i >= 1 && hasl && s_lab[i - 1] != li) ? ((j == 0) ? first : 1.0f) : 0.0f;
-                tdl[j] = hasl ? Tb - (L - i) : (i == L ? Tb : -1);  // label alive iff t <= tdl; blank alive iff t < tdl
                 pl[j] = a_lat + 4u * (i <= L ? 1 + 2 * i : HI);
                 ab[j] = 0.0f; al[j] = 0.0f;
             }
@@ -621,13 +631,8 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 float mloc = 0.0f;
 #pragma unroll
                 for (int j = 0; j < NP; ++j) {
-                    if constexpr (decltype(masked)::value) {
-                        ab[j] = (t < tdl[j]) ? nbv[j] : 0.0f;
-                        al[j] = (t <= tdl[j]) ? nlv[j] : 0.0f;
-                    } else {
-                        ab[j] = nbv[j];
-                        al[j] = nlv[j];
-                    }
+                    ab[j] = nbv[j];
+                    al[j] = nlv[j];
                     mloc = fmaxf(mloc, fmaxf(ab[j], al[j]));
                 }
                 rs.next(mloc);
@@ -649,19 +654,21 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                     const float el0 = el_n[j];
                     pe[j] += pes[j];
                     el_n[j] = lds(pe[j]);
-                    ab[j] = (i == 0 && 0 < tdl[j]) ? eb0 * kinv : 0.0f;
-                    al[j] = (i == 0 && 0 <= tdl[j] && L > 0) ? el0 * kinv : 0.0f;
+                    ab[j] = (i == 0) ? eb0 * kinv : 0.0f;
+                    al[j] = (i == 0 && L > 0) ? el0 * kinv : 0.0f;
                 }
                 float mloc = 0.0f;
 #pragma unroll
                 for (int j = 0; j < NP; ++j) mloc = fmaxf(mloc, fmaxf(ab[j], al[j]));
                 rs.next(mloc);
             }
-            const int tm0 = max(1, Tb - L);  // states start dying (cannot reach the end any more) at t = Tb - L
             int t = 1;
             store();  // mid >= 1
-            for (; t < min(mid, tm0); ++t) { step(t, std::false_type()); store(); }
-            for (; t < mid; ++t) { step(t, std::true_type()); store(); }
+            // (no alive-masks: a state that cannot reach the end any more has beta = 0, so its product is zero whatever its
+            // alpha; it only takes part in the rescale maximum, and the exactness guard covers that.  The masked loop forms
+            // doubled the code of the chains: 9 % of the kernel's stall samples were instruction-cache misses.)
+#pragma unroll 2
+            for (; t < mid; ++t) { step(t, std::false_type()); store(); }
             ctc_mark(tl, 4);
             pair_barrier(1 + s);  // partner has stored beta_t (and its exponents) for t >= mid
             ctc_mark(tl, 5);
@@ -691,12 +698,12 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 pex += LSB;
             };
             if (t < Tb) {
-                if (t < tm0) step(t, std::false_type()); else step(t, std::true_type());
+                step(t, std::false_type());
                 consume(std::true_type());
                 ++t;
             }
-            for (; t < min(Tb, tm0); ++t) { step(t, std::false_type()); consume(std::false_type()); }
-            for (; t < Tb; ++t) { step(t, std::true_type()); consume(std::false_type()); }
+#pragma unroll 2
+            for (; t < Tb; ++t) { step(t, std::false_type()); consume(std::false_type()); }
             // p(z|x) in e-units: alpha(2L) + alpha(2L-1) at the last frame
             float up = __shfl_up_sync(kFullMask, al[NP - 1], 1);
             if (lane == 0) up = 0.0f;
@@ -725,7 +732,6 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
             // pair i = lane*NP + j : (bl = beta(label i-1), bb = beta(blank after label i-1))
             float bb[NP], bl[NP], skp[NP], c1[NP];
             unsigned pe[NP], pes[NP], pl[NP];
-            int tbl[NP], tbb[NP];
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
                 const int i = lane * NP + j;
@@ -735,8 +741,6 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 pes[j] = hasl ? RSB : 0u;
                 skp[j] = (hasl && i < L && s_lab[i] != li) ? 1.0f : 0.0f;
                 c1[j] = hasl ? 1.0f : 0.0f;
-                tbl[j] = hasl ? i - 1 : 0x7fffffff;   // label i-1 alive iff t >= i-1
-                tbb[j] = (i <= L) ? i : 0x7fffffff;   // blank i alive iff t >= i
                 pl[j] = a_lat + (unsigned)(Tb - 1) * LSB + 4u * (i <= L ? 2 * i : HI);
                 bb[j] = 0.0f; bl[j] = 0.0f;
             }
@@ -771,13 +775,8 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                     const float nx = (j == NP - 1) ? dn : wl[j + 1];
                     const float nbb = wb[j] + nx;
                     const float nbl = fmaf(skp[j], nx, fmaf(c1[j], wb[j], wl[j]));
-                    if constexpr (decltype(masked)::value) {
-                        bb[j] = (t >= tbb[j]) ? nbb : 0.0f;
-                        bl[j] = (t >= tbl[j]) ? nbl : 0.0f;
-                    } else {
-                        bb[j] = nbb;
-                        bl[j] = nbl;
-                    }
+                    bb[j] = nbb;
+                    bl[j] = nbl;
                     mloc = fmaxf(mloc, fmaxf(bb[j], bl[j]));
                 }
                 rs.next(mloc);
@@ -792,8 +791,8 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
                 const int i = lane * NP + j;
-                bb[j] = (i == L && Tb - 1 >= tbb[j]) ? 1.0f : 0.0f;
-                bl[j] = (i == L && L >= 1 && Tb - 1 >= tbl[j]) ? 1.0f : 0.0f;
+                bb[j] = (i == L) ? 1.0f : 0.0f;
+                bl[j] = (i == L && L >= 1) ? 1.0f : 0.0f;
             }
             rs.next(1.0f);
             int Pt = 0;
@@ -826,14 +825,14 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
             if (t >= mid) {
                 store();
                 --t;
-                for (; t >= max(mid, L); --t) { step(t, std::false_type()); store(); }
-                for (; t >= mid; --t) { step(t, std::true_type()); store(); }
+#pragma unroll 2
+                for (; t >= mid; --t) { step(t, std::false_type()); store(); }
                 ctc_mark(tl, 4);
                 pair_barrier(1 + s);  // partner has stored alpha_t (and its exponents) for t < mid
                 ctc_mark(tl, 5);
                 consume_prefetch();
                 // t = mid - 1 >= 0: the frame where the chains meet fixes Pt
-                if (t >= L) step(t, std::false_type()); else step(t, std::true_type());
+                step(t, std::false_type());
                 consume(std::true_type());
                 --t;
             } else {
@@ -842,8 +841,8 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 consume(std::true_type());
                 --t;
             }
-            for (; t >= L; --t) { step(t, std::false_type()); consume(std::false_type()); }
-            for (; t >= 0; --t) { step(t, std::true_type()); consume(std::false_type()); }
+#pragma unroll 2
+            for (; t >= 0; --t) { step(t, std::false_type()); consume(std::false_type()); }
             if (lane == 0) infoi[6] = Pt;
             ctc_mark(tl, 6);
             pair_barrier(1 + s);

@@ -32,7 +32,7 @@ preprocess_train_kernel(const unsigned char* __restrict__ in, int B, int Hin, in
         const int b = (int)(p / (Hin + 1));
         const int src = r > 0 ? r - 1 : 0;
         float v = 0.0f;
-        if (x < __ldg(widths + b)) v = (float)__ldg(in + ((size_t)b * Hin + src) * W + x) * kInv255 - 0.5f;
+        if (x < __ldg(widths + b)) v = __fsub_rn(__fmul_rn((float)__ldg(in + ((size_t)b * Hin + src) * W + x), kInv255), 0.5f);   // two roundings, as TF's multiply then subtract (no FMA contraction)
         out[idx] = v;
     }
 }
@@ -59,7 +59,7 @@ conv1_kernel(const void* __restrict__ in_, int B, int H, int W, const float* __r
             for (int j = 0; j < 3; ++j) {
                 const size_t o = ((size_t)b * H + (y + i)) * W + (x + j);
                 float v;
-                if (kU8) v = (float)__ldg(reinterpret_cast<const unsigned char*>(in_) + o) * kInv255 - 0.5f;
+                if (kU8) v = __fsub_rn(__fmul_rn((float)__ldg(reinterpret_cast<const unsigned char*>(in_) + o), kInv255), 0.5f);
                 else v = __ldg(reinterpret_cast<const float*>(in_) + o);
                 const float4 ww = __ldg(reinterpret_cast<const float4*>(w + (i * 3 + j) * Co) + c4);
                 acc.x = fmaf(v, ww.x, acc.x); acc.y = fmaf(v, ww.y, acc.y); acc.z = fmaf(v, ww.z, acc.z); acc.w = fmaf(v, ww.w, acc.w);

@@ -82,6 +82,9 @@ int ocr_debug_ctc_inline_redo(int on);
 /* Tuning aid: the fast kernel requests every TMA box of a group before its sequence lengths are known (1, default) or only
  * the boxes up to the group's longest sequence, after reading the lengths (0). */
 int ocr_debug_ctc_speculate(int on);
+/* Tuning aid: ring depth (16-frame boxes in flight per CTA) of the streaming CTC kernel (0 = automatic: 2, or the whole
+ * sequence block when the grid is a single wave).  ocr_ctc_loss_set_path(7) keeps the streaming kernel out altogether. */
+int ocr_debug_ctc_stream_nbuf(int n);
 
 /* ---------------------------------------------------------------------------------------------
  * CTC greedy decoder.  Replaces tf.nn.ctc_greedy_decoder(merge_repeated=True) at

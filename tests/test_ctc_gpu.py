@@ -45,7 +45,7 @@ def test_loss_tf_unit_vectors():
     np.testing.assert_allclose(grad[:, 1], G["loss_g1"], atol=2e-6)
 
 
-@pytest.mark.parametrize("path", [0, 2, 1])
+@pytest.mark.parametrize("path", [0, 2, 1, 8])   # 8: the streaming kernel (csrc/ctc_loss_stream.cuh)
 @pytest.mark.parametrize("C,ragged,relu", [(63, False, False), (63, True, False), (63, True, True), (96, True, False)])
 def test_loss_cfg2_vs_oracle(oracle, C, ragged, relu, path):
     x, labels, seq_len = cfg2_inputs(seed=1, T=64, B=256, C=C, ragged=ragged, relu=relu)
@@ -102,6 +102,7 @@ def test_loss_many_waves_prefetch_and_pdl(oracle):
     (200, 9, 30, 60, 0),     # 2 label pairs per lane
     (250, 5, 20, 100, 0),    # 4 label pairs per lane
     (3, 4, 5, 2, 0), (1, 4, 5, 1, 0), (2, 3, 4, 1, 2),
+    (64, 8, 63, 16, 8), (61, 36, 63, 20, 8), (125, 64, 63, 24, 8), (48, 6, 66, 30, 8),   # streaming kernel: partial last box, G = 4 and 2
 ])
 def test_loss_shapes_vs_f64(oracle, T, B, C, maxlen, path):
     rng = np.random.default_rng(T * 1000 + B)
