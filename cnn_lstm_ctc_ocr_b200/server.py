@@ -67,11 +67,18 @@ class Bucket(object):
 class LocalServer(object):
     """Synchronous version of server.py:60-145 around a `model.Model`."""
 
-    def __init__(self, recognizer, bucket_size=32, bucket_max_time=0.5, device="cuda"):
+    def __init__(self, recognizer, bucket_size=32, bucket_max_time=0.5, device="cuda", shard=None):
+        """shard = (rank, world): multi-GPU dispatch with one server process per GPU and no collective.  Every process is
+        handed the same stream of crops; a crop's batch is known when it arrives (bucket k, the n-th crop of that bucket ->
+        batch n // bucket_size), and batch (k, j) belongs to process (k + j) % world.  Whole BATCHES are dealt, so the
+        fillers are the same as on one GPU (only a bucket's last batch is ever short) and neighbouring widths -- similar
+        cost -- land on different GPUs.  A process keeps only its own crops; `take` returns only its own strings."""
         self.model = recognizer
         self.bucket_size = bucket_size
         self.device = torch.device(device)
         self.buckets = [Bucket(bucket_max_time, bucket_size, (w, w + 32)) for w in range(32, 1000, 32)]  # server.py:64-65
+        self.rank, self.world = shard if shard is not None else (0, 1)
+        self._seen = [0] * len(self.buckets)   # crops offered to each bucket so far, owned or not
         self.results = {}
         self._pending = []
         self.padded_pixels = 0
@@ -81,9 +88,21 @@ class LocalServer(object):
         img = np.asarray(img)
         if img.dtype != np.uint8 or img.shape[0] != 32:
             raise ValueError("crops must be uint8 with height 32 (pagepredictor2.py:102-105)")
+        if self.world > 1:
+            w = img.shape[1]
+            k = (w - 1) // 32 - 1    # bucket k holds widths in (32k+32, 32k+64]
+            if w <= 32 or k >= len(self.buckets):
+                raise ValueError("crop width %d falls in no bucket: widths must be in (32, 1024]" % w)
+            j = self._seen[k] // self.bucket_size
+            self._seen[k] += 1
+            if (k + j) % self.world != self.rank:
+                return False
+            self.buckets[k].addImgToBucket(clientid, imgid, time.time() if imgtime is None else imgtime, img)
+            return True
         ok = sum(b.addImgToBucket(clientid, imgid, time.time() if imgtime is None else imgtime, img) for b in self.buckets)
         if ok != 1:
             raise ValueError("crop width %d falls in no bucket: widths must be in (32, 1024]" % img.shape[1])
+        return True
 
     def _run_batch(self, infos, batch, widths):
         n = batch.shape[0]
@@ -150,4 +169,6 @@ class BatchLinePredictor(object):
             self.server.submit(self.clientid, batch_name + "_" + str(i), img)
         self.server.flush()
         got = self.server.take(self.clientid)
+        if self.server.world > 1:   # this process's share; the caller gathers the dictionaries of all processes on the host
+            return {i: got[batch_name + "_" + str(i)] for i in range(len(img_list)) if batch_name + "_" + str(i) in got}
         return {i: got[batch_name + "_" + str(i)] for i in range(len(img_list))}

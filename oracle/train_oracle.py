@@ -136,10 +136,11 @@ def adam_step(p, g, m, v, t, lr, beta1=0.9, beta2=0.999, eps=1e-8):
 TRAINABLE = lambda name: not ("moving_mean" in name or "moving_variance" in name)
 
 
-def train_step_reference(params_np, images_u8, widths, labels, step, cell_type="lstm", sizes=(512, 512), adam_state=None):
-    """One reference training step in float64.  Returns dict(loss, grads, new_params, new_stats, adam_state)."""
-    params = {k: torch.tensor(np.asarray(v, np.float64), requires_grad=TRAINABLE(k)) for k, v in params_np.items()}
-    x = torch.tensor(mo.preprocess_image(images_u8))
+def train_step_reference(params_np, images_u8, widths, labels, step, cell_type="lstm", sizes=(512, 512), adam_state=None, dtype=np.float64):
+    """One reference training step, float64 by default (the parity oracle); dtype=np.float32 is the reference's own arithmetic type
+    (bench.py's CPU baseline leg).  Returns dict(loss, grads, new_params, new_stats, adam_state)."""
+    params = {k: torch.tensor(np.asarray(v, dtype), requires_grad=TRAINABLE(k)) for k, v in params_np.items()}
+    x = torch.tensor(mo.preprocess_image(images_u8).astype(dtype))
     logits, seq_len, new_stats = forward_train(params, x, widths, cell_type, sizes)
     loss, losses = ctc_mean_loss(logits, labels, seq_len)
     loss.backward()
@@ -149,7 +150,7 @@ def train_step_reference(params_np, images_u8, widths, labels, step, cell_type="
     new_params, new_adam = {}, {}
     for k, v in params_np.items():
         if k in grads:
-            pnew, m, vv = adam_step(np.asarray(v, np.float64), grads[k], adam_state[k][0], adam_state[k][1], step + 1, lr)
+            pnew, m, vv = adam_step(np.asarray(v, dtype), grads[k], adam_state[k][0], adam_state[k][1], step + 1, lr)
             new_params[k], new_adam[k] = pnew, (m, vv)
         else:
             new_params[k] = new_stats[k].numpy()

@@ -44,6 +44,32 @@ def test_bucket_boundaries_padding_and_fillers():
     assert got == {0: "w33", 1: "w64", 2: "w65", 3: "w1024", 4: "w40"}       # fillers dropped
 
 
+def test_multi_gpu_dispatch_deals_whole_batches():
+    """shard=(rank, world): every process sees the same crops and runs the batches (bucket k, batch j) with
+    (k + j) % world == rank.  Union of the shares == the one-process result; the padded pixels add up to the one-process
+    figure (fillers only in a bucket's last batch), and the shares are balanced."""
+    rng = np.random.default_rng(3)
+    widths = rng.integers(64, 1025, 900)
+    crops = [_crop(int(w), i % 251) for i, w in enumerate(widths)]
+    one = server.LocalServer(_Stub(), bucket_size=8, device="cpu")
+    ref = server.BatchLinePredictor(one).predict_batch("s", crops)
+    for world in (2, 4, 8):
+        union, padded, real, calls = {}, 0, 0, []
+        for rank in range(world):
+            stub = _Stub()
+            srv = server.LocalServer(stub, bucket_size=8, device="cpu", shard=(rank, world))
+            got = server.BatchLinePredictor(srv).predict_batch("s", crops)
+            assert not (set(got) & set(union))
+            union.update(got)
+            padded += srv.padded_pixels
+            real += srv.real_pixels
+            calls.append(len(stub.calls))
+            assert all(c[0][0] == 8 for c in stub.calls)          # fixed batch, as on one GPU
+        assert union == ref
+        assert (padded, real) == (one.padded_pixels, one.real_pixels)
+        assert max(calls) - min(calls) <= 4
+
+
 def test_release_rule_is_strictly_more_than_batchsize_or_age():
     stub = _Stub()
     srv = server.LocalServer(stub, bucket_size=2, bucket_max_time=0.05, device="cpu")
