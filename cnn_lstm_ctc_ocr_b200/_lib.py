@@ -30,6 +30,8 @@ SIGNATURES = {
     "ocr_debug_ctc_stream_nbuf": (_i, [_i]),
     "ocr_ctc_greedy_decode": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "ocr_ctc_beam_search_workspace_bytes": (_i, [_i, _i, _i, _i, _c.POINTER(_sz)]),
+    "ocr_debug_beam_path": (_i, [_i]),
+    "ocr_debug_beam_profile": (_i, [_vp, _i]),
     "ocr_ctc_beam_search": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ocr_gemm_tf32": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ocr_preprocess_train": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),

@@ -108,6 +108,11 @@ int ocr_ctc_greedy_decode(const float* logits, int T, int B, int C, const int32_
  * Limits: beam_width in {1..128}, top_paths <= beam_width, C <= 512.
  */
 int ocr_ctc_beam_search_workspace_bytes(int T, int B, int C, int beam_width, size_t* bytes);
+/* Tuning / cross-check aid: 0 = one CTA per sequence (default), 1 = one warp per sequence replaying TensorFlow's list updates
+ * one insertion at a time.  Same bits either way (tests/test_beam_gpu.py). */
+int ocr_debug_beam_path(int path);
+/* Tuning aid: cycles per phase of CTA 0 of the CTA-per-sequence kernel, summed over its frames (host array of 16). */
+int ocr_debug_beam_profile(long long* host16, int reset);
 int ocr_ctc_beam_search(const float* logits, int T, int B, int C, const int32_t* seq_len, int beam_width,
                         int top_paths, int merge_repeated, int normalize, int64_t* decoded,
                         int32_t* decoded_len, float* log_prob, void* workspace, size_t workspace_bytes,

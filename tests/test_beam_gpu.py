@@ -76,3 +76,24 @@ def test_beam_api_and_metrics(oracle):
     assert (dist == ref).all()
     with pytest.raises(ValueError):
         ctc.ctc_beam_search_decoder(torch.tensor(x, device=dev), torch.tensor(seq_len), beam_width=2, top_paths=3)
+
+
+def test_cta_kernel_equals_the_replay_kernel():
+    """The default kernel (one CTA per sequence: counts, selection and TF's reset rule stated in closed form) against the
+    warp-per-sequence kernel that replays TensorFlow's list updates one insertion at a time: same labels, lengths and score
+    bits on flat, peaked and ReLU-tied inputs, several widths and alphabets."""
+    from cnn_lstm_ctc_ocr_b200 import _lib
+    lib = _lib.load()
+    cases = [(63, 3.0, False, 128, 64, 64), (63, 8.0, False, 128, 64, 48), (96, 0.3, True, 128, 61, 32), (20, 2.0, True, 37, 40, 64),
+             (5, 1.0, False, 128, 120, 8), (200, 2.0, False, 64, 30, 8), (63, 0.05, False, 128, 64, 32), (63, 20.0, True, 100, 64, 32)]
+    for C, scale, relu, K, T, B in cases:
+        x, _, seq_len = cfg2_inputs(seed=7 * C + K, T=T, B=B, C=C, relu=relu, scale=scale)
+        outs = []
+        try:
+            for path in (0, 1):
+                _lib.check(lib.ocr_debug_beam_path(path), "beam_path")
+                outs.append(_gpu_beam(x, seq_len, K, min(3, K), True))
+        finally:
+            lib.ocr_debug_beam_path(0)
+        for a, b_ in zip(outs[0], outs[1]):
+            assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a, b_.view(np.uint32) if b_.dtype == np.float32 else b_), (C, scale, relu, K)
