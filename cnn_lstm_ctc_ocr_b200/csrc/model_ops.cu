@@ -200,6 +200,12 @@ int lstm_permute_wh(const float* wh, int H, float* whp, cudaStream_t st);
 int lstm_persistent_run(const float* xp, const float* wh, const float* wh_perm, const int32_t* seq_len, int T, int B, int H,
                         float* out, float* ws, cudaStream_t st, float* gates_out = nullptr, float* cs_out = nullptr);
 
+// gru_persistent.cu
+bool gru_persistent_supported(int T, int B, int H);
+size_t gru_persistent_workspace_floats(int B, int H);
+int gru_persistent_run(const float* xp, const float* whg, const float* whc, const int32_t* seq_len, int T, int B, int H,
+                       float* out, float* ws, cudaStream_t st);
+
 int lstm_set_timeline(long long* buf);
 int lstm_bptt_set_timeline(long long* buf);
 
@@ -282,6 +288,7 @@ extern "C" int ocr_birnn_workspace_bytes(int cell, int T, int B, int H, size_t* 
     // xp [T*B, 2*G*H] + gh [2B, 2*(cell?2:4)*H] + h, c/u, rh [2B,H] each + ch [2B,2H]
     size_t step = (size_t)2 * B * 8 * H + (size_t)2 * B * H * 3 + (size_t)2 * B * 2 * H;
     if (cell == 0 && lstm_persistent_supported(T, B, H)) step = step > lstm_persistent_workspace_floats(B, H) ? step : lstm_persistent_workspace_floats(B, H);
+    if (cell == 1 && gru_persistent_supported(T, B, H)) step = step > gru_persistent_workspace_floats(B, H) ? step : gru_persistent_workspace_floats(B, H);
     *bytes = sizeof(float) * ((size_t)T * B * 2 * G * H + step) + 256;
     return OCR_OK;
 }
@@ -322,6 +329,8 @@ extern "C" int ocr_birnn_layer(int cell, const float* x, int T, int B, int I, in
     if (rc != OCR_OK) return rc;
     if (cell == 0 && g_birnn_path == 0 && lstm_persistent_supported(T, B, H))
         return lstm_persistent_run(xp, wh, cell == 0 ? wh2 : nullptr, seq_len, T, B, H, out, gh, st);   // one launch for all T frames
+    if (cell == 1 && g_birnn_path == 0 && gru_persistent_supported(T, B, H))
+        return gru_persistent_run(xp, wh, wh2, seq_len, T, B, H, out, gh, st);                          // likewise: two phases per frame
     OCR_CHECK_CUDA(cudaMemsetAsync(h, 0, sizeof(float) * (size_t)2 * B * H * 3, st));
     OCR_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)T * B * 2 * H, st));
     const int cg = grid_for((long long)2 * B * H);

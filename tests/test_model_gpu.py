@@ -85,6 +85,35 @@ def test_rnn_layer_masks_and_directions(path):
         assert (o[sl[b]:, b] == 0).all()
 
 
+@pytest.mark.parametrize("path", [0, 1])
+@pytest.mark.parametrize("layer,I,H", [(0, 256, 512), (1, 1024, 256)])
+def test_gru_layer_masks_and_directions(path, layer, I, H):
+    """The GRU model's two layers (model.py:167-199, 213-214; H = 512 and 256) against the numpy oracle: per-example lengths,
+    zeros past the length, backward direction from len-1.  path 0 = persistent tcgen05 GRU kernel (two products per frame with
+    a grid-wide exchange of r*h between them), path 1 = frame-by-frame launches."""
+    from cnn_lstm_ctc_ocr_b200 import model, _lib
+    _lib.check(_lib.load().ocr_birnn_set_path(path), "ocr_birnn_set_path")
+    rng = np.random.default_rng(6 + layer)
+    params = mo.init_params(seed=3, cell_type="gru", sizes=(512, 256), dtype=np.float64)
+    for k in list(params):
+        if "gru_cell" in k and k.endswith("kernel"):
+            params[k] = params[k] * 8      # make the recurrence matter (TruncNormal(0.01) is nearly linear)
+    T, B = 13, 37
+    feats = rng.standard_normal((B, T, I))
+    sl = rng.integers(0, T + 1, B).astype(np.int32)
+    sl[:4] = [13, 1, 7, 0]
+    scope = "bdrnn%d" % (layer + 1)
+    ref = mo.rnn_layer(np.transpose(feats, (1, 0, 2)), sl, params, scope, "gru", H)
+    m = model.Model(params, cell_type="gru", rnn_sizes=(512, 256))
+    dev = torch.device("cuda:0")
+    out = m.rnn_layer(torch.tensor(feats, device=dev, dtype=torch.float32).transpose(0, 1).contiguous(), torch.tensor(sl, device=dev), layer)
+    o = out.cpu().numpy()
+    _lib.load().ocr_birnn_set_path(0)
+    assert np.abs(o - ref).max() <= 5e-3 * np.abs(ref).max()
+    for b in range(B):
+        assert (o[sl[b]:, b] == 0).all()
+
+
 def test_conv_paths_agree():
     """Implicit GEMM (default) and explicit im2col + GEMM are the same contraction in the same order of k."""
     from cnn_lstm_ctc_ocr_b200 import model
