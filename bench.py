@@ -352,6 +352,22 @@ def run_ours(args, cfg):
     windows = []
 
     # ---- headline: the training step (configs[2])
+    if args.blocks_only:
+        blocks = {}
+        if not args.skip_ctc:
+            blocks["ctc_cfg2"] = ctc_cfg2_block(args, dev, rank, world, windows)
+        if not args.skip_infer:
+            blocks["inference_gru"] = inference_block(dev, world, windows, cell="gru", with_cpu=False)
+        if not args.skip_extra:
+            blocks["beam_search"] = beam_block(dev, rank, world, windows, with_cpu=False)
+            blocks["sweep"] = sweep_block(dev, rank, world, windows)
+        sampler.stop()
+        if rank == 0:
+            _emit(json.dumps({"blocks_only": True, "n_gpus": world, "blocks": {k: _short(v) for k, v in blocks.items()}}))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     training = training_block(dev, rank, world, windows, global_batch=cfg["B"], W=cfg["W"], steps=K, warmup=W,
                               with_cpu=(rank == 0 and world == 1))
     # ---- the metric's named kernel: CTC loss + gradient, bandwidth regime (rank 0) and configs[1]
@@ -586,12 +602,12 @@ def sweep_block(dev, rank, world, windows, n_crops=10000, bucket_size=32):
     # (bucket k, batch j -> process (k + j) % world), so the fillers are those of a single server
     pix = rng.integers(0, 256, (32, 1024), dtype=np.uint8)
     crops = [pix[:, :int(w)] for w in widths]
+    # like the reference's server, which builds its graph once at start-up: one batch per bucket shape before the clock
+    # starts (records the per-shape CUDA graphs in the model -- on every process, whichever batches it will be dealt)
+    server.BatchLinePredictor(server.LocalServer(m, bucket_size=bucket_size, device=dev)).predict_batch(
+        "warm", [np.zeros((32, w), np.uint8) for w in range(64, 1025, 32)])
     srv = server.LocalServer(m, bucket_size=bucket_size, device=dev, shard=(rank, world))
     pred = server.BatchLinePredictor(srv)
-    # like the reference's server, which builds its graph once at start-up: one batch per bucket shape before the clock
-    # starts (records the per-shape CUDA graphs)
-    pred.predict_batch("warm", [np.zeros((32, w), np.uint8) for w in range(64, 1025, 32)])
-    srv.padded_pixels = srv.real_pixels = 0
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
@@ -790,6 +806,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-ctc", action="store_true", help="skip the CTC-only block (BASELINE configs[1])")
+    ap.add_argument("--blocks-only", action="store_true", help="tuning: skip the headline training step, print the blocks")
     ap.add_argument("--skip-bw", action="store_true", help="skip the bandwidth-regime measurement")
     ap.add_argument("--bw-batch", type=int, default=65536)
     ap.add_argument("--skip-infer", action="store_true", help="skip the recognizer-inference block (BASELINE configs[0])")

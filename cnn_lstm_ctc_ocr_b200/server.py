@@ -152,6 +152,7 @@ class LocalServer(object):
                     break
                 self._run_batch(*b)
         self._drain()
+        self._seen = [0] * len(self.buckets)   # every bucket is empty again: batch numbering restarts (the same on every process)
 
     def take(self, clientid):
         return self.results.pop(clientid, {})
