@@ -1015,98 +1015,66 @@ ctc_beam_cta_kernel(const float* __restrict__ logits, int T, int B, int C, const
         }
 
         if (blockIdx.x == 0 && tid == 0) { const long long now = clock64(); g_beam_prof[4] += now - tprev; tprev = now; }
-        // ---- rebuild the beam state from the sorted list (warp 0; as in the kernel above)
-        int nb_new = 0;
-        if (warp == 0) {
-            u64 key[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) key[r] = s_skey[lane * 4 + r];
-            int live_cnt = 0;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int p = lane * 4 + r;
-                const u64 kk = key[r];
-                if ((kk >> 32) != 0) {
-                    ++live_cnt;
-                    const unsigned seq = ~(unsigned)kk;
-                    if (seq < (unsigned)nb) {
-                        const int ii = (int)seq;
-                        s_tot[no + p] = n_tot[ii]; s_blk[no + p] = n_blk[ii]; s_labp[no + p] = n_lab[ii];
-                        s_label[no + p] = s_label[co + ii];
-                        s_hash[no + p] = s_hash[co + ii]; s_phash[no + p] = s_phash[co + ii];
-                        s_pool[no + p] = s_pool[co + ii];
-                        s_newpos[ii] = p;
-                    } else {
-                        const unsigned cc = seq - (unsigned)nb;
-                        const int ii = (int)(cc / (unsigned)C);
-                        const int k = (int)(cc - (unsigned)ii * (unsigned)C);
-                        const float sc = unord((unsigned)(kk >> 32));
-                        s_tot[no + p] = sc; s_blk[no + p] = NEG; s_labp[no + p] = sc;
-                        s_label[no + p] = k;
-                        const u64 ph = s_hash[co + ii];
-                        s_phash[no + p] = ph;
-                        s_hash[no + p] = mix_hash(ph, k);
-                        const int id = 1 + t * K + p;
-                        s_pool[no + p] = id;
-                        pool[id] = make_int2(s_pool[co + ii], k);
+        // ---- rebuild the beam state from the sorted list (as in the kernel above; thread p builds slot p)
+        {
+            const int p = tid;
+            const u64 kk = s_skey[p];
+            const bool live = (kk >> 32) != 0;
+            const unsigned seq = ~(unsigned)kk;
+            const bool carried = live && seq < (unsigned)nb;
+            int src = -1, kcls = -1;   // the old slot this entry continues / is a child of
+            if (live) {
+                if (carried) {
+                    src = (int)seq;
+                    s_tot[no + p] = n_tot[src]; s_blk[no + p] = n_blk[src]; s_labp[no + p] = n_lab[src];
+                    s_label[no + p] = s_label[co + src];
+                    s_hash[no + p] = s_hash[co + src]; s_phash[no + p] = s_phash[co + src];
+                    s_pool[no + p] = s_pool[co + src];
+                    s_newpos[src] = p;
+                } else {
+                    const unsigned cc = seq - (unsigned)nb;
+                    src = (int)(cc / (unsigned)C);
+                    kcls = (int)(cc - (unsigned)src * (unsigned)C);
+                    const float sc = unord((unsigned)(kk >> 32));
+                    s_tot[no + p] = sc; s_blk[no + p] = NEG; s_labp[no + p] = sc;
+                    s_label[no + p] = kcls;
+                    const u64 ph = s_hash[co + src];
+                    s_phash[no + p] = ph;
+                    s_hash[no + p] = mix_hash(ph, kcls);
+                    const int id = 1 + t * K + p;
+                    s_pool[no + p] = id;
+                    pool[id] = make_int2(s_pool[co + src], kcls);
+                }
+            }
+            const int nb_new = block_sum(live ? 1 : 0);   // (barrier: s_newpos and the new hashes are visible)
+            bool orphan = false;   // a surviving beam whose parent was not in the beam
+            if (live) {
+                int psn;
+                if (carried) {
+                    const int po = s_ps[co + src];
+                    psn = (po >= 0) ? s_newpos[po] : -1;
+                    orphan = po < 0 && s_label[co + src] >= 0;
+                } else {
+                    psn = s_newpos[src];
+                }
+                // a surviving beam whose parent prefix was re-created in this frame gets its parent back
+                if (orphan) {
+                    const u64 ph = s_phash[no + p];
+                    for (int q = 0; q < kSlots; ++q) {
+                        const u64 kq = s_skey[q];
+                        if ((kq >> 32) != 0 && (~(unsigned)kq) >= (unsigned)nb && s_hash[no + q] == ph) psn = q;
                     }
                 }
+                s_ps[no + p] = psn;
             }
-            nb_new = warp_sum_int(live_cnt);
-            __syncwarp();
-            unsigned orphan_r = 0;  // bit r: my slot r is a surviving beam whose parent was not in the beam
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int p = lane * 4 + r;
-                const u64 kk = key[r];
-                if ((kk >> 32) != 0) {
-                    const unsigned seq = ~(unsigned)kk;
-                    int psn;
-                    if (seq < (unsigned)nb) {
-                        const int po = s_ps[co + (int)seq];
-                        psn = (po >= 0) ? s_newpos[po] : -1;
-                        if (po < 0 && s_label[co + (int)seq] >= 0) orphan_r |= 1u << r;
-                    } else {
-                        const int ii = (int)((seq - (unsigned)nb) / (unsigned)C);
-                        psn = s_newpos[ii];
-                    }
-                    s_ps[no + p] = psn;
-                }
+            for (int q = tid; q < kSlots * CW; q += kCtaThreads) s_cm[q] = 0;
+            __syncthreads();
+            if (live) {
+                const int psn = s_ps[no + p];
+                const int lbn = s_label[no + p];
+                if (psn >= 0 && lbn >= 0) atomicOr(&s_cm[psn * CW + (lbn >> 5)], 1u << (lbn & 31));
             }
-            __syncwarp();
-            // a surviving beam whose parent prefix was re-created in this frame gets its parent back
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                unsigned om = __ballot_sync(kFullMask, (orphan_r >> r) & 1u);
-                while (om) {
-                    const int src = __ffs(om) - 1;
-                    om &= om - 1;
-                    const int po = src * 4 + r;
-                    const u64 ph = s_phash[no + po];
-                    int found = -1;
-#pragma unroll
-                    for (int r2 = 0; r2 < 4; ++r2) {
-                        const u64 kk = key[r2];
-                        const bool isnew = (kk >> 32) != 0 && (~(unsigned)kk) >= (unsigned)nb;
-                        const bool mt = isnew && s_hash[no + lane * 4 + r2] == ph;
-                        const unsigned bm = __ballot_sync(kFullMask, mt);
-                        if (bm) found = (__ffs(bm) - 1) * 4 + r2;
-                    }
-                    if (found >= 0 && lane == 0) s_ps[no + po] = found;
-                }
-            }
-            for (int q = lane; q < kSlots * CW; q += 32) s_cm[q] = 0;
-            __syncwarp();
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int p = lane * 4 + r;
-                if ((key[r] >> 32) != 0) {
-                    const int psn = s_ps[no + p];
-                    const int lbn = s_label[no + p];
-                    if (psn >= 0 && lbn >= 0) atomicOr(&s_cm[psn * CW + (lbn >> 5)], 1u << (lbn & 31));
-                }
-            }
-            if (lane == 0) s_misc[2] = nb_new;
+            if (tid == 0) s_misc[2] = nb_new;
         }
         __syncthreads();
         nb = s_misc[2];

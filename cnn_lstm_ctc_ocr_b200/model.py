@@ -97,6 +97,38 @@ def preprocess_image(image):
     return image.to(torch.float32) * float(np.float32(1.0 / 255.0)) - 0.5     # convert_image_dtype multiplies by float32(1/255)
 
 
+class Placeholders(object):
+    """validate._get_input (validate.py:71-78): the pair of placeholders the reference's graph is fed through --
+    image uint8 [bucket_size, 32, None, 1], width int32 [bucket_size].  TensorFlow checks a feed against the placeholder's
+    dtype and static shape and raises ValueError; `feed` applies the same checks (the width axis is free) and hands back the
+    pair as tensors on `device`, ready for Model.convnet_layers / Model.recognize."""
+
+    def __init__(self, bucket_size):
+        self.bucket_size = int(bucket_size)
+        self.image_shape = (self.bucket_size, 32, None, 1)
+        self.width_shape = (self.bucket_size,)
+
+    def feed(self, image, width, device=None):
+        image = torch.as_tensor(image)
+        width = torch.as_tensor(width)
+        if image.dtype != torch.uint8:
+            raise ValueError("image: placeholder is uint8, got %s" % image.dtype)
+        if image.dim() != 4 or image.shape[0] != self.bucket_size or image.shape[1] != 32 or image.shape[3] != 1:
+            raise ValueError("Cannot feed value of shape %s for a placeholder of shape %s" % (tuple(image.shape), self.image_shape))
+        if width.dtype not in (torch.int32, torch.int64) or tuple(width.shape) != self.width_shape:
+            raise ValueError("Cannot feed value of shape %s / dtype %s for the int32 placeholder of shape %s"
+                             % (tuple(width.shape), width.dtype, self.width_shape))
+        width = width.to(torch.int32)
+        if device is not None:
+            image, width = image.to(device), width.to(device)
+        return image, width
+
+
+def get_input(bucket_size):
+    """validate._get_input(bucket_size) -> the (image, width) placeholder pair, here one object with a checked `feed`."""
+    return Placeholders(bucket_size)
+
+
 def get_string(labels):
     """validate._get_string: label ids -> text."""
     return "".join(out_charset[int(c)] for c in labels)
