@@ -483,9 +483,21 @@ static int launch_fast(const FastPlan& fp, const float* logits, int T, int B, in
     // routine's 128 threads and shared-memory layout fit it; otherwise (and on path 3) the caller launches the redo gate
     const int inl = (g_ctc_inline_redo && g_ctc_path != 3 && 64 * fp.G >= kCtcThreads && ctc_layout(T, C, Lmax, true).total <= fp.smem) ? 1 : 0;
     *redo_inlined = inl;
+    if (g_ctc_timeline != nullptr && NP == 1 && CR == 64) {   // the instantiation with the phase marks compiled in (tuning aid)
+        static int configured_tl = -1;
+        if (configured_tl != dev) {
+            OCR_CHECK_CUDA(cudaFuncSetAttribute(ctc_loss_fast_kernel<1, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+            configured_tl = dev;
+        }
+    OCR_CHECK_CUDA(launch_pdl(ctc_loss_fast_kernel<1, 64, true>, grid, 64 * fp.G, (size_t)fp.smem + 128, st, logits, T, B, C, labels, label_offsets,
+                              seq_len, Lmax, fp.G, bulk, loss, grad, status, grad_scale, tmIn, tmOut, pf, inl | ((g_ctc_pdl == 2 && grid * 2 <= sms_of(dev)) ? 2 : 0) | (g_ctc_speculate ? 4 : 0),
+                              g_ctc_timeline, lay));
+        count_launch();
+        return OCR_OK;
+    }
     OCR_CHECK_CUDA(launch_pdl(ctc_loss_fast_kernel<NP, CR>, grid, 64 * fp.G, (size_t)fp.smem + 128, st, logits, T, B, C, labels, label_offsets,
                               seq_len, Lmax, fp.G, bulk, loss, grad, status, grad_scale, tmIn, tmOut, pf, inl | ((g_ctc_pdl == 2 && grid * 2 <= sms_of(dev)) ? 2 : 0) | (g_ctc_speculate ? 4 : 0),
-                              g_ctc_timeline));
+                              g_ctc_timeline, lay));
     count_launch();
     return OCR_OK;
 }

@@ -306,13 +306,14 @@ __device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsign
     return r;
 }
 
-template <int NP, int CR>
+// TL: the phase timeline of ocr_debug_ctc_timeline is compiled in (fifteen marks cost ~3 % of the kernel's instructions even when off)
+template <int NP, int CR, bool TL = false>
 __global__ void __launch_bounds__(CR > 64 ? 64 * 4 : 64 * kFastMaxG)
 ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, const int32_t* __restrict__ labels,
                      const int32_t* __restrict__ label_offsets, const int32_t* __restrict__ seq_len, int Lmax, int G,
                      int use_bulk, float* __restrict__ loss, float* __restrict__ grad, int32_t* __restrict__ status,
                      float grad_scale, const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut, int pf_stride, int inline_redo,
-                     long long* const tl)
+                     long long* const tl, const __grid_constant__ FastLayout lay)
 {
     // programmatic dependent launch (launch_pdl): this grid may have been scheduled while its predecessor was still running;
     // nothing here touches global memory before the predecessor's results are visible
@@ -324,7 +325,7 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
     // tensor-map TMA wants 128-byte aligned shared-memory boxes: align by hand (the launch adds 128 bytes)
     // (pointer arithmetic, not an integer round trip: the compiler keeps the shared address space and emits LDS/STS, not generic LD/ST)
     unsigned char* smem = smem_f + ((128u - (smem_u32(smem_f) & 127u)) & 127u);
-    const FastLayout lay = fast_layout(T, C, Lmax, G);
+    // (the layout comes as a kernel parameter: computing it took ~100 instructions per warp, 1.5 % of the kernel)
     float* stage = reinterpret_cast<float*>(smem + lay.stage);
     float* s_info = reinterpret_cast<float*>(smem + lay.info);
     float* s_zero = reinterpret_cast<float*>(smem + lay.zero);
@@ -333,7 +334,7 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = warp >> 1, role = warp & 1;  // role 0: alpha (forward), 1: beta (backward)
-    ctc_mark(tl, 0);
+    if constexpr (TL) ctc_mark(tl, 0);
     const int b0 = blockIdx.x * G;
     const int nb = min(G, B - b0);
     const bool bulk = use_bulk && nb == G;
@@ -355,7 +356,9 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
     // ---- group frame count, TMA loads (warp 0: one bulk copy per frame, spread over the lanes)
     __shared__ int s_tmax;
     __shared__ int s_redo[kFastMaxG];   // sequences of this CTA whose lattice left the float32 range (redone in the tail)
-    if (tid < kFastMaxG) s_redo[tid] = 0;   // ordered before the first write by the CTA barrier below
+    __shared__ int s_anyredo;
+    if (tid < kFastMaxG) s_redo[tid] = 0;
+    if (tid == 0) s_anyredo = 0;   // ordered before the first write by the CTA barrier below
     // Speculative requests (tensor-map path): all T/16 boxes go out at once instead of after the lengths have come back
     // from global memory (a dependent load of ~800 cycles at the head of every CTA).  The rows past the group's longest
     // sequence are wasted L2 -> shared-memory traffic only: the predecessor's L2 prefetch fetched them anyway.
@@ -452,7 +455,7 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
     } else if (tmax > 0 || spec) {
         mbar_wait_sleep(bar, 0);
     }
-    ctc_mark(tl, 1);
+    if constexpr (TL) ctc_mark(tl, 1);
     // L2 prefetch for the successor group: its load phase becomes an L2 hit instead of a DRAM round trip under load, and
     // DRAM sees requests while this CTA computes.  Issued after this CTA's own loads landed, so never queued ahead of them.
     if (pf) {
@@ -574,9 +577,9 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 }
             }
         }
-        ctc_mark(tl, 2);
+        if constexpr (TL) ctc_mark(tl, 2);
         pair_barrier(1 + s);  // both halves of the staged block now hold y * grad_scale
-        ctc_mark(tl, 3);
+        if constexpr (TL) ctc_mark(tl, 3);
 
         // ================= pass 2: lattice chains =================
         // lattice row t: position 1+u holds state u (blank i -> 1+2i, label i -> 2+2i); positions 0 and HI,HI+1
@@ -669,9 +672,9 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
             // doubled the code of the chains: 9 % of the kernel's stall samples were instruction-cache misses.)
 #pragma unroll 2
             for (; t < mid; ++t) { step(t, std::false_type()); store(); }
-            ctc_mark(tl, 4);
+            if constexpr (TL) ctc_mark(tl, 4);
             pair_barrier(1 + s);  // partner has stored beta_t (and its exponents) for t >= mid
-            ctc_mark(tl, 5);
+            if constexpr (TL) ctc_mark(tl, 5);
             int Pt = 0;
             // the partner's beta_t for the frame about to be consumed is fetched one frame ahead
             float wb_n[NP], wl_n[NP];
@@ -715,14 +718,14 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 if (i == L) pev = ab[j] + pv;
             }
             pev = __shfl_sync(kFullMask, pev, L / NP);
-            ctc_mark(tl, 6);
+            if constexpr (TL) ctc_mark(tl, 6);
             pair_barrier(1 + s);  // both chains done: products complete
             novalid = !(pev > 0.0f);
             if (lane == 0) {
                 const float lp = novalid ? -INFINITY : (logf(pev) + (float)rs.E * 0.6931471805599453f);
                 loss[b] = -lp;
                 status[b] = novalid ? kCtcRedo : 0;  // an all-zero lattice may be underflow: the exact kernel decides
-                if (novalid) s_redo[s] = 1;
+                if (novalid) { s_redo[s] = 1; s_anyredo = 1; }
                 info[2] = novalid ? 1.0f : 0.0f;
                 info[3] = novalid ? 0.0f : log2f(pev);
                 infoi[4] = rs.E;
@@ -827,9 +830,9 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 --t;
 #pragma unroll 2
                 for (; t >= mid; --t) { step(t, std::false_type()); store(); }
-                ctc_mark(tl, 4);
+                if constexpr (TL) ctc_mark(tl, 4);
                 pair_barrier(1 + s);  // partner has stored alpha_t (and its exponents) for t < mid
-                ctc_mark(tl, 5);
+                if constexpr (TL) ctc_mark(tl, 5);
                 consume_prefetch();
                 // t = mid - 1 >= 0: the frame where the chains meet fixes Pt
                 step(t, std::false_type());
@@ -844,11 +847,11 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
 #pragma unroll 2
             for (; t >= 0; --t) { step(t, std::false_type()); consume(std::false_type()); }
             if (lane == 0) infoi[6] = Pt;
-            ctc_mark(tl, 6);
+            if constexpr (TL) ctc_mark(tl, 6);
             pair_barrier(1 + s);
         }
         pair_barrier(1 + s);  // flags / log2 p written by the alpha warp
-        ctc_mark(tl, 7);
+        if constexpr (TL) ctc_mark(tl, 7);
         novalid = info[2] != 0.0f;
     } else if (have_seq && role == 0 && lane == 0) {
         // TF: zero-length sequence -> loss 0, grad 0.  Infeasible / invalid -> flagged, zero outputs.
@@ -892,9 +895,9 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 }
             }
         }
-        if (run && !novalid && __any_sync(kFullMask, lost) && lane == 0) { status[b] = kCtcRedo; s_redo[s] = 1; }
+        if (run && !novalid && __any_sync(kFullMask, lost) && lane == 0) { status[b] = kCtcRedo; s_redo[s] = 1; s_anyredo = 1; }
     }
-    ctc_mark(tl, 8);
+    if constexpr (TL) ctc_mark(tl, 8);
     // Tail of a CTA that flagged a sequence (rare): once the CTA's own gradient block has left shared memory, its first
     // 128 threads recompute the flagged sequences with the exact log-domain routine, in place of a second kernel launch
     // that would have to visit every sequence's flag (inline_redo: the routine's layout fits this CTA's allocation).
@@ -922,14 +925,12 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                     for (int k = 0; k + lane < C; k += 32) p[k] = 0.0f;
             }
         }
-        ctc_mark(tl, 9);
+        if constexpr (TL) ctc_mark(tl, 9);
         if (bulk) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
-            ctc_mark(tl, 10);
-            bool redo = false;
-            if (inline_redo)
-                for (int i = 0; i < nb; ++i) redo = redo || s_redo[i] != 0;   // CTA-uniform
+            if constexpr (TL) ctc_mark(tl, 10);
+            const bool redo = inline_redo && s_anyredo != 0;   // CTA-uniform
             if (warp == 0) {
                 const unsigned row_bytes = (unsigned)(G * C * 4);
                 float* dst = grad + (size_t)b0 * C;
@@ -944,7 +945,7 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 if (redo) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the block has reached global memory: the redo overwrites part of it
                 else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             }
-            ctc_mark(tl, 11);
+            if constexpr (TL) ctc_mark(tl, 11);
             if (redo) {
                 __syncthreads();
                 do_redo = true;

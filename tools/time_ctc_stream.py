@@ -56,5 +56,5 @@ def run(B, K, configs):
     lib.ocr_ctc_loss_set_path(0); lib.ocr_debug_ctc_stream_nbuf(0)
 
 nb = [int(a) for a in sys.argv[1:]] or [0]
-run(256, 100, [(0, 0)] + [(8, n) for n in nb])
-run(65536, 4, [(0, 0)] + [(8, n) for n in nb])
+run(256, 100, [(0, 0), (7, 0)] + [(8, n) for n in nb])
+run(65536, 4, [(0, 0), (7, 0)] + [(8, n) for n in nb])
