@@ -884,9 +884,9 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                     }
                     Bs += lds_pure(rp + 8u * L);
                     S += Bs;
-                    lost = lost || !(fabsf(log2f(S) - l2pe + dexp) < thr);
+                    lost = lost || !(fabsf(__log2f(S) - l2pe + dexp) < thr);   // (MUFU.LG2: 2^-22 absolute, far inside thr)
                     if (grad) {
-                        const float r = (S > 0.0f) ? grad_scale / S : 0.0f;
+                        const float r = (S > 0.0f) ? __fdividef(grad_scale, S) : 0.0f;
                         row[blank] -= Bs * r;
                         // in label order: a class that occurs twice is updated twice, one after the other
 #pragma unroll 4
