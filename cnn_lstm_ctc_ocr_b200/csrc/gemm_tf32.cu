@@ -45,6 +45,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const GemmSplit sp)
 {
     using S = GemmSmem<BN, STAGES>;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // (programmatic dependent launch: the successor may be scheduled; see below)
     extern __shared__ unsigned char gemm_smem_raw[];
     // 128-byte swizzle wants 1024-byte aligned tiles
     unsigned char* smem = gemm_smem_raw + ((1024u - (g_smem_u32(gemm_smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
@@ -77,6 +78,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem_d = *tmem_slot;
+    // Programmatic dependent launch (GemmPlan::pdl): the prologue above (barriers, TMEM) may have run while the predecessor in
+    // the stream was still finishing; nothing below touches global memory before the predecessor's results are visible.
+    // (No-ops in an ordinary launch.)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0) {
         if (lane == 0) {
@@ -193,6 +198,21 @@ static int launch_planned(const GemmPlan& p, cudaStream_t st)
     sp.split_stride = p.split_stride;
     sp.a_box_bytes = p.a_box_rows * kGemmBK * 4;
     sp.batch_stride = p.batch_stride;
+    if (p.pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = S::kTotal;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, STAGES>, p.tmA, p.tmB, p.bias, p.D, p.M, p.N, p.K, p.ldd, p.relu, sp));
+        count_launch();
+        return OCR_OK;
+    }
     gemm_tf32_kernel<BN, STAGES><<<grid, kGemmThreads, S::kTotal, st>>>(p.tmA, p.tmB, p.bias, p.D, p.M, p.N, p.K, p.ldd, p.relu, sp);
     OCR_CHECK_LAUNCH();
     return OCR_OK;

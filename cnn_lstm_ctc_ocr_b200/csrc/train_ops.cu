@@ -361,6 +361,9 @@ lstm_cell_bwd_kernel(float* __restrict__ act, const float* __restrict__ cs, cons
                      const int32_t* __restrict__ seq_len, int s, int last, int T, int B, int H, int splits, float* __restrict__ dh,
                      float* __restrict__ dc, float* __restrict__ dgs)
 {
+    // programmatic dependent launch: scheduled while the recurrent product of the previous step was finishing (see the frame loop)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int total = 2 * B * H;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int j = idx % H;
@@ -963,6 +966,12 @@ extern "C" int ocr_birnn_lstm_train_fwd(const float* x, int T, int B, int I, int
 
 // wh_rows [2H, 4H]: the h-part of the TensorFlow kernels (rows = hidden unit, columns = gates i,j,f,o), forward
 // direction's H rows then the backward direction's.  gates: activations in, d(pre-activation) out.
+static int g_bptt_pdl = 1;   // programmatic dependent launch on the frame-by-frame BPTT chain (0: ordinary launches)
+extern "C" int ocr_debug_bptt_pdl(int on) {
+    g_bptt_pdl = on ? 1 : 0;
+    return OCR_OK;
+}
+
 extern "C" int ocr_birnn_lstm_bwd(const float* dout, int T, int B, int H, const int32_t* seq_len, float* gates, const float* cstate,
                                   const float* wh_rows, void* workspace, size_t workspace_bytes, ocr_stream_t stream)
 {
@@ -994,9 +1003,27 @@ extern "C" int ocr_birnn_lstm_bwd(const float* dout, int T, int B, int H, const 
     if (rc != OCR_OK) return rc;
     const int splits = p1.splits;
     const int cg = grid_cap((long long)2 * B * H);
+    // The 2T launches of this loop are one dependent chain of short kernels: each is launched with programmatic stream
+    // serialization, so its CTAs are scheduled (and the product's prologue -- barriers, TMEM allocation -- runs) while the
+    // predecessor drains; both kernels order themselves with griddepcontrol.wait before their first global access.
+    p1.pdl = g_bptt_pdl;
     for (int s = T - 1; s >= 0; --s) {
-        lstm_cell_bwd_kernel<<<cg, 256, 0, st>>>(gates, cstate, dout, dh_rec, seq_len, s, s == T - 1 ? 1 : 0, T, B, H, splits, dh, dc, dgs);
-        OCR_CHECK_LAUNCH();
+        if (g_bptt_pdl && s < T - 1) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(cg);
+            cfg.blockDim = dim3(256);
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_cell_bwd_kernel, gates, (const float*)cstate, dout, (const float*)dh_rec, seq_len, s, 0, T, B, H, splits, dh, dc, dgs));
+            count_launch();
+        } else {
+            lstm_cell_bwd_kernel<<<cg, 256, 0, st>>>(gates, cstate, dout, dh_rec, seq_len, s, s == T - 1 ? 1 : 0, T, B, H, splits, dh, dc, dgs);
+            OCR_CHECK_LAUNCH();
+        }
         if (s > 0) { rc = gemm_run(p1, st); if (rc != OCR_OK) return rc; }
     }
     return OCR_OK;

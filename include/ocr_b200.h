@@ -270,6 +270,8 @@ int ocr_adam_step(float* params, const float* grads, float* m, float* v, long lo
  * ocr_birnn_lstm_bwd: back-propagation through time.  dout [T,B,2H]; gates is overwritten with the gradient of the
  * gate pre-activations (zero past each example's length), from which d kernel / d bias / d input follow as dense
  * contractions.  wh_rows [2H, 4H]: rows I.. of the forward cell's TensorFlow kernel, then the backward cell's. */
+/* Tuning aid: programmatic dependent launch on the frame-by-frame BPTT chain on (1, default) / off (0); same bits either way. */
+int ocr_debug_bptt_pdl(int on);
 int ocr_birnn_lstm_train_workspace_bytes(int T, int B, int H, size_t* bytes);
 int ocr_birnn_lstm_train_fwd(const float* x, int T, int B, int I, int H, const int32_t* seq_len, const float* wx, const float* wh,
                              const float* bias, float* out, float* gates, float* cstate, void* workspace, size_t workspace_bytes,
