@@ -179,6 +179,36 @@ int tma_map_chunks(CUtensorMap* tm, const float* base, long long rows, long long
 }
 }  // namespace ocr
 
+// binary16 forms of the two views (64 elements per 128-byte swizzle row)
+namespace ocr {
+int tma_map_2d_h(CUtensorMap* tm, const void* base, long long rows, long long K, long long ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (enc == nullptr) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return OCR_ECUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kGemmBKh, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (binary16) failed (%d) rows=%lld K=%lld ld=%lld", (int)r, rows, K, ld); return OCR_ECUDA; }
+    return OCR_OK;
+}
+int tma_map_chunks_h(CUtensorMap* tm, const void* base, long long rows, long long K, long long ld, int box_rows, int box_chunks) {
+    EncodeTiledFn enc = get_encode();
+    if (enc == nullptr) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return OCR_ECUDA; }
+    cuuint64_t dims[3] = {(cuuint64_t)kGemmBKh, (cuuint64_t)rows, (cuuint64_t)(K / kGemmBKh)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)kGemmBKh * 2};
+    cuuint32_t box[3] = {(cuuint32_t)kGemmBKh, (cuuint32_t)box_rows, (cuuint32_t)box_chunks};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (3-D, binary16) failed (%d) rows=%lld K=%lld ld=%lld", (int)r, rows, K, ld); return OCR_ECUDA; }
+    return OCR_OK;
+}
+}  // namespace ocr
+
 template <int BN, int STAGES>
 static int launch_planned(const GemmPlan& p, cudaStream_t st)
 {

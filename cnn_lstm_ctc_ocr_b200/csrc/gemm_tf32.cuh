@@ -45,6 +45,11 @@ int tma_map_2d(CUtensorMap* tm, const float* base, long long rows, long long K, 
 // 3-D view [K/32][rows][32]: one request loads box_chunks consecutive swizzled k-chunk tiles of box_rows rows
 int tma_map_chunks(CUtensorMap* tm, const float* base, long long rows, long long K, long long ld, int box_rows, int box_chunks);
 
+// the same two views of a half-precision (IEEE binary16) matrix: a 128-byte swizzle row holds 64 elements
+constexpr int kGemmBKh = 64;
+int tma_map_2d_h(CUtensorMap* tm, const void* base, long long rows, long long K, long long ld, int box_rows);
+int tma_map_chunks_h(CUtensorMap* tm, const void* base, long long rows, long long K, long long ld, int box_rows, int box_chunks);
+
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned g_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -90,6 +95,14 @@ __device__ __forceinline__ void umma_tf32(unsigned tmem_d, unsigned long long da
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+}
+// binary16 operands (K = 16 per instruction: the same 32 bytes of a swizzle row as eight tf32), float32 accumulation
+__device__ __forceinline__ void umma_f16(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc, unsigned acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc), "r"(0u) : "memory");
 }
 __device__ __forceinline__ void umma_commit(unsigned bar) {

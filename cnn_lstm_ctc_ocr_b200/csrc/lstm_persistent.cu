@@ -16,6 +16,18 @@
 //     guarantees co-residency), both directions run concurrently in the same launch.
 // Per-example sequence lengths follow dynamic_rnn: an example is updated only while s < len (its state is carried
 // unchanged afterwards, outputs past the length stay zero); the backward direction visits frame len-1-s at step s.
+//
+// Operand precision (round 2): with F16 the recurrent operands are IEEE binary16 -- h_{t-1} is published in binary16 by the
+// epilogue (round to nearest; |h| < 1) and W_h is converted once per weight update.  binary16 carries the same 10 explicit
+// mantissa bits the tensor core keeps of a TF32 operand (which it truncates), so the products are as exact as before,
+// but a tcgen05.mma.kind::f16 covers K = 16 per instruction instead of 8: half the MMA instructions per frame (the
+// frame's critical path is their issue rate, ~70 cycles each from one thread), half the h bytes through L2 -> TMA ->
+// shared memory, half the resident weight bytes.  Accumulation, cell state, gate arithmetic and the layer output stay
+// float32.  Shapes with H % 64 != 0, or ocr_debug_lstm_operands(0), take the TF32 instantiation.
+#include <cuda_fp16.h>
+
+#include <type_traits>
+
 #include "gemm_tf32.cuh"
 
 namespace ocr {
@@ -51,32 +63,34 @@ __device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned targe
     __trap();
 }
 
-template <int HS, bool TRAIN>  // hidden units per CTA; N = 4*HS gate columns.  TRAIN: keep gate activations + cell states
+template <int HS, bool TRAIN, bool F16>  // hidden units per CTA; N = 4*HS gate columns.  TRAIN: keep gate activations + cell states.  F16: binary16 operands
 __global__ void __launch_bounds__(kRnnThreads, 1)
 lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH00,
                        const __grid_constant__ CUtensorMap tmH01, const __grid_constant__ CUtensorMap tmH10,
                        const __grid_constant__ CUtensorMap tmH11, const float* __restrict__ xp, const int32_t* __restrict__ seq_len,
-                       float* __restrict__ hbuf /*[2 parity][2 dir][B][H]*/, float* __restrict__ out /*[T,B,2H]*/,
+                       void* __restrict__ hbuf_v /*[2 parity][2 dir][B][H], float32 or binary16*/, float* __restrict__ out /*[T,B,2H]*/,
                        unsigned* __restrict__ counters /*[2]*/, int T, int B, int H, int NS, int a_rows, int n_stages, int gc, int MT,
                        float* gates_out /*[T*B, 8H], may alias xp*/, float* __restrict__ cs_out /*[T,B,2H]*/)
 {
     constexpr int N = 4 * HS;
-    const int nk = H / kGemmBK;
+    constexpr int BK = F16 ? kGemmBKh : kGemmBK;   // elements per 128-byte swizzle row
+    constexpr unsigned kRowB = 128;
+    const int nk = H / BK;
     long long* const tl = blockIdx.x == 0 ? g_lstm_timeline : nullptr;
     extern __shared__ unsigned char rnn_smem_raw[];
     unsigned char* smem = rnn_smem_raw + ((1024u - (g_smem_u32(rnn_smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space (LDS/STS, not generic LD/ST)
     const unsigned s_base = g_smem_u32(smem);
-    const unsigned w_bytes = (unsigned)N * kGemmBK * 4;          // one k-chunk of the weight slice
+    const unsigned w_bytes = (unsigned)N * kRowB;                // one k-chunk of the weight slice
     // one k-chunk of h: only the a_rows (>= B, multiple of 8) real batch rows are fetched; the MMA still reads 128
     // rows, the rest is whatever follows in shared memory and lands in TMEM lanes no thread looks at
-    const unsigned a_bytes = (unsigned)a_rows * kGemmBK * 4;
+    const unsigned a_bytes = (unsigned)a_rows * kRowB;
     const unsigned s_w = s_base;                                 // nk resident weight tiles
     // ring of n_stages groups of gc k-chunk tiles of h; ONE 3-D TMA request per group (issuing sixteen 4 KB requests one by
     // one cost the producer lane ~450 cycles each: measured with ocr_debug_lstm_timeline)
     const unsigned s_a = s_w + (unsigned)nk * w_bytes;
     const unsigned g_bytes = (unsigned)gc * a_bytes;
     const int ng = nk / gc;                                      // groups per frame
-    const unsigned s_bar = s_a + (unsigned)n_stages * g_bytes + (a_rows < kGemmBM ? kGemmBM * kGemmBK * 4 : 0);  // + one tile of slack for the 128-row read of a short tile
+    const unsigned s_bar = s_a + (unsigned)n_stages * g_bytes + (a_rows < kGemmBM ? kGemmBM * kRowB : 0);  // + one tile of slack for the 128-row read of a short tile
     const unsigned bar_full = s_bar, bar_empty = s_bar + kRnnMaxStages * 8, bar_w = bar_empty + kRnnMaxStages * 8, bar_acc = bar_w + 8;
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(smem + (s_bar - s_base) + (2 * kRnnMaxStages + 2) * 8);
 
@@ -90,6 +104,12 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
     // N..2N); the epilogue adds the two.
     const bool dual = n_stages == 1 && gc == nk && nk >= 2;
     const unsigned tmem_cols = (unsigned)(2 * N < 32 ? 32 : 2 * N);
+    // instruction descriptor: float32 accumulator; operand formats TF32 (2) or binary16 (0); N, M
+    constexpr unsigned kIdesc = (1u << 4) | ((F16 ? 0u : 2u) << 7) | ((F16 ? 0u : 2u) << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(kGemmBM >> 4) << 24);
+    auto mma = [](unsigned td, unsigned long long da, unsigned long long db, unsigned acc) {
+        if constexpr (F16) umma_f16(td, da, db, kIdesc, acc);
+        else umma_tf32(td, da, db, kIdesc, acc);
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < n_stages; ++s) { g_mbar_init(bar_full + s * 8, 1); g_mbar_init(bar_empty + s * 8, dual ? 2 : 1); }
@@ -110,7 +130,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
         if (lane == 0) {
             // resident weight slice: rows [(d*NS + j)*N, +N) of the gate-major permuted W_h
             g_mbar_expect_tx(bar_w, (unsigned)nk * w_bytes);
-            for (int k = 0; k < nk; ++k) tma_load_2d(s_w + k * w_bytes, &tmW, k * kGemmBK, (d * NS + j) * N, bar_w);
+            for (int k = 0; k < nk; ++k) tma_load_2d(s_w + k * w_bytes, &tmW, k * BK, (d * NS + j) * N, bar_w);
             int it = 0;
             for (int s = 0; s < T; ++s) {
                 if (s > 0) {
@@ -127,15 +147,14 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
                 }
                 lstm_mark(tl, s, 1);
                 if (dual) {   // second MMA issuer: odd k-chunks -> accumulator 1
-                    const unsigned idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(kGemmBM >> 4) << 24);
                     if (s == 0) g_mbar_wait(bar_w, 0);
                     g_mbar_wait(bar_full, s & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     for (int k = 1; k < nk; k += 2) {
                         const unsigned long long da = umma_desc_k128(s_a + k * a_bytes), db = umma_desc_k128(s_w + k * w_bytes);
 #pragma unroll
-                        for (int kk = 0; kk < kGemmBK / 8; ++kk)
-                            umma_tf32(tmem_d + (unsigned)N, da + (unsigned long long)(kk * 2), db + (unsigned long long)(kk * 2), idesc2, (k > 1 || kk) ? 1u : 0u);
+                        for (int kk = 0; kk < 4; ++kk)   // 32 bytes of the swizzle row per MMA (8 tf32 / 16 binary16)
+                            mma(tmem_d + (unsigned)N, da + (unsigned long long)(kk * 2), db + (unsigned long long)(kk * 2), (k > 1 || kk) ? 1u : 0u);
                     }
                     umma_commit(bar_empty);
                     umma_commit(bar_acc);
@@ -144,7 +163,6 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(kGemmBM >> 4) << 24);
             g_mbar_wait(bar_w, 0);
             int it = 0;
             for (int s = 0; s < T; ++s) {
@@ -157,8 +175,8 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
                         const int k = gi * gc + c;
                         const unsigned long long da = umma_desc_k128(s_a + st * g_bytes + c * a_bytes), db = umma_desc_k128(s_w + k * w_bytes);
 #pragma unroll
-                        for (int kk = 0; kk < kGemmBK / 8; ++kk)
-                            umma_tf32(tmem_d, da + (unsigned long long)(kk * 2), db + (unsigned long long)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+                        for (int kk = 0; kk < 4; ++kk)
+                            mma(tmem_d, da + (unsigned long long)(kk * 2), db + (unsigned long long)(kk * 2), (k | kk) ? 1u : 0u);
                     }
                     umma_commit(bar_empty + st * 8);
                 }
@@ -192,7 +210,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
                 }
             }
             g_mbar_wait(bar_acc, s & 1);
-            if (threadIdx.x == 64) lstm_mark(tl, s, 4);
+            if (threadIdx.x == 128) lstm_mark(tl, s, 4);   // (warp 4 = TMEM lanes 0..31: live at every batch size)
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             unsigned g[N];
 #pragma unroll
@@ -221,9 +239,9 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
                     for (int i = 0; i < 16; ++i) g[c0 + i] = __float_as_uint(__uint_as_float(g[c0 + i]) + __uint_as_float(g2[i]));
                 }
             }
-            if (threadIdx.x == 64) lstm_mark(tl, s, 5);
+            if (threadIdx.x == 128) lstm_mark(tl, s, 5);
             if (live_row) {
-                float* hn = hbuf + (((size_t)((s + 1) & 1) * 2 + d) * B + r) * H + j * HS;
+                const size_t hoff = (((size_t)((s + 1) & 1) * 2 + d) * B + r) * H + j * HS;
                 if (upd) {
 #pragma unroll
                     for (int u = 0; u < HS; ++u) {
@@ -236,32 +254,48 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
                         h[u] = go * tanh_fast(c[u]);
                         if (TRAIN) { xi[u] = gi; xj[u] = gj; xf[u] = gf; xo[u] = go; }
                     }
-                    float* o = out + ((size_t)t * B + r) * 2 * H + (size_t)d * H + j * HS;
-#pragma unroll
-                    for (int u = 0; u < HS; u += 4) *reinterpret_cast<float4*>(o + u) = make_float4(h[u], h[u + 1], h[u + 2], h[u + 3]);
-                    if (TRAIN) {   // what back-propagation through time needs: gate activations (in place of the pre-activations) and c_t
-                        float* ga = gates_out + ((size_t)t * B + r) * 8 * H + (size_t)d * 4 * H + j * HS;
-                        float* cso = cs_out + ((size_t)t * B + r) * 2 * H + (size_t)d * H + j * HS;
-#pragma unroll
-                        for (int u = 0; u < HS; u += 4) {
-                            *reinterpret_cast<float4*>(ga + u) = *reinterpret_cast<float4*>(xi + u);
-                            *reinterpret_cast<float4*>(ga + H + u) = *reinterpret_cast<float4*>(xj + u);
-                            *reinterpret_cast<float4*>(ga + 2 * H + u) = *reinterpret_cast<float4*>(xf + u);
-                            *reinterpret_cast<float4*>(ga + 3 * H + u) = *reinterpret_cast<float4*>(xo + u);
-                            *reinterpret_cast<float4*>(cso + u) = make_float4(c[u], c[u + 1], c[u + 2], c[u + 3]);
-                        }
-                    }
                 }
                 // carried or updated, the state is the next frame's operand
+                if constexpr (F16) {
+                    __half* hn = reinterpret_cast<__half*>(hbuf_v) + hoff;
 #pragma unroll
-                for (int u = 0; u < HS; u += 4) *reinterpret_cast<float4*>(hn + u) = make_float4(h[u], h[u + 1], h[u + 2], h[u + 3]);
+                    for (int u = 0; u < HS; u += 8) {
+                        const __half2 p0 = __floats2half2_rn(h[u], h[u + 1]), p1 = __floats2half2_rn(h[u + 2], h[u + 3]);
+                        const __half2 p2 = __floats2half2_rn(h[u + 4], h[u + 5]), p3 = __floats2half2_rn(h[u + 6], h[u + 7]);
+                        *reinterpret_cast<uint4*>(hn + u) = make_uint4(*reinterpret_cast<const unsigned*>(&p0), *reinterpret_cast<const unsigned*>(&p1),
+                                                                       *reinterpret_cast<const unsigned*>(&p2), *reinterpret_cast<const unsigned*>(&p3));
+                    }
+                } else {
+                    float* hn = reinterpret_cast<float*>(hbuf_v) + hoff;
+#pragma unroll
+                    for (int u = 0; u < HS; u += 4) *reinterpret_cast<float4*>(hn + u) = make_float4(h[u], h[u + 1], h[u + 2], h[u + 3]);
+                }
             }
-            if (threadIdx.x == 64) lstm_mark(tl, s, 6);
+            if (threadIdx.x == 128) lstm_mark(tl, s, 6);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps: their h stores are ordered before...
             if (warp == 2 && lane == 0) {                    // ...this gpu-scope release (cumulative) that publishes the slice
                 asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counters + d) : "memory");
                 lstm_mark(tl, s, 7);
+            }
+            // everything only later kernels read leaves AFTER the slice is published: the release above waits for the stores
+            // issued before it, and the other CTAs of the direction wait for the release
+            if (upd) {
+                float* o = out + ((size_t)t * B + r) * 2 * H + (size_t)d * H + j * HS;
+#pragma unroll
+                for (int u = 0; u < HS; u += 4) *reinterpret_cast<float4*>(o + u) = make_float4(h[u], h[u + 1], h[u + 2], h[u + 3]);
+                if (TRAIN) {   // what back-propagation through time needs: gate activations (in place of the pre-activations) and c_t
+                    float* ga = gates_out + ((size_t)t * B + r) * 8 * H + (size_t)d * 4 * H + j * HS;
+                    float* cso = cs_out + ((size_t)t * B + r) * 2 * H + (size_t)d * H + j * HS;
+#pragma unroll
+                    for (int u = 0; u < HS; u += 4) {
+                        *reinterpret_cast<float4*>(ga + u) = *reinterpret_cast<float4*>(xi + u);
+                        *reinterpret_cast<float4*>(ga + H + u) = *reinterpret_cast<float4*>(xj + u);
+                        *reinterpret_cast<float4*>(ga + 2 * H + u) = *reinterpret_cast<float4*>(xf + u);
+                        *reinterpret_cast<float4*>(ga + 3 * H + u) = *reinterpret_cast<float4*>(xo + u);
+                        *reinterpret_cast<float4*>(cso + u) = make_float4(c[u], c[u + 1], c[u + 2], c[u + 3]);
+                    }
+                }
             }
         }
     }
@@ -274,7 +308,8 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
 }
 
 // gate-major permutation of the recurrent weights: row ((d*NS + j)*4 + g)*HS + u  <-  wh[d*4H + g*H + j*HS + u]
-__global__ void permute_wh_kernel(const float* __restrict__ wh, float* __restrict__ whp, int H, int HS, int NS)
+template <typename TO>
+__global__ void permute_wh_kernel(const float* __restrict__ wh, TO* __restrict__ whp, int H, int HS, int NS)
 {
     const long long total = (long long)8 * H * H;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -284,7 +319,9 @@ __global__ void permute_wh_kernel(const float* __restrict__ wh, float* __restric
         const int g = (int)(row % 4); row /= 4;
         const int j = (int)(row % NS);
         const int d = (int)(row / NS);
-        whp[idx] = wh[((size_t)d * 4 * H + (size_t)g * H + j * HS + u) * H + k];
+        const float v = wh[((size_t)d * 4 * H + (size_t)g * H + j * HS + u) * H + k];
+        if constexpr (std::is_same<TO, __half>::value) whp[idx] = __float2half_rn(v);
+        else whp[idx] = v;
     }
 }
 
@@ -296,6 +333,14 @@ constexpr int kHS = 16;
 
 namespace ocr {
 
+static int g_lstm_f16 = 1;   // binary16 recurrent operands where the shape allows (H % 64 == 0); 0: TF32 everywhere
+
+int lstm_set_operands(int f16) {
+    g_lstm_f16 = f16 ? 1 : 0;
+    return OCR_OK;
+}
+static bool lstm_f16(int H) { return g_lstm_f16 && (H % kGemmBKh) == 0; }
+
 int lstm_set_timeline(long long* buf) {
     OCR_CHECK_CUDA(cudaMemcpyToSymbol(g_lstm_timeline, &buf, sizeof(buf)));
     return OCR_OK;
@@ -305,25 +350,47 @@ bool lstm_persistent_supported(int T, int B, int H) {
     if ((H % kGemmBK) != 0 || (H % kHS) != 0 || B < 1) return false;
     const int NS = H / kHS, MT = (B + kGemmBM - 1) / kGemmBM;
     if (2 * NS * MT > 148) return false;   // one CTA per SM, all co-resident
-    if (H / kGemmBK > kRnnMaxStages) return false;
-    const size_t w = (size_t)H / kGemmBK * (4 * kHS) * kGemmBK * 4;
-    const size_t a = (size_t)(B >= kGemmBM ? kGemmBM : (B + 7) / 8 * 8) * kGemmBK * 4;
+    const int bk = lstm_f16(H) ? kGemmBKh : kGemmBK;
+    if (H / bk > kRnnMaxStages) return false;
+    const size_t w = (size_t)H / bk * (4 * kHS) * 128;
+    const size_t a = (size_t)(B >= kGemmBM ? kGemmBM : (B + 7) / 8 * 8) * 128;
     // weights + at least 2 stages of h + the slack tile + barriers + alignment
-    return w + 2 * a + kGemmBM * kGemmBK * 4 + 1024 + 1024 <= (size_t)kMaxDynSmem && T >= 1;
+    return w + 2 * a + kGemmBM * 128 + 1024 + 1024 <= (size_t)kMaxDynSmem && T >= 1;
 }
 
 size_t lstm_persistent_workspace_floats(int B, int H) {
-    // permuted W_h [8H, H] + h double buffer [2][2][B][H] + counters (64 floats)
+    // permuted W_h [8H, H] + h double buffer [2][2][B][H] + counters (64 floats); the binary16 forms use half of each
     return (size_t)8 * H * H + (size_t)4 * B * H + 64;
 }
 
 // xp [T*B, 8H] (input projection + bias), wh [8H, H] (fw i,j,f,o | bw), out [T,B,2H] (pre-zeroed by this call)
+// whp: [8H, H] gate-major rows, float32 or (lstm_f16(H)) binary16 -- the form lstm_persistent_run expects for this H
 int lstm_permute_wh(const float* wh, int H, float* whp, cudaStream_t st)
 {
     const long long total = (long long)8 * H * H;
     long long gsz = (total + 255) / 256;
-    permute_wh_kernel<<<(int)(gsz > 148 * 16 ? 148 * 16 : gsz), 256, 0, st>>>(wh, whp, H, kHS, H / kHS);
+    const int grid = (int)(gsz > 148 * 16 ? 148 * 16 : gsz);
+    if (lstm_f16(H)) permute_wh_kernel<__half><<<grid, 256, 0, st>>>(wh, reinterpret_cast<__half*>(whp), H, kHS, H / kHS);
+    else permute_wh_kernel<float><<<grid, 256, 0, st>>>(wh, whp, H, kHS, H / kHS);
     OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+template <bool TRAIN, bool F16>
+static int lstm_launch(const cudaLaunchConfig_t& cfg, const CUtensorMap& tmW, const CUtensorMap (&tmH)[2][2], const float* xp,
+                       const int32_t* seq_len, void* hbuf, float* out, unsigned* counters, int T, int B, int H, int NS, int a_rows,
+                       int n_stages, int gc, int MT, float* gates_out, float* cs_out)
+{
+    static int configured = -1;
+    int dev = 0;
+    OCR_CHECK_CUDA(cudaGetDevice(&dev));
+    if (configured != dev) {
+        OCR_CHECK_CUDA(cudaFuncSetAttribute(lstm_persistent_kernel<kHS, TRAIN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        configured = dev;
+    }
+    OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_persistent_kernel<kHS, TRAIN, F16>, tmW, tmH[0][0], tmH[0][1], tmH[1][0], tmH[1][1], xp, seq_len,
+                                      hbuf, out, counters, T, B, H, NS, a_rows, n_stages, gc, MT, gates_out, cs_out));
+    count_launch();
     return OCR_OK;
 }
 
@@ -333,6 +400,7 @@ int lstm_persistent_run(const float* xp, const float* wh, const float* wh_perm, 
 {
     const int NS = H / kHS, MT = (B + kGemmBM - 1) / kGemmBM;
     const bool train = gates_out != nullptr;
+    const bool f16 = lstm_f16(H);
     float* whp_ws = ws;
     float* hbuf = whp_ws + (size_t)8 * H * H;
     unsigned* counters = reinterpret_cast<unsigned*>(hbuf + (size_t)4 * B * H);
@@ -344,10 +412,11 @@ int lstm_persistent_run(const float* xp, const float* wh, const float* wh_perm, 
     }
     OCR_CHECK_CUDA(cudaMemsetAsync(hbuf, 0, sizeof(float) * ((size_t)4 * B * H + 64), st));
     OCR_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)T * B * 2 * H, st));
-    const int nk = H / kGemmBK;
+    const int bk = f16 ? kGemmBKh : kGemmBK;
+    const int nk = H / bk;
     const int a_rows = B >= kGemmBM ? kGemmBM : (B + 7) / 8 * 8;
-    const size_t w_bytes = (size_t)nk * (4 * kHS) * kGemmBK * 4, a_bytes = (size_t)a_rows * kGemmBK * 4;
-    const size_t fixed = w_bytes + (a_rows < kGemmBM ? kGemmBM * kGemmBK * 4 : 0) + 1024 + 1024;
+    const size_t w_bytes = (size_t)nk * (4 * kHS) * 128, a_bytes = (size_t)a_rows * 128;
+    const size_t fixed = w_bytes + (a_rows < kGemmBM ? kGemmBM * 128 : 0) + 1024 + 1024;
     // h streams in groups of gc k-chunk tiles, one TMA request each: the whole row block as one group when it fits,
     // else two ring stages of the largest group (a divisor of nk) that fits twice
     const int fit = (int)(((size_t)kMaxDynSmem - fixed) / a_bytes);     // chunk tiles that fit beside the weights
@@ -361,22 +430,15 @@ int lstm_persistent_run(const float* xp, const float* wh, const float* wh_perm, 
         if (n_stages > kRnnMaxStages) n_stages = kRnnMaxStages;
     }
     CUtensorMap tmW, tmH[2][2];
-    int rc = tma_map_2d(&tmW, whp, (long long)8 * H, H, H, 4 * kHS);
+    int rc = f16 ? tma_map_2d_h(&tmW, whp, (long long)8 * H, H, H, 4 * kHS) : tma_map_2d(&tmW, whp, (long long)8 * H, H, H, 4 * kHS);
     if (rc != OCR_OK) return rc;
     for (int p = 0; p < 2; ++p)
         for (int d = 0; d < 2; ++d) {
-            rc = tma_map_chunks(&tmH[p][d], hbuf + ((size_t)p * 2 + d) * B * H, B, H, H, a_rows, gc);
+            rc = f16 ? tma_map_chunks_h(&tmH[p][d], reinterpret_cast<__half*>(hbuf) + ((size_t)p * 2 + d) * B * H, B, H, H, a_rows, gc)
+                     : tma_map_chunks(&tmH[p][d], hbuf + ((size_t)p * 2 + d) * B * H, B, H, H, a_rows, gc);
             if (rc != OCR_OK) return rc;
         }
     const size_t smem = fixed + (size_t)n_stages * gc * a_bytes;
-    static int configured = -1;
-    int dev = 0;
-    OCR_CHECK_CUDA(cudaGetDevice(&dev));
-    if (configured != dev) {
-        OCR_CHECK_CUDA(cudaFuncSetAttribute(lstm_persistent_kernel<kHS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-        OCR_CHECK_CUDA(cudaFuncSetAttribute(lstm_persistent_kernel<kHS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-        configured = dev;
-    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * NS * MT);
     cfg.blockDim = dim3(kRnnThreads);
@@ -387,14 +449,12 @@ int lstm_persistent_run(const float* xp, const float* wh, const float* wh_perm, 
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (train)
-        OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_persistent_kernel<kHS, true>, tmW, tmH[0][0], tmH[0][1], tmH[1][0], tmH[1][1], xp, seq_len, hbuf,
-                                          out, counters, T, B, H, NS, a_rows, n_stages, gc, MT, gates_out, cs_out));
-    else
-        OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_persistent_kernel<kHS, false>, tmW, tmH[0][0], tmH[0][1], tmH[1][0], tmH[1][1], xp, seq_len, hbuf,
-                                          out, counters, T, B, H, NS, a_rows, n_stages, gc, MT, (float*)nullptr, (float*)nullptr));
-    count_launch();
-    return OCR_OK;
+    float* g0 = train ? gates_out : nullptr;
+    float* c0 = train ? cs_out : nullptr;
+    if (train) return f16 ? lstm_launch<true, true>(cfg, tmW, tmH, xp, seq_len, hbuf, out, counters, T, B, H, NS, a_rows, n_stages, gc, MT, g0, c0)
+                          : lstm_launch<true, false>(cfg, tmW, tmH, xp, seq_len, hbuf, out, counters, T, B, H, NS, a_rows, n_stages, gc, MT, g0, c0);
+    return f16 ? lstm_launch<false, true>(cfg, tmW, tmH, xp, seq_len, hbuf, out, counters, T, B, H, NS, a_rows, n_stages, gc, MT, g0, c0)
+               : lstm_launch<false, false>(cfg, tmW, tmH, xp, seq_len, hbuf, out, counters, T, B, H, NS, a_rows, n_stages, gc, MT, g0, c0);
 }
 
 }  // namespace ocr

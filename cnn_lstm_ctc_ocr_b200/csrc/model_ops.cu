@@ -208,6 +208,8 @@ int gru_persistent_run(const float* xp, const float* whg, const float* whc, cons
 
 int lstm_set_timeline(long long* buf);
 int lstm_bptt_set_timeline(long long* buf);
+int lstm_set_operands(int f16);
+int gru_set_operands(int f16);
 
 static inline int grid_for(long long total, int threads = 256) {
     long long g = (total + threads - 1) / threads;
@@ -279,6 +281,14 @@ extern "C" int ocr_birnn_set_path(int path) {
 extern "C" int ocr_debug_lstm_timeline(long long* device_buffer) {
     const int rc = lstm_set_timeline(device_buffer);
     return rc != OCR_OK ? rc : lstm_bptt_set_timeline(device_buffer);     // the persistent BPTT kernel stamps the same buffer
+}
+
+// Operand precision of the persistent recurrence kernels: 1 (default) = IEEE binary16 h and W_h where H % 64 == 0 (K = 16 per
+// tcgen05.mma: half the instructions and half the h bytes per frame; same 10 mantissa bits as a TF32 operand), 0 = TF32.
+// Takes effect for weights prepared (ocr_lstm_prepare_wh) and layers run after the call.
+extern "C" int ocr_debug_lstm_operands(int f16) {
+    const int rc = lstm_set_operands(f16);
+    return rc != OCR_OK ? rc : gru_set_operands(f16);
 }
 
 extern "C" int ocr_birnn_workspace_bytes(int cell, int T, int B, int H, size_t* bytes)

@@ -187,6 +187,10 @@ int ocr_birnn_set_path(int path);
  * barrier, last h tile requested, first tile landed, last MMA issued, accumulator complete, TMEM read, cell update + stores
  * done, slice published); NULL switches it off.  Not part of the product path. */
 int ocr_debug_lstm_timeline(long long* device_buffer);
+/* Operand precision of the persistent recurrence kernels (LSTM and GRU): 1 (default) = IEEE binary16 h and W_h where
+ * H % 64 == 0 (tcgen05.mma.kind::f16, K = 16 per instruction; the same 10 explicit mantissa bits a TF32 operand keeps),
+ * 0 = TF32 operands.  Applies to weights prepared (ocr_lstm_prepare_wh) and layers run after the call. */
+int ocr_debug_lstm_operands(int f16);
 int ocr_birnn_layer(int cell, const float* x, int T, int B, int I, int H, const int32_t* seq_len, const float* wx,
                     const float* wh, const float* wh2, const float* bias, float* out, void* workspace,
                     size_t workspace_bytes, ocr_stream_t stream);

@@ -60,12 +60,14 @@ def test_full_graph_vs_oracle(cell, sizes):
     assert len(texts) == B and all(isinstance(t, str) for t in texts)
 
 
-@pytest.mark.parametrize("path", [0, 1])
+@pytest.mark.parametrize("path", [0, 10, 1])
 def test_rnn_layer_masks_and_directions(path):
     """Per-example lengths: zeros past the length, backward direction starts at len-1 (bidirectional_dynamic_rnn).
-    path 0 = persistent tcgen05 LSTM kernel, path 1 = frame-by-frame launches."""
+    path 0 = persistent tcgen05 LSTM kernel (binary16 recurrent operands, the default), 10 = the same kernel with TF32
+    operands (ocr_debug_lstm_operands(0)), path 1 = frame-by-frame launches."""
     from cnn_lstm_ctc_ocr_b200 import model, _lib
-    _lib.check(_lib.load().ocr_birnn_set_path(path), "ocr_birnn_set_path")
+    _lib.check(_lib.load().ocr_debug_lstm_operands(0 if path >= 10 else 1), "ocr_debug_lstm_operands")
+    _lib.check(_lib.load().ocr_birnn_set_path(path % 10), "ocr_birnn_set_path")
     rng = np.random.default_rng(5)
     params = mo.init_params(seed=2, cell_type="lstm", sizes=(512, 512), dtype=np.float64)
     for k in list(params):
@@ -80,19 +82,22 @@ def test_rnn_layer_masks_and_directions(path):
     out = m.rnn_layer(torch.tensor(feats, device=dev, dtype=torch.float32).transpose(0, 1).contiguous(), torch.tensor(sl, device=dev), 0)
     o = out.cpu().numpy()
     _lib.load().ocr_birnn_set_path(0)
+    _lib.load().ocr_debug_lstm_operands(1)
     assert np.abs(o - ref).max() <= 5e-3 * np.abs(ref).max()
     for b in range(B):
         assert (o[sl[b]:, b] == 0).all()
 
 
-@pytest.mark.parametrize("path", [0, 1])
+@pytest.mark.parametrize("path", [0, 10, 1])
 @pytest.mark.parametrize("layer,I,H", [(0, 256, 512), (1, 1024, 256)])
 def test_gru_layer_masks_and_directions(path, layer, I, H):
     """The GRU model's two layers (model.py:167-199, 213-214; H = 512 and 256) against the numpy oracle: per-example lengths,
     zeros past the length, backward direction from len-1.  path 0 = persistent tcgen05 GRU kernel (two products per frame with
-    a grid-wide exchange of r*h between them), path 1 = frame-by-frame launches."""
+    a grid-wide exchange of r*h between them; binary16 recurrent operands, the default), 10 = the same kernel with TF32
+    operands, path 1 = frame-by-frame launches."""
     from cnn_lstm_ctc_ocr_b200 import model, _lib
-    _lib.check(_lib.load().ocr_birnn_set_path(path), "ocr_birnn_set_path")
+    _lib.check(_lib.load().ocr_debug_lstm_operands(0 if path >= 10 else 1), "ocr_debug_lstm_operands")
+    _lib.check(_lib.load().ocr_birnn_set_path(path % 10), "ocr_birnn_set_path")
     rng = np.random.default_rng(6 + layer)
     params = mo.init_params(seed=3, cell_type="gru", sizes=(512, 256), dtype=np.float64)
     for k in list(params):
@@ -109,6 +114,7 @@ def test_gru_layer_masks_and_directions(path, layer, I, H):
     out = m.rnn_layer(torch.tensor(feats, device=dev, dtype=torch.float32).transpose(0, 1).contiguous(), torch.tensor(sl, device=dev), layer)
     o = out.cpu().numpy()
     _lib.load().ocr_birnn_set_path(0)
+    _lib.load().ocr_debug_lstm_operands(1)
     assert np.abs(o - ref).max() <= 5e-3 * np.abs(ref).max()
     for b in range(B):
         assert (o[sl[b]:, b] == 0).all()

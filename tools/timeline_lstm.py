@@ -1,4 +1,4 @@
-"""Per-frame phase timeline of the persistent LSTM kernel (CTA 0): python tools/timeline_lstm.py [B] [T]"""
+"""Per-frame phase timeline of the persistent LSTM kernel (CTA 0): python tools/timeline_lstm.py [B] [T] [f16 operands: 1|0]"""
 import sys, ctypes
 sys.path.insert(0, ".")
 import numpy as np, torch
@@ -7,6 +7,8 @@ lib = _lib.load()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 61
 I, H = 256, 512
+F16 = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+lib.ocr_debug_lstm_operands(F16)
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev); g.manual_seed(0)
 x = torch.randn((T, B, I), device=dev, generator=g)
@@ -31,6 +33,7 @@ lib.ocr_debug_lstm_timeline(None)
 a = tl.cpu().numpy().reshape(T, 8).astype(np.float64)
 names = ["barrier->", "tma issued", "1st tile landed", "mma issued", "acc done", "tmem read", "cell+stores", "published"]
 fr = a[5:T - 2]
+print("operands: %s" % ("binary16" if F16 else "tf32"))
 print("B=%d T=%d: frame period %.0f cycles (%.2f us at 1.965 GHz)" % (B, T, np.diff(a[5:T - 2, 0]).mean(), np.diff(a[5:T - 2, 0]).mean() / 1965))
 for i in range(1, 8):
     print("  %-16s +%6.0f cycles after the previous mark" % (names[i], (fr[:, i] - fr[:, i - 1]).mean()))
