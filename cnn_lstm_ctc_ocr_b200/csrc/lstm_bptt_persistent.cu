@@ -16,6 +16,13 @@
 //   * the owner of a slice adds the NS partials of its 16 units in a fixed order (deterministic) at the start of the next
 //     frame; the CTAs of a (direction, batch tile) meet at a per-frame grid barrier (release/acquire on a global counter;
 //     cooperative launch guarantees co-residency).  Partials are double buffered by frame parity.
+//   * small batches (round 2): TMEM lane = accumulator row, so with B <= 32 live rows only a quarter of the 128 epilogue
+//     threads had work.  The A tile now holds R = 4 (B <= 32) or 2 (B <= 64) COPIES of every batch row -- the MMA costs the
+//     same (M = 128 whatever the batch) and every copy of a row receives the same partial d h_{prev}.  Copy rho of a row
+//     owns 16/R of the CTA's units for the partial sums and the cell backward (it writes its gate gradients into all R
+//     copies of the row in the A tile) and the destination slices [rho*NS/R, +NS/R) for the scatter: a quarter (half) of
+//     the loads, arithmetic, stores and TMEM reads per thread, nothing computed twice, sums in the same order (same bits).
+//     The exchange blocks are laid out [4 column groups][128 rows][4 floats]: a warp's 16-byte accesses are contiguous.
 // Sequence lengths follow dynamic_rnn: an example is touched only while s < len (processing order s = T-1 .. 0), the
 // backward direction visits frame len-1-s at step s; rows past their length contribute zero gate gradients.
 #include "gemm_tf32.cuh"
@@ -42,6 +49,7 @@ __device__ __forceinline__ void bp_wait_counter(const unsigned* ctr, unsigned ta
     __trap();
 }
 
+template <int R>   // copies of a batch row in the A tile: 1, 2 or 4 (one batch tile when R > 1)
 __global__ void __launch_bounds__(kBpThreads, 1)
 lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW, float* act /*[T*B, 8H]: activations in, d pre-activations out*/,
                  const float* __restrict__ cs /*[T,B,2H]*/, const float* __restrict__ dout /*[T,B,2H]*/, const int32_t* __restrict__ seq_len,
@@ -112,47 +120,56 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW, float* act /*[T*B, 8H]
             }
         }
     } else {
+        constexpr int U = kBpHS / R;                     // units per thread
+        constexpr int per = 4 / R;                       // warps per copy
         const int q = warp & 3;
         const int rl = q * 32 + lane;                    // row of the A tile / accumulator = TMEM lane
-        // batch rows are dealt round-robin to the four lane quarters: with a small batch (the case this kernel is for) the
-        // live rows -- and with them the partial-sum reads, the cell backward and the scatter -- spread over all four
-        // epilogue warps instead of filling one (measured at B = 32, H = 512: 19300 -> 17050 cycles per frame)
-        const int r = m0 + lane * 4 + q;
+        // R == 1: batch rows are dealt round-robin to the four lane quarters, so that with a partly filled tile the live rows
+        // spread over all four epilogue warps (measured at B = 32, H = 512: 19300 -> 17050 cycles per frame).
+        // R > 1: copy rho of row `slot`: units [rho*U, +U) of the CTA's 16, destination slices [rho*NS/R, +NS/R).
+        const int rho = q / per;
+        const int slot = R > 1 ? (q % per) * 32 + lane : rl;     // row index inside the exchange blocks
+        const int r = R > 1 ? slot : m0 + lane * 4 + q;
+        const int u0 = rho * U;
+        const int nsr = NS / R;
         const bool in_batch = r < B;
         const int len = in_batch ? min(max(seq_len[r], 0), T) : 0;
-        const size_t part_tile = (size_t)128 * kBpHS;    // floats of one [128][16] block
+        const size_t part_tile = (size_t)128 * kBpHS;    // floats of one [4][128][4] block
         const size_t part_pd = (size_t)MT * NS * NS * part_tile;          // per (parity, direction)
-        float dc[kBpHS];
+        float dc[U];
 #pragma unroll
-        for (int u = 0; u < kBpHS; ++u) dc[u] = 0.f;
+        for (int u = 0; u < U; ++u) dc[u] = 0.f;
         for (int f = 0; f < T; ++f) {
             const int s = T - 1 - f;
             const bool live = s < len;
             const int t = d ? len - 1 - s : s;
-            // ---- d h of my 16 units: the layer's output gradient + what step s+1 sent back through W_h
-            float dh[kBpHS];
+            // ---- d h of my units: the layer's output gradient + what step s+1 sent back through W_h
+            float dh[U];
 #pragma unroll
-            for (int u = 0; u < kBpHS; ++u) dh[u] = 0.f;
+            for (int u = 0; u < U; ++u) dh[u] = 0.f;
             if (live) {   // this frame's records do not depend on the other CTAs: pull them towards the SM while waiting at the barrier
-                const size_t o = ((size_t)t * B + r) * 2 * H + (size_t)d * H + j * kBpHS;
-                const float* a = act + ((size_t)t * B + r) * 8 * H + (size_t)d * 4 * H + j * kBpHS;
+                const size_t o = ((size_t)t * B + r) * 2 * H + (size_t)d * H + j * kBpHS + u0;
+                const float* a = act + ((size_t)t * B + r) * 8 * H + (size_t)d * 4 * H + j * kBpHS + u0;
 #pragma unroll
                 for (int gq = 0; gq < 4; ++gq) asm volatile("prefetch.global.L1 [%0];" ::"l"(a + gq * H));
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(cs + o));
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(dout + o));
-                if (s > 0) { const int tp = d ? t + 1 : t - 1; asm volatile("prefetch.global.L1 [%0];" ::"l"(cs + ((size_t)tp * B + r) * 2 * H + (size_t)d * H + j * kBpHS)); }
+                if (s > 0) { const int tp = d ? t + 1 : t - 1; asm volatile("prefetch.global.L1 [%0];" ::"l"(cs + ((size_t)tp * B + r) * 2 * H + (size_t)d * H + j * kBpHS + u0)); }
             }
             if (f > 0) {
                 if (threadIdx.x == 64) bp_wait_counter(counters + d * MT + mt, (unsigned)NS * (unsigned)f);
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (threadIdx.x == 64) bp_mark(tl, f, 0);
                 if (live && s + 1 < len) {
-                    const float* src = part + ((size_t)((f - 1) & 1) * 2 + d) * part_pd + (((size_t)mt * NS + j) * NS) * part_tile + (size_t)rl * kBpHS;
+                    // block [4 column groups][128 rows][4 floats]: my column groups rho*U/4 .., row `slot`
+                    const float4* src = reinterpret_cast<const float4*>(part + ((size_t)((f - 1) & 1) * 2 + d) * part_pd + (((size_t)mt * NS + j) * NS) * part_tile) +
+                                        (size_t)(u0 / 4) * 128 + slot;
+#pragma unroll 4
                     for (int js = 0; js < NS; ++js) {     // fixed order: deterministic sums
-                        const float4* p4 = reinterpret_cast<const float4*>(src + (size_t)js * part_tile);
+                        const float4* p4 = src + (size_t)js * (part_tile / 4);
 #pragma unroll
-                        for (int v = 0; v < kBpHS / 4; ++v) {
-                            const float4 a = __ldcg(p4 + v);   // written by other SMs this launch: L2, never a stale L1 line
+                        for (int v = 0; v < U / 4; ++v) {
+                            const float4 a = __ldcg(p4 + v * 128);   // written by other SMs this launch: L2, never a stale L1 line
                             dh[4 * v] += a.x; dh[4 * v + 1] += a.y; dh[4 * v + 2] += a.z; dh[4 * v + 3] += a.w;
                         }
                     }
@@ -160,14 +177,14 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW, float* act /*[T*B, 8H]
             }
             if (threadIdx.x == 64) bp_mark(tl, f, 1);
             // ---- cell backward for my units; gate gradients to global memory and into the A tile (k = gate*16 + unit)
-            float dg[kBpK];
+            float dg[4 * U];
             if (live) {
-                const size_t o = ((size_t)t * B + r) * 2 * H + (size_t)d * H + j * kBpHS;
-                float* a = act + ((size_t)t * B + r) * 8 * H + (size_t)d * 4 * H + j * kBpHS;
+                const size_t o = ((size_t)t * B + r) * 2 * H + (size_t)d * H + j * kBpHS + u0;
+                float* a = act + ((size_t)t * B + r) * 8 * H + (size_t)d * 4 * H + j * kBpHS + u0;
                 const float* cprev_p = nullptr;
-                if (s > 0) { const int tp = d ? t + 1 : t - 1; cprev_p = cs + ((size_t)tp * B + r) * 2 * H + (size_t)d * H + j * kBpHS; }
+                if (s > 0) { const int tp = d ? t + 1 : t - 1; cprev_p = cs + ((size_t)tp * B + r) * 2 * H + (size_t)d * H + j * kBpHS + u0; }
 #pragma unroll
-                for (int u = 0; u < kBpHS; u += 4) {
+                for (int u = 0; u < U; u += 4) {
                     const float4 gi = *reinterpret_cast<const float4*>(a + u), gj = *reinterpret_cast<const float4*>(a + H + u);
                     const float4 gf = *reinterpret_cast<const float4*>(a + 2 * H + u), go = *reinterpret_cast<const float4*>(a + 3 * H + u);
                     const float4 cn = __ldg(reinterpret_cast<const float4*>(cs + o + u)), dO = __ldg(reinterpret_cast<const float4*>(dout + o + u));
@@ -179,9 +196,9 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW, float* act /*[T*B, 8H]
                         const float d_o = dht * tc * go.f_ * (1.f - go.f_);       \
                         const float dct = dc[u + k_] + dht * go.f_ * (1.f - tc * tc); \
                         dg[u + k_] = dct * gj.f_ * gi.f_ * (1.f - gi.f_);         \
-                        dg[kBpHS + u + k_] = dct * gi.f_ * (1.f - gj.f_ * gj.f_); \
-                        dg[2 * kBpHS + u + k_] = dct * cp.f_ * gf.f_ * (1.f - gf.f_); \
-                        dg[3 * kBpHS + u + k_] = d_o;                             \
+                        dg[U + u + k_] = dct * gi.f_ * (1.f - gj.f_ * gj.f_);     \
+                        dg[2 * U + u + k_] = dct * cp.f_ * gf.f_ * (1.f - gf.f_); \
+                        dg[3 * U + u + k_] = d_o;                                 \
                         dc[u + k_] = dct * gf.f_;                                 \
                     }
                     OCR_BP1(x, 0) OCR_BP1(y, 1) OCR_BP1(z, 2) OCR_BP1(w, 3)
@@ -190,22 +207,29 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW, float* act /*[T*B, 8H]
 #pragma unroll
                 for (int g = 0; g < 4; ++g)
 #pragma unroll
-                    for (int u = 0; u < kBpHS; u += 4)
-                        *reinterpret_cast<float4*>(a + g * H + u) = make_float4(dg[g * kBpHS + u], dg[g * kBpHS + u + 1], dg[g * kBpHS + u + 2], dg[g * kBpHS + u + 3]);
+                    for (int u = 0; u < U; u += 4)
+                        *reinterpret_cast<float4*>(a + g * H + u) = make_float4(dg[g * U + u], dg[g * U + u + 1], dg[g * U + u + 2], dg[g * U + u + 3]);
             } else {
 #pragma unroll
-                for (int k = 0; k < kBpK; ++k) dg[k] = 0.f;
+                for (int k = 0; k < 4 * U; ++k) dg[k] = 0.f;
             }
-            // A tile row rl: chunk c = k / 32, 16-byte group (k % 32) / 4 XOR (row & 7)  (128-byte swizzle, tile 1024-aligned)
+            // A tile, every copy of my row (rows c*(128/R) + slot): k = gate*16 + unit -> chunk k / 32, 16-byte group
+            // (k % 32) / 4 XOR (row & 7)  (128-byte swizzle, tile 1024-aligned)
             {
-                unsigned char* arow = smem + (s_a - s_base) + (size_t)rl * 128;
 #pragma unroll
-                for (int c = 0; c < 2; ++c)
+                for (int c = 0; c < R; ++c) {
+                    const int row = R > 1 ? c * (128 / R) + slot : rl;
+                    unsigned char* arow = smem + (s_a - s_base) + (size_t)row * 128;
 #pragma unroll
-                    for (int g4 = 0; g4 < 8; ++g4) {
-                        const int k = c * 32 + g4 * 4;
-                        *reinterpret_cast<float4*>(arow + c * (128 * 128) + ((g4 ^ (rl & 7)) << 4)) = make_float4(dg[k], dg[k + 1], dg[k + 2], dg[k + 3]);
-                    }
+                    for (int g = 0; g < 4; ++g)
+#pragma unroll
+                        for (int u = 0; u < U; u += 4) {
+                            const int k = g * kBpHS + u0 + u;     // multiple of 4
+                            const int grp = (k & 31) >> 2;
+                            *reinterpret_cast<float4*>(arow + (k >> 5) * (128 * 128) + ((grp ^ (row & 7)) << 4)) =
+                                make_float4(dg[g * U + u], dg[g * U + u + 1], dg[g * U + u + 2], dg[g * U + u + 3]);
+                        }
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -215,13 +239,13 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW, float* act /*[T*B, 8H]
                 bp_mark(tl, f, 2);
             }
             if (f == T - 1) break;                        // the last step's product has no consumer (no MMA is issued for it)
-            // ---- partial d h_{prev}[row, all H units] over my K-slice: scatter 16 columns to each slice owner
+            // ---- partial d h_{prev}[row, all H units] over my K-slice: scatter 16 columns to each slice owner (my share of them)
             g_mbar_wait(bar_acc, f & 1);
             if (threadIdx.x == 64) bp_mark(tl, f, 4);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             {
-                float* dst = part + ((size_t)(f & 1) * 2 + d) * part_pd + ((size_t)mt * NS * NS + j) * part_tile + (size_t)rl * kBpHS;
-                for (int jd0 = 0; jd0 < NS; jd0 += 2) {       // 32 columns (two destination slices) per TMEM load; NS is even (H % 32 == 0)
+                float4* dst = reinterpret_cast<float4*>(part + ((size_t)(f & 1) * 2 + d) * part_pd + ((size_t)mt * NS * NS + j) * part_tile) + slot;
+                for (int jd0 = rho * nsr; jd0 < (rho + 1) * nsr; jd0 += 2) {   // 32 columns (two destination slices) per TMEM load; NS / R is even
                     unsigned v[32];
                     const unsigned taddr = tmem_d + ((unsigned)(q * 32) << 16) + (unsigned)(jd0 * kBpHS);
                     asm volatile(
@@ -237,11 +261,11 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW, float* act /*[T*B, 8H]
                     if (live) {                            // dead rows have zero gate gradients and nobody reads their partials
 #pragma unroll
                         for (int i = 0; i < 2; ++i) {
-                            float4* d4 = reinterpret_cast<float4*>(dst + (size_t)(jd0 + i) * NS * part_tile);
+                            float4* d4 = dst + (size_t)(jd0 + i) * NS * (part_tile / 4);
 #pragma unroll
                             for (int w = 0; w < 4; ++w)
-                                __stcg(d4 + w, make_float4(__uint_as_float(v[16 * i + 4 * w]), __uint_as_float(v[16 * i + 4 * w + 1]),
-                                                           __uint_as_float(v[16 * i + 4 * w + 2]), __uint_as_float(v[16 * i + 4 * w + 3])));
+                                __stcg(d4 + w * 128, make_float4(__uint_as_float(v[16 * i + 4 * w]), __uint_as_float(v[16 * i + 4 * w + 1]),
+                                                                 __uint_as_float(v[16 * i + 4 * w + 2]), __uint_as_float(v[16 * i + 4 * w + 3])));
                         }
                     }
                 }
@@ -276,6 +300,12 @@ __global__ void bptt_permute_kernel(const float* __restrict__ wh_rows, float* __
         const int g = k / kBpHS, u = k % kBpHS;
         whp[idx] = wh_rows[((size_t)d * H + n) * 4 * H + (size_t)g * H + j * kBpHS + u];
     }
+}
+
+static int g_bptt_copies = 1;   // row copies in the A tile at small batches (0: one copy, the round-1 form)
+int lstm_bptt_set_copies(int on) {
+    g_bptt_copies = on ? 1 : 0;
+    return OCR_OK;
 }
 
 int lstm_bptt_set_timeline(long long* buf) {
@@ -319,7 +349,9 @@ int lstm_bptt_run(const float* dout, int T, int B, int H, const int32_t* seq_len
     int dev = 0;
     OCR_CHECK_CUDA(cudaGetDevice(&dev));
     if (configured != dev) {
-        OCR_CHECK_CUDA(cudaFuncSetAttribute(lstm_bptt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        OCR_CHECK_CUDA(cudaFuncSetAttribute(lstm_bptt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        OCR_CHECK_CUDA(cudaFuncSetAttribute(lstm_bptt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        OCR_CHECK_CUDA(cudaFuncSetAttribute(lstm_bptt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
         configured = dev;
     }
     cudaLaunchConfig_t cfg = {};
@@ -332,7 +364,15 @@ int lstm_bptt_run(const float* dout, int T, int B, int H, const int32_t* seq_len
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_bptt_kernel, tmW, act, cstate, dout, seq_len, part, counters, T, B, H, NS, MT));
+    // copies of a batch row in the A tile (small batches): the largest R in {4, 2, 1} with B <= 128 / R and NS / R even
+    int R = 1;
+    if (g_bptt_copies && MT == 1) {
+        if (B <= 32 && (NS % 8) == 0) R = 4;
+        else if (B <= 64 && (NS % 4) == 0) R = 2;
+    }
+    if (R == 4) OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_bptt_kernel<4>, tmW, act, cstate, dout, seq_len, part, counters, T, B, H, NS, MT));
+    else if (R == 2) OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_bptt_kernel<2>, tmW, act, cstate, dout, seq_len, part, counters, T, B, H, NS, MT));
+    else OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_bptt_kernel<1>, tmW, act, cstate, dout, seq_len, part, counters, T, B, H, NS, MT));
     count_launch();
     return OCR_OK;
 }

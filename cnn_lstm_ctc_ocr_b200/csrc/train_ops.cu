@@ -971,6 +971,9 @@ extern "C" int ocr_debug_bptt_pdl(int on) {
     g_bptt_pdl = on ? 1 : 0;
     return OCR_OK;
 }
+namespace ocr { int lstm_bptt_set_copies(int on); }
+// Tuning aid: the persistent BPTT kernel's row copies at small batches (1, default) / one copy per row (0); same bits either way.
+extern "C" int ocr_debug_bptt_copies(int on) { return lstm_bptt_set_copies(on); }
 
 extern "C" int ocr_birnn_lstm_bwd(const float* dout, int T, int B, int H, const int32_t* seq_len, float* gates, const float* cstate,
                                   const float* wh_rows, void* workspace, size_t workspace_bytes, ocr_stream_t stream)

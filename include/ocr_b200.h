@@ -276,6 +276,10 @@ int ocr_adam_step(float* params, const float* grads, float* m, float* v, long lo
  * contractions.  wh_rows [2H, 4H]: rows I.. of the forward cell's TensorFlow kernel, then the backward cell's. */
 /* Tuning aid: programmatic dependent launch on the frame-by-frame BPTT chain on (1, default) / off (0); same bits either way. */
 int ocr_debug_bptt_pdl(int on);
+/* Tuning aid: in the persistent BPTT kernel a batch of <= 32 (<= 64) rows is held four (two) times in the 128-row operand
+ * tile so that all 128 epilogue threads share the partial-sum reads and the scatter (1, default); 0 = one copy per row.
+ * Same bits either way. */
+int ocr_debug_bptt_copies(int on);
 int ocr_birnn_lstm_train_workspace_bytes(int T, int B, int H, size_t* bytes);
 int ocr_birnn_lstm_train_fwd(const float* x, int T, int B, int I, int H, const int32_t* seq_len, const float* wx, const float* wh,
                              const float* bias, float* out, float* gates, float* cstate, void* workspace, size_t workspace_bytes,

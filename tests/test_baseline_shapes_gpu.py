@@ -89,6 +89,37 @@ def test_lstm_training_kernels_at_cfg3_shapes(B, I):
     _close(dx, xt.grad.numpy(), 2e-2, "dx")
 
 
+@pytest.mark.parametrize("B,H,T", [(32, 512, 40), (23, 512, 17), (64, 512, 24), (40, 256, 19), (5, 64, 9)])
+def test_bptt_row_copies_leave_every_bit_unchanged(B, H, T):
+    """Persistent BPTT kernel: with B <= 32 (<= 64) rows the 128-row operand tile holds four (two) copies of every row and the
+    copies share the partial-sum reads and the scatter (ocr_debug_bptt_copies).  The sums are added in the same fixed order
+    either way: identical gate gradients, bit for bit."""
+    from cnn_lstm_ctc_ocr_b200 import _lib as L
+    lib, sh = L.load(), L.stream_handle()
+    g = torch.Generator(device=DEV); g.manual_seed(B * 1000 + H)
+    act = torch.rand((T * B, 8 * H), device=DEV, generator=g) * 0.8 + 0.1
+    cs = torch.randn((T, B, 2 * H), device=DEV, generator=g) * 0.5
+    dout = torch.randn((T, B, 2 * H), device=DEV, generator=g) * 0.01
+    wh_rows = torch.randn((2 * H, 4 * H), device=DEV, generator=g) * 0.05
+    sl = torch.randint(1, T + 1, (B,), dtype=torch.int32, device=DEV, generator=g)
+    sl[0] = T
+    need = ctypes.c_size_t(0)
+    L.check(lib.ocr_birnn_lstm_train_workspace_bytes(T, B, H, ctypes.byref(need)), "ws")
+    ws = torch.empty(need.value, dtype=torch.uint8, device=DEV)
+    L.check(lib.ocr_birnn_set_path(3), "path")          # persistent BPTT whenever the shape fits
+    res = []
+    for copies in (1, 0):
+        L.check(lib.ocr_debug_bptt_copies(copies), "copies")
+        a = act.clone()
+        L.check(lib.ocr_birnn_lstm_bwd(L.ptr(dout), T, B, H, L.ptr(sl), L.ptr(a), L.ptr(cs), L.ptr(wh_rows), L.ptr(ws), need.value, sh), "bwd")
+        torch.cuda.synchronize()
+        res.append(a)
+    L.check(lib.ocr_debug_bptt_copies(1), "copies")
+    L.check(lib.ocr_birnn_set_path(0), "path")
+    assert torch.isfinite(res[0]).all()
+    assert torch.equal(res[0], res[1])
+
+
 def test_whole_training_step_lstm512_w256():
     """One step of train.py's graph at cfg3's layer sizes and crop width (LSTM 512/512, 32x256 crops, 96 logits), batch 8."""
     from cnn_lstm_ctc_ocr_b200 import train
