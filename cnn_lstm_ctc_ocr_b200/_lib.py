@@ -68,6 +68,7 @@ SIGNATURES = {
     "ocr_conv_filter_layouts": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "ocr_adam_step": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _vp, _f, _f, _f, _f, _vp]),
     "ocr_debug_bptt_pdl": (_i, [_i]),
+    "ocr_debug_gemm_tma_store": (_i, [_i]),
     "ocr_debug_bptt_copies": (_i, [_i]),
     "ocr_debug_lstm_operands": (_i, [_i]),
     "ocr_birnn_lstm_train_workspace_bytes": (_i, [_i, _i, _i, _c.POINTER(_sz)]),

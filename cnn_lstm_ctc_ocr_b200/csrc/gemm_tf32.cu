@@ -26,6 +26,7 @@ struct GemmSplit {
     int ksteps_per_split, nbatch;
     int a_shift[9], a_row[9], b_row[9];
     int a_box_bytes;   // bytes one A box delivers (boxes shorter than 128 rows when M < 128: no over-fetch of foreign rows)
+    int tma_store;     // 1: TMA-store epilogue through tmD
     long long split_stride, batch_stride;
 };
 
@@ -40,7 +41,7 @@ struct GemmSmem {
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kGemmThreads)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
                  const float* __restrict__ bias, float* __restrict__ D, int M, int N, int K, int ldd, int relu,
                  const GemmSplit sp)
 {
@@ -115,7 +116,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int q = warp & 3;
         g_mbar_wait(bar_acc, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        gemm_epilogue<BN>(tmem_d, q, lane, m0, n0, M, N, bias, D, ldd, relu);
+        // (the pipeline stages are idle by now: every TMA load has been consumed and every MMA has retired)
+        if (sp.tma_store) gemm_epilogue_tma<BN>(tmem_d, q, lane, m0, n0, N, bias, relu, &tmD, s_base);
+        else gemm_epilogue<BN>(tmem_d, q, lane, m0, n0, M, N, bias, D, ldd, relu);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -209,6 +212,26 @@ int tma_map_chunks_h(CUtensorMap* tm, const void* base, long long rows, long lon
 }
 }  // namespace ocr
 
+namespace ocr {
+int tma_map_out(CUtensorMap* tm, float* base, long long rows, long long cols, long long ld) {
+    EncodeTiledFn enc = get_encode();
+    if (enc == nullptr) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return OCR_ECUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (output) failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld); return OCR_ECUDA; }
+    return OCR_OK;
+}
+static int g_gemm_tma_store = 1;   // TMA-store epilogue where the plan allows it (0: one STG per lane and row everywhere)
+int gemm_set_tma_store(int on) {
+    g_gemm_tma_store = on ? 1 : 0;
+    return OCR_OK;
+}
+}  // namespace ocr
+
 template <int BN, int STAGES>
 static int launch_planned(const GemmPlan& p, cudaStream_t st)
 {
@@ -228,6 +251,7 @@ static int launch_planned(const GemmPlan& p, cudaStream_t st)
     sp.split_stride = p.split_stride;
     sp.a_box_bytes = p.a_box_rows * kGemmBK * 4;
     sp.batch_stride = p.batch_stride;
+    sp.tma_store = (p.tma_store && g_gemm_tma_store && p.nbatch == 1 && p.splits == 1) ? 1 : 0;
     if (p.pdl) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid;
@@ -239,11 +263,11 @@ static int launch_planned(const GemmPlan& p, cudaStream_t st)
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, STAGES>, p.tmA, p.tmB, p.bias, p.D, p.M, p.N, p.K, p.ldd, p.relu, sp));
+        OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, STAGES>, p.tmA, p.tmB, p.tmD, p.bias, p.D, p.M, p.N, p.K, p.ldd, p.relu, sp));
         count_launch();
         return OCR_OK;
     }
-    gemm_tf32_kernel<BN, STAGES><<<grid, kGemmThreads, S::kTotal, st>>>(p.tmA, p.tmB, p.bias, p.D, p.M, p.N, p.K, p.ldd, p.relu, sp);
+    gemm_tf32_kernel<BN, STAGES><<<grid, kGemmThreads, S::kTotal, st>>>(p.tmA, p.tmB, p.tmD, p.bias, p.D, p.M, p.N, p.K, p.ldd, p.relu, sp);
     OCR_CHECK_LAUNCH();
     return OCR_OK;
 }
@@ -272,6 +296,14 @@ int gemm_plan(GemmPlan* p, const float* A, int lda, const float* W, int ldw, con
     p->bn = bn; p->bias = bias; p->D = D; p->M = M; p->N = N; p->K = K; p->ldd = ldd; p->relu = relu;
     int rc = tma_map_2d(&p->tmA, A, M, K, lda, kGemmBM);
     if (rc != OCR_OK) return rc;
+    // TMA-store epilogue: output rows must be 16-byte aligned (tensor-map stride rule) and N a multiple of 4 (a bulk tensor
+    // store writes whole 16-byte units: with N = 50 it zeroed columns 50 and 51 of a wider row; measured)
+    p->tma_store = 0;
+    if ((ldd % 4) == 0 && (N % 4) == 0 && ((uintptr_t)D % 16) == 0) {
+        rc = tma_map_out(&p->tmD, D, M, N, ldd);
+        if (rc != OCR_OK) return rc;
+        p->tma_store = 1;
+    }
     return tma_map_2d(&p->tmB, W, N, K, ldw, bn);
 }
 
@@ -385,6 +417,9 @@ int gemm_wgrad(const float* A, long long lda, const float* W, long long ldw, flo
 }
 
 }  // namespace ocr
+
+// Tuning aid: TMA-store epilogue of ocr_gemm_tf32 on (1, default) / off (0); same bits either way.
+extern "C" int ocr_debug_gemm_tma_store(int on) { return gemm_set_tma_store(on); }
 
 extern "C" int ocr_gemm_tf32(const float* A, int lda, const float* W, int ldw, const float* bias, float* D, int ldd, int M, int N,
                              int K, int relu, ocr_stream_t stream)

@@ -9,6 +9,8 @@ namespace ocr {
 
 struct GemmPlan {
     CUtensorMap tmA, tmB;
+    CUtensorMap tmD;       // output [M, N] as 32-column x 32-row boxes, 128-byte swizzle (tma_store)
+    int tma_store = 0;     // 1: the epilogue stages 32x32 blocks in shared memory and stores them with cp.async.bulk.tensor (plain products with 16-byte aligned output rows)
     const float* bias;
     float* D;
     int M, N, K, ldd, relu, bn;
@@ -44,6 +46,8 @@ int tma_map_2d(CUtensorMap* tm, const float* base, long long rows, long long K, 
 
 // 3-D view [K/32][rows][32]: one request loads box_chunks consecutive swizzled k-chunk tiles of box_rows rows
 int tma_map_chunks(CUtensorMap* tm, const float* base, long long rows, long long K, long long ld, int box_rows, int box_chunks);
+// output tensor [rows, cols] fp32 with row pitch ld elements; box = [32 rows, 32 floats], 128-byte swizzle (TMA-store epilogues)
+int tma_map_out(CUtensorMap* tm, float* base, long long rows, long long cols, long long ld);
 
 // the same two views of a half-precision (IEEE binary16) matrix: a 128-byte swizzle row holds 64 elements
 constexpr int kGemmBKh = 64;
@@ -107,6 +111,64 @@ __device__ __forceinline__ void umma_f16(unsigned tmem_d, unsigned long long da,
 }
 __device__ __forceinline__ void umma_commit(unsigned bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, unsigned src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+
+// TMA-store epilogue: accumulator tile -> + bias, ReLU -> 32x32 blocks staged in shared memory (128-byte rows, 16-byte groups
+// XOR (row & 7): the SWIZZLE_128B layout, conflict-free for a warp writing one row per lane) -> cp.async.bulk.tensor stores.
+// Each epilogue warp owns its 32 rows and two 4 KB staging blocks at `slab` (1024-byte aligned; the CTA's pipeline stages,
+// idle once the accumulator is complete): no CTA-wide barrier.  Against one 16-byte STG per lane and row (32 rows x 16 bytes
+// per instruction, every 128-byte line touched by eight instructions) the stores leave as whole lines.  Rows >= M and columns
+// >= N are clipped by the tensor map.
+template <int BN>
+__device__ __forceinline__ void gemm_epilogue_tma(unsigned tmem_d, int q, int lane, int m0, int n0, int N, const float* __restrict__ bias,
+                                                  int relu, const CUtensorMap* tmD, unsigned slab)
+{
+    const unsigned my = slab + (unsigned)q * 8192u;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= N) break;
+        unsigned r[32];
+        const unsigned taddr = tmem_d + ((unsigned)(q * 32) << 16) + (unsigned)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const unsigned blk = my + (unsigned)((c0 >> 5) & 1) * 4096u;
+        if (c0 >= 64) {   // the block is being reused: the store issued two steps ago must have read it
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+        }
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(r[j]);
+            const int col = n0 + c0 + j;
+            if (bias != nullptr && col < N) x += __ldg(bias + col);
+            v[j] = relu ? fmaxf(x, 0.0f) : x;
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(blk + (unsigned)lane * 128u + (unsigned)((j4 ^ (lane & 7)) << 4)),
+                         "f"(v[4 * j4]), "f"(v[4 * j4 + 1]), "f"(v[4 * j4 + 2]), "f"(v[4 * j4 + 3]) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy (TMA) reads
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_2d(tmD, n0 + c0, m0 + q * 32, blk);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the reads
+    __syncwarp();
 }
 
 // accumulator tile (TMEM lanes q*32.., BN columns) -> + bias, ReLU -> global rows; called by the four epilogue warps

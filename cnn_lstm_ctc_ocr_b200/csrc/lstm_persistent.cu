@@ -24,6 +24,13 @@
 // frame's critical path is their issue rate, ~70 cycles each from one thread), half the h bytes through L2 -> TMA ->
 // shared memory, half the resident weight bytes.  Accumulation, cell state, gate arithmetic and the layer output stay
 // float32.  Shapes with H % 64 != 0, or ocr_debug_lstm_operands(0), take the TF32 instantiation.
+//
+// Measured dead end (round 2, kept out of the tree): replacing the counter barrier + TMA by a flagged-word exchange (8-byte words
+// {two binary16 values, frame tag} written with st.relaxed.gpu and polled with 16-byte ld.relaxed.gpu by the epilogue threads,
+// which then fill the swizzled operand tile themselves).  Same bits, and slower: a frame at B = 32 took 10900 cycles against
+// 7240 -- a round of polls is a ~1000-1500 cycle L2 round trip under load, the 2048 16-byte groups of the h block need two
+// batches per thread plus the wait for the slowest slice, and that is no shorter than release (1100) + counter poll (1900) +
+// TMA (1400).  (`volatile` accesses compile to system-scope LDG/STG.STRONG.SYS: 30700 cycles per frame.)
 #include <cuda_fp16.h>
 
 #include <type_traits>

@@ -62,3 +62,31 @@ def test_gemm_tf32_strided_operands_and_padding():
     ref = A.double() @ W.double().t()
     assert (D[:, :50].double() - ref).abs().max() < 0.1
     assert torch.isnan(D[:, 50:]).all()
+
+
+@pytest.mark.parametrize("M,N,K,relu,ldd", [(32000, 4096, 256, False, 4096), (1952, 96, 1024, True, 96), (777, 100, 64, True, 104), (130, 36, 40, False, 36),
+                                            (257, 52, 36, False, 64)])
+def test_gemm_tma_store_epilogue_equals_stg_epilogue(M, N, K, relu, ldd):
+    """The epilogue that stages 32x32 blocks in shared memory and stores them with cp.async.bulk.tensor writes the same bits as
+    the one-STG-per-lane-and-row epilogue, clips at M and N, and leaves the columns between N and the row pitch untouched."""
+    from cnn_lstm_ctc_ocr_b200 import _lib as L
+    lib = L.load()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(M + N + K)
+    A = torch.randn((M, K), device="cuda", generator=g)
+    W = torch.randn((N, K), device="cuda", generator=g) * 0.1
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = []
+    for on in (1, 0):
+        L.check(lib.ocr_debug_gemm_tma_store(on), "store path")
+        D = torch.full((M + 3, ldd), float("nan"), device="cuda")
+        L.check(lib.ocr_gemm_tf32(L.ptr(A), K, L.ptr(W), K, L.ptr(bias), L.ptr(D), ldd, M, N, K, int(relu), L.stream_handle()), "gemm")
+        torch.cuda.synchronize()
+        res.append(D)
+    L.check(lib.ocr_debug_gemm_tma_store(1), "store path")
+    assert torch.equal(res[0][:M, :N], res[1][:M, :N])
+    assert torch.isnan(res[0][M:]).all() and torch.isnan(res[0][:, N:]).all()
+    ref = torch.addmm(bias.double(), A.double(), W.double().t())
+    if relu:
+        ref = ref.clamp(min=0)
+    assert (res[0][:M, :N].double() - ref).abs().max() <= 5e-3 * max(1.0, ref.abs().max().item())
