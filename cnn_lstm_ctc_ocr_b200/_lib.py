@@ -41,6 +41,9 @@ SIGNATURES = {
     "ocr_conv3x3_same": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "ocr_maxpool": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "ocr_conv_set_path": (_i, [_i]),
+    "ocr_conv3x3_pool_fused": (_i, [_i, _i, _i, _i, _i, _i]),
+    "ocr_conv3x3_same_pool": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "ocr_debug_conv_tma_store": (_i, [_i]),
     "ocr_birnn_workspace_bytes": (_i, [_i, _i, _i, _i, _c.POINTER(_sz)]),
     "ocr_birnn_set_path": (_i, [_i]),
     "ocr_debug_lstm_timeline": (_i, [_vp]),

@@ -16,6 +16,15 @@
 //                       k order as conv_igemm.cu, so both kernels produce bit-identical sums) through a small ring
 //   warp 1 / one lane : tcgen05.mma.kind::tf32, accumulator in TMEM
 //   warps 2..5        : epilogue, TMEM lane m = ty*8 + tx -> out[b, y0+ty, x0+tx, :] (+ bias, ReLU)
+//
+// Round 2: the epilogue stages each warp's 4 x 8 pixels x 32 channels in shared memory (the halo tiles are idle by then) and
+// stores them with ONE cp.async.bulk.tensor (4-D map over the NHWC output, box {32 ch, 8 x, 4 y, 1}: clipping at the image
+// border comes with the map), and it can apply the max-pool that follows the layer (model.py:111-116, pool_layer) on the way:
+//   POOL 1 = window 2x2, stride (2,2) (pool2): a warp's 4 x 8 pixels hold eight whole windows (lanes l, l^1, l^8, l^9): two
+//            shuffles per value, the warp stores a 2 x 4 block of the pooled tensor;
+//   POOL 2 = window 2x2, stride (2,1) (pool4): horizontal stride 1 needs the right-hand neighbour, so the patches overlap by
+//            one column (x0 = 7 * tile): 7 pooled columns per patch, a 2 x 7 block per warp.
+// conv -> (folded batch-norm) -> ReLU -> pool then is one launch and the unpooled activation never reaches memory.
 #include "gemm_tf32.cuh"
 
 namespace ocr {
@@ -41,10 +50,15 @@ __device__ __forceinline__ unsigned long long umma_desc_view(unsigned smem_addr,
     return d;
 }
 
-template <int BN, int WSTAGES>
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3, unsigned src) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+template <int BN, int WSTAGES, int POOL>   // POOL: 0 = none, 1 = max 2x2 stride (2,2), 2 = max 2x2 stride (2,1) fused into the epilogue
 __global__ void __launch_bounds__(kHaloThreads)
-conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW, int B, int H, int W, int C,
-                    const float* __restrict__ bias, float* __restrict__ out, int Cout, int relu, int tiles_x, int tiles_y)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut,
+                    int B, int H, int W, int C, const float* __restrict__ bias, float* __restrict__ out, int Cout, int relu, int tiles_x,
+                    int tiles_y, int tma_store)
 {
     constexpr int kWB = BN * kGemmBK * 4;                       // one filter tile
     extern __shared__ unsigned char halo_smem_raw[];
@@ -62,7 +76,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
     const int tx_i = tile % tiles_x; tile /= tiles_x;
     const int ty_i = tile % tiles_y;
     const int b = tile / tiles_y;
-    const int x0 = tx_i * kHaloTX, y0 = ty_i * kHaloTY;
+    const int x0 = tx_i * (POOL == 2 ? kHaloTX - 1 : kHaloTX), y0 = ty_i * kHaloTY;   // POOL 2: patches overlap by one column
     const int n0 = blockIdx.y * BN;
     const int nk = 9 * cpt;
 
@@ -121,8 +135,17 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
         g_mbar_wait(bar_acc, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float* drow = out + (((size_t)b * H + y) * W + x) * Cout + n0;
+        // staging: two 4 KB blocks per warp in the (idle) halo tiles; rows of 128 bytes, 16-byte groups XOR (row & 7)
+        const unsigned my = s_halo + (unsigned)q * 8192u;
+        const int tyl = lane >> 3, tx = lane & 7;
+        // the staged row this lane writes (-1: none) and the block's origin in the output tensor
+        int srow, ox, oy;
+        if (POOL == 0) { srow = lane; ox = x0; oy = y0 + 4 * q; }
+        else if (POOL == 1) { srow = ((tyl | tx) & 1) ? -1 : (tyl >> 1) * 4 + (tx >> 1); ox = x0 >> 1; oy = (y0 + 4 * q) >> 1; }
+        else { srow = ((tyl & 1) || tx == 7) ? -1 : (tyl >> 1) * 7 + tx; ox = x0; oy = (y0 + 4 * q) >> 1; }
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
+            if ((POOL != 0 || tma_store) && n0 + c0 >= Cout) break;
             unsigned r[32];
             const unsigned taddr = tmem_d + ((unsigned)(q * 32) << 16) + (unsigned)c0;
             asm volatile(
@@ -135,19 +158,61 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_const
                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                 : "r"(taddr) : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (live) {
+            if (POOL == 0 && !tma_store) {
+                if (live) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    if (n0 + c0 + j < Cout) {            // Cout % 4 == 0
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
-                        float4 v = make_float4(__uint_as_float(r[j]) + bb.x, __uint_as_float(r[j + 1]) + bb.y,
-                                               __uint_as_float(r[j + 2]) + bb.z, __uint_as_float(r[j + 3]) + bb.w);
-                        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                        *reinterpret_cast<float4*>(drow + c0 + j) = v;
+                    for (int j = 0; j < 32; j += 4) {
+                        if (n0 + c0 + j < Cout) {            // Cout % 4 == 0
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
+                            float4 v = make_float4(__uint_as_float(r[j]) + bb.x, __uint_as_float(r[j + 1]) + bb.y,
+                                                   __uint_as_float(r[j + 2]) + bb.z, __uint_as_float(r[j + 3]) + bb.w);
+                            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                            *reinterpret_cast<float4*>(drow + c0 + j) = v;
+                        }
                     }
                 }
+                continue;
+            }
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float xv = __uint_as_float(r[j]);
+                if (n0 + c0 + j < Cout) xv += __ldg(bias + n0 + c0 + j);
+                v[j] = relu ? fmaxf(xv, 0.0f) : xv;
+            }
+            if (POOL == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = fmaxf(v[j], __shfl_xor_sync(kFullMask, v[j], 1));   // (x, x+1)
+                    v[j] = fmaxf(v[j], __shfl_xor_sync(kFullMask, v[j], 8));   // (y, y+1)
+                }
+            } else if (POOL == 2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = fmaxf(v[j], __shfl_down_sync(kFullMask, v[j], 1));  // (x, x+1); lanes with tx == 7 are not stored
+                    v[j] = fmaxf(v[j], __shfl_xor_sync(kFullMask, v[j], 8));   // (y, y+1)
+                }
+            }
+            const unsigned blk = my + (unsigned)((c0 >> 5) & 1) * 4096u;
+            if (c0 >= 64) {   // the block is being reused: the store issued two steps ago must have read it
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+            }
+            if (srow >= 0) {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(blk + (unsigned)srow * 128u + (unsigned)((j4 ^ (srow & 7)) << 4)),
+                                 "f"(v[4 * j4]), "f"(v[4 * j4 + 1]), "f"(v[4 * j4 + 2]), "f"(v[4 * j4 + 3]) : "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async-proxy (TMA) reads
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_4d(&tmOut, n0 + c0, ox, oy, b, blk);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the reads
+        __syncwarp();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -182,12 +247,43 @@ static int tma_map_nhwc_halo(CUtensorMap* tm, const float* base, int B, int H, i
     return OCR_OK;
 }
 
-template <int BN, int WSTAGES>
+// NHWC output [B, Ho, Wo, C] as a 4-D tensor {C, Wo, Ho, B}; box {32 channels, bx, by, 1}, 128-byte swizzle (TMA-store epilogue)
+static int tma_map_nhwc_out(CUtensorMap* tm, float* base, int B, int Ho, int Wo, int C, int bx, int by) {
+    EncodeTiledFn4 enc = nullptr;
+    {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            enc = reinterpret_cast<EncodeTiledFn4>(p);
+    }
+    if (enc == nullptr) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return OCR_ECUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)Wo * C * 4, (cuuint64_t)Ho * Wo * C * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)bx, (cuuint32_t)by, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (NHWC output) failed (%d) B=%d H=%d W=%d C=%d", (int)r, B, Ho, Wo, C); return OCR_ECUDA; }
+    return OCR_OK;
+}
+
+static int g_halo_tma_store = 1;   // TMA-store epilogue (0: one STG per lane and 16 bytes; pooling always stores through TMA)
+int conv_halo_set_tma_store(int on) {
+    g_halo_tma_store = on ? 1 : 0;
+    return OCR_OK;
+}
+
+template <int BN, int WSTAGES, int POOL>
 static int launch_halo(const float* in, int B, int H, int W, int C, const float* w, const float* bias, int Cout, int relu, float* out,
                        cudaStream_t st)
 {
-    CUtensorMap tmIn, tmW;
+    CUtensorMap tmIn, tmW, tmOut;
     int rc = tma_map_nhwc_halo(&tmIn, in, B, H, W, C);
+    if (rc != OCR_OK) return rc;
+    // output tensor: the layer's own, or the pooled one ('valid' pooling: floor)
+    const int Ho = POOL == 0 ? H : (H - 2) / 2 + 1, Wo = POOL == 0 ? W : (POOL == 1 ? (W - 2) / 2 + 1 : W - 1);
+    const int tma_store = (POOL != 0 || g_halo_tma_store) ? 1 : 0;
+    rc = tma_map_nhwc_out(&tmOut, out, B, Ho, Wo, Cout, POOL == 0 ? 8 : (POOL == 1 ? 4 : 7), POOL == 0 ? 4 : 2);
     if (rc != OCR_OK) return rc;
     rc = tma_map_2d(&tmW, w, Cout, 9 * C, 9 * C, BN);
     if (rc != OCR_OK) return rc;
@@ -197,12 +293,13 @@ static int launch_halo(const float* in, int B, int H, int W, int C, const float*
     int dev = 0;
     OCR_CHECK_CUDA(cudaGetDevice(&dev));
     if (configured != dev) {
-        OCR_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<BN, WSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        OCR_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<BN, WSTAGES, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
         configured = dev;
     }
-    const int tiles_x = (W + kHaloTX - 1) / kHaloTX, tiles_y = (H + kHaloTY - 1) / kHaloTY;
+    // POOL 2: a patch yields 7 pooled columns (the 8th output column is the right-hand neighbour of the 7th)
+    const int tiles_x = POOL == 2 ? (W - 1 + kHaloTX - 2) / (kHaloTX - 1) : (W + kHaloTX - 1) / kHaloTX, tiles_y = (H + kHaloTY - 1) / kHaloTY;
     dim3 grid((unsigned)((long long)tiles_x * tiles_y * B), (unsigned)((Cout + BN - 1) / BN));
-    conv3x3_halo_kernel<BN, WSTAGES><<<grid, kHaloThreads, smem, st>>>(tmIn, tmW, B, H, W, C, bias, out, Cout, relu, tiles_x, tiles_y);
+    conv3x3_halo_kernel<BN, WSTAGES, POOL><<<grid, kHaloThreads, smem, st>>>(tmIn, tmW, tmOut, B, H, W, C, bias, out, Cout, relu, tiles_x, tiles_y, tma_store);
     OCR_CHECK_LAUNCH();
     return OCR_OK;
 }
@@ -216,9 +313,13 @@ bool conv_halo_supported(int B, int H, int W, int C, int Cout) {
     return tiles < 0x7fffffffLL;
 }
 
-int conv_halo_run(const float* in, int B, int H, int W, int C, const float* w, const float* bias, int Cout, int relu, float* out, cudaStream_t st) {
-    if (Cout <= 32) return launch_halo<32, 4>(in, B, H, W, C, w, bias, Cout, relu, out, st);
-    return launch_halo<64, 4>(in, B, H, W, C, w, bias, Cout, relu, out, st);
+// pool: 0 = none, 1 = max-pool 2x2 stride (2,2), 2 = max-pool 2x2 stride (2,1) applied to the layer's output in the epilogue
+int conv_halo_run(const float* in, int B, int H, int W, int C, const float* w, const float* bias, int Cout, int relu, float* out, cudaStream_t st,
+                  int pool) {
+    if (pool == 1) return Cout <= 32 ? launch_halo<32, 4, 1>(in, B, H, W, C, w, bias, Cout, relu, out, st) : launch_halo<64, 4, 1>(in, B, H, W, C, w, bias, Cout, relu, out, st);
+    if (pool == 2) return Cout <= 32 ? launch_halo<32, 4, 2>(in, B, H, W, C, w, bias, Cout, relu, out, st) : launch_halo<64, 4, 2>(in, B, H, W, C, w, bias, Cout, relu, out, st);
+    if (Cout <= 32) return launch_halo<32, 4, 0>(in, B, H, W, C, w, bias, Cout, relu, out, st);
+    return launch_halo<64, 4, 0>(in, B, H, W, C, w, bias, Cout, relu, out, st);
 }
 
 }  // namespace ocr

@@ -38,10 +38,12 @@ struct ConvSmem {
     static constexpr int kTotal = kBars + (2 * STAGES + 1) * 8 + 16 + 1024;
 };
 
+static int g_conv_tma_store = 1;   // TMA-store epilogue (0: one STG per lane and row)
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kConvThreads)
-conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const float* __restrict__ in, int B, int H, int W, int C,
-                     const float* __restrict__ bias, float* __restrict__ out, int Cout, int relu)
+conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const float* __restrict__ in, int B, int H,
+                     int W, int C, const float* __restrict__ bias, float* __restrict__ out, int Cout, int relu, int tma_store)
 {
     using S = ConvSmem<BN, STAGES>;
     extern __shared__ unsigned char conv_smem_raw[];
@@ -103,7 +105,9 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const float* __res
         const int q = warp & 3;
         g_mbar_wait(bar_acc, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        gemm_epilogue<BN>(tmem_d, q, lane, m0, n0, M, Cout, bias, out, Cout, relu);
+        // NHWC output = a [pixels, Cout] matrix: the TMA-store epilogue of the GEMM (blocks staged in the idle pipeline stages)
+        if (tma_store) gemm_epilogue_tma<BN>(tmem_d, q, lane, m0, n0, Cout, bias, relu, &tmOut, s_base);
+        else gemm_epilogue<BN>(tmem_d, q, lane, m0, n0, M, Cout, bias, out, Cout, relu);
     } else {
         // patch gatherers: thread pr owns tile row pr = output pixel m0 + pr
         const int pr = threadIdx.x - 192;
@@ -166,9 +170,14 @@ static int launch_conv(const float* in, int B, int H, int W, int C, const float*
                        cudaStream_t st)
 {
     using S = ConvSmem<BN, STAGES>;
-    CUtensorMap tmW;
+    CUtensorMap tmW, tmOut;
     int rc = tma_map_2d(&tmW, w, Cout, 9 * C, 9 * C, BN);
     if (rc != OCR_OK) return rc;
+    const int tma_store = (g_conv_tma_store && (Cout % 4) == 0) ? 1 : 0;
+    if (tma_store) {
+        rc = tma_map_out(&tmOut, out, (long long)B * H * W, Cout, Cout);
+        if (rc != OCR_OK) return rc;
+    }
     static int configured = -1;
     int dev = 0;
     OCR_CHECK_CUDA(cudaGetDevice(&dev));
@@ -178,14 +187,16 @@ static int launch_conv(const float* in, int B, int H, int W, int C, const float*
     }
     const long long M = (long long)B * H * W;
     dim3 grid((unsigned)((M + kGemmBM - 1) / kGemmBM), (unsigned)((Cout + BN - 1) / BN));
-    conv3x3_igemm_kernel<BN, STAGES><<<grid, kConvThreads, S::kTotal, st>>>(tmW, in, B, H, W, C, bias, out, Cout, relu);
+    conv3x3_igemm_kernel<BN, STAGES><<<grid, kConvThreads, S::kTotal, st>>>(tmW, tmOut, in, B, H, W, C, bias, out, Cout, relu, tma_store);
     OCR_CHECK_LAUNCH();
     return OCR_OK;
 }
 
 namespace ocr {   // conv_halo.cu
 bool conv_halo_supported(int B, int H, int W, int C, int Cout);
-int conv_halo_run(const float* in, int B, int H, int W, int C, const float* w, const float* bias, int Cout, int relu, float* out, cudaStream_t st);
+int conv_halo_run(const float* in, int B, int H, int W, int C, const float* w, const float* bias, int Cout, int relu, float* out, cudaStream_t st,
+                  int pool = 0);
+int conv_halo_set_tma_store(int on);
 }
 // 0 = automatic (halo-tile kernel for the wide shallow layers, gather kernel otherwise), 1 = gather kernel only, 2 = halo kernel only
 static int g_conv_path = 0;
@@ -204,7 +215,7 @@ extern "C" int ocr_conv3x3_same(const float* in, int B, int H, int W, int C, con
     OCR_CHECK_ARG(((uintptr_t)in % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)out % 16) == 0, "ocr_conv3x3_same: pointers must be 16-byte aligned");
     OCR_CHECK_ARG((long long)B * H * W < 0x7fffffffLL, "ocr_conv3x3_same: too many output pixels");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (g_conv_path != 1 && conv_halo_supported(B, H, W, C, Cout)) return conv_halo_run(in, B, H, W, C, w, bias, Cout, relu, out, st);
+    if (g_conv_path != 1 && conv_halo_supported(B, H, W, C, Cout)) return conv_halo_run(in, B, H, W, C, w, bias, Cout, relu, out, st, 0);
     OCR_CHECK_ARG(g_conv_path != 2, "ocr_conv3x3_same: the halo-tile kernel does not take this shape (B=%d H=%d W=%d C=%d Cout=%d)", B, H, W, C, Cout);
     const long long mt = ((long long)B * H * W + kGemmBM - 1) / kGemmBM;
     // The main loop is bound by the bytes an SM pulls in per k-step (patch tile 16 KB + filter tile BN * 128 B at ~35 B/clk),
@@ -226,6 +237,31 @@ extern "C" int ocr_conv3x3_same(const float* in, int B, int H, int W, int C, con
         case 128: return launch_conv<128, 3>(in, B, H, W, C, w, bias, Cout, relu, out, st);
         default: return launch_conv<256, 4>(in, B, H, W, C, w, bias, Cout, relu, out, st);
     }
+}
+
+// conv3x3 'same' + bias + ReLU followed by the layer's max-pool (window 2x2, stride (2, stride_w) with stride_w 2 or 1, 'valid':
+// pool2 / pool4 of model.py:111-116) as ONE launch when the halo-tile kernel takes the shape (ocr_conv3x3_pool_fused tells);
+// out: [B, (H-2)/2+1, stride_w == 2 ? (W-2)/2+1 : W-1, Cout].
+extern "C" int ocr_conv3x3_pool_fused(int B, int H, int W, int C, int Cout, int stride_w)
+{
+    return (g_conv_path != 1 && (stride_w == 1 || stride_w == 2) && H >= 2 && W >= 2 && conv_halo_supported(B, H, W, C, Cout)) ? 1 : 0;
+}
+extern "C" int ocr_conv3x3_same_pool(const float* in, int B, int H, int W, int C, const float* w, const float* bias, int Cout, int relu,
+                                     int stride_w, float* out, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(B >= 0 && H >= 2 && W >= 2 && C >= 32 && (C % 32) == 0 && Cout >= 1 && (stride_w == 1 || stride_w == 2),
+                  "ocr_conv3x3_same_pool: bad shape B=%d H=%d W=%d C=%d Cout=%d stride_w=%d", B, H, W, C, Cout, stride_w);
+    if (B == 0) return OCR_OK;
+    OCR_CHECK_ARG(in && w && bias && out, "ocr_conv3x3_same_pool: NULL argument");
+    OCR_CHECK_ARG(((uintptr_t)in % 16) == 0 && ((uintptr_t)w % 16) == 0 && ((uintptr_t)out % 16) == 0, "ocr_conv3x3_same_pool: pointers must be 16-byte aligned");
+    OCR_CHECK_ARG(ocr_conv3x3_pool_fused(B, H, W, C, Cout, stride_w), "ocr_conv3x3_same_pool: the halo-tile kernel does not take this shape (B=%d H=%d W=%d C=%d Cout=%d); run ocr_conv3x3_same + ocr_maxpool", B, H, W, C, Cout);
+    return conv_halo_run(in, B, H, W, C, w, bias, Cout, relu, out, static_cast<cudaStream_t>(stream), stride_w == 2 ? 1 : 2);
+}
+// Tuning aid: TMA-store epilogues of the convolution kernels on (1, default) / off (0); same bits either way.
+extern "C" int ocr_debug_conv_tma_store(int on)
+{
+    g_conv_tma_store = on ? 1 : 0;
+    return conv_halo_set_tma_store(on);
 }
 
 extern "C" int ocr_maxpool(const float* in, int B, int H, int W, int C, int pool_h, int pool_w, int stride_h, int stride_w, float* out,

@@ -172,9 +172,11 @@ class _Pending:
 class Model:
     """Weights of the recognizer + the reference's graph-building functions as methods."""
 
-    def __init__(self, params, cell_type="lstm", rnn_sizes=(512, 512), device="cuda", conv_path="igemm"):
+    def __init__(self, params, cell_type="lstm", rnn_sizes=(512, 512), device="cuda", conv_path="igemm", fuse_pool=True):
         # conv_path: "igemm" = implicit GEMM (patches gathered inside the kernel); "im2col" = explicit patch matrix + GEMM
+        # fuse_pool: pool2 / pool4 applied in the epilogue of conv2 / conv4 (ocr_conv3x3_same_pool); False = separate ocr_maxpool launches
         self.conv_path = conv_path
+        self.fuse_pool = fuse_pool
         if cell_type not in ("lstm", "gru"):
             raise ValueError("cell_type must be 'lstm' (model_bu.py) or 'gru' (model.py)")
         self.cell_type = cell_type
@@ -261,8 +263,11 @@ class Model:
         a = torch.empty((B, H - 2, W - 2, w1.shape[-1]), dtype=torch.float32, device=dev)
         _lib.check(lib.ocr_conv1_3x3_valid(_lib.ptr(x), int(is_u8), B, H, W, _lib.ptr(w1), _lib.ptr(b1), w1.shape[-1], _lib.ptr(a), sh),
                    "ocr_conv1_3x3_valid")
+        names = [lp[3] for lp in LAYER_PARAMS]
+        pooled_already = False      # the previous layer's launch applied this layer's pool in its epilogue
         for (filters, k, padding, name, bn) in LAYER_PARAMS[1:]:
-            ph, pw, s_h, s_w = _POOL_BEFORE[name]
+            ph, pw, s_h, s_w = (1, 1, 1, 1) if pooled_already else _POOL_BEFORE[name]
+            pooled_already = False
             Bn, Hn, Wn, Cn = a.shape
             Hp, Wp = (Hn - ph) // s_h + 1, (Wn - pw) // s_w + 1
             if Hp < 1 or Wp < 1:
@@ -273,9 +278,20 @@ class Model:
                     pooled = torch.empty((Bn, Hp, Wp, Cn), dtype=torch.float32, device=dev)
                     _lib.check(lib.ocr_maxpool(_lib.ptr(a), Bn, Hn, Wn, Cn, ph, pw, s_h, s_w, _lib.ptr(pooled), sh), "ocr_maxpool")
                     a = pooled
-                out = torch.empty((Bn, Hp, Wp, filters), dtype=torch.float32, device=dev)
-                _lib.check(lib.ocr_conv3x3_same(_lib.ptr(a), Bn, Hp, Wp, Cn, _lib.ptr(wk), _lib.ptr(bk), filters, 1, _lib.ptr(out), sh),
-                           "ocr_conv3x3_same")
+                # conv -> (folded batch-norm) -> ReLU -> the pool in front of the next layer as ONE launch where the halo-tile
+                # kernel takes the shape (conv2 + pool2, conv4 + pool4): model.py:105-116
+                nxt = names.index(name) + 1
+                npool = _POOL_BEFORE[names[nxt]] if nxt < len(names) else (1, 1, 1, 1)
+                if self.fuse_pool and npool[:3] == (2, 2, 2) and Hp >= 2 and Wp >= 2 and lib.ocr_conv3x3_pool_fused(Bn, Hp, Wp, Cn, filters, npool[3]):
+                    Ho, Wo = (Hp - 2) // 2 + 1, (Wp - 2) // npool[3] + 1
+                    out = torch.empty((Bn, Ho, Wo, filters), dtype=torch.float32, device=dev)
+                    _lib.check(lib.ocr_conv3x3_same_pool(_lib.ptr(a), Bn, Hp, Wp, Cn, _lib.ptr(wk), _lib.ptr(bk), filters, 1, npool[3],
+                                                         _lib.ptr(out), sh), "ocr_conv3x3_same_pool")
+                    pooled_already = True
+                else:
+                    out = torch.empty((Bn, Hp, Wp, filters), dtype=torch.float32, device=dev)
+                    _lib.check(lib.ocr_conv3x3_same(_lib.ptr(a), Bn, Hp, Wp, Cn, _lib.ptr(wk), _lib.ptr(bk), filters, 1, _lib.ptr(out), sh),
+                               "ocr_conv3x3_same")
                 a = out
             else:
                 patches = torch.empty((Bn * Hp * Wp, 9 * Cn), dtype=torch.float32, device=dev)

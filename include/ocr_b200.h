@@ -177,6 +177,17 @@ int ocr_conv3x3_same(const float* in, int B, int H, int W, int C, const float* w
                      float* out, ocr_stream_t stream);
 int ocr_maxpool(const float* in, int B, int H, int W, int C, int pool_h, int pool_w, int stride_h, int stride_w, float* out,
                 ocr_stream_t stream);
+/* ocr_conv3x3_same_pool: ocr_conv3x3_same followed by the max-pool that follows the layer in convnet_layers (window 2x2,
+ * stride (2, stride_w), stride_w = 2: pool2, stride_w = 1: pool4 / pool6; 'valid'; model.py:105-116) as ONE launch: the pool
+ * is taken in the epilogue of the halo-tile kernel and the unpooled activation never reaches memory.
+ * out [B, (H-2)/2+1, stride_w == 2 ? (W-2)/2+1 : W-1, Cout].  Only shapes the halo-tile kernel takes (C = 32 / 64, H >= 12,
+ * W >= 8): ocr_conv3x3_pool_fused returns 1 for them, otherwise run ocr_conv3x3_same + ocr_maxpool. */
+int ocr_conv3x3_pool_fused(int B, int H, int W, int C, int Cout, int stride_w);
+int ocr_conv3x3_same_pool(const float* in, int B, int H, int W, int C, const float* w, const float* bias, int Cout, int relu,
+                          int stride_w, float* out, ocr_stream_t stream);
+/* Tuning aid: TMA-store epilogues of the convolution kernels (32-pixel x 32-channel blocks staged in shared memory, one
+ * cp.async.bulk.tensor per block) on (1, default) / off (0); same bits either way. */
+int ocr_debug_conv_tma_store(int on);
 /* Kernel-path override of ocr_conv3x3_same for tests: 0 = automatic (the wide shallow layers, C = 32 / 64 and H >= 12, run a
  * kernel that TMA-loads the input halo of a 16x8 pixel patch once and feeds all nine taps from it as shifted views; other
  * shapes gather each tap's patch rows with cp.async), 1 = gather kernel only, 2 = halo kernel only.  Same sums, bit for bit. */

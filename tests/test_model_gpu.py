@@ -202,3 +202,58 @@ def test_conv_halo_kernel_equals_gather_kernel(B, H, W, C, Co, relu):
         ref = np.maximum(ref, 0)
     assert np.abs(outs[1] - ref).max() <= 3e-3 * np.abs(ref).max()
     assert (outs[0] == outs[1]).all()
+
+
+@pytest.mark.parametrize("B,H,W,C,Co,relu,stride_w", [(2, 30, 37, 32, 32, 1, 2), (2, 30, 254, 32, 32, 1, 2), (3, 15, 21, 64, 64, 1, 1), (2, 15, 126, 64, 64, 1, 1),
+                                                       (1, 12, 8, 64, 32, 0, 2), (2, 13, 15, 32, 64, 0, 1), (1, 30, 1022, 32, 32, 1, 2)])
+def test_conv_with_fused_pool_equals_conv_then_pool(B, H, W, C, Co, relu, stride_w):
+    """ocr_conv3x3_same_pool (the pool taken in the halo-tile kernel's epilogue; pool2 = stride (2,2), pool4 = stride (2,1)) writes
+    the bits of ocr_conv3x3_same followed by ocr_maxpool, touches nothing outside the pooled tensor, and the TMA-store and STG
+    epilogues of both convolution kernels write the same bits."""
+    from cnn_lstm_ctc_ocr_b200 import _lib as L
+    lib, sh = L.load(), L.stream_handle()
+    rng = np.random.default_rng(B * 1000 + W + stride_w)
+    dx = torch.tensor(rng.standard_normal((B, H, W, C)).astype(np.float32), device="cuda:0")
+    dw = torch.tensor(np.ascontiguousarray((rng.standard_normal((3, 3, C, Co)) * 0.1).astype(np.float32).reshape(9 * C, Co).T), device="cuda:0")
+    dbias = torch.tensor(rng.standard_normal(Co).astype(np.float32), device="cuda:0")
+    assert lib.ocr_conv3x3_pool_fused(B, H, W, C, Co, stride_w) == 1
+    plain = {}
+    for path in (1, 2):                      # gather kernel, halo-tile kernel
+        for store in (1, 0):                 # TMA-store epilogue, STG epilogue
+            L.check(lib.ocr_conv_set_path(path), "path")
+            L.check(lib.ocr_debug_conv_tma_store(store), "store")
+            out = torch.full((B, H, W, Co), float("nan"), device="cuda:0")
+            L.check(lib.ocr_conv3x3_same(L.ptr(dx), B, H, W, C, L.ptr(dw), L.ptr(dbias), Co, relu, L.ptr(out), sh), "conv")
+            plain[(path, store)] = out
+    L.check(lib.ocr_conv_set_path(0), "path")
+    L.check(lib.ocr_debug_conv_tma_store(1), "store")
+    ref = plain[(1, 0)]
+    assert torch.isfinite(ref).all()
+    for k, v in plain.items():
+        assert torch.equal(v, ref), k
+    Hp, Wp = (H - 2) // 2 + 1, (W - 2) // stride_w + 1
+    want = torch.empty((B, Hp, Wp, Co), device="cuda:0")
+    L.check(lib.ocr_maxpool(L.ptr(ref), B, H, W, Co, 2, 2, 2, stride_w, L.ptr(want), sh), "pool")
+    buf = torch.full((B * Hp * Wp * Co + 64,), float("nan"), device="cuda:0")
+    got = buf[:B * Hp * Wp * Co].view(B, Hp, Wp, Co)
+    L.check(lib.ocr_conv3x3_same_pool(L.ptr(dx), B, H, W, C, L.ptr(dw), L.ptr(dbias), Co, relu, stride_w, L.ptr(got), sh), "conv+pool")
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    assert torch.isnan(buf[B * Hp * Wp * Co:]).all()
+
+
+@pytest.mark.parametrize("cell,sizes", [("lstm", (512, 512)), ("gru", (512, 256))])
+def test_fused_pool_graph_equals_unfused_graph(cell, sizes):
+    """Model(fuse_pool=True) (conv2 + pool2 and conv4 + pool4 as one launch each) == Model(fuse_pool=False), bit for bit."""
+    from cnn_lstm_ctc_ocr_b200 import model, _lib
+    params = model.init_params(0, cell, sizes)
+    img, widths = _inputs(5, 150, 9)
+    widths[1], widths[3] = 97, 64
+    res = []
+    for fuse in (True, False):
+        m = model.Model(params, cell_type=cell, rnn_sizes=sizes, fuse_pool=fuse)
+        n0 = _lib.launch_count()
+        f, sl = m.convnet_layers(torch.tensor(img, device="cuda:0"), torch.tensor(widths))
+        res.append((f.clone(), _lib.launch_count() - n0))
+    assert torch.equal(res[0][0], res[1][0])
+    assert res[0][1] == res[1][1] - 2        # two launches fewer
