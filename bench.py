@@ -361,6 +361,7 @@ def run_ours(args, cfg):
         if not args.skip_extra:
             blocks["beam_search"] = beam_block(dev, rank, world, windows, with_cpu=False)
             blocks["sweep"] = sweep_block(dev, rank, world, windows)
+            blocks["sweep_b128"] = sweep_block(dev, rank, world, windows, bucket_size=128)
         sampler.stop()
         if rank == 0:
             _emit(json.dumps({"blocks_only": True, "n_gpus": world, "blocks": {k: _short(v) for k, v in blocks.items()}}))
@@ -388,6 +389,8 @@ def run_ours(args, cfg):
     if not args.skip_extra:
         blocks["beam_search"] = beam_block(dev, rank, world, windows, with_cpu=(rank == 0 and world == 1))
         blocks["sweep"] = sweep_block(dev, rank, world, windows)
+        # "batch per bucket 32 (and a tuned size)": the recurrence costs a frame the same at 32 and at 128 rows
+        blocks["sweep_b128"] = sweep_block(dev, rank, world, windows, bucket_size=128)
     sampler.stop()
     if rank == 0:
         cfg2 = blocks.get("ctc_cfg2")

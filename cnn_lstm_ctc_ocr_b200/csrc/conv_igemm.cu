@@ -39,6 +39,7 @@ struct ConvSmem {
 };
 
 static int g_conv_tma_store = 1;   // TMA-store epilogue (0: one STG per lane and row)
+static int g_conv_deep = 1;        // deep gather ring for one-wave grids (ocr_debug_conv_tma_store(2) switches it off for measurements)
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kConvThreads)
@@ -109,25 +110,35 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_const
         if (tma_store) gemm_epilogue_tma<BN>(tmem_d, q, lane, m0, n0, Cout, bias, relu, &tmOut, s_base);
         else gemm_epilogue<BN>(tmem_d, q, lane, m0, n0, M, Cout, bias, out, Cout, relu);
     } else {
-        // patch gatherers: thread pr owns tile row pr = output pixel m0 + pr
-        const int pr = threadIdx.x - 192;
-        const int m = m0 + pr;
-        const bool valid = m < M;
-        int x = 0, y = 0, b = 0;
-        if (valid) { x = m % W; const int t = m / W; y = t % H; b = t / H; }
-        const unsigned row_off = (unsigned)(pr >> 3) * 1024u + (unsigned)(pr & 7) * 128u;
-        const unsigned sw = (unsigned)(pr & 7);
+        // patch gatherers.  Eight consecutive lanes fetch the eight 16-byte groups of ONE pixel's 128-byte channel chunk, so a
+        // warp instruction reads four whole lines (round 2; with one pixel per lane each instruction touched 32 lines for 16
+        // bytes apiece and every 32-byte sector crossed L2 -> SM twice: the k-step was bound by that traffic, 32 KB of patch
+        // sectors + the filter tile at ~35 B/clk).  Thread g owns group g % 8 of the tile rows g / 8 + 16 i, i = 0..7.
+        const int g = threadIdx.x - 192;
+        const unsigned grp = (unsigned)(g & 7);
+        const int r0 = g >> 3;
+        int px[8], py[8], pb[8];      // pixel of row r0 + 16 i (pb < 0: past M)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = m0 + r0 + 16 * i;
+            px[i] = 0; py[i] = 0; pb[i] = -1;
+            if (m < M) { px[i] = m % W; const int t = m / W; py[i] = t % H; pb[i] = t / H; }
+        }
+        // row r of the tile: 8-row atoms of 1024 bytes, 128 bytes per row, 16-byte groups XOR (r & 7); (r0 + 16 i) & 7 == r0 & 7
+        const unsigned row_off0 = (unsigned)(r0 >> 3) * 1024u + (unsigned)(r0 & 7) * 128u + ((grp ^ (unsigned)(r0 & 7)) << 4);
         for (int k = 0; k < nk; ++k) {
             const int s = k % STAGES;
             if (k >= STAGES) g_mbar_wait(bar_empty + s * 8, ((k / STAGES) - 1) & 1);
             const int tap = k / cpt, c0 = (k - tap * cpt) * kGemmBK;
-            const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-            const bool inb = valid && yy >= 0 && yy < H && xx >= 0 && xx < W;
-            const float* src = inb ? in + (((size_t)b * H + yy) * W + xx) * C + c0 : in;
-            const unsigned nbytes = inb ? 16u : 0u;   // 0 source bytes = zero fill (padding ring, rows past M)
-            const unsigned dst = s_base + s * S::kStage + row_off;
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            const unsigned dst = s_base + s * S::kStage + row_off0;
 #pragma unroll
-            for (unsigned j = 0; j < 8; ++j) cp_async16_zfill(dst + ((j ^ sw) << 4), src + j * 4, nbytes);
+            for (int i = 0; i < 8; ++i) {
+                const int yy = py[i] + dy, xx = px[i] + dx;
+                const bool inb = pb[i] >= 0 && yy >= 0 && yy < H && xx >= 0 && xx < W;
+                const float* src = inb ? in + (((size_t)pb[i] * H + yy) * W + xx) * C + c0 + grp * 4 : in;
+                cp_async16_zfill(dst + (unsigned)i * 2048u, src, inb ? 16u : 0u);   // 0 source bytes = zero fill (padding ring, rows past M)
+            }
             cp_async_arrive_noinc(bar_full + s * 8);
         }
     }
@@ -229,6 +240,18 @@ extern "C" int ocr_conv3x3_same(const float* in, int B, int H, int W, int C, con
         const long long cost = ((tiles + 147) / 148) * (128 + cand);
         if (best < 0 || cost < best) { best = cost; bn = cand; }
     }
+    // A grid that puts at most one CTA on an SM (the deep layers at serving batch sizes: conv5..conv8 at B = 32 are 92..109 CTAs
+    // of 18..72 k-steps) has nothing to overlap a tile with but its own pipeline: a deep ring keeps the gathers of six k-steps
+    // in flight instead of three (each is an L2 round trip).
+    const long long ctas = mt * ((Cout + bn - 1) / bn);
+    if (ctas <= 148 && g_conv_deep) {
+        switch (bn) {
+            case 32: return launch_conv<32, 8>(in, B, H, W, C, w, bias, Cout, relu, out, st);
+            case 64: return launch_conv<64, 8>(in, B, H, W, C, w, bias, Cout, relu, out, st);
+            case 128: return launch_conv<128, 6>(in, B, H, W, C, w, bias, Cout, relu, out, st);
+            default: return launch_conv<256, 4>(in, B, H, W, C, w, bias, Cout, relu, out, st);
+        }
+    }
     switch (bn) {
         // few stages per CTA, several CTAs per SM (3, 3, 2, 1): a tile is short (9..72 k-steps), so the prologue /
         // epilogue of one CTA hides behind the main loop of its neighbours
@@ -260,8 +283,9 @@ extern "C" int ocr_conv3x3_same_pool(const float* in, int B, int H, int W, int C
 // Tuning aid: TMA-store epilogues of the convolution kernels on (1, default) / off (0); same bits either way.
 extern "C" int ocr_debug_conv_tma_store(int on)
 {
-    g_conv_tma_store = on ? 1 : 0;
-    return conv_halo_set_tma_store(on);
+    g_conv_tma_store = (on & 1) ? 1 : 0;
+    g_conv_deep = (on & 2) ? 0 : 1;        // bit 1: shallow gather ring everywhere (tuning)
+    return conv_halo_set_tma_store(on & 1);
 }
 
 extern "C" int ocr_maxpool(const float* in, int B, int H, int W, int C, int pool_h, int pool_w, int stride_h, int stride_w, float* out,
