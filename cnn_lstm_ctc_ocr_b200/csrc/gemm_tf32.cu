@@ -27,6 +27,7 @@ struct GemmSplit {
     int a_shift[9], a_row[9], b_row[9];
     int a_box_bytes;   // bytes one A box delivers (boxes shorter than 128 rows when M < 128: no over-fetch of foreign rows)
     int tma_store;     // 1: TMA-store epilogue through tmD
+    int tp, ntaps;     // tp > 1: a tile stacks the a_box_rows-row slices of tp consecutive views (of ntaps in all) in its 128 rows
     long long split_stride, batch_stride;
 };
 
@@ -63,7 +64,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int nk_all = (K + kGemmBK - 1) / kGemmBK;
     const int k_begin = sp.ksteps_per_split > 0 ? blockIdx.z * sp.ksteps_per_split : 0;
     const int nk = sp.ksteps_per_split > 0 ? min(sp.ksteps_per_split, nk_all - k_begin) : nk_all;
-    const int a_shift = sp.a_shift[batch], a_row = sp.a_row[batch], b_row = sp.b_row[batch];
+    // Stacked views (weight gradients of the shallow layers, C_in <= 64): the A tile's 128 rows are tp slices of a_box_rows rows,
+    // one per tap view, each its own TMA box; ONE MMA then contracts tp taps against the same d-output tile (a tile per tap
+    // left 3/4 of the MMA rows and of the B-operand traffic unused: conv2's filter gradient ran 1184 us).
+    const int tp = sp.tp;
+    const int v0 = batch * tp;                                            // first view of this tile
+    const int nview = tp > 1 ? min(tp, sp.ntaps - v0) : 1;
+    const int b_row = sp.b_row[v0];
     D += (size_t)batch * sp.batch_stride + (size_t)blockIdx.z * sp.split_stride;
 
     if (threadIdx.x == 0) {
@@ -89,8 +96,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int k = 0; k < nk; ++k) {
                 const int s = k % STAGES;
                 if (k >= STAGES) g_mbar_wait(bar_empty + s * 8, ((k / STAGES) - 1) & 1);
-                g_mbar_expect_tx(bar_full + s * 8, (unsigned)(sp.a_box_bytes + S::kB));
-                tma_load_2d(s_base + s * S::kStage, &tmA, (k_begin + k) * kGemmBK + a_shift, m0 + a_row, bar_full + s * 8);
+                g_mbar_expect_tx(bar_full + s * 8, (unsigned)(nview * sp.a_box_bytes + S::kB));
+                for (int i = 0; i < nview; ++i)
+                    tma_load_2d(s_base + s * S::kStage + i * sp.a_box_bytes, &tmA, (k_begin + k) * kGemmBK + sp.a_shift[v0 + i], m0 + sp.a_row[v0 + i],
+                                bar_full + s * 8);
                 tma_load_2d(s_base + s * S::kStage + S::kA, &tmB, (k_begin + k) * kGemmBK, n0 + b_row, bar_full + s * 8);
             }
         }
@@ -118,7 +127,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // (the pipeline stages are idle by now: every TMA load has been consumed and every MMA has retired)
         if (sp.tma_store) gemm_epilogue_tma<BN>(tmem_d, q, lane, m0, n0, N, bias, relu, &tmD, s_base);
-        else gemm_epilogue<BN>(tmem_d, q, lane, m0, n0, M, N, bias, D, ldd, relu);
+        else gemm_epilogue<BN>(tmem_d, q, lane, m0, n0, tp > 1 ? nview * (sp.a_box_bytes >> 7) : M, N, bias, D, ldd, relu);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -252,6 +261,8 @@ static int launch_planned(const GemmPlan& p, cudaStream_t st)
     sp.a_box_bytes = p.a_box_rows * kGemmBK * 4;
     sp.batch_stride = p.batch_stride;
     sp.tma_store = (p.tma_store && g_gemm_tma_store && p.nbatch == 1 && p.splits == 1) ? 1 : 0;
+    sp.tp = p.tp;
+    sp.ntaps = p.ntaps;
     if (p.pdl) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid;
@@ -353,23 +364,31 @@ int gemm_run(const GemmPlan& p, cudaStream_t st)
 // D[b][i] = sum_z partials[b][z][i] in a fixed order (deterministic split-K)
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partials, int splits, int M, int N, int ldd, long long batch_stride, int nbatch,
-                     float* __restrict__ D)
+                     float* __restrict__ D, long long in_batch_stride, long long in_split_stride)
 {
     const long long per = (long long)M * N, total = per * nbatch;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int b = (int)(idx / per);
         const long long i = idx - (long long)b * per;
-        const float* src = partials + (size_t)b * splits * per + i;
+        const float* src = partials + (size_t)b * in_batch_stride + i;
         float acc = 0.0f;
-        for (int z = 0; z < splits; ++z) acc += src[(size_t)z * per];
+        for (int z = 0; z < splits; ++z) acc += src[(size_t)z * in_split_stride];
         D[(size_t)b * batch_stride + (size_t)(i / N) * ldd + (i % N)] = acc;
     }
 }
 
+static int g_wgrad_stack = 1;   // stack the tap views of shallow layers in one tile (0: one tile per tap, the round-1 form)
+// taps per tile: views of at most 64 rows (a multiple of 8) are stacked in the 128 rows of an A tile
+static int wgrad_tp(int M, int nbatch) {
+    if (!g_wgrad_stack || nbatch < 2 || M > 64 || (M % 8) != 0) return 1;
+    return kGemmBM / M;
+}
 static int wgrad_splits(int M, int N, long long R, int nbatch, int* ksteps_per_split) {
     const long long nk = (R + kGemmBK - 1) / kGemmBK;
     const int bn = N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
-    const long long tiles = (long long)((M + kGemmBM - 1) / kGemmBM) * ((N + bn - 1) / bn) * nbatch;
+    const int tp = wgrad_tp(M, nbatch);
+    const long long tiles = tp > 1 ? (long long)((nbatch + tp - 1) / tp) * ((N + bn - 1) / bn)
+                                   : (long long)((M + kGemmBM - 1) / kGemmBM) * ((N + bn - 1) / bn) * nbatch;
     long long want = 148 / tiles;                               // one full wave of CTAs (one CTA per SM): no ragged last wave
     if (want > nk / 8) want = nk / 8;                           // at least 8 k-steps per split
     if (want < 1) want = 1;
@@ -401,7 +420,18 @@ int gemm_wgrad(const float* A, long long lda, const float* W, long long ldw, flo
     p.D = partials; p.ldd = N;
     p.split_stride = (long long)M * N;
     p.batch_stride = (long long)p.splits * M * N;
+    long long in_batch_stride = p.batch_stride, in_split_stride = p.split_stride;
     p.a_box_rows = M >= kGemmBM ? kGemmBM : (M + 7) / 8 * 8;   // rows past M belong to other views: do not fetch them
+    const int tp = wgrad_tp(M, nbatch);
+    if (tp > 1) {
+        // tile = tp stacked views; partials laid out [split][view][M][N] so that a tile's rows are contiguous
+        p.tp = tp; p.ntaps = nbatch;
+        p.nbatch = (nbatch + tp - 1) / tp;
+        p.batch_stride = (long long)tp * M * N;
+        p.split_stride = (long long)nbatch * M * N;
+        in_batch_stride = (long long)M * N;
+        in_split_stride = p.split_stride;
+    }
     int rc = tma_map_2d(&p.tmA, A, a_rows, R, lda, p.a_box_rows);
     if (rc != OCR_OK) return rc;
     rc = tma_map_2d(&p.tmB, W, N, R, ldw, p.bn);
@@ -411,15 +441,19 @@ int gemm_wgrad(const float* A, long long lda, const float* W, long long ldw, flo
     if (rc != OCR_OK) return rc;
     const long long total = (long long)M * N * nbatch;
     long long g = (total + 255) / 256;
-    splitk_reduce_kernel<<<(int)(g > 148 * 8 ? 148 * 8 : g), 256, 0, st>>>(partials, p.splits, M, N, ldd, batch_stride, nbatch, D);
+    splitk_reduce_kernel<<<(int)(g > 148 * 8 ? 148 * 8 : g), 256, 0, st>>>(partials, p.splits, M, N, ldd, batch_stride, nbatch, D, in_batch_stride, in_split_stride);
     OCR_CHECK_LAUNCH();
     return OCR_OK;
 }
 
 }  // namespace ocr
 
-// Tuning aid: TMA-store epilogue of ocr_gemm_tf32 on (1, default) / off (0); same bits either way.
-extern "C" int ocr_debug_gemm_tma_store(int on) { return gemm_set_tma_store(on); }
+// Tuning aid: bit 0 = TMA-store epilogue of ocr_gemm_tf32 (default on), bit 1 = one tile per tap view in ocr_gemm_tf32_wgrad
+// (default off: the views of layers with at most 64 input channels are stacked in one tile).
+extern "C" int ocr_debug_gemm_tma_store(int on) {
+    g_wgrad_stack = (on & 2) ? 0 : 1;
+    return gemm_set_tma_store(on & 1);
+}
 
 extern "C" int ocr_gemm_tf32(const float* A, int lda, const float* W, int ldw, const float* bias, float* D, int ldd, int M, int N,
                              int K, int relu, ocr_stream_t stream)

@@ -17,6 +17,7 @@ struct GemmPlan {
     // split-K / shifted-operand form used by the weight-gradient contractions (gemm_plan_wgrad):
     //   D[batch][split] (M x N) = sum over the split's k range of A[m, k + a_shift[batch]] * W[n, k]
     int splits = 1, ksteps_per_split = 0, nbatch = 1, a_box_rows = 128;
+    int tp = 1, ntaps = 0;   // stacked views (gemm_wgrad, shallow layers): tp views of a_box_rows rows per A tile, ntaps views in all
     int pdl = 0;       // 1: launch with programmatic stream serialization (the kernel orders itself with griddepcontrol.wait after its prologue)
     int shallow = 0;   // 1: take the shallow pipeline (small shared-memory footprint) even for a one-wave grid, to leave room for co-running kernels
     int a_shift[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, a_row[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, b_row[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};

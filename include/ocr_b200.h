@@ -134,9 +134,10 @@ int ocr_edit_distance(const int64_t* hyp, int hyp_stride, const int32_t* hyp_len
  *   A [M,K] fp32 row-major, row pitch lda;  W [N,K] fp32 row-major (K-major weights), row pitch ldw;
  *   bias [N] or NULL;  D [M,N] fp32, row pitch ldd;  relu != 0 applies max(x,0).
  * A and W rows must be 16-byte aligned (pointer % 16 == 0, lda % 4 == 0, ldw % 4 == 0). */
-/* Tuning aid: the epilogue of ocr_gemm_tf32 stages 32x32 output blocks in shared memory and stores them with
- * cp.async.bulk.tensor (1, default; needs 16-byte aligned output rows) or writes one 16-byte STG per lane and row (0).
- * Same bits either way. */
+/* Tuning aid, a bit mask.  Bit 0 (default set): the epilogue of ocr_gemm_tf32 stages 32x32 output blocks in shared memory and
+ * stores them with cp.async.bulk.tensor (needs 16-byte aligned output rows); clear = one 16-byte STG per lane and row; same
+ * bits either way.  Bit 1 (default clear): ocr_gemm_tf32_wgrad runs one tile per tap view; clear = the views of operands
+ * with at most 64 rows are stacked in one 128-row tile (several taps per MMA). */
 int ocr_debug_gemm_tma_store(int on);
 int ocr_gemm_tf32(const float* A, int lda, const float* W, int ldw, const float* bias, float* D, int ldd, int M,
                   int N, int K, int relu, ocr_stream_t stream);

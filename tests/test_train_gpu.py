@@ -71,10 +71,16 @@ def test_transpose_and_planar_pad():
     assert (o[2][:, :-1] == flat[:, 1:]).all() and (o[2][:, -1] == 0).all()     # copy 2 holds pixel r+1 at r
 
 
+@pytest.mark.parametrize("stack", [1, 0])
 @pytest.mark.parametrize("M,N,R,shifts", [(40, 24, 1000, [0]), (256, 128, 33000, [0]), (70, 300, 5000, [-4, 0, 12]),
-                                          (32, 32, 70001, [-68, -68, -68, 0, 0, 0, 68, 68, 68])])
-def test_wgrad_gemm(M, N, R, shifts):
+                                          (32, 32, 70001, [-68, -68, -68, 0, 0, 0, 68, 68, 68]),
+                                          (64, 64, 20000, [-68, -64, -60, -4, 0, 4, 60, 64, 68]), (48, 40, 9000, [-4, 0, 4, 8, 12]),
+                                          (40, 24, 1000, [0, 4, 8])])
+def test_wgrad_gemm(M, N, R, shifts, stack):
+    """stack = 1 (default): views of at most 64 rows are stacked in one 128-row operand tile (one MMA contracts several taps);
+    stack = 0: one tile per view."""
     L, lib, sh = _lib()
+    L.check(lib.ocr_debug_gemm_tma_store(1 if stack else 3), "stack")
     rng = np.random.default_rng(1)
     ld = (R + 3) // 4 * 4
     At = np.zeros((M, ld), np.float32); At[:, :R] = rng.standard_normal((M, R))
@@ -98,6 +104,7 @@ def test_wgrad_gemm(M, N, R, shifts):
             Ash[:, -s:] = A64[:, :R + s]
         ref = Ash @ W64.T
         _close(D[i].cpu().numpy(), ref, 3e-3, "wgrad shift %d" % s)
+    L.check(lib.ocr_debug_gemm_tma_store(1), "stack")
 
 
 def test_batch_norm_train_and_backward():
