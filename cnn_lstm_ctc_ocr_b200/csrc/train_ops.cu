@@ -942,7 +942,7 @@ extern "C" int ocr_birnn_lstm_train_fwd(const float* x, int T, int B, int I, int
     float* c = h + (size_t)2 * B * H;
     int rc = ocr_gemm_tf32(x, I, wx, I, bias, gates, 8 * H, T * B, 8 * H, I, 0, stream);
     if (rc != OCR_OK) return rc;
-    if ((g_birnn_path == 0 || g_birnn_path == 2) && lstm_persistent_supported(T, B, H)) {
+    if ((g_birnn_path == 0 || g_birnn_path == 2 || g_birnn_path == 3) && lstm_persistent_supported(T, B, H)) {
         // all T frames of both directions in ONE cooperative launch, W_h resident in shared memory (lstm_persistent.cu)
         OCR_CHECK_CUDA(cudaMemsetAsync(cstate, 0, sizeof(float) * (size_t)T * B * 2 * H, st));
         return lstm_persistent_run(gates, wh, nullptr, seq_len, T, B, H, out, ws, st, gates, cstate);
@@ -967,8 +967,10 @@ extern "C" int ocr_birnn_lstm_train_fwd(const float* x, int T, int B, int I, int
 // wh_rows [2H, 4H]: the h-part of the TensorFlow kernels (rows = hidden unit, columns = gates i,j,f,o), forward
 // direction's H rows then the backward direction's.  gates: activations in, d(pre-activation) out.
 static int g_bptt_pdl = 1;   // programmatic dependent launch on the frame-by-frame BPTT chain (0: ordinary launches)
+static int g_bptt_bn = 0;    // tile width of the frame-by-frame recurrent product (0: automatic)
 extern "C" int ocr_debug_bptt_pdl(int on) {
-    g_bptt_pdl = on ? 1 : 0;
+    g_bptt_pdl = (on & 1) ? 1 : 0;
+    g_bptt_bn = on >> 4 << 4;             // tuning: on = 1 + 64 / 128 / 256 overrides the tile width
     return OCR_OK;
 }
 namespace ocr { int lstm_bptt_set_copies(int on); }
@@ -999,10 +1001,11 @@ extern "C" int ocr_birnn_lstm_bwd(const float* dout, int T, int B, int H, const 
     GemmPlan p1;
     // dh_rec[d][b, n] = sum_g dgs[d*B + b, g] * wh_rows[d*H + n, g]: K = 4H is long and the tile count small, so the
     // contraction is split over K across the SMs; the cell kernel of the next step adds the partials up
-    int want = 148 / (2 * ((B + 127) / 128) * ((H + 63) / 64));     // one full wave of CTAs, no ragged second wave
+    const int bn = g_bptt_bn ? g_bptt_bn : (H > 32 ? 64 : 32);
+    int want = 148 / (2 * ((B + 127) / 128) * ((H + bn - 1) / bn));     // one full wave of CTAs, no ragged second wave
     if (want > 8) want = 8;
     if (want < 1) want = 1;
-    int rc = gemm_plan_dirs(&p1, dgs, 4 * H, wh_rows, 4 * H, dh_rec, B, H, 4 * H, 2, want, H > 32 ? 64 : 32);
+    int rc = gemm_plan_dirs(&p1, dgs, 4 * H, wh_rows, 4 * H, dh_rec, B, H, 4 * H, 2, want, bn);
     if (rc != OCR_OK) return rc;
     const int splits = p1.splits;
     const int cg = grid_cap((long long)2 * B * H);

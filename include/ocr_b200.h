@@ -197,7 +197,7 @@ int ocr_birnn_workspace_bytes(int cell, int T, int B, int H, size_t* bytes);
 int ocr_lstm_prepare_wh(const float* wh, int H, float* wh_perm, ocr_stream_t stream);
 /* Kernel-path override for tests: 0 = automatic (LSTM forward frames with B <= 256, H <= 512 run as ONE persistent
  * tcgen05 kernel for all frames; back-propagation through time likewise for B <= 64), 1 = one recurrent GEMM + one cell
- * kernel per frame everywhere, 2 = persistent forward only, 3 = persistent BPTT whenever the shape fits. */
+ * kernel per frame everywhere, 2 = persistent forward only, 3 = persistent forward and persistent BPTT whenever the shape fits. */
 int ocr_birnn_set_path(int path);
 /* Tuning aid: per-frame clock64() stamps of CTA 0 of the persistent LSTM kernel (8 int64 per frame: producer past the grid
  * barrier, last h tile requested, first tile landed, last MMA issued, accumulator complete, TMEM read, cell update + stores

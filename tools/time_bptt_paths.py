@@ -18,8 +18,9 @@ for B in [int(a) for a in sys.argv[1:]] or [32, 64, 128, 256]:
     ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
     a = act.clone()
     out = {}
-    for path in (1, 3):
-        lib.ocr_birnn_set_path(path)
+    for path in (1, 129, 257, 3):
+        lib.ocr_birnn_set_path(min(path, 3) if path <= 3 else 1)
+        lib.ocr_debug_bptt_pdl(1 if path <= 3 else path)
         def run():
             a.copy_(act)
             _lib.check(lib.ocr_birnn_lstm_bwd(_lib.ptr(dout), T, B, H, _lib.ptr(sl), _lib.ptr(a), _lib.ptr(cs), _lib.ptr(wh_rows), _lib.ptr(ws), need.value,
@@ -30,7 +31,8 @@ for B in [int(a) for a in sys.argv[1:]] or [32, 64, 128, 256]:
         for _ in range(5): run()
         e1.record(); torch.cuda.synchronize()
         out[path] = (e0.elapsed_time(e1) / 5, a.clone())
-    lib.ocr_birnn_set_path(0)
+    lib.ocr_birnn_set_path(0); lib.ocr_debug_bptt_pdl(1)
+    print("   tile width 128: %.2f us/frame, 256: %.2f us/frame" % (out[129][0] * 1e3 / T, out[257][0] * 1e3 / T))
     d = (out[1][1] - out[3][1]).abs().max().item() / out[1][1].abs().max().item()
     print("B=%3d: frame-by-frame %.3f ms (%.2f us/frame), persistent %.3f ms (%.2f us/frame), max rel diff %.2e" % (
         B, out[1][0], out[1][0] * 1e3 / T, out[3][0], out[3][0] * 1e3 / T, d), flush=True)

@@ -1,4 +1,4 @@
-"""Times Trainer.train_step (cfg3-shaped) on one GPU: python tools/time_train.py [B] [W] [steps]."""
+"""Times Trainer.train_step (cfg3-shaped) on one GPU: python tools/time_train.py [B] [W] [steps] [birnn path: 0 automatic, 3 persistent BPTT forced]."""
 import sys, time
 sys.path.insert(0, ".")
 import numpy as np, torch
@@ -10,6 +10,8 @@ from util import make_labels
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 W = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+if len(sys.argv) > 4:
+    _lib.load().ocr_birnn_set_path(int(sys.argv[4]))
 rng = np.random.default_rng(0)
 params = _model.init_params(0, "lstm", (512, 512))
 tr = train.Trainer(params)
