@@ -40,7 +40,7 @@ struct GemmSmem {
     static constexpr int kTotal = kBars + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool H16 = false>   // H16: bfloat16 operands, 64 elements per swizzle row
 __global__ void __launch_bounds__(kGemmThreads)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
                  const float* __restrict__ bias, float* __restrict__ D, int M, int N, int K, int ldd, int relu,
@@ -61,7 +61,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // blockIdx.x = m-tile * nbatch + batch (the batches of one tile run side by side and share operand tiles in L2)
     const int batch = blockIdx.x % sp.nbatch;
     const int m0 = (blockIdx.x / sp.nbatch) * kGemmBM, n0 = blockIdx.y * BN;
-    const int nk_all = (K + kGemmBK - 1) / kGemmBK;
+    constexpr int kBKe = H16 ? kGemmBKh : kGemmBK;   // elements per k-step (one 128-byte row)
+    const int nk_all = (K + kBKe - 1) / kBKe;
     const int k_begin = sp.ksteps_per_split > 0 ? blockIdx.z * sp.ksteps_per_split : 0;
     const int nk = sp.ksteps_per_split > 0 ? min(sp.ksteps_per_split, nk_all - k_begin) : nk_all;
     // Stacked views (weight gradients of the shallow layers, C_in <= 64): the A tile's 128 rows are tp slices of a_box_rows rows,
@@ -98,15 +99,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (k >= STAGES) g_mbar_wait(bar_empty + s * 8, ((k / STAGES) - 1) & 1);
                 g_mbar_expect_tx(bar_full + s * 8, (unsigned)(nview * sp.a_box_bytes + S::kB));
                 for (int i = 0; i < nview; ++i)
-                    tma_load_2d(s_base + s * S::kStage + i * sp.a_box_bytes, &tmA, (k_begin + k) * kGemmBK + sp.a_shift[v0 + i], m0 + sp.a_row[v0 + i],
+                    tma_load_2d(s_base + s * S::kStage + i * sp.a_box_bytes, &tmA, (k_begin + k) * kBKe + sp.a_shift[v0 + i], m0 + sp.a_row[v0 + i],
                                 bar_full + s * 8);
-                tma_load_2d(s_base + s * S::kStage + S::kA, &tmB, (k_begin + k) * kGemmBK, n0 + b_row, bar_full + s * 8);
+                tma_load_2d(s_base + s * S::kStage + S::kA, &tmB, (k_begin + k) * kBKe, n0 + b_row, bar_full + s * 8);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // instruction descriptor: fp32 accumulate, tf32 x tf32, both K-major, N = BN, M = 128
-            const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(kGemmBM >> 4) << 24);
+            // instruction descriptor: fp32 accumulate, tf32 x tf32 (H16: bfloat16 x bfloat16 -- measured: mixing bfloat16 and
+            // binary16 operands in one tcgen05.mma.kind::f16 is an illegal instruction), both K-major, N = BN, M = 128
+            const unsigned idesc = (1u << 4) | ((H16 ? 1u : 2u) << 7) | ((H16 ? 1u : 2u) << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(kGemmBM >> 4) << 24);
             for (int k = 0; k < nk; ++k) {
                 const int s = k % STAGES;
                 g_mbar_wait(bar_full + s * 8, (k / STAGES) & 1);
@@ -114,8 +116,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const unsigned a_addr = s_base + s * S::kStage, b_addr = a_addr + S::kA;
                 const unsigned long long da = umma_desc_k128(a_addr), db = umma_desc_k128(b_addr);
 #pragma unroll
-                for (int kk = 0; kk < kGemmBK / 8; ++kk)  // 8 tf32 = 32 bytes per MMA: advance the start address inside the swizzle row
-                    umma_tf32(tmem_d, da + (unsigned long long)(kk * 2), db + (unsigned long long)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+                for (int kk = 0; kk < 4; ++kk) {  // 8 tf32 / 16 halves = 32 bytes per MMA: advance the start address inside the swizzle row
+                    if constexpr (H16) umma_f16(tmem_d, da + (unsigned long long)(kk * 2), db + (unsigned long long)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+                    else umma_tf32(tmem_d, da + (unsigned long long)(kk * 2), db + (unsigned long long)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+                }
                 umma_commit(bar_empty + s * 8);  // frees the stage when the MMAs that read it retire
             }
             umma_commit(bar_acc);
@@ -241,7 +245,7 @@ int gemm_set_tma_store(int on) {
 }
 }  // namespace ocr
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool H16 = false>
 static int launch_planned(const GemmPlan& p, cudaStream_t st)
 {
     using S = GemmSmem<BN, STAGES>;
@@ -249,7 +253,7 @@ static int launch_planned(const GemmPlan& p, cudaStream_t st)
     int dev = 0;
     OCR_CHECK_CUDA(cudaGetDevice(&dev));
     if (configured != dev) {
-        OCR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+        OCR_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES, H16>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
         configured = dev;
     }
     dim3 grid(((p.M + kGemmBM - 1) / kGemmBM) * p.nbatch, (p.N + BN - 1) / BN, p.splits);
@@ -274,11 +278,11 @@ static int launch_planned(const GemmPlan& p, cudaStream_t st)
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, STAGES>, p.tmA, p.tmB, p.tmD, p.bias, p.D, p.M, p.N, p.K, p.ldd, p.relu, sp));
+        OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, STAGES, H16>, p.tmA, p.tmB, p.tmD, p.bias, p.D, p.M, p.N, p.K, p.ldd, p.relu, sp));
         count_launch();
         return OCR_OK;
     }
-    gemm_tf32_kernel<BN, STAGES><<<grid, kGemmThreads, S::kTotal, st>>>(p.tmA, p.tmB, p.tmD, p.bias, p.D, p.M, p.N, p.K, p.ldd, p.relu, sp);
+    gemm_tf32_kernel<BN, STAGES, H16><<<grid, kGemmThreads, S::kTotal, st>>>(p.tmA, p.tmB, p.tmD, p.bias, p.D, p.M, p.N, p.K, p.ldd, p.relu, sp);
     OCR_CHECK_LAUNCH();
     return OCR_OK;
 }
@@ -338,8 +342,27 @@ int gemm_plan_dirs(GemmPlan* p, const float* A, int lda, const float* W, int ldw
     return tma_map_2d(&p->tmB, W, (long long)ndir * N, K, ldw, bn);
 }
 
+int gemm_plan_dirs_h16(GemmPlan* p, const void* A, int lda, const void* W, int ldw, float* D, int M, int N, int K, int ndir, int splits, int bn)
+{
+    OCR_CHECK_ARG(M >= 1 && N >= 1 && K >= 1 && ndir >= 1 && ndir <= 9 && splits >= 1 && (bn == 32 || bn == 64), "gemm_plan_dirs_h16: bad shape");
+    OCR_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0, "gemm_plan_dirs_h16: operands need 16-byte aligned rows");
+    const int nk = (K + kGemmBKh - 1) / kGemmBKh;
+    if (splits > nk) splits = nk;
+    const int kps = (nk + splits - 1) / splits;
+    splits = (nk + kps - 1) / kps;
+    p->bn = bn; p->bias = nullptr; p->D = D; p->M = M; p->N = N; p->K = K; p->ldd = N; p->relu = 0; p->h16 = 1;
+    p->splits = splits; p->ksteps_per_split = splits > 1 ? kps : 0; p->nbatch = ndir;
+    for (int d = 0; d < ndir; ++d) { p->a_shift[d] = 0; p->a_row[d] = d * M; p->b_row[d] = d * N; }
+    p->split_stride = (long long)M * N;
+    p->batch_stride = (long long)splits * M * N;
+    int rc = tma_map_2d_h(&p->tmA, A, (long long)ndir * M, K, lda, kGemmBM);
+    if (rc != OCR_OK) return rc;
+    return tma_map_2d_h(&p->tmB, W, (long long)ndir * N, K, ldw, bn);
+}
+
 int gemm_run(const GemmPlan& p, cudaStream_t st)
 {
+    if (p.h16) return p.bn == 32 ? launch_planned<32, 8, true>(p, st) : launch_planned<64, 6, true>(p, st);
     // Two shapes of pipeline.  Grids that put at most one CTA on an SM (split-K contractions, the small per-frame
     // products) get a deep TMA ring: the k loop is all there is.  Grids of many short tiles get a shallow ring so that
     // 2-3 CTAs share an SM (shared memory and the 512 TMEM columns allow it) and the epilogue of one tile -- one thread per

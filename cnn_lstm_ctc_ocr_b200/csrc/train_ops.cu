@@ -10,6 +10,11 @@
 //
 // The memory-bound kernels are coalesced grid-stride loops; per-channel reductions accumulate float partials per thread,
 // combine them per CTA in shared memory and finish in double-precision atomics (order-independent to ~1e-16).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <type_traits>
+
 #include "gemm_tf32.cuh"
 
 namespace ocr {
@@ -356,11 +361,18 @@ lstm_cell_train_kernel(const float* __restrict__ gh, float* __restrict__ xp, con
 // [2][splits][B][H] holds the split-K partial products dG_step * W_h of the step processed just before; dh, dc [2B,H] carry the
 // state gradients; dgs [2B, 4H] receives this step's gate gradients as the A operand of the next recurrent product
 // (zero rows for examples that are past their length).
+// GS = float: dgs float32 (TF32 product); GS = __nv_bfloat16: dgs bfloat16 (float32's exponent range -- gradients span many
+// orders of magnitude -- with 8 mantissa bits; the 16-bit product, gemm_plan_dirs_h16).
+template <typename GS>
 __global__ void __launch_bounds__(256)
 lstm_cell_bwd_kernel(float* __restrict__ act, const float* __restrict__ cs, const float* __restrict__ dout, const float* __restrict__ dh_rec,
                      const int32_t* __restrict__ seq_len, int s, int last, int T, int B, int H, int splits, float* __restrict__ dh,
-                     float* __restrict__ dc, float* __restrict__ dgs)
+                     float* __restrict__ dc, GS* __restrict__ dgs)
 {
+    auto cvt = [](float v) -> GS {
+        if constexpr (std::is_same<GS, float>::value) return v;
+        else return __float2bfloat16_rn(v);
+    };
     // programmatic dependent launch: scheduled while the recurrent product of the previous step was finishing (see the frame loop)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -370,7 +382,7 @@ lstm_cell_bwd_kernel(float* __restrict__ act, const float* __restrict__ cs, cons
         const int r = idx / H;
         const int dir = r >= B, b = dir ? r - B : r;
         const int len = min(seq_len[b], T);
-        float* gs = dgs + (size_t)r * 4 * H;
+        GS* gs = dgs + (size_t)r * 4 * H;
         // gradient flowing into h_s from step s+1 (only if that step was live for this example)
         float dhv = 0.f, dcv = 0.f;
         if (!last && s + 1 < len) {
@@ -378,7 +390,7 @@ lstm_cell_bwd_kernel(float* __restrict__ act, const float* __restrict__ cs, cons
             for (int z = 0; z < splits; ++z) dhv += pr[(size_t)z * B * H];
             dcv = dc[idx];
         }
-        if (s >= len) { gs[j] = 0.f; gs[H + j] = 0.f; gs[2 * H + j] = 0.f; gs[3 * H + j] = 0.f; continue; }
+        if (s >= len) { gs[j] = cvt(0.f); gs[H + j] = cvt(0.f); gs[2 * H + j] = cvt(0.f); gs[3 * H + j] = cvt(0.f); continue; }
         const int t = dir ? len - 1 - s : s;
         const size_t o = ((size_t)t * B + b) * 2 * H + dir * H + j;
         float* a = act + ((size_t)t * B + b) * 8 * H + dir * 4 * H;
@@ -394,7 +406,7 @@ lstm_cell_bwd_kernel(float* __restrict__ act, const float* __restrict__ cs, cons
         const float d_j = dct * gi * (1.f - gj * gj);
         const float d_f = dct * cprev * gf * (1.f - gf);
         a[j] = d_i; a[H + j] = d_j; a[2 * H + j] = d_f; a[3 * H + j] = d_o;
-        gs[j] = d_i; gs[H + j] = d_j; gs[2 * H + j] = d_f; gs[3 * H + j] = d_o;
+        gs[j] = cvt(d_i); gs[H + j] = cvt(d_j); gs[2 * H + j] = cvt(d_f); gs[3 * H + j] = cvt(d_o);
         dc[idx] = dct * gf;
         dh[idx] = dht;   // kept for inspection; the recurrent product is taken from dgs
     }
@@ -919,7 +931,8 @@ extern "C" int ocr_birnn_lstm_train_workspace_bytes(int T, int B, int H, size_t*
 {
     OCR_CHECK_ARG(bytes && T >= 0 && B >= 0 && H >= 1, "ocr_birnn_lstm_train_workspace_bytes: bad argument");
     // gh [2B, 8H] (backward: split-K partials of dh_rec, at most 8 x [2B, H]) + h, c, dh, dc [2B,H] + dgs [2B,4H]
-    size_t fl = (size_t)2 * B * 8 * H + (size_t)2 * B * H * 4 + (size_t)2 * B * 4 * H;
+    // + the bfloat16 copy of wh_rows [2H, 4H] for the 16-bit frame-by-frame product (4 H^2 floats)
+    size_t fl = (size_t)2 * B * 8 * H + (size_t)2 * B * H * 4 + (size_t)2 * B * 4 * H + (size_t)4 * H * H + 64;
     if (T >= 1 && B >= 1 && lstm_persistent_supported(T, B, H) && lstm_persistent_workspace_floats(B, H) > fl) fl = lstm_persistent_workspace_floats(B, H);
     if (T >= 1 && B >= 1 && lstm_bptt_supported(T, B, H) && lstm_bptt_workspace_floats(B, H) > fl) fl = lstm_bptt_workspace_floats(B, H);
     *bytes = sizeof(float) * fl + 256;
@@ -968,8 +981,14 @@ extern "C" int ocr_birnn_lstm_train_fwd(const float* x, int T, int B, int I, int
 // direction's H rows then the backward direction's.  gates: activations in, d(pre-activation) out.
 static int g_bptt_pdl = 1;   // programmatic dependent launch on the frame-by-frame BPTT chain (0: ordinary launches)
 static int g_bptt_bn = 0;    // tile width of the frame-by-frame recurrent product (0: automatic)
+static int g_bptt_h16 = 1;   // bfloat16 operands (dG, W_h) in the frame-by-frame recurrent product where 4H % 64 == 0
+__global__ void to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = __float2bfloat16_rn(in[i]);
+}
 extern "C" int ocr_debug_bptt_pdl(int on) {
     g_bptt_pdl = (on & 1) ? 1 : 0;
+    g_bptt_h16 = (on & 2) ? 0 : 1;
     g_bptt_bn = on >> 4 << 4;             // tuning: on = 1 + 64 / 128 / 256 overrides the tile width
     return OCR_OK;
 }
@@ -990,7 +1009,8 @@ extern "C" int ocr_birnn_lstm_bwd(const float* dout, int T, int B, int H, const 
     float* dh_rec = ws;                               // [2][splits][B][H], splits <= 8
     float* dh = dh_rec + (size_t)2 * B * 8 * H;
     float* dc = dh + (size_t)2 * B * H;
-    float* dgs = dc + (size_t)2 * B * H * 3;          // [2B, 4H]
+    float* dgs = dc + (size_t)2 * B * H * 3;          // [2B, 4H] float32 or bfloat16
+    __nv_bfloat16* wh16 = reinterpret_cast<__nv_bfloat16*>(dgs + (size_t)2 * B * 4 * H);   // [2H, 4H] bfloat16 copy of wh_rows
     OCR_CHECK_CUDA(cudaMemsetAsync(dh, 0, sizeof(float) * (size_t)2 * B * H * 2, st));
     zero_past_len_kernel<<<grid_cap((long long)T * B * 2 * H), 256, 0, st>>>(gates, seq_len, T, B, 2 * H);
     OCR_CHECK_LAUNCH();
@@ -1005,7 +1025,17 @@ extern "C" int ocr_birnn_lstm_bwd(const float* dout, int T, int B, int H, const 
     int want = 148 / (2 * ((B + 127) / 128) * ((H + bn - 1) / bn));     // one full wave of CTAs, no ragged second wave
     if (want > 8) want = 8;
     if (want < 1) want = 1;
-    int rc = gemm_plan_dirs(&p1, dgs, 4 * H, wh_rows, 4 * H, dh_rec, B, H, 4 * H, 2, want, bn);
+    // 16-bit operands: the product is bound by the operand bytes an SM pulls through L2 (A tile re-read by every N tile, W by
+    // every M tile: 48 MB per frame at B = 256 in float32); bfloat16 gate gradients x bfloat16 weights halve them
+    const bool h16 = g_bptt_h16 && (H % 16) == 0 && bn <= 64;
+    int rc;
+    if (h16) {
+        to_bf16_kernel<<<grid_cap((long long)8 * H * H), 256, 0, st>>>(wh_rows, wh16, (long long)8 * H * H);
+        OCR_CHECK_LAUNCH();
+        rc = gemm_plan_dirs_h16(&p1, dgs, 4 * H, wh16, 4 * H, dh_rec, B, H, 4 * H, 2, want, bn);
+    } else {
+        rc = gemm_plan_dirs(&p1, dgs, 4 * H, wh_rows, 4 * H, dh_rec, B, H, 4 * H, 2, want, bn);
+    }
     if (rc != OCR_OK) return rc;
     const int splits = p1.splits;
     const int cg = grid_cap((long long)2 * B * H);
@@ -1024,10 +1054,12 @@ extern "C" int ocr_birnn_lstm_bwd(const float* dout, int T, int B, int H, const 
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_cell_bwd_kernel, gates, (const float*)cstate, dout, (const float*)dh_rec, seq_len, s, 0, T, B, H, splits, dh, dc, dgs));
+            if (h16) OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_cell_bwd_kernel<__nv_bfloat16>, gates, (const float*)cstate, dout, (const float*)dh_rec, seq_len, s, 0, T, B, H, splits, dh, dc, reinterpret_cast<__nv_bfloat16*>(dgs)));
+            else OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_cell_bwd_kernel<float>, gates, (const float*)cstate, dout, (const float*)dh_rec, seq_len, s, 0, T, B, H, splits, dh, dc, dgs));
             count_launch();
         } else {
-            lstm_cell_bwd_kernel<<<cg, 256, 0, st>>>(gates, cstate, dout, dh_rec, seq_len, s, s == T - 1 ? 1 : 0, T, B, H, splits, dh, dc, dgs);
+            if (h16) lstm_cell_bwd_kernel<__nv_bfloat16><<<cg, 256, 0, st>>>(gates, cstate, dout, dh_rec, seq_len, s, s == T - 1 ? 1 : 0, T, B, H, splits, dh, dc, reinterpret_cast<__nv_bfloat16*>(dgs));
+            else lstm_cell_bwd_kernel<float><<<cg, 256, 0, st>>>(gates, cstate, dout, dh_rec, seq_len, s, s == T - 1 ? 1 : 0, T, B, H, splits, dh, dc, dgs);
             OCR_CHECK_LAUNCH();
         }
         if (s > 0) { rc = gemm_run(p1, st); if (rc != OCR_OK) return rc; }
