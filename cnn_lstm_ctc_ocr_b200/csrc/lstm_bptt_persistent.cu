@@ -164,14 +164,20 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW, float* act /*[T*B, 8H]
                     // block [4 column groups][128 rows][4 floats]: my column groups rho*U/4 .., row `slot`
                     const float4* src = reinterpret_cast<const float4*>(part + ((size_t)((f - 1) & 1) * 2 + d) * part_pd + (((size_t)mt * NS + j) * NS) * part_tile) +
                                         (size_t)(u0 / 4) * 128 + slot;
-#pragma unroll 4
-                    for (int js = 0; js < NS; ++js) {     // fixed order: deterministic sums
-                        const float4* p4 = src + (size_t)js * (part_tile / 4);
+                    // 16 loads in flight per thread (each batch is one L2 round trip), added in slice order: deterministic sums
+                    constexpr int JB = 16 / (U / 4);
+                    for (int js0 = 0; js0 < NS; js0 += JB) {
+                        float4 a[JB][U / 4];
 #pragma unroll
-                        for (int v = 0; v < U / 4; ++v) {
-                            const float4 a = __ldcg(p4 + v * 128);   // written by other SMs this launch: L2, never a stale L1 line
-                            dh[4 * v] += a.x; dh[4 * v + 1] += a.y; dh[4 * v + 2] += a.z; dh[4 * v + 3] += a.w;
-                        }
+                        for (int i = 0; i < JB; ++i)
+#pragma unroll
+                            for (int v = 0; v < U / 4; ++v)
+                                if (js0 + i < NS) a[i][v] = __ldcg(src + (size_t)(js0 + i) * (part_tile / 4) + v * 128);   // written by other SMs this launch: L2, never a stale L1 line
+#pragma unroll
+                        for (int i = 0; i < JB; ++i)
+#pragma unroll
+                            for (int v = 0; v < U / 4; ++v)
+                                if (js0 + i < NS) { dh[4 * v] += a[i][v].x; dh[4 * v + 1] += a[i][v].y; dh[4 * v + 2] += a[i][v].z; dh[4 * v + 3] += a[i][v].w; }
                     }
                 }
             }
