@@ -23,11 +23,23 @@
 //     copies of the row in the A tile) and the destination slices [rho*NS/R, +NS/R) for the scatter: a quarter (half) of
 //     the loads, arithmetic, stores and TMEM reads per thread, nothing computed twice, sums in the same order (same bits).
 //     The exchange blocks are laid out [4 column groups][128 rows][4 floats]: a warp's 16-byte accesses are contiguous.
+//   * XB (default): the partials cross L2 as bfloat16 ([2 column groups][128 rows][8 values]).  Scatter and gather are bound by
+//     the bytes an SM writes and reads per frame (64 KB each way at 32 rows: ~2000 + ~3500 of 13400 cycles); bfloat16 keeps
+//     float32's exponent range (gradients) and halves them.  The sums themselves stay float32.
 // Sequence lengths follow dynamic_rnn: an example is touched only while s < len (processing order s = T-1 .. 0), the
 // backward direction visits frame len-1-s at step s; rows past their length contribute zero gate gradients.
+#include <cuda_bf16.h>
+
 #include "gemm_tf32.cuh"
 
 namespace ocr {
+
+__device__ __forceinline__ unsigned bp_pack2(float lo, float hi) {
+    const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const unsigned*>(&p);
+}
+__device__ __forceinline__ float bp_lo(unsigned v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bp_hi(unsigned v) { return __uint_as_float(v & 0xffff0000u); }
 
 constexpr int kBpThreads = 192;
 constexpr int kBpHS = 16;                 // hidden units per CTA
@@ -49,7 +61,7 @@ __device__ __forceinline__ void bp_wait_counter(const unsigned* ctr, unsigned ta
     __trap();
 }
 
-template <int R>   // copies of a batch row in the A tile: 1, 2 or 4 (one batch tile when R > 1)
+template <int R, bool XB>   // R: copies of a batch row in the A tile: 1, 2 or 4 (one batch tile when R > 1); XB: partials exchanged as bfloat16
 __global__ void __launch_bounds__(kBpThreads, 1)
 lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW, float* act /*[T*B, 8H]: activations in, d pre-activations out*/,
                  const float* __restrict__ cs /*[T,B,2H]*/, const float* __restrict__ dout /*[T,B,2H]*/, const int32_t* __restrict__ seq_len,
@@ -165,6 +177,35 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW, float* act /*[T*B, 8H]
                     const float4* src = reinterpret_cast<const float4*>(part + ((size_t)((f - 1) & 1) * 2 + d) * part_pd + (((size_t)mt * NS + j) * NS) * part_tile) +
                                         (size_t)(u0 / 4) * 128 + slot;
                     // 16 loads in flight per thread (each batch is one L2 round trip), added in slice order: deterministic sums
+                    if constexpr (XB) {
+                        // bfloat16 blocks [2 groups][128 rows][8 values]: my U units = 32 / 16 / 8 bytes of row `slot`
+                        const unsigned char* srcb = reinterpret_cast<const unsigned char*>(part) + (((size_t)((f - 1) & 1) * 2 + d) * part_pd + (((size_t)mt * NS + j) * NS) * part_tile) * 2 +
+                               ((size_t)(u0 >> 3) * 128 + slot) * 16 + (size_t)(u0 & 7) * 2;
+                        constexpr int NV = U == 16 ? 2 : 1;                  // 16-byte (8-byte for U = 4) loads per source slice
+                        constexpr int JB = 16 / NV;
+                        for (int js0 = 0; js0 < NS; js0 += JB) {
+                            uint4 a[JB][NV];
+#pragma unroll
+                            for (int i = 0; i < JB; ++i)
+#pragma unroll
+                                for (int v = 0; v < NV; ++v)
+                                    if (js0 + i < NS) {
+                                        const unsigned char* p = srcb + (size_t)(js0 + i) * part_tile * 2 + (size_t)v * 128 * 16;
+                                        if constexpr (U == 4) { const uint2 t2 = __ldcg(reinterpret_cast<const uint2*>(p)); a[i][v] = make_uint4(t2.x, t2.y, 0u, 0u); }
+                                        else a[i][v] = __ldcg(reinterpret_cast<const uint4*>(p));
+                                    }
+#pragma unroll
+                            for (int i = 0; i < JB; ++i)
+#pragma unroll
+                                for (int v = 0; v < NV; ++v)
+                                    if (js0 + i < NS) {
+                                        dh[8 * v] += bp_lo(a[i][v].x); dh[8 * v + 1] += bp_hi(a[i][v].x); dh[8 * v + 2] += bp_lo(a[i][v].y); dh[8 * v + 3] += bp_hi(a[i][v].y);
+                                        if constexpr (U > 4) {
+                                            dh[8 * v + 4] += bp_lo(a[i][v].z); dh[8 * v + 5] += bp_hi(a[i][v].z); dh[8 * v + 6] += bp_lo(a[i][v].w); dh[8 * v + 7] += bp_hi(a[i][v].w);
+                                        }
+                                    }
+                        }
+                    } else {
                     constexpr int JB = 16 / (U / 4);
                     for (int js0 = 0; js0 < NS; js0 += JB) {
                         float4 a[JB][U / 4];
@@ -178,6 +219,7 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW, float* act /*[T*B, 8H]
 #pragma unroll
                             for (int v = 0; v < U / 4; ++v)
                                 if (js0 + i < NS) { dh[4 * v] += a[i][v].x; dh[4 * v + 1] += a[i][v].y; dh[4 * v + 2] += a[i][v].z; dh[4 * v + 3] += a[i][v].w; }
+                    }
                     }
                 }
             }
@@ -264,7 +306,20 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW, float* act /*[T*B, 8H]
                           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                         : "r"(taddr) : "memory");
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (live) {                            // dead rows have zero gate gradients and nobody reads their partials
+                    if (live && XB) {
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(part) +
+                                                                 (((size_t)(f & 1) * 2 + d) * part_pd + ((size_t)mt * NS * NS + j) * part_tile + (size_t)(jd0 + i) * NS * part_tile) * 2) + slot;
+#pragma unroll
+                            for (int w = 0; w < 2; ++w) {
+                                const int c = 16 * i + 8 * w;
+                                __stcg(d4 + w * 128, make_uint4(bp_pack2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), bp_pack2(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])),
+                                                                bp_pack2(__uint_as_float(v[c + 4]), __uint_as_float(v[c + 5])), bp_pack2(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7]))));
+                            }
+                        }
+                    }
+                    if (live && !XB) {                     // dead rows have zero gate gradients and nobody reads their partials
 #pragma unroll
                         for (int i = 0; i < 2; ++i) {
                             float4* d4 = dst + (size_t)(jd0 + i) * NS * (part_tile / 4);
@@ -309,8 +364,10 @@ __global__ void bptt_permute_kernel(const float* __restrict__ wh_rows, float* __
 }
 
 static int g_bptt_copies = 1;   // row copies in the A tile at small batches (0: one copy, the round-1 form)
-int lstm_bptt_set_copies(int on) {
-    g_bptt_copies = on ? 1 : 0;
+static int g_bptt_xb = 1;       // partials exchanged as bfloat16 (0: float32)
+int lstm_bptt_set_copies(int on) {      // bit 0: row copies, bit 1: float32 exchange
+    g_bptt_copies = (on & 1) ? 1 : 0;
+    g_bptt_xb = (on & 2) ? 0 : 1;
     return OCR_OK;
 }
 
@@ -355,9 +412,12 @@ int lstm_bptt_run(const float* dout, int T, int B, int H, const int32_t* seq_len
     int dev = 0;
     OCR_CHECK_CUDA(cudaGetDevice(&dev));
     if (configured != dev) {
-        OCR_CHECK_CUDA(cudaFuncSetAttribute(lstm_bptt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-        OCR_CHECK_CUDA(cudaFuncSetAttribute(lstm_bptt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-        OCR_CHECK_CUDA(cudaFuncSetAttribute(lstm_bptt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        OCR_CHECK_CUDA(cudaFuncSetAttribute(lstm_bptt_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        OCR_CHECK_CUDA(cudaFuncSetAttribute(lstm_bptt_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        OCR_CHECK_CUDA(cudaFuncSetAttribute(lstm_bptt_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        OCR_CHECK_CUDA(cudaFuncSetAttribute(lstm_bptt_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        OCR_CHECK_CUDA(cudaFuncSetAttribute(lstm_bptt_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        OCR_CHECK_CUDA(cudaFuncSetAttribute(lstm_bptt_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
         configured = dev;
     }
     cudaLaunchConfig_t cfg = {};
@@ -376,9 +436,13 @@ int lstm_bptt_run(const float* dout, int T, int B, int H, const int32_t* seq_len
         if (B <= 32 && (NS % 8) == 0) R = 4;
         else if (B <= 64 && (NS % 4) == 0) R = 2;
     }
-    if (R == 4) OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_bptt_kernel<4>, tmW, act, cstate, dout, seq_len, part, counters, T, B, H, NS, MT));
-    else if (R == 2) OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_bptt_kernel<2>, tmW, act, cstate, dout, seq_len, part, counters, T, B, H, NS, MT));
-    else OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_bptt_kernel<1>, tmW, act, cstate, dout, seq_len, part, counters, T, B, H, NS, MT));
+#define OCR_BP_GO(R_, X_) OCR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_bptt_kernel<R_, X_>, tmW, act, cstate, dout, seq_len, part, counters, T, B, H, NS, MT))
+    if (g_bptt_xb) {
+        if (R == 4) OCR_BP_GO(4, true); else if (R == 2) OCR_BP_GO(2, true); else OCR_BP_GO(1, true);
+    } else {
+        if (R == 4) OCR_BP_GO(4, false); else if (R == 2) OCR_BP_GO(2, false); else OCR_BP_GO(1, false);
+    }
+#undef OCR_BP_GO
     count_launch();
     return OCR_OK;
 }
