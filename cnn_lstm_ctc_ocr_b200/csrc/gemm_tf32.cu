@@ -162,6 +162,7 @@ static EncodeTiledFn get_encode() {
 
 // 2-D fp32 tensor [rows, K] row-major with row pitch ld elements; box = [box_rows, 32 floats], 128-byte swizzle
 namespace ocr {
+static int g_tma_promo256 = 0;   // tuning: L2 promotion of the 2-D operand maps (0: 128 bytes, 1: 256 bytes)
 int tma_map_2d(CUtensorMap* tm, const float* base, long long rows, long long K, long long ld, int box_rows) {
     EncodeTiledFn enc = get_encode();
     if (enc == nullptr) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return OCR_ECUDA; }
@@ -170,8 +171,8 @@ int tma_map_2d(CUtensorMap* tm, const float* base, long long rows, long long K, 
     cuuint32_t box[2] = {(cuuint32_t)kGemmBK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     g_tma_promo256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld K=%lld ld=%lld", (int)r, rows, K, ld); return OCR_ECUDA; }
     return OCR_OK;
 }
@@ -475,6 +476,7 @@ int gemm_wgrad(const float* A, long long lda, const float* W, long long ldw, flo
 // (default off: the views of layers with at most 64 input channels are stacked in one tile).
 extern "C" int ocr_debug_gemm_tma_store(int on) {
     g_wgrad_stack = (on & 2) ? 0 : 1;
+    g_tma_promo256 = (on & 4) ? 1 : 0;
     return gemm_set_tma_store(on & 1);
 }
 

@@ -230,14 +230,19 @@ bn_relu_apply_kernel(const float* __restrict__ y, long long rows, int C, const f
 }
 
 // dy = gamma * inv_std * (dz - dbeta/n - xhat * dgamma/n), dz = g * (z > 0)
+// BIAS: also the per-channel sums of dy (the bias gradient of the convolution in front of the batch-norm: one pass less over
+// dy).  The grid stride is a multiple of C/4, so a thread keeps ITS four channels for the whole loop: float partials in
+// registers, one shared-memory pass per CTA, double atomics per channel (as channel_reduce_kernel does).
+template <bool BIAS>
 __global__ void __launch_bounds__(256)
 bn_relu_bwd_apply_kernel(const float* __restrict__ y, const float* __restrict__ g, long long rows, long long n, int C, const float* __restrict__ mean,
                          const float* __restrict__ inv_std, const float* __restrict__ gamma, const float* __restrict__ beta,
-                         const double* __restrict__ sums, float* __restrict__ dy)
+                         const double* __restrict__ sums, float* __restrict__ dy, double* __restrict__ dy_sums)
 {
     const int c4n = C >> 2;
     const long long total = rows * c4n;
     const double inv_n = 1.0 / (double)n;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(idx % c4n) * 4;
         const float4 yv = reinterpret_cast<const float4*>(y)[idx], gv = reinterpret_cast<const float4*>(g)[idx];
@@ -254,6 +259,18 @@ bn_relu_bwd_apply_kernel(const float* __restrict__ y, const float* __restrict__ 
         OCR_BNB(x, 0) OCR_BNB(y, 1) OCR_BNB(z, 2) OCR_BNB(w, 3)
 #undef OCR_BNB
         reinterpret_cast<float4*>(dy)[idx] = o;
+        if (BIAS) { acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+    }
+    if (BIAS) {
+        __shared__ float4 red[256];
+        red[threadIdx.x] = acc;
+        __syncthreads();
+        if ((int)threadIdx.x < c4n) {          // threads t, t + c4n, t + 2 c4n, ... hold the same four channels (256 % c4n == 0)
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+            for (int k = threadIdx.x; k < 256; k += c4n) { t0 += (double)red[k].x; t1 += (double)red[k].y; t2 += (double)red[k].z; t3 += (double)red[k].w; }
+            const int c = (int)threadIdx.x * 4;
+            atomicAdd(dy_sums + c, t0); atomicAdd(dy_sums + c + 1, t1); atomicAdd(dy_sums + c + 2, t2); atomicAdd(dy_sums + c + 3, t3);
+        }
     }
 }
 
@@ -823,7 +840,24 @@ extern "C" int ocr_bn_relu_bwd_apply(const float* y, const float* dout, long lon
 {
     OCR_CHECK_ARG(rows >= 1 && n >= rows && C >= 1 && y && dout && mean && inv_std && gamma && beta && sums && dy, "ocr_bn_relu_bwd_apply: bad argument");
     OCR_CHECK_ARG((C % 4) == 0, "ocr_bn_relu_bwd_apply: C must be a multiple of 4");
-    bn_relu_bwd_apply_kernel<<<grid_cap(rows * (C / 4)), 256, 0, ST(stream)>>>(y, dout, rows, n, C, mean, inv_std, gamma, beta, reinterpret_cast<const double*>(sums), dy);
+    bn_relu_bwd_apply_kernel<false><<<grid_cap(rows * (C / 4)), 256, 0, ST(stream)>>>(y, dout, rows, n, C, mean, inv_std, gamma, beta, reinterpret_cast<const double*>(sums), dy, nullptr);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+// the same, and dbias [C] = per-channel sums of dy (what ocr_colsum(dy) gives: the bias gradient of the convolution whose output
+// the batch-norm normalises) from the same pass; scratch: C doubles.  Needs 256 % (C / 4) == 0 (C = 32 .. 1024 in powers of two).
+extern "C" int ocr_bn_relu_bwd_apply_bias(const float* y, const float* dout, long long rows, long long n, int C, const float* mean,
+                                          const float* inv_std, const float* gamma, const float* beta, const void* sums, float* dy,
+                                          float* dbias, void* scratch, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(rows >= 1 && n >= rows && C >= 4 && y && dout && mean && inv_std && gamma && beta && sums && dy && dbias && scratch, "ocr_bn_relu_bwd_apply_bias: bad argument");
+    OCR_CHECK_ARG((C % 4) == 0 && (256 % (C / 4)) == 0, "ocr_bn_relu_bwd_apply_bias: C / 4 must divide 256 (C = %d)", C);
+    double* ds = reinterpret_cast<double*>(scratch);
+    OCR_CHECK_CUDA(cudaMemsetAsync(ds, 0, sizeof(double) * C, ST(stream)));
+    bn_relu_bwd_apply_kernel<true><<<grid_cap(rows * (C / 4)), 256, 0, ST(stream)>>>(y, dout, rows, n, C, mean, inv_std, gamma, beta, reinterpret_cast<const double*>(sums), dy, ds);
+    OCR_CHECK_LAUNCH();
+    sums_to_float_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(ds, C, dbias, nullptr);
     OCR_CHECK_LAUNCH();
     return OCR_OK;
 }

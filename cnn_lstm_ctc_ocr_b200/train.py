@@ -669,9 +669,13 @@ class Trainer:
                 if self.sync_bn:
                     self._allreduce(sums)
                 dy = da
-                self._c(lib.ocr_bn_relu_bwd_apply(_lib.ptr(S["y"]), _lib.ptr(da), rows, S["n_stat"], filters, *args, _lib.ptr(sums), _lib.ptr(dy), sh),
-                        "ocr_bn_relu_bwd_apply")
-                self._c(lib.ocr_colsum(_lib.ptr(dy), rows, filters, filters, _lib.ptr(G["convnet/%s/bias" % name]), scr, sh), "ocr_colsum")
+                if 256 % (filters // 4) == 0:      # the bias gradient (column sums of dy) comes out of the same pass
+                    self._c(lib.ocr_bn_relu_bwd_apply_bias(_lib.ptr(S["y"]), _lib.ptr(da), rows, S["n_stat"], filters, *args, _lib.ptr(sums), _lib.ptr(dy),
+                                                           _lib.ptr(G["convnet/%s/bias" % name]), scr, sh), "ocr_bn_relu_bwd_apply_bias")
+                else:
+                    self._c(lib.ocr_bn_relu_bwd_apply(_lib.ptr(S["y"]), _lib.ptr(da), rows, S["n_stat"], filters, *args, _lib.ptr(sums), _lib.ptr(dy), sh),
+                            "ocr_bn_relu_bwd_apply")
+                    self._c(lib.ocr_colsum(_lib.ptr(dy), rows, filters, filters, _lib.ptr(G["convnet/%s/bias" % name]), scr, sh), "ocr_colsum")
             else:
                 dy = da
                 self._c(lib.ocr_relu_bwd_bias(_lib.ptr(S["out"]), _lib.ptr(da), rows, filters, _lib.ptr(dy), _lib.ptr(G["convnet/%s/bias" % name]), scr, sh),

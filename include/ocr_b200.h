@@ -263,6 +263,12 @@ int ocr_bn_relu_bwd_sums(const float* y, const float* dout, long long rows, int 
 int ocr_bn_relu_bwd_apply(const float* y, const float* dout, long long rows, long long n, int C, const float* mean,
                           const float* inv_std, const float* gamma, const float* beta, const void* sums, float* dy,
                           ocr_stream_t stream);
+/* ocr_bn_relu_bwd_apply_bias: ocr_bn_relu_bwd_apply that also returns dbias [C] = the per-channel sums of dy (the bias gradient of
+ * the convolution in front of the batch-norm, what ocr_colsum(dy) gives) from the same pass; scratch: C doubles; C / 4 must
+ * divide 256. */
+int ocr_bn_relu_bwd_apply_bias(const float* y, const float* dout, long long rows, long long n, int C, const float* mean,
+                               const float* inv_std, const float* gamma, const float* beta, const void* sums, float* dy,
+                               float* dbias, void* scratch, ocr_stream_t stream);
 int ocr_copy_2d(const float* src, long long ld_src, float* dst, long long ld_dst, long long rows, long long cols, ocr_stream_t stream);
 /* ReLU + bias-add gradients: dy = dout * (out > 0) (dy may alias dout), dbias[c] = sum_rows dy;  ocr_colsum: plain column
  * sums of x [rows, C] (row pitch ldx);  ocr_relu_bwd: dz = g * (z > 0) elementwise. */
@@ -290,11 +296,13 @@ int ocr_adam_step(float* params, const float* grads, float* m, float* v, long lo
  * ocr_birnn_lstm_bwd: back-propagation through time.  dout [T,B,2H]; gates is overwritten with the gradient of the
  * gate pre-activations (zero past each example's length), from which d kernel / d bias / d input follow as dense
  * contractions.  wh_rows [2H, 4H]: rows I.. of the forward cell's TensorFlow kernel, then the backward cell's. */
-/* Tuning aid: programmatic dependent launch on the frame-by-frame BPTT chain on (1, default) / off (0); same bits either way. */
+/* Tuning aid for the frame-by-frame BPTT chain (B > 64), a bit mask; default 1.  Bit 0: programmatic dependent launch (same bits
+ * either way).  Bit 1: float32 / TF32 operands in the recurrent product dG x W_h (clear, the default: bfloat16 operands with
+ * float32 sums; gate gradients within 4e-4 of their max-norm of the TF32 product).  Bits 4..: tile width override (64/128/256). */
 int ocr_debug_bptt_pdl(int on);
-/* Tuning aid: in the persistent BPTT kernel a batch of <= 32 (<= 64) rows is held four (two) times in the 128-row operand
- * tile so that all 128 epilogue threads share the partial-sum reads and the scatter (1, default); 0 = one copy per row.
- * Same bits either way. */
+/* Tuning aid for the persistent BPTT kernel (B <= 64), a bit mask; default 1.  Bit 0: a batch of <= 32 (<= 64) rows is held four
+ * (two) times in the 128-row operand tile so that all 128 epilogue threads share the partial-sum reads, the cell backward and
+ * the scatter (same bits either way).  Bit 1: the partial sums cross L2 as float32 (clear, the default: bfloat16). */
 int ocr_debug_bptt_copies(int on);
 int ocr_birnn_lstm_train_workspace_bytes(int T, int B, int H, size_t* bytes);
 int ocr_birnn_lstm_train_fwd(const float* x, int T, int B, int I, int H, const int32_t* seq_len, const float* wx, const float* wh,

@@ -137,6 +137,16 @@ def test_batch_norm_train_and_backward():
     _close(dgam.cpu().numpy(), gt.grad.numpy(), 1e-5, "dgamma")
     _close(dbet.cpu().numpy(), bt.grad.numpy(), 1e-5, "dbeta")
     _close(dy.cpu().numpy(), yt.grad.numpy(), 2e-5, "dy")
+    # the same pass also yields the bias gradient of the convolution in front (column sums of dy): same dy bits, sums as ocr_colsum's
+    dy2, db2, db_ref = torch.empty((rows, C), device=DEV), torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    scr = torch.zeros(1 << 16, dtype=torch.uint8, device=DEV)
+    L.check(lib.ocr_bn_relu_bwd_apply_bias(L.ptr(d_y), L.ptr(dg), rows, rows, C, L.ptr(d_mean), L.ptr(d_is), L.ptr(d_g), L.ptr(d_b), L.ptr(sums), L.ptr(dy2),
+                                           L.ptr(db2), L.ptr(scr), sh), "bab")
+    L.check(lib.ocr_colsum(L.ptr(dy), rows, C, C, L.ptr(db_ref), L.ptr(scr), sh), "colsum")
+    assert torch.equal(dy2, dy)
+    want = dy.double().sum(0).cpu().numpy()
+    scale = float(dy.double().abs().sum(0).max())       # the sums cancel almost completely (sum of xhat = 0): compare on the scale of the terms
+    assert np.abs(db2.cpu().numpy() - want).max() <= 1e-6 * scale and np.abs(db_ref.cpu().numpy() - want).max() <= 1e-6 * scale
 
 
 def test_relu_bias_colsum_pool_gradients():
