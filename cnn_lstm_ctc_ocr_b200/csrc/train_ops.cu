@@ -229,6 +229,47 @@ bn_relu_apply_kernel(const float* __restrict__ y, long long rows, int C, const f
     }
 }
 
+// z = relu(batch-norm(y)) written to `out` AND the max-pool that follows the layer (window 2x2, stride (2, sw), 'valid';
+// model.py:105-116) written to `pooled`, in one pass over y: the thread of a window's top-left pixel normalises the window's
+// other three pixels too (their y values are its neighbours' own loads: cache hits) and stores the maximum.
+__global__ void __launch_bounds__(256)
+bn_relu_apply_pool_kernel(const float* __restrict__ y, int B, int H, int W, int C, const float* __restrict__ mean, const float* __restrict__ inv_std,
+                          const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out, int sw, int Hp, int Wp,
+                          float* __restrict__ pooled)
+{
+    const int c4n = C >> 2;
+    const long long total = (long long)B * H * W * c4n;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % c4n), c = c4 * 4;
+        long long p = idx / c4n;
+        const int x = (int)(p % W); p /= W;
+        const int yy = (int)(p % H);
+        const int b = (int)(p / H);
+        const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(inv_std + c);
+        const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+        auto act = [&](const float4 v) {
+            float4 o;
+            o.x = fmaxf(ga.x * ((v.x - mu.x) * is.x) + be.x, 0.f);
+            o.y = fmaxf(ga.y * ((v.y - mu.y) * is.y) + be.y, 0.f);
+            o.z = fmaxf(ga.z * ((v.z - mu.z) * is.z) + be.z, 0.f);
+            o.w = fmaxf(ga.w * ((v.w - mu.w) * is.w) + be.w, 0.f);
+            return o;
+        };
+        const float4 z0 = act(reinterpret_cast<const float4*>(y)[idx]);
+        reinterpret_cast<float4*>(out)[idx] = z0;
+        const int py = yy >> 1, px = sw == 2 ? x >> 1 : x;
+        if ((yy & 1) == 0 && py < Hp && px < Wp && (sw == 1 || (x & 1) == 0)) {     // top-left pixel of a window
+            const float4 z1 = act(__ldg(reinterpret_cast<const float4*>(y) + idx + c4n));
+            const float4 z2 = act(__ldg(reinterpret_cast<const float4*>(y) + idx + (long long)W * c4n));
+            const float4 z3 = act(__ldg(reinterpret_cast<const float4*>(y) + idx + (long long)W * c4n + c4n));
+            float4 m;
+            m.x = fmaxf(fmaxf(z0.x, z1.x), fmaxf(z2.x, z3.x)); m.y = fmaxf(fmaxf(z0.y, z1.y), fmaxf(z2.y, z3.y));
+            m.z = fmaxf(fmaxf(z0.z, z1.z), fmaxf(z2.z, z3.z)); m.w = fmaxf(fmaxf(z0.w, z1.w), fmaxf(z2.w, z3.w));
+            reinterpret_cast<float4*>(pooled)[(((size_t)b * Hp + py) * Wp + px) * c4n + c4] = m;
+        }
+    }
+}
+
 // dy = gamma * inv_std * (dz - dbeta/n - xhat * dgamma/n), dz = g * (z > 0)
 // BIAS: also the per-channel sums of dy (the bias gradient of the convolution in front of the batch-norm: one pass less over
 // dy).  The grid stride is a multiple of C/4, so a thread keeps ITS four channels for the whole loop: float partials in
@@ -815,6 +856,19 @@ extern "C" int ocr_bn_relu_apply(const float* y, long long rows, int C, const fl
 {
     OCR_CHECK_ARG(rows >= 1 && C >= 4 && (C % 4) == 0 && y && mean && inv_std && gamma && beta && out, "ocr_bn_relu_apply: bad argument");
     bn_relu_apply_kernel<<<grid_cap(rows * (C / 4)), 256, 0, ST(stream)>>>(y, rows, C, mean, inv_std, gamma, beta, out);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+// ocr_bn_relu_apply followed by ocr_maxpool(2, 2, 2, stride_w) in one pass: out [B,H,W,C] = relu(bn(y)) (kept for the pool's
+// gradient), pooled [B, (H-2)/2+1, (W-2)/stride_w+1, C]
+extern "C" int ocr_bn_relu_apply_pool(const float* y, int B, int H, int W, int C, const float* mean, const float* inv_std, const float* gamma,
+                                      const float* beta, float* out, int stride_w, float* pooled, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(B >= 1 && H >= 2 && W >= 2 && C >= 4 && (C % 4) == 0 && (stride_w == 1 || stride_w == 2) && y && mean && inv_std && gamma && beta && out && pooled,
+                  "ocr_bn_relu_apply_pool: bad argument");
+    const int Hp = (H - 2) / 2 + 1, Wp = (W - 2) / stride_w + 1;
+    bn_relu_apply_pool_kernel<<<grid_cap((long long)B * H * W * (C / 4)), 256, 0, ST(stream)>>>(y, B, H, W, C, mean, inv_std, gamma, beta, out, stride_w, Hp, Wp, pooled);
     OCR_CHECK_LAUNCH();
     return OCR_OK;
 }

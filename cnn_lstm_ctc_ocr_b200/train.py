@@ -473,12 +473,15 @@ class Trainer:
         a = self._new(B, Hh - 2, Ww - 2, w1.shape[-1])
         self._c(lib.ocr_conv1_3x3_valid(_lib.ptr(x), int(is_u8), B, Hh, Ww, _lib.ptr(w1), _lib.ptr(b1), w1.shape[-1], _lib.ptr(a), sh), "ocr_conv1_3x3_valid")
         saved["conv1"] = dict(out=a)
+        names = [lp[3] for lp in LAYER_PARAMS]
+        pre_pooled = None            # the pool in front of this layer, already taken by the previous layer's batch-norm pass
         for (filters, k, padding, name, bn) in LAYER_PARAMS[1:]:
             S = {}
             ph, pw, s_h, s_w = _POOL_BEFORE[name]
             if (ph, pw, s_h, s_w) != (1, 1, 1, 1):
                 S["pool_in"], S["pool"] = a, (ph, pw, s_h, s_w)
-                a = self._pool(a, ph, pw, s_h, s_w)
+                a = pre_pooled if pre_pooled is not None else self._pool(a, ph, pw, s_h, s_w)
+            pre_pooled = None
             S["x"] = a
             wf, _ = self.conv_w[name]
             bias = P["convnet/%s/bias" % name]
@@ -499,8 +502,17 @@ class Trainer:
                 self._c(lib.ocr_bn_finalize(_lib.ptr(sums), n_stat, filters, BN_EPS, BN_MOMENTUM, _lib.ptr(mean), _lib.ptr(inv_std),
                                             _lib.ptr(self.stats[q + "moving_mean"]), _lib.ptr(self.stats[q + "moving_variance"]), sh), "ocr_bn_finalize")
                 a = self._new(*y.shape)
-                self._c(lib.ocr_bn_relu_apply(_lib.ptr(y), rows, filters, _lib.ptr(mean), _lib.ptr(inv_std), _lib.ptr(P[q + "gamma"]),
-                                              _lib.ptr(P[q + "beta"]), _lib.ptr(a), sh), "ocr_bn_relu_apply")
+                nxt = names.index(name) + 1
+                npool = _POOL_BEFORE[names[nxt]] if nxt < len(names) else (1, 1, 1, 1)
+                Bn, Hn, Wn, _ = y.shape
+                if npool[:3] == (2, 2, 2) and Hn >= 2 and Wn >= 2:
+                    # normalise + ReLU + the pool in front of the next layer in one pass over y (model.py:105-116)
+                    pre_pooled = self._new(Bn, (Hn - 2) // 2 + 1, (Wn - 2) // npool[3] + 1, filters)
+                    self._c(lib.ocr_bn_relu_apply_pool(_lib.ptr(y), Bn, Hn, Wn, filters, _lib.ptr(mean), _lib.ptr(inv_std), _lib.ptr(P[q + "gamma"]),
+                                                       _lib.ptr(P[q + "beta"]), _lib.ptr(a), npool[3], _lib.ptr(pre_pooled), sh), "ocr_bn_relu_apply_pool")
+                else:
+                    self._c(lib.ocr_bn_relu_apply(_lib.ptr(y), rows, filters, _lib.ptr(mean), _lib.ptr(inv_std), _lib.ptr(P[q + "gamma"]),
+                                                  _lib.ptr(P[q + "beta"]), _lib.ptr(a), sh), "ocr_bn_relu_apply")
                 S.update(y=y, mean=mean, inv_std=inv_std, out=a, n_stat=n_stat)
             saved[name] = S
         Bn, Hn, Wn, Cn = a.shape

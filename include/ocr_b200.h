@@ -258,6 +258,11 @@ int ocr_bn_finalize(const void* sums, long long n, int C, float eps, float momen
                     float* moving_mean, float* moving_var, ocr_stream_t stream);
 int ocr_bn_relu_apply(const float* y, long long rows, int C, const float* mean, const float* inv_std, const float* gamma,
                       const float* beta, float* out, ocr_stream_t stream);
+/* ocr_bn_relu_apply_pool: ocr_bn_relu_apply followed by ocr_maxpool(2, 2, 2, stride_w) (the pool_layer behind conv2 / conv4 /
+ * conv6, model.py:105-116) in one pass over y: out [B,H,W,C] = relu(bn(y)) (kept: the pool's gradient needs it), pooled
+ * [B, (H-2)/2+1, (W-2)/stride_w+1, C]. */
+int ocr_bn_relu_apply_pool(const float* y, int B, int H, int W, int C, const float* mean, const float* inv_std, const float* gamma,
+                           const float* beta, float* out, int stride_w, float* pooled, ocr_stream_t stream);
 int ocr_bn_relu_bwd_sums(const float* y, const float* dout, long long rows, int C, const float* mean, const float* inv_std,
                          const float* gamma, const float* beta, void* sums, float* dgamma, float* dbeta, ocr_stream_t stream);
 int ocr_bn_relu_bwd_apply(const float* y, const float* dout, long long rows, long long n, int C, const float* mean,

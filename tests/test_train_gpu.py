@@ -149,6 +149,26 @@ def test_batch_norm_train_and_backward():
     assert np.abs(db2.cpu().numpy() - want).max() <= 1e-6 * scale and np.abs(db_ref.cpu().numpy() - want).max() <= 1e-6 * scale
 
 
+@pytest.mark.parametrize("B,H,W,C,sw", [(2, 30, 37, 32, 2), (3, 15, 21, 64, 1), (2, 7, 62, 128, 1), (1, 2, 2, 4, 2), (2, 5, 9, 8, 2)])
+def test_bn_relu_apply_pool_equals_apply_then_pool(B, H, W, C, sw):
+    """ocr_bn_relu_apply_pool == ocr_bn_relu_apply followed by ocr_maxpool(2, 2, 2, sw), bit for bit, and nothing else is written."""
+    L, lib, sh = _lib()
+    rng = np.random.default_rng(B * 100 + W)
+    y = _t(rng.standard_normal((B, H, W, C)) * 2)
+    mean, inv_std = _t(rng.normal(0, 0.5, C)), _t(rng.uniform(0.5, 2, C))
+    gamma, beta = _t(rng.uniform(0.5, 1.5, C)), _t(rng.normal(0, 0.3, C))
+    Hp, Wp = (H - 2) // 2 + 1, (W - 2) // sw + 1
+    z_ref, p_ref = torch.empty((B, H, W, C), device=DEV), torch.empty((B, Hp, Wp, C), device=DEV)
+    L.check(lib.ocr_bn_relu_apply(L.ptr(y), B * H * W, C, L.ptr(mean), L.ptr(inv_std), L.ptr(gamma), L.ptr(beta), L.ptr(z_ref), sh), "apply")
+    L.check(lib.ocr_maxpool(L.ptr(z_ref), B, H, W, C, 2, 2, 2, sw, L.ptr(p_ref), sh), "pool")
+    z = torch.full((B * H * W * C + 16,), float("nan"), device=DEV)
+    pz = torch.full((B * Hp * Wp * C + 16,), float("nan"), device=DEV)
+    L.check(lib.ocr_bn_relu_apply_pool(L.ptr(y), B, H, W, C, L.ptr(mean), L.ptr(inv_std), L.ptr(gamma), L.ptr(beta), L.ptr(z), sw, L.ptr(pz), sh), "fused")
+    torch.cuda.synchronize()
+    assert torch.equal(z[:-16].view(B, H, W, C), z_ref) and torch.isnan(z[-16:]).all()
+    assert torch.equal(pz[:-16].view(B, Hp, Wp, C), p_ref) and torch.isnan(pz[-16:]).all()
+
+
 def test_relu_bias_colsum_pool_gradients():
     L, lib, sh = _lib()
     rng = np.random.default_rng(3)
