@@ -54,7 +54,6 @@ __device__ __forceinline__ void gru_wait_counter(const unsigned* ctr, unsigned t
         unsigned v;
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
         if (v >= target) return;
-        __nanosleep(20);
     }
     __trap();
 }
@@ -145,7 +144,7 @@ gru_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
                 const int s = hf >> 1, ph = hf & 1;
                 if (hf > 0) {
                     gru_wait_counter(counters + d, (unsigned)(NS * MT) * (unsigned)hf);   // every slice / batch tile of this direction published its part
-                    asm volatile("fence.proxy.async;" ::: "memory");                     // generic-proxy writes -> async-proxy (TMA) reads
+                    asm volatile("fence.proxy.async.global;" ::: "memory");              // generic-proxy writes -> async-proxy (TMA) reads (global state space only)
                 }
                 const CUtensorMap* tm = ph ? (d ? &tmR1 : &tmR0) : ((s & 1) ? (d ? &tmH11 : &tmH10) : (d ? &tmH01 : &tmH00));
                 for (int gi = 0; gi < ng; ++gi, ++it) {
