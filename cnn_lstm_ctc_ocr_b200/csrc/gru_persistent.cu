@@ -142,6 +142,11 @@ gru_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
             int it = 0;
             for (int hf = 0; hf < 2 * T; ++hf) {   // half-frames: phase A of frame s = hf/2, then its phase B
                 const int s = hf >> 1, ph = hf & 1;
+                {   // the first group's stage is armed before the grid barrier (see lstm_persistent.cu)
+                    const int st0 = it % n_stages;
+                    if (it >= n_stages) g_mbar_wait(bar_empty + st0 * 8, ((it / n_stages) - 1) & 1);
+                    g_mbar_expect_tx(bar_full + st0 * 8, g_bytes);
+                }
                 if (hf > 0) {
                     gru_wait_counter(counters + d, (unsigned)(NS * MT) * (unsigned)hf);   // every slice / batch tile of this direction published its part
                     asm volatile("fence.proxy.async.global;" ::: "memory");              // generic-proxy writes -> async-proxy (TMA) reads (global state space only)
@@ -149,8 +154,10 @@ gru_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
                 const CUtensorMap* tm = ph ? (d ? &tmR1 : &tmR0) : ((s & 1) ? (d ? &tmH11 : &tmH10) : (d ? &tmH01 : &tmH00));
                 for (int gi = 0; gi < ng; ++gi, ++it) {
                     const int st = it % n_stages;
-                    if (it >= n_stages) g_mbar_wait(bar_empty + st * 8, ((it / n_stages) - 1) & 1);
-                    g_mbar_expect_tx(bar_full + st * 8, g_bytes);
+                    if (gi > 0) {
+                        if (it >= n_stages) g_mbar_wait(bar_empty + st * 8, ((it / n_stages) - 1) & 1);
+                        g_mbar_expect_tx(bar_full + st * 8, g_bytes);
+                    }
                     tma_load_3d(s_a + st * g_bytes, tm, 0, m0, gi * gc, bar_full + st * 8);
                 }
                 if (dual) {   // second MMA issuer: odd k-chunks -> the phase's second accumulator

@@ -139,6 +139,13 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
             for (int k = 0; k < nk; ++k) tma_load_2d(s_w + k * w_bytes, &tmW, k * BK, (d * NS + j) * N, bar_w);
             int it = 0;
             for (int s = 0; s < T; ++s) {
+                // the first group's stage is armed BEFORE the grid barrier (its release by the previous frame's MMAs and the
+                // expect_tx do not depend on the other CTAs): after the barrier only the fence and the request remain
+                {
+                    const int st0 = it % n_stages;
+                    if (it >= n_stages) g_mbar_wait(bar_empty + st0 * 8, ((it / n_stages) - 1) & 1);
+                    g_mbar_expect_tx(bar_full + st0 * 8, g_bytes);
+                }
                 if (s > 0) {
                     wait_counter(counters + d, (unsigned)(NS * MT) * (unsigned)s);   // every slice / batch tile of this direction wrote h_s
                     // generic-proxy writes -> async-proxy (TMA) reads; global state space only (measured: the all-spaces form
@@ -149,8 +156,10 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_con
                 lstm_mark(tl, s, 0);
                 for (int gi = 0; gi < ng; ++gi, ++it) {
                     const int st = it % n_stages;
-                    if (it >= n_stages) g_mbar_wait(bar_empty + st * 8, ((it / n_stages) - 1) & 1);
-                    g_mbar_expect_tx(bar_full + st * 8, g_bytes);
+                    if (gi > 0) {
+                        if (it >= n_stages) g_mbar_wait(bar_empty + st * 8, ((it / n_stages) - 1) & 1);
+                        g_mbar_expect_tx(bar_full + st * 8, g_bytes);
+                    }
                     tma_load_3d(s_a + st * g_bytes, tm, 0, m0, gi * gc, bar_full + st * 8);
                 }
                 lstm_mark(tl, s, 1);
