@@ -23,12 +23,16 @@
 //     copies of the row in the A tile) and the destination slices [rho*NS/R, +NS/R) for the scatter: a quarter (half) of
 //     the loads, arithmetic, stores and TMEM reads per thread, nothing computed twice, sums in the same order (same bits).
 //     The exchange blocks are laid out [4 column groups][128 rows][4 floats]: a warp's 16-byte accesses are contiguous.
-//   * XB (default): the partials cross L2 as bfloat16 ([2 column groups][128 rows][8 values]).  Scatter and gather are bound by
+//   * XB (default): the partials cross L2 as bfloat16 ([2 column groups][128 rows][8 values]; with four row copies
+//     [4 groups][128 rows][4 values], so that a copy's 8-byte loads use whole sectors: the gather is bound by the sectors an SM
+//     pulls through L2, ~35 B/clk).  Scatter and gather are bound by
 //     the bytes an SM writes and reads per frame (64 KB each way at 32 rows: ~2000 + ~3500 of 13400 cycles); bfloat16 keeps
 //     float32's exponent range (gradients) and halves them.  The sums themselves stay float32.
 // Sequence lengths follow dynamic_rnn: an example is touched only while s < len (processing order s = T-1 .. 0), the
 // backward direction visits frame len-1-s at step s; rows past their length contribute zero gate gradients.
 #include <cuda_bf16.h>
+
+#include <type_traits>
 
 #include "gemm_tf32.cuh"
 
@@ -37,6 +41,20 @@ namespace ocr {
 __device__ __forceinline__ unsigned bp_pack2(float lo, float hi) {
     const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<const unsigned*>(&p);
+}
+// WEAK loads of the partials (no L1 allocation).  They are ordered after the other CTAs' stores by the acquire of the polling thread
+// (ld.acquire.gpu invalidates this SM's L1) and the CTA barrier that follows it.  Strong loads (ld.global.cg / ld.relaxed.gpu) do not
+// pipeline: measured ~110 cycles per load and thread, 3600 cycles for the 32 partials of a unit against one round trip for weak loads.
+template <typename T> __device__ __forceinline__ T bp_ld_weak(const void* p);
+template <> __device__ __forceinline__ uint2 bp_ld_weak<uint2>(const void* p) {
+    uint2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+template <> __device__ __forceinline__ uint4 bp_ld_weak<uint4>(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
 }
 __device__ __forceinline__ float bp_lo(unsigned v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bp_hi(unsigned v) { return __uint_as_float(v & 0xffff0000u); }
@@ -56,7 +74,7 @@ __device__ __forceinline__ void bp_wait_counter(const unsigned* ctr, unsigned ta
     for (unsigned it = 0; it < (1u << 27); ++it) {
         unsigned v;
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-        if (v >= target) return;
+        if (v >= target) return;     // (relaxed polls + one fence.acq_rel.gpu at the end measured slower: the fence is a ~1000-cycle membar)
     }
     __trap();
 }
@@ -180,20 +198,20 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW, float* act /*[T*B, 8H]
                     if constexpr (XB) {
                         // bfloat16 blocks [2 groups][128 rows][8 values]: my U units = 32 / 16 / 8 bytes of row `slot`
                         const unsigned char* srcb = reinterpret_cast<const unsigned char*>(part) + (((size_t)((f - 1) & 1) * 2 + d) * part_pd + (((size_t)mt * NS + j) * NS) * part_tile) * 2 +
-                               ((size_t)(u0 >> 3) * 128 + slot) * 16 + (size_t)(u0 & 7) * 2;
+                               (U == 4 ? ((size_t)(u0 >> 2) * 128 + slot) * 8                                   // [4 groups][128 rows][4 values]: my group, whole
+                                       : ((size_t)(u0 >> 3) * 128 + slot) * 16 + (size_t)(u0 & 7) * 2);           // [2 groups][128 rows][8 values]
                         constexpr int NV = U == 16 ? 2 : 1;                  // 16-byte (8-byte for U = 4) loads per source slice
-                        constexpr int JB = 16 / NV;
+                        // loads in flight per thread: a batch comes back in ~2000 cycles whatever its size (measured with the
+                        // timeline), so the batches are as large as the registers allow -- all 32 slices at once for U = 4
+                        constexpr int JB = U == 4 ? 32 : 16 / NV;
+                        using LT = typename std::conditional<U == 4, uint2, uint4>::type;
                         for (int js0 = 0; js0 < NS; js0 += JB) {
-                            uint4 a[JB][NV];
+                            LT a[JB][NV];
 #pragma unroll
                             for (int i = 0; i < JB; ++i)
 #pragma unroll
                                 for (int v = 0; v < NV; ++v)
-                                    if (js0 + i < NS) {
-                                        const unsigned char* p = srcb + (size_t)(js0 + i) * part_tile * 2 + (size_t)v * 128 * 16;
-                                        if constexpr (U == 4) { const uint2 t2 = __ldcg(reinterpret_cast<const uint2*>(p)); a[i][v] = make_uint4(t2.x, t2.y, 0u, 0u); }
-                                        else a[i][v] = __ldcg(reinterpret_cast<const uint4*>(p));
-                                    }
+                                    if (js0 + i < NS) a[i][v] = bp_ld_weak<LT>(srcb + (size_t)(js0 + i) * part_tile * 2 + (size_t)v * 128 * 16);
 #pragma unroll
                             for (int i = 0; i < JB; ++i)
 #pragma unroll
@@ -204,6 +222,7 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW, float* act /*[T*B, 8H]
                                             dh[8 * v + 4] += bp_lo(a[i][v].z); dh[8 * v + 5] += bp_hi(a[i][v].z); dh[8 * v + 6] += bp_lo(a[i][v].w); dh[8 * v + 7] += bp_hi(a[i][v].w);
                                         }
                                     }
+                            if (js0 == 0 && threadIdx.x == 64 && dh[0] != 12345.678f) bp_mark(tl, f, 7);   // (timeline: first batch of partials summed)
                         }
                     } else {
                     constexpr int JB = 16 / (U / 4);
@@ -309,13 +328,23 @@ lstm_bptt_kernel(const __grid_constant__ CUtensorMap tmW, float* act /*[T*B, 8H]
                     if (live && XB) {
 #pragma unroll
                         for (int i = 0; i < 2; ++i) {
-                            uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(part) +
-                                                                 (((size_t)(f & 1) * 2 + d) * part_pd + ((size_t)mt * NS * NS + j) * part_tile + (size_t)(jd0 + i) * NS * part_tile) * 2) + slot;
+                            unsigned char* blk = reinterpret_cast<unsigned char*>(part) +
+                                                 (((size_t)(f & 1) * 2 + d) * part_pd + ((size_t)mt * NS * NS + j) * part_tile + (size_t)(jd0 + i) * NS * part_tile) * 2;
+                            if constexpr (R == 4) {      // [4 groups][128 rows][4 values]
+                                uint2* d2 = reinterpret_cast<uint2*>(blk) + slot;
 #pragma unroll
-                            for (int w = 0; w < 2; ++w) {
-                                const int c = 16 * i + 8 * w;
-                                __stcg(d4 + w * 128, make_uint4(bp_pack2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), bp_pack2(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])),
-                                                                bp_pack2(__uint_as_float(v[c + 4]), __uint_as_float(v[c + 5])), bp_pack2(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7]))));
+                                for (int w = 0; w < 4; ++w) {
+                                    const int c = 16 * i + 4 * w;
+                                    __stcg(d2 + w * 128, make_uint2(bp_pack2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), bp_pack2(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]))));
+                                }
+                            } else {                     // [2 groups][128 rows][8 values]
+                                uint4* d4 = reinterpret_cast<uint4*>(blk) + slot;
+#pragma unroll
+                                for (int w = 0; w < 2; ++w) {
+                                    const int c = 16 * i + 8 * w;
+                                    __stcg(d4 + w * 128, make_uint4(bp_pack2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), bp_pack2(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])),
+                                                                    bp_pack2(__uint_as_float(v[c + 4]), __uint_as_float(v[c + 5])), bp_pack2(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7]))));
+                                }
                             }
                         }
                     }

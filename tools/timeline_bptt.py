@@ -34,4 +34,5 @@ print("B=%d T=%d: frame period %.0f cycles (%.2f us at 1.965 GHz)" % (B, T, per,
 names = ["barrier passed", "partials summed", "cell + A tile + fence", "MMAs issued (MMA lane)", "accumulator ready", "scatter done", "published"]
 for i in range(1, 7):
     print("  %-26s +%6.0f cycles after the previous mark" % (names[i], (fr[:, i] - fr[:, i - 1]).mean()))
+print("  %-26s +%6.0f cycles after the barrier (first batch of 16 partial loads per thread summed)" % ("(first batch)", (fr[:, 7] - fr[:, 0]).mean()))
 print("  %-26s +%6.0f cycles (published -> next frame's barrier passed)" % ("grid barrier", (a[6:T - 2, 0] - a[5:T - 3, 6]).mean()))
