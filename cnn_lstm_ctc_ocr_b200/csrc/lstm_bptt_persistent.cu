@@ -23,6 +23,11 @@
 //     copies of the row in the A tile) and the destination slices [rho*NS/R, +NS/R) for the scatter: a quarter (half) of
 //     the loads, arithmetic, stores and TMEM reads per thread, nothing computed twice, sums in the same order (same bits).
 //     The exchange blocks are laid out [4 column groups][128 rows][4 floats]: a warp's 16-byte accesses are contiguous.
+//   * Measured dead end (kept out): fetching the NS partial blocks with one cp.async.bulk per lane of the idle warp 0 into shared
+//     memory ([row][16 values] blocks, the live rows of a source one contiguous kilobyte) instead of per-thread global loads: the
+//     blocks land 3750 cycles after the counter is seen -- the same as 32 loads per thread (3500; 16 loads: 2000), whether strong,
+//     weak or sector-exact -- and the two-store rows of that layout slow the scatter (1050 -> 2000): frame 12080 -> 14030 cycles.
+//     What the gather waits for is the memory system's turn-around on lines other SMs have just written, not the load instructions.
 //   * XB (default): the partials cross L2 as bfloat16 ([2 column groups][128 rows][8 values]; with four row copies
 //     [4 groups][128 rows][4 values], so that a copy's 8-byte loads use whole sectors: the gather is bound by the sectors an SM
 //     pulls through L2, ~35 B/clk).  Scatter and gather are bound by
