@@ -18,9 +18,9 @@
 //   * the lattice runs in the LINEAR domain on y, register resident: lane i holds the state pair
 //     (blank before label i, label i), one shuffle per frame carries the neighbour state,
 //     the chain per frame is shuffle + 3 dependent FP ops.  Dynamic range is handled with an
-//     exact power-of-two rescale every frame (warp max by one redux.sync, applied one frame
-//     late, exponent summed as an integer) -- no exp/log inside the chain and no rounding from
-//     the scaling;
+//     exact power-of-two rescale every second frame (warp max by one redux.sync, applied two
+//     frames late, exponent summed as an integer; struct Rescale) -- no exp/log inside the chain
+//     and no rounding from the scaling;
 //   * the alpha warp walks forward while the beta warp walks backward; they meet in the middle:
 //     each stores its half of the lattice, then over the other half multiplies its live values
 //     into what the partner stored, so shared memory holds ONE lattice of products
@@ -199,7 +199,27 @@ struct Rescale {
         sc = __uint_as_float((unsigned)(127 - c) << 23);
         mb = __reduce_max_sync(kFullMask, __float_as_uint(mloc));
     }
+    // Every-second-frame form (kCtcRescaleAlt): only the "A" frames carry a factor, the frames between them run
+    // unscaled.  An A frame takes the exponent of the maximum left by the previous A frame (its redux.sync was issued
+    // two frames earlier) as its factor: nothing was applied in between, so c_t = x_{t-2} and the maximum after frame t
+    // is again growth_{t-1} + growth_t -- the same two-frame bound as the every-frame form, with the maximum, the
+    // redux and the exponent arithmetic on half the frames.
+    __device__ __forceinline__ void begin_a() {
+        const int x = (int)(mb >> 23) - 127;
+        c = max(-126, min(126, x));
+        sc = __uint_as_float((unsigned)(127 - c) << 23);
+    }
+    __device__ __forceinline__ void end_a(float mloc) {
+        E += c;
+        mb = __reduce_max_sync(kFullMask, __float_as_uint(mloc));
+    }
 };
+#ifndef OCR_CTC_RESCALE_ALT
+#define OCR_CTC_RESCALE_ALT 1
+#endif
+constexpr bool kCtcRescaleAlt = OCR_CTC_RESCALE_ALT != 0;
+using FrameA = std::true_type;   // chain frame that carries the rescale factor
+using FrameB = std::false_type;  // chain frame without one (every second frame when kCtcRescaleAlt)
 
 // The stored lattice halves are scaled: alpha_t = v_t * 2^Ea_t, beta_t = w_t * 2^Eb_t with max(v), max(w) ~ 1,
 // but the two maxima usually sit on different states, so v*w at the states that matter can be far below the
@@ -612,8 +632,10 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
 #pragma unroll
             for (int j = 0; j < NP; ++j) el_n[j] = lds(pe[j]);
             // one forward step: alpha_t from alpha_{t-1}; stored value v_t = alpha_t * 2^-E
-            auto step = [&](int t, auto masked) {
-                const float sck = rs.sc * kinv;  // staged rows hold y * grad_scale
+            auto step = [&](auto frame) {
+                constexpr bool kA = !kCtcRescaleAlt || decltype(frame)::value;
+                if constexpr (kCtcRescaleAlt && kA) rs.begin_a();
+                const float sck = kA ? rs.sc * kinv : kinv;  // staged rows hold y * grad_scale
                 const float ebs = eb_n * sck;
                 float els[NP];
 #pragma unroll
@@ -636,9 +658,10 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 for (int j = 0; j < NP; ++j) {
                     ab[j] = nbv[j];
                     al[j] = nlv[j];
-                    mloc = fmaxf(mloc, fmaxf(ab[j], al[j]));
+                    if constexpr (kA) mloc = fmaxf(mloc, fmaxf(ab[j], al[j]));
                 }
-                rs.next(mloc);
+                if constexpr (!kCtcRescaleAlt) rs.next(mloc);
+                else if constexpr (kA) rs.end_a(mloc);
             };
             auto store = [&]() {
 #pragma unroll
@@ -663,15 +686,17 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 float mloc = 0.0f;
 #pragma unroll
                 for (int j = 0; j < NP; ++j) mloc = fmaxf(mloc, fmaxf(ab[j], al[j]));
-                rs.next(mloc);
+                if constexpr (kCtcRescaleAlt) rs.end_a(mloc); else rs.next(mloc);
             }
             int t = 1;
             store();  // mid >= 1
             // (no alive-masks: a state that cannot reach the end any more has beta = 0, so its product is zero whatever its
             // alpha; it only takes part in the rescale maximum, and the exactness guard covers that.  The masked loop forms
             // doubled the code of the chains: 9 % of the kernel's stall samples were instruction-cache misses.)
-#pragma unroll 2
-            for (; t < mid; ++t) { step(t, std::false_type()); store(); }
+            // frames in (B, A) pairs; a single frame left over runs as B (one three-frame gap between factors)
+#pragma unroll 1
+            for (; t + 1 < mid; t += 2) { step(FrameB()); store(); step(FrameA()); store(); }
+            if (t < mid) { step(FrameB()); store(); ++t; }
             if constexpr (TL) ctc_mark(tl, 4);
             pair_barrier(1 + s);  // partner has stored beta_t (and its exponents) for t >= mid
             if constexpr (TL) ctc_mark(tl, 5);
@@ -701,12 +726,16 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 pex += LSB;
             };
             if (t < Tb) {
-                step(t, std::false_type());
+                step(FrameB());
                 consume(std::true_type());
                 ++t;
             }
-#pragma unroll 2
-            for (; t < Tb; ++t) { step(t, std::false_type()); consume(std::false_type()); }
+#pragma unroll 1
+            for (; t + 1 < Tb; t += 2) {
+                step(FrameA()); consume(std::false_type());
+                step(FrameB()); consume(std::false_type());
+            }
+            if (t < Tb) { step(FrameA()); consume(std::false_type()); }
             // p(z|x) in e-units: alpha(2L) + alpha(2L-1) at the last frame
             float up = __shfl_up_sync(kFullMask, al[NP - 1], 1);
             if (lane == 0) up = 0.0f;
@@ -754,8 +783,10 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
 #pragma unroll
             for (int j = 0; j < NP; ++j) el_n[j] = lds(pe[j]);
             // one backward step: beta_t from beta_{t+1} and y_{t+1}; stored value w_t = beta_t * 2^-E
-            auto step = [&](int t, auto masked) {
-                const float sck = rs.sc * kinv;  // staged rows hold y * grad_scale
+            auto step = [&](auto frame) {
+                constexpr bool kA = !kCtcRescaleAlt || decltype(frame)::value;
+                if constexpr (kCtcRescaleAlt && kA) rs.begin_a();
+                const float sck = kA ? rs.sc * kinv : kinv;  // staged rows hold y * grad_scale
                 const float ebs = eb_n * sck;
                 float els[NP];
 #pragma unroll
@@ -780,9 +811,10 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                     const float nbl = fmaf(skp[j], nx, fmaf(c1[j], wb[j], wl[j]));
                     bb[j] = nbb;
                     bl[j] = nbl;
-                    mloc = fmaxf(mloc, fmaxf(bb[j], bl[j]));
+                    if constexpr (kA) mloc = fmaxf(mloc, fmaxf(bb[j], bl[j]));
                 }
-                rs.next(mloc);
+                if constexpr (!kCtcRescaleAlt) rs.next(mloc);
+                else if constexpr (kA) rs.end_a(mloc);
             };
             auto store = [&]() {
 #pragma unroll
@@ -797,7 +829,7 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 bb[j] = (i == L) ? 1.0f : 0.0f;
                 bl[j] = (i == L && L >= 1) ? 1.0f : 0.0f;
             }
-            rs.next(1.0f);
+            if constexpr (kCtcRescaleAlt) rs.end_a(1.0f); else rs.next(1.0f);
             int Pt = 0;
             float vl_n[NP], vb_n[NP];
             int ex_n = 0;
@@ -828,14 +860,15 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
             if (t >= mid) {
                 store();
                 --t;
-#pragma unroll 2
-                for (; t >= mid; --t) { step(t, std::false_type()); store(); }
+#pragma unroll 1
+                for (; t - 1 >= mid; t -= 2) { step(FrameB()); store(); step(FrameA()); store(); }
+                if (t >= mid) { step(FrameB()); store(); --t; }
                 if constexpr (TL) ctc_mark(tl, 4);
                 pair_barrier(1 + s);  // partner has stored alpha_t (and its exponents) for t < mid
                 if constexpr (TL) ctc_mark(tl, 5);
                 consume_prefetch();
                 // t = mid - 1 >= 0: the frame where the chains meet fixes Pt
-                step(t, std::false_type());
+                step(FrameB());
                 consume(std::true_type());
                 --t;
             } else {
@@ -844,8 +877,12 @@ ctc_loss_fast_kernel(const float* __restrict__ logits, int T, int B, int C, cons
                 consume(std::true_type());
                 --t;
             }
-#pragma unroll 2
-            for (; t >= 0; --t) { step(t, std::false_type()); consume(std::false_type()); }
+#pragma unroll 1
+            for (; t - 1 >= 0; t -= 2) {
+                step(FrameA()); consume(std::false_type());
+                step(FrameB()); consume(std::false_type());
+            }
+            if (t >= 0) { step(FrameA()); consume(std::false_type()); }
             if (lane == 0) infoi[6] = Pt;
             if constexpr (TL) ctc_mark(tl, 6);
             pair_barrier(1 + s);
