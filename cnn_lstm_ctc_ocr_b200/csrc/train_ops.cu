@@ -272,8 +272,36 @@ bn_relu_apply_pool_kernel(const float* __restrict__ y, int B, int H, int W, int 
 
 // dy = gamma * inv_std * (dz - dbeta/n - xhat * dgamma/n), dz = g * (z > 0)
 // BIAS: also the per-channel sums of dy (the bias gradient of the convolution in front of the batch-norm: one pass less over
-// dy).  The grid stride is a multiple of C/4, so a thread keeps ITS four channels for the whole loop: float partials in
-// registers, one shared-memory pass per CTA, double atomics per channel (as channel_reduce_kernel does).
+// dy).  When C/4 divides 256 the grid stride is a multiple of C/4, so a thread keeps ITS four channels for the whole loop:
+// the per-channel constants (eight of them from float64 sums) are set up once per thread instead of once per element, two
+// elements are in flight per thread, the float partials stay in registers, one shared-memory pass per CTA, double atomics per
+// channel (as channel_reduce_kernel does).  The atomics are C per CTA whatever the tensor size: the BIAS launch uses four waves
+// of CTAs, not sixteen (at per-GPU batch 32 the sixteen-wave grid spent 60-100 us per layer on 1.2 M atomics to 512 addresses).
+struct BnBwdConst { float4 mu, is, ga, be, db, dg; };
+__device__ __forceinline__ BnBwdConst bn_bwd_const(int c, int C, const float* __restrict__ mean, const float* __restrict__ inv_std,
+                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                   const double* __restrict__ sums, double inv_n)
+{
+    BnBwdConst k;
+    k.mu = *reinterpret_cast<const float4*>(mean + c); k.is = *reinterpret_cast<const float4*>(inv_std + c);
+    k.ga = *reinterpret_cast<const float4*>(gamma + c); k.be = *reinterpret_cast<const float4*>(beta + c);
+    k.db = make_float4((float)(sums[c] * inv_n), (float)(sums[c + 1] * inv_n), (float)(sums[c + 2] * inv_n), (float)(sums[c + 3] * inv_n));
+    k.dg = make_float4((float)(sums[C + c] * inv_n), (float)(sums[C + c + 1] * inv_n), (float)(sums[C + c + 2] * inv_n), (float)(sums[C + c + 3] * inv_n));
+    return k;
+}
+__device__ __forceinline__ float4 bn_bwd_one(const float4 yv, const float4 gv, const BnBwdConst& k)
+{
+    float4 o;
+#define OCR_BNB(f)                                                       \
+    {                                                                    \
+        const float xh = (yv.f - k.mu.f) * k.is.f;                       \
+        const float dz = (k.ga.f * xh + k.be.f > 0.f) ? gv.f : 0.f;      \
+        o.f = k.ga.f * k.is.f * (dz - k.db.f - xh * k.dg.f);             \
+    }
+    OCR_BNB(x) OCR_BNB(y) OCR_BNB(z) OCR_BNB(w)
+#undef OCR_BNB
+    return o;
+}
 template <bool BIAS>
 __global__ void __launch_bounds__(256)
 bn_relu_bwd_apply_kernel(const float* __restrict__ y, const float* __restrict__ g, long long rows, long long n, int C, const float* __restrict__ mean,
@@ -284,23 +312,29 @@ bn_relu_bwd_apply_kernel(const float* __restrict__ y, const float* __restrict__ 
     const long long total = rows * c4n;
     const double inv_n = 1.0 / (double)n;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(idx % c4n) * 4;
-        const float4 yv = reinterpret_cast<const float4*>(y)[idx], gv = reinterpret_cast<const float4*>(g)[idx];
-        const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(inv_std + c);
-        const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
-        float4 o;
-#define OCR_BNB(f, k)                                                                    \
-        {                                                                                \
-            const float xh = (yv.f - mu.f) * is.f;                                       \
-            const float dz = (ga.f * xh + be.f > 0.f) ? gv.f : 0.f;                      \
-            const float db = (float)(sums[c + k] * inv_n), dg = (float)(sums[C + c + k] * inv_n); \
-            o.f = ga.f * is.f * (dz - db - xh * dg);                                     \
+    const long long first = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    if ((256 % c4n) == 0) {        // BIAS launches always (checked by the caller)
+        const BnBwdConst k = bn_bwd_const((int)(first % c4n) * 4, C, mean, inv_std, gamma, beta, sums, inv_n);
+        long long idx = first;
+        for (; idx + stride < total; idx += 2 * stride) {
+            const float4 y0 = y4[idx], g0 = g4[idx], y1 = y4[idx + stride], g1 = g4[idx + stride];
+            const float4 o0 = bn_bwd_one(y0, g0, k), o1 = bn_bwd_one(y1, g1, k);
+            reinterpret_cast<float4*>(dy)[idx] = o0;
+            reinterpret_cast<float4*>(dy)[idx + stride] = o1;
+            if (BIAS) { acc.x += o0.x; acc.y += o0.y; acc.z += o0.z; acc.w += o0.w; acc.x += o1.x; acc.y += o1.y; acc.z += o1.z; acc.w += o1.w; }
         }
-        OCR_BNB(x, 0) OCR_BNB(y, 1) OCR_BNB(z, 2) OCR_BNB(w, 3)
-#undef OCR_BNB
-        reinterpret_cast<float4*>(dy)[idx] = o;
-        if (BIAS) { acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+        if (idx < total) {
+            const float4 o = bn_bwd_one(y4[idx], g4[idx], k);
+            reinterpret_cast<float4*>(dy)[idx] = o;
+            if (BIAS) { acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+        }
+    } else {
+        for (long long idx = first; idx < total; idx += stride) {
+            const BnBwdConst k = bn_bwd_const((int)(idx % c4n) * 4, C, mean, inv_std, gamma, beta, sums, inv_n);
+            reinterpret_cast<float4*>(dy)[idx] = bn_bwd_one(y4[idx], g4[idx], k);
+        }
     }
     if (BIAS) {
         __shared__ float4 red[256];
@@ -909,7 +943,7 @@ extern "C" int ocr_bn_relu_bwd_apply_bias(const float* y, const float* dout, lon
     OCR_CHECK_ARG((C % 4) == 0 && (256 % (C / 4)) == 0, "ocr_bn_relu_bwd_apply_bias: C / 4 must divide 256 (C = %d)", C);
     double* ds = reinterpret_cast<double*>(scratch);
     OCR_CHECK_CUDA(cudaMemsetAsync(ds, 0, sizeof(double) * C, ST(stream)));
-    bn_relu_bwd_apply_kernel<true><<<grid_cap(rows * (C / 4)), 256, 0, ST(stream)>>>(y, dout, rows, n, C, mean, inv_std, gamma, beta, reinterpret_cast<const double*>(sums), dy, ds);
+    bn_relu_bwd_apply_kernel<true><<<grid_cap(rows * (C / 4), 256, 4), 256, 0, ST(stream)>>>(y, dout, rows, n, C, mean, inv_std, gamma, beta, reinterpret_cast<const double*>(sums), dy, ds);
     OCR_CHECK_LAUNCH();
     sums_to_float_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(ds, C, dbias, nullptr);
     OCR_CHECK_LAUNCH();
