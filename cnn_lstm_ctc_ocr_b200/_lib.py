@@ -61,6 +61,9 @@ SIGNATURES = {
     "ocr_bn_relu_apply": (_i, [_vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ocr_bn_relu_bwd_sums": (_i, [_vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ocr_bn_relu_apply_pool": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "ocr_bn_relu_apply_pool_arg": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "ocr_bn_relu_bwd_sums_pool": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ocr_bn_relu_bwd_apply_bias_pool": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ocr_bn_relu_bwd_apply": (_i, [_vp, _vp, _ll, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ocr_bn_relu_bwd_apply_bias": (_i, [_vp, _vp, _ll, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ocr_copy_2d": (_i, [_vp, _ll, _vp, _ll, _ll, _ll, _vp]),

@@ -270,6 +270,134 @@ bn_relu_apply_pool_kernel(const float* __restrict__ y, int B, int H, int W, int 
     }
 }
 
+// The same pass WITHOUT the full-size activation: pooled [B,Hp,Wp,C] and, per pooled element, which of its window's four
+// pixels is the FIRST maximum in row-major window order (TensorFlow's MaxPoolGrad rule; 2 bits per channel, the four channels of
+// a float4 in one byte: arg [B,Hp,Wp,C/4]).  With the argument of the maximum kept, the pool's gradient needs neither the
+// activation nor a tensor of its own (pool_arg_grad below): the layer's backward pass reads y and writes dy, nothing else of
+// that size.  One thread per pooled float4; the y values of a window are read once (stride 2) or twice (stride 1, cache hits).
+__global__ void __launch_bounds__(256)
+bn_relu_pool_arg_kernel(const float* __restrict__ y, int B, int H, int W, int C, const float* __restrict__ mean, const float* __restrict__ inv_std,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, int sw, int Hp, int Wp,
+                        float* __restrict__ pooled, unsigned char* __restrict__ arg)
+{
+    const int c4n = C >> 2;
+    const long long total = (long long)B * Hp * Wp * c4n;
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % c4n), c = c4 * 4;
+        long long p = idx / c4n;
+        const int px = (int)(p % Wp); p /= Wp;
+        const int py = (int)(p % Hp);
+        const int b = (int)(p / Hp);
+        const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(inv_std + c);
+        const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+        auto act = [&](const float4 v) {
+            float4 o;
+            o.x = fmaxf(ga.x * ((v.x - mu.x) * is.x) + be.x, 0.f);
+            o.y = fmaxf(ga.y * ((v.y - mu.y) * is.y) + be.y, 0.f);
+            o.z = fmaxf(ga.z * ((v.z - mu.z) * is.z) + be.z, 0.f);
+            o.w = fmaxf(ga.w * ((v.w - mu.w) * is.w) + be.w, 0.f);
+            return o;
+        };
+        const long long i00 = (((long long)b * H + 2 * py) * W + (long long)px * sw) * c4n + c4;
+        const float4 z0 = act(__ldg(y4 + i00)), z1 = act(__ldg(y4 + i00 + c4n));
+        const float4 z2 = act(__ldg(y4 + i00 + (long long)W * c4n)), z3 = act(__ldg(y4 + i00 + (long long)W * c4n + c4n));
+        float4 m = z0;
+        unsigned a = 0;
+#define OCR_PA(f, sh_)                                              \
+        {                                                          \
+            unsigned k = 0;                                        \
+            if (z1.f > m.f) { m.f = z1.f; k = 1; }                 \
+            if (z2.f > m.f) { m.f = z2.f; k = 2; }                 \
+            if (z3.f > m.f) { m.f = z3.f; k = 3; }                 \
+            a |= k << sh_;                                         \
+        }
+        OCR_PA(x, 0) OCR_PA(y, 2) OCR_PA(z, 4) OCR_PA(w, 6)
+#undef OCR_PA
+        reinterpret_cast<float4*>(pooled)[idx] = m;
+        arg[idx] = (unsigned char)a;
+    }
+}
+
+// gradient of the 2x2 / stride (2, sw) max-pool w.r.t. its input pixel (b, yy, x), channels 4*c4 .. 4*c4+3, from the pooled
+// gradient and the arguments of the maxima: the sum over the windows that contain the pixel (one, or two when sw == 1, in
+// ascending window order as maxpool_bwd_kernel adds them) of dpool where the window's first maximum is this pixel.
+__device__ __forceinline__ float4 pool_arg_grad(const float4* __restrict__ dpool4, const unsigned char* __restrict__ arg, int b, int yy, int x,
+                                                int c4, int c4n, int sw, int Hp, int Wp)
+{
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int oy = yy >> 1;
+    if (oy >= Hp) return acc;
+    const unsigned dy = (unsigned)(yy & 1) * 2;
+    auto add = [&](int ox, unsigned code) {
+        const long long o = (((long long)b * Hp + oy) * Wp + ox) * c4n + c4;
+        const unsigned a = arg[o];
+        const float4 d = __ldg(dpool4 + o);
+        if ((a & 3u) == code) acc.x += d.x;
+        if (((a >> 2) & 3u) == code) acc.y += d.y;
+        if (((a >> 4) & 3u) == code) acc.z += d.z;
+        if (((a >> 6) & 3u) == code) acc.w += d.w;
+    };
+    if (sw == 2) {
+        const int ox = x >> 1;
+        if (ox < Wp) add(ox, dy + (unsigned)(x & 1));
+    } else {
+        if (x >= 1 && x - 1 < Wp) add(x - 1, dy + 1u);
+        if (x < Wp) add(x, dy);
+    }
+    return acc;
+}
+
+// ocr_bn_relu_bwd_sums for a layer whose output went through the pool: the gradient w.r.t. the activation is pool_arg_grad,
+// never materialised.  float4 form (a thread keeps its four channels: 256 % (C/4) == 0), Kahan-compensated float partials per
+// thread, one shared-memory pass per CTA, double atomics per channel.
+__global__ void __launch_bounds__(256)
+bn_bwd_sums_pool_kernel(const float* __restrict__ y, const float* __restrict__ dpool, const unsigned char* __restrict__ arg, int B, int H, int W,
+                        int C, int sw, int Hp, int Wp, const float* __restrict__ mean, const float* __restrict__ inv_std,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, double* __restrict__ sums /*[2][C]*/)
+{
+    const int c4n = C >> 2;
+    const long long total = (long long)B * H * W * c4n;
+    const long long first = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    const int c4 = (int)(first % c4n), c = c4 * 4;
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(inv_std + c);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c), be = *reinterpret_cast<const float4*>(beta + c);
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    const float4* dpool4 = reinterpret_cast<const float4*>(dpool);
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, k0[4] = {0.f, 0.f, 0.f, 0.f}, k1[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long idx = first; idx < total; idx += stride) {
+        unsigned p = (unsigned)(idx / c4n);                 // pixel index < 2^31 (checked by the caller)
+        const int x = (int)(p % (unsigned)W); p /= (unsigned)W;
+        const int yy = (int)(p % (unsigned)H);
+        const int b = (int)(p / (unsigned)H);
+        const float4 yv = y4[idx];
+        const float4 gv = pool_arg_grad(dpool4, arg, b, yy, x, c4, c4n, sw, Hp, Wp);
+#define OCR_BS(f, j)                                                                   \
+        {                                                                              \
+            const float xh = (yv.f - mu.f) * is.f;                                     \
+            const float dz = (ga.f * xh + be.f > 0.f) ? gv.f : 0.f;                    \
+            { const float v = dz - k0[j]; const float t = s0[j] + v; k0[j] = (t - s0[j]) - v; s0[j] = t; }       \
+            { const float v = dz * xh - k1[j]; const float t = s1[j] + v; k1[j] = (t - s1[j]) - v; s1[j] = t; }  \
+        }
+        OCR_BS(x, 0) OCR_BS(y, 1) OCR_BS(z, 2) OCR_BS(w, 3)
+#undef OCR_BS
+    }
+    __shared__ float4 red0[256], red1[256];
+    red0[threadIdx.x] = make_float4(s0[0], s0[1], s0[2], s0[3]);
+    red1[threadIdx.x] = make_float4(s1[0], s1[1], s1[2], s1[3]);
+    __syncthreads();
+    if ((int)threadIdx.x < c4n) {
+        double t0[4] = {0.0, 0.0, 0.0, 0.0}, t1[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int k = threadIdx.x; k < 256; k += c4n) {
+            t0[0] += (double)red0[k].x; t0[1] += (double)red0[k].y; t0[2] += (double)red0[k].z; t0[3] += (double)red0[k].w;
+            t1[0] += (double)red1[k].x; t1[1] += (double)red1[k].y; t1[2] += (double)red1[k].z; t1[3] += (double)red1[k].w;
+        }
+        const int cc = (int)threadIdx.x * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { atomicAdd(sums + cc + j, t0[j]); atomicAdd(sums + C + cc + j, t1[j]); }
+    }
+}
+
 // dy = gamma * inv_std * (dz - dbeta/n - xhat * dgamma/n), dz = g * (z > 0)
 // BIAS: also the per-channel sums of dy (the bias gradient of the convolution in front of the batch-norm: one pass less over
 // dy).  When C/4 divides 256 the grid stride is a multiple of C/4, so a thread keeps ITS four channels for the whole loop:
@@ -346,6 +474,42 @@ bn_relu_bwd_apply_kernel(const float* __restrict__ y, const float* __restrict__ 
             const int c = (int)threadIdx.x * 4;
             atomicAdd(dy_sums + c, t0); atomicAdd(dy_sums + c + 1, t1); atomicAdd(dy_sums + c + 2, t2); atomicAdd(dy_sums + c + 3, t3);
         }
+    }
+}
+
+// bn_relu_bwd_apply_kernel<true> with the gradient w.r.t. the activation taken from the pool (pool_arg_grad)
+__global__ void __launch_bounds__(256)
+bn_relu_bwd_apply_pool_kernel(const float* __restrict__ y, const float* __restrict__ dpool, const unsigned char* __restrict__ arg, int B, int H,
+                              int W, int C, int sw, int Hp, int Wp, long long n, const float* __restrict__ mean,
+                              const float* __restrict__ inv_std, const float* __restrict__ gamma, const float* __restrict__ beta,
+                              const double* __restrict__ sums, float* __restrict__ dy, double* __restrict__ dy_sums)
+{
+    const int c4n = C >> 2;
+    const long long total = (long long)B * H * W * c4n;
+    const double inv_n = 1.0 / (double)n;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long first = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    const float4* dpool4 = reinterpret_cast<const float4*>(dpool);
+    const int c4 = (int)(first % c4n);
+    const BnBwdConst k = bn_bwd_const(c4 * 4, C, mean, inv_std, gamma, beta, sums, inv_n);
+    for (long long idx = first; idx < total; idx += stride) {
+        unsigned p = (unsigned)(idx / c4n);
+        const int x = (int)(p % (unsigned)W); p /= (unsigned)W;
+        const int yy = (int)(p % (unsigned)H);
+        const int b = (int)(p / (unsigned)H);
+        const float4 o = bn_bwd_one(y4[idx], pool_arg_grad(dpool4, arg, b, yy, x, c4, c4n, sw, Hp, Wp), k);
+        reinterpret_cast<float4*>(dy)[idx] = o;
+        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    __shared__ float4 red[256];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if ((int)threadIdx.x < c4n) {
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+        for (int kk = threadIdx.x; kk < 256; kk += c4n) { t0 += (double)red[kk].x; t1 += (double)red[kk].y; t2 += (double)red[kk].z; t3 += (double)red[kk].w; }
+        const int c = (int)threadIdx.x * 4;
+        atomicAdd(dy_sums + c, t0); atomicAdd(dy_sums + c + 1, t1); atomicAdd(dy_sums + c + 2, t2); atomicAdd(dy_sums + c + 3, t3);
     }
 }
 
@@ -949,6 +1113,59 @@ extern "C" int ocr_bn_relu_bwd_apply_bias(const float* y, const float* dout, lon
     OCR_CHECK_LAUNCH();
     return OCR_OK;
 }
+
+// ---- the pooled batch-norm layers without the full-size activation and without a pool-gradient tensor (see bn_relu_pool_arg_kernel)
+#define OCR_POOL_ARG_SHAPE(fn)                                                                                                              \
+    OCR_CHECK_ARG(B >= 1 && H >= 2 && W >= 2 && C >= 4 && (C % 4) == 0 && (256 % (C / 4)) == 0 && (stride_w == 1 || stride_w == 2) &&       \
+                  (long long)B * H * W < 0x7fffffffLL, fn ": bad shape B=%d H=%d W=%d C=%d stride_w=%d (C / 4 must divide 256)", B, H, W, C, stride_w)
+
+extern "C" int ocr_bn_relu_apply_pool_arg(const float* y, int B, int H, int W, int C, const float* mean, const float* inv_std, const float* gamma,
+                                          const float* beta, int stride_w, float* pooled, void* arg, ocr_stream_t stream)
+{
+    OCR_POOL_ARG_SHAPE("ocr_bn_relu_apply_pool_arg");
+    OCR_CHECK_ARG(y && mean && inv_std && gamma && beta && pooled && arg, "ocr_bn_relu_apply_pool_arg: NULL argument");
+    const int Hp = (H - 2) / 2 + 1, Wp = (W - 2) / stride_w + 1;
+    bn_relu_pool_arg_kernel<<<grid_cap((long long)B * Hp * Wp * (C / 4)), 256, 0, ST(stream)>>>(y, B, H, W, C, mean, inv_std, gamma, beta, stride_w, Hp, Wp, pooled,
+                                                                                            reinterpret_cast<unsigned char*>(arg));
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+extern "C" int ocr_bn_relu_bwd_sums_pool(const float* y, const float* dpooled, const void* arg, int B, int H, int W, int C, int stride_w,
+                                         const float* mean, const float* inv_std, const float* gamma, const float* beta, void* sums,
+                                         float* dgamma, float* dbeta, ocr_stream_t stream)
+{
+    OCR_POOL_ARG_SHAPE("ocr_bn_relu_bwd_sums_pool");
+    OCR_CHECK_ARG(y && dpooled && arg && mean && inv_std && gamma && beta && sums && dgamma && dbeta, "ocr_bn_relu_bwd_sums_pool: NULL argument");
+    const int Hp = (H - 2) / 2 + 1, Wp = (W - 2) / stride_w + 1;
+    OCR_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, ST(stream)));
+    bn_bwd_sums_pool_kernel<<<grid_cap((long long)B * H * W * (C / 4), 256, 4), 256, 0, ST(stream)>>>(
+        y, dpooled, reinterpret_cast<const unsigned char*>(arg), B, H, W, C, stride_w, Hp, Wp, mean, inv_std, gamma, beta, reinterpret_cast<double*>(sums));
+    OCR_CHECK_LAUNCH();
+    sums_to_float_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(reinterpret_cast<const double*>(sums), C, dbeta, dgamma);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+extern "C" int ocr_bn_relu_bwd_apply_bias_pool(const float* y, const float* dpooled, const void* arg, int B, int H, int W, int C, int stride_w,
+                                               long long n, const float* mean, const float* inv_std, const float* gamma, const float* beta,
+                                               const void* sums, float* dy, float* dbias, void* scratch, ocr_stream_t stream)
+{
+    OCR_POOL_ARG_SHAPE("ocr_bn_relu_bwd_apply_bias_pool");
+    OCR_CHECK_ARG(n >= (long long)B * H * W && y && dpooled && arg && mean && inv_std && gamma && beta && sums && dy && dbias && scratch,
+                  "ocr_bn_relu_bwd_apply_bias_pool: bad argument");
+    const int Hp = (H - 2) / 2 + 1, Wp = (W - 2) / stride_w + 1;
+    double* ds = reinterpret_cast<double*>(scratch);
+    OCR_CHECK_CUDA(cudaMemsetAsync(ds, 0, sizeof(double) * C, ST(stream)));
+    bn_relu_bwd_apply_pool_kernel<<<grid_cap((long long)B * H * W * (C / 4), 256, 4), 256, 0, ST(stream)>>>(
+        y, dpooled, reinterpret_cast<const unsigned char*>(arg), B, H, W, C, stride_w, Hp, Wp, n, mean, inv_std, gamma, beta,
+        reinterpret_cast<const double*>(sums), dy, ds);
+    OCR_CHECK_LAUNCH();
+    sums_to_float_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(ds, C, dbias, nullptr);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+#undef OCR_POOL_ARG_SHAPE
 
 extern "C" int ocr_copy_2d(const float* src, long long ld_src, float* dst, long long ld_dst, long long rows, long long cols, ocr_stream_t stream)
 {

@@ -134,6 +134,9 @@ class Trainer:
         # all-reduce / Adam), while the chain of input gradients -- above all the frame-by-frame BPTT loops -- leaves most
         # SMs idle: the transposes and split-K contractions of every layer's weight gradient run on a side stream.
         self.overlap = bool(overlap_weight_gradients)
+        # pooled batch-norm layers keep the arguments of the pool's maxima instead of the full-size activation (tests switch it
+        # off to compare with the separate max-pool gradient)
+        self.pool_arg = True
         self.side = torch.cuda.Stream(device=dev) if self.overlap else None
         self.scratch_side = torch.zeros_like(self.scratch)
         self._side_keep = []
@@ -475,13 +478,16 @@ class Trainer:
         saved["conv1"] = dict(out=a)
         names = [lp[3] for lp in LAYER_PARAMS]
         pre_pooled = None            # the pool in front of this layer, already taken by the previous layer's batch-norm pass
+        pre_arg = None               # ... and the arguments of its maxima (ocr_bn_relu_apply_pool_arg)
         for (filters, k, padding, name, bn) in LAYER_PARAMS[1:]:
             S = {}
             ph, pw, s_h, s_w = _POOL_BEFORE[name]
             if (ph, pw, s_h, s_w) != (1, 1, 1, 1):
                 S["pool_in"], S["pool"] = a, (ph, pw, s_h, s_w)
                 a = pre_pooled if pre_pooled is not None else self._pool(a, ph, pw, s_h, s_w)
-            pre_pooled = None
+                if pre_arg is not None:
+                    saved[pre_arg[0]]["pool_arg"] = pre_arg[1:]     # the layer in front back-propagates through this pool itself
+            pre_pooled = pre_arg = None
             S["x"] = a
             wf, _ = self.conv_w[name]
             bias = P["convnet/%s/bias" % name]
@@ -501,16 +507,28 @@ class Trainer:
                 mean, inv_std = self._new(filters), self._new(filters)
                 self._c(lib.ocr_bn_finalize(_lib.ptr(sums), n_stat, filters, BN_EPS, BN_MOMENTUM, _lib.ptr(mean), _lib.ptr(inv_std),
                                             _lib.ptr(self.stats[q + "moving_mean"]), _lib.ptr(self.stats[q + "moving_variance"]), sh), "ocr_bn_finalize")
-                a = self._new(*y.shape)
                 nxt = names.index(name) + 1
                 npool = _POOL_BEFORE[names[nxt]] if nxt < len(names) else (1, 1, 1, 1)
                 Bn, Hn, Wn, _ = y.shape
-                if npool[:3] == (2, 2, 2) and Hn >= 2 and Wn >= 2:
-                    # normalise + ReLU + the pool in front of the next layer in one pass over y (model.py:105-116)
+                fused_pool = npool[:3] == (2, 2, 2) and npool[3] in (1, 2) and Hn >= 2 and Wn >= 2
+                if fused_pool and self.pool_arg and 256 % (filters // 4) == 0 and Bn * Hn * Wn < 2 ** 31 - 1:
+                    # normalise + ReLU + the pool in front of the next layer in one pass over y (model.py:105-116); the full-size
+                    # activation is never written: the arguments of the maxima (a byte per four pooled channels) carry the pool's
+                    # gradient into this layer's batch-norm backward
+                    Hp_, Wp_ = (Hn - 2) // 2 + 1, (Wn - 2) // npool[3] + 1
+                    pre_pooled = self._new(Bn, Hp_, Wp_, filters)
+                    arg = torch.empty(Bn * Hp_ * Wp_ * (filters // 4), dtype=torch.uint8, device=self.device)
+                    self._c(lib.ocr_bn_relu_apply_pool_arg(_lib.ptr(y), Bn, Hn, Wn, filters, _lib.ptr(mean), _lib.ptr(inv_std), _lib.ptr(P[q + "gamma"]),
+                                                           _lib.ptr(P[q + "beta"]), npool[3], _lib.ptr(pre_pooled), _lib.ptr(arg), sh), "ocr_bn_relu_apply_pool_arg")
+                    pre_arg = (name, arg, (Bn, Hn, Wn, filters), npool[3])
+                    a = None
+                elif fused_pool:
+                    a = self._new(*y.shape)
                     pre_pooled = self._new(Bn, (Hn - 2) // 2 + 1, (Wn - 2) // npool[3] + 1, filters)
                     self._c(lib.ocr_bn_relu_apply_pool(_lib.ptr(y), Bn, Hn, Wn, filters, _lib.ptr(mean), _lib.ptr(inv_std), _lib.ptr(P[q + "gamma"]),
                                                        _lib.ptr(P[q + "beta"]), _lib.ptr(a), npool[3], _lib.ptr(pre_pooled), sh), "ocr_bn_relu_apply_pool")
                 else:
+                    a = self._new(*y.shape)
                     self._c(lib.ocr_bn_relu_apply(_lib.ptr(y), rows, filters, _lib.ptr(mean), _lib.ptr(inv_std), _lib.ptr(P[q + "gamma"]),
                                                   _lib.ptr(P[q + "beta"]), _lib.ptr(a), sh), "ocr_bn_relu_apply")
                 S.update(y=y, mean=mean, inv_std=inv_std, out=a, n_stat=n_stat)
@@ -672,7 +690,23 @@ class Trainer:
             S = saved[name]
             xin = S["x"]
             rows = da.numel() // filters
-            if bn:
+            if bn and "pool_arg" in S:
+                # the gradient w.r.t. the activation is MaxPoolGrad(dpool): formed from the arguments of the maxima inside the two
+                # batch-norm backward passes (dpool = the input gradient of the layer behind the pool, held in `da`)
+                q = "convnet/%s/batch_norm/" % name
+                arg, (Bn, Hn, Wn, _), sw_ = S["pool_arg"]
+                rows = Bn * Hn * Wn
+                sums = torch.empty(2 * filters, dtype=torch.float64, device=self.device)
+                args = (_lib.ptr(S["mean"]), _lib.ptr(S["inv_std"]), _lib.ptr(P[q + "gamma"]), _lib.ptr(P[q + "beta"]))
+                self._c(lib.ocr_bn_relu_bwd_sums_pool(_lib.ptr(S["y"]), _lib.ptr(da), _lib.ptr(arg), Bn, Hn, Wn, filters, sw_, *args, _lib.ptr(sums),
+                                                      _lib.ptr(G[q + "gamma"]), _lib.ptr(G[q + "beta"]), sh), "ocr_bn_relu_bwd_sums_pool")
+                if self.sync_bn:
+                    self._allreduce(sums)
+                dy = self._new(Bn, Hn, Wn, filters)
+                self._c(lib.ocr_bn_relu_bwd_apply_bias_pool(_lib.ptr(S["y"]), _lib.ptr(da), _lib.ptr(arg), Bn, Hn, Wn, filters, sw_, S["n_stat"], *args,
+                                                            _lib.ptr(sums), _lib.ptr(dy), _lib.ptr(G["convnet/%s/bias" % name]), scr, sh),
+                        "ocr_bn_relu_bwd_apply_bias_pool")
+            elif bn:
                 q = "convnet/%s/batch_norm/" % name
                 sums = torch.empty(2 * filters, dtype=torch.float64, device=self.device)
                 args = (_lib.ptr(S["mean"]), _lib.ptr(S["inv_std"]), _lib.ptr(P[q + "gamma"]), _lib.ptr(P[q + "beta"]))
@@ -696,7 +730,9 @@ class Trainer:
                 self._conv_wgrad(xin, dy, name)
             _, wd = self.conv_w[name]
             dxin = self._conv(dy, wd, self.zero_bias, xin.shape[3], relu=False)
-            if "pool" in S:
+            if "pool" in S and S["pool_in"] is None:
+                da = dxin                  # the layer in front takes the pool's gradient from its stored arguments of the maxima
+            elif "pool" in S:
                 ph, pw, s_h, s_w = S["pool"]
                 pin = S["pool_in"]
                 da = self._new(*pin.shape)

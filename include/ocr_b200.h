@@ -274,6 +274,21 @@ int ocr_bn_relu_bwd_apply(const float* y, const float* dout, long long rows, lon
 int ocr_bn_relu_bwd_apply_bias(const float* y, const float* dout, long long rows, long long n, int C, const float* mean,
                                const float* inv_std, const float* gamma, const float* beta, const void* sums, float* dy,
                                float* dbias, void* scratch, ocr_stream_t stream);
+/* The pooled batch-norm layers (conv2 / conv4 / conv6, model.py:105-116) without the full-size activation and without a tensor for
+ * the pool's gradient.  C / 4 must divide 256; pool window 2x2, stride (2, stride_w), 'valid'.
+ *   ocr_bn_relu_apply_pool_arg       pooled [B,Hp,Wp,C] = maxpool(relu(bn(y))) and arg [B,Hp,Wp,C/4] BYTES: per pooled element
+ *                                    which window pixel (row-major 0..3) holds the first maximum -- TensorFlow's MaxPoolGrad
+ *                                    rule -- two bits per channel, the four channels of a float4 in one byte
+ *   ocr_bn_relu_bwd_sums_pool        ocr_bn_relu_bwd_sums with dout = MaxPoolGrad(dpooled) formed on the fly from arg
+ *   ocr_bn_relu_bwd_apply_bias_pool  ocr_bn_relu_bwd_apply_bias, likewise (dy [B,H,W,C]; scratch: C doubles) */
+int ocr_bn_relu_apply_pool_arg(const float* y, int B, int H, int W, int C, const float* mean, const float* inv_std, const float* gamma,
+                               const float* beta, int stride_w, float* pooled, void* arg, ocr_stream_t stream);
+int ocr_bn_relu_bwd_sums_pool(const float* y, const float* dpooled, const void* arg, int B, int H, int W, int C, int stride_w,
+                              const float* mean, const float* inv_std, const float* gamma, const float* beta, void* sums,
+                              float* dgamma, float* dbeta, ocr_stream_t stream);
+int ocr_bn_relu_bwd_apply_bias_pool(const float* y, const float* dpooled, const void* arg, int B, int H, int W, int C, int stride_w,
+                                    long long n, const float* mean, const float* inv_std, const float* gamma, const float* beta,
+                                    const void* sums, float* dy, float* dbias, void* scratch, ocr_stream_t stream);
 int ocr_copy_2d(const float* src, long long ld_src, float* dst, long long ld_dst, long long rows, long long cols, ocr_stream_t stream);
 /* ReLU + bias-add gradients: dy = dout * (out > 0) (dy may alias dout), dbias[c] = sum_rows dy;  ocr_colsum: plain column
  * sums of x [rows, C] (row pitch ldx);  ocr_relu_bwd: dz = g * (z > 0) elementwise. */

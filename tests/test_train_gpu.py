@@ -169,6 +169,57 @@ def test_bn_relu_apply_pool_equals_apply_then_pool(B, H, W, C, sw):
     assert torch.equal(pz[:-16].view(B, Hp, Wp, C), p_ref) and torch.isnan(pz[-16:]).all()
 
 
+@pytest.mark.parametrize("B,H,W,C,sw", [(2, 30, 37, 32, 2), (3, 15, 21, 64, 1), (2, 7, 62, 128, 1), (1, 2, 2, 4, 2), (2, 5, 9, 8, 2), (1, 3, 126, 256, 1)])
+def test_pool_arg_path_equals_separate_pool_gradient(B, H, W, C, sw):
+    """Pooled batch-norm layer without the full-size activation: ocr_bn_relu_apply_pool_arg gives the bits of apply + maxpool, and
+    the two backward passes that form MaxPoolGrad from the stored arguments of the maxima give the bits (dy) / the sums (float64
+    accumulators, 1e-6) of ocr_maxpool_bwd followed by ocr_bn_relu_bwd_sums / _apply_bias.  Values are quantised so that windows
+    hold ties (TensorFlow's first-maximum rule decides) and whole windows of zeros."""
+    L, lib, sh = _lib()
+    rng = np.random.default_rng(B * 1000 + W * 10 + C)
+    y = _t(np.round(rng.standard_normal((B, H, W, C)) * 2) / 2)
+    mean, inv_std = _t(np.round(rng.normal(0, 0.5, C) * 2) / 2), _t(rng.choice([0.5, 1.0, 2.0], C))
+    gamma, beta = _t(rng.choice([0.5, 1.0, 1.5], C)), _t(np.round(rng.normal(0, 0.3, C) * 2) / 2)
+    Hp, Wp = (H - 2) // 2 + 1, (W - 2) // sw + 1
+    rows = B * H * W
+    z_ref, p_ref = torch.empty((B, H, W, C), device=DEV), torch.empty((B, Hp, Wp, C), device=DEV)
+    L.check(lib.ocr_bn_relu_apply(L.ptr(y), rows, C, L.ptr(mean), L.ptr(inv_std), L.ptr(gamma), L.ptr(beta), L.ptr(z_ref), sh), "apply")
+    L.check(lib.ocr_maxpool(L.ptr(z_ref), B, H, W, C, 2, 2, 2, sw, L.ptr(p_ref), sh), "pool")
+    pz = torch.full((B * Hp * Wp * C + 16,), float("nan"), device=DEV)
+    arg = torch.full((B * Hp * Wp * (C // 4) + 16,), 0xEE, dtype=torch.uint8, device=DEV)
+    L.check(lib.ocr_bn_relu_apply_pool_arg(L.ptr(y), B, H, W, C, L.ptr(mean), L.ptr(inv_std), L.ptr(gamma), L.ptr(beta), sw, L.ptr(pz), L.ptr(arg), sh), "fwd")
+    torch.cuda.synchronize()
+    assert torch.equal(pz[:-16].view(B, Hp, Wp, C), p_ref) and torch.isnan(pz[-16:]).all() and (arg[-16:] == 0xEE).all()
+    assert (z_ref == 0).float().mean() > 0.2      # the case does hold zero windows / ties
+    # backward, reference: separate pool gradient, then the two batch-norm passes
+    dpool = _t(rng.standard_normal((B, Hp, Wp, C)))
+    da = torch.empty_like(z_ref)
+    L.check(lib.ocr_maxpool_bwd(L.ptr(z_ref), L.ptr(dpool), B, H, W, C, 2, 2, 2, sw, L.ptr(da), sh), "pool bwd")
+    sums_ref = torch.empty(2 * C, dtype=torch.float64, device=DEV)
+    dg_ref, db_ref = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    L.check(lib.ocr_bn_relu_bwd_sums(L.ptr(y), L.ptr(da), rows, C, L.ptr(mean), L.ptr(inv_std), L.ptr(gamma), L.ptr(beta), L.ptr(sums_ref),
+                                     L.ptr(dg_ref), L.ptr(db_ref), sh), "sums")
+    dy_ref, dbias_ref = torch.empty_like(z_ref), torch.empty(C, device=DEV)
+    scratch = torch.zeros(2 * C, dtype=torch.float64, device=DEV)
+    L.check(lib.ocr_bn_relu_bwd_apply_bias(L.ptr(y), L.ptr(da), rows, rows, C, L.ptr(mean), L.ptr(inv_std), L.ptr(gamma), L.ptr(beta), L.ptr(sums_ref),
+                                           L.ptr(dy_ref), L.ptr(dbias_ref), L.ptr(scratch), sh), "apply bias")
+    # fused
+    sums = torch.empty(2 * C, dtype=torch.float64, device=DEV)
+    dg, db = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    L.check(lib.ocr_bn_relu_bwd_sums_pool(L.ptr(y), L.ptr(dpool), L.ptr(arg), B, H, W, C, sw, L.ptr(mean), L.ptr(inv_std), L.ptr(gamma), L.ptr(beta),
+                                          L.ptr(sums), L.ptr(dg), L.ptr(db), sh), "sums pool")
+    dy = torch.full((rows * C + 16,), float("nan"), device=DEV)
+    dbias = torch.empty(C, device=DEV)
+    L.check(lib.ocr_bn_relu_bwd_apply_bias_pool(L.ptr(y), L.ptr(dpool), L.ptr(arg), B, H, W, C, sw, rows, L.ptr(mean), L.ptr(inv_std), L.ptr(gamma),
+                                                L.ptr(beta), L.ptr(sums_ref), L.ptr(dy), L.ptr(dbias), L.ptr(scratch), sh), "apply bias pool")
+    torch.cuda.synchronize()
+    scale = float(sums_ref.abs().max()) + 1.0
+    assert float((sums - sums_ref).abs().max()) <= 1e-6 * scale
+    assert float((dg - dg_ref).abs().max()) <= 1e-6 * scale and float((db - db_ref).abs().max()) <= 1e-6 * scale
+    assert torch.equal(dy[:-16].view(B, H, W, C), dy_ref) and torch.isnan(dy[-16:]).all()
+    assert float((dbias - dbias_ref).abs().max()) <= 1e-5 * (float(dbias_ref.abs().max()) + 1.0)
+
+
 def test_relu_bias_colsum_pool_gradients():
     L, lib, sh = _lib()
     rng = np.random.default_rng(3)
@@ -386,6 +437,25 @@ def test_train_step_vs_oracle(B, cell, sizes):
     assert np.isfinite(last) and last < loss
     m = tr.to_model()
     assert len(m.recognize(torch.tensor(img, device=DEV), torch.tensor(widths))) == len(labels)
+
+
+def test_pool_arg_step_matches_separate_pool_step():
+    """The whole backward pass with the pooled layers on the arguments-of-the-maxima path against the same pass with the
+    full-size activations and ocr_maxpool_bwd: same losses bit for bit (the forward bits are the same), gradients equal up to the
+    summation order of the batch-norm sums (float64 accumulators of float partials)."""
+    from cnn_lstm_ctc_ocr_b200 import train
+    params, img, widths, labels = _small_problem(B=4, cell="lstm", sizes=(32, 32))
+    out = []
+    for flag in (True, False):
+        tr = train.Trainer(params, cell_type="lstm", rnn_sizes=(32, 32))
+        tr.pool_arg = flag
+        losses = tr.forward_backward(torch.tensor(img, device=DEV), widths, labels)
+        torch.cuda.synchronize()
+        out.append((losses.cpu().numpy(), {k: v.cpu().numpy().copy() for k, v in tr.grads.items()}))
+    assert np.array_equal(out[0][0], out[1][0])
+    for k, g in out[0][1].items():
+        ref = out[1][1][k]
+        assert np.abs(g - ref).max() <= 2e-5 * (np.abs(ref).max() + 1e-12), k
 
 
 def test_captured_step_matches_eager_step():
