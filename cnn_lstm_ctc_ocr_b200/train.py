@@ -137,6 +137,7 @@ class Trainer:
         # pooled batch-norm layers keep the arguments of the pool's maxima instead of the full-size activation (tests switch it
         # off to compare with the separate max-pool gradient)
         self.pool_arg = True
+        self.early_planar = True     # planar copies of the conv inputs (weight-gradient operands) made during the recurrent layers
         self.side = torch.cuda.Stream(device=dev) if self.overlap else None
         self.scratch_side = torch.zeros_like(self.scratch)
         self._side_keep = []
@@ -385,14 +386,14 @@ class Trainer:
         self._c(self.lib.ocr_nhwc_to_planar_pad(_lib.ptr(x), B, H, W, C, _lib.ptr(out), R, ncopies, C * R, self._sh()), "ocr_nhwc_to_planar_pad")
         return out, R
 
-    def _conv_wgrad(self, x, dy, name):
+    def _conv_wgrad(self, x, dy, name, xp=None):
         """d kernel [3,3,C,Cout] = sum over pixels of (3x3 patch of x) x dy.  Tap (i, j) is the zero-ringed planar copy of x
         shifted by j-1 pixels (three copies: TMA box origins must be 16-byte aligned) and by i-1 padded rows (a multiple of
         four elements): nine views, one launch."""
         B, H, W, C = x.shape
         Co = dy.shape[3]
         Wp = self.lib.ocr_planar_pad_pitch(W)
-        xp, R = self._planar(x, 3)
+        xp, R = xp if xp is not None else self._planar(x, 3)
         dyp, _ = self._planar(dy, 1)
         shifts = [(i - 1) * Wp for i in range(3) for j in range(3)]
         a_row = [j * C for i in range(3) for j in range(3)]
@@ -533,6 +534,14 @@ class Trainer:
                                                   _lib.ptr(P[q + "beta"]), _lib.ptr(a), sh), "ocr_bn_relu_apply")
                 S.update(y=y, mean=mean, inv_std=inv_std, out=a, n_stat=n_stat)
             saved[name] = S
+        if self.overlap and self.early_planar:
+            # the planar copies of the layer INPUTS that the weight gradients contract over depend on the forward pass only: they
+            # are made on the side stream now, beside the recurrent layers (latency-bound, bandwidth idle), instead of at the end
+            # of the step, where the side stream -- planar copies + the split-K contractions of conv4 .. conv2 -- is what the
+            # optimizer waits for (0.6 ms of copies at B = 256)
+            with self._on_side(*[saved[n]["x"] for n in names[1:]]):
+                for n in names[1:]:
+                    saved[n]["xp"] = self._planar(saved[n]["x"], 3)
         Bn, Hn, Wn, Cn = a.shape
         seq = self._new(Wn, Bn, Cn)
         self._c(lib.ocr_rows_max_to_seq(_lib.ptr(a), Bn, Hn, Wn, Cn, _lib.ptr(seq), sh), "ocr_rows_max_to_seq")
@@ -727,7 +736,7 @@ class Trainer:
                 self._c(lib.ocr_relu_bwd_bias(_lib.ptr(S["out"]), _lib.ptr(da), rows, filters, _lib.ptr(dy), _lib.ptr(G["convnet/%s/bias" % name]), scr, sh),
                         "ocr_relu_bwd_bias")
             with self._on_side(xin, dy):
-                self._conv_wgrad(xin, dy, name)
+                self._conv_wgrad(xin, dy, name, S.get("xp"))
             _, wd = self.conv_w[name]
             dxin = self._conv(dy, wd, self.zero_bias, xin.shape[3], relu=False)
             if "pool" in S and S["pool_in"] is None:
