@@ -34,6 +34,9 @@ SIGNATURES = {
     "ocr_debug_beam_profile": (_i, [_vp, _i]),
     "ocr_ctc_beam_search": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ocr_gemm_tf32": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "ocr_float_to_half": (_i, [_vp, _vp, _ll, _vp]),
+    "ocr_gemm_f16": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "ocr_debug_proj_f16": (_i, [_i]),
     "ocr_preprocess_train": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "ocr_conv1_3x3_valid": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "ocr_im2col3x3_same": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),

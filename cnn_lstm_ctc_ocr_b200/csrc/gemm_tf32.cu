@@ -16,6 +16,7 @@
 // Out-of-range rows / columns / k are zero-filled by TMA, so M, N, K need no padding (K*4 bytes must be a
 // multiple of 16 for the tensor map).  TF32 keeps fp32 storage end to end: activations and weights stay the
 // reference's float32 tensors, products are rounded to 10-bit mantissas inside the tensor core, sums are fp32.
+#include <cuda_fp16.h>
 #include "gemm_tf32.cuh"
 
 namespace ocr {
@@ -40,7 +41,7 @@ struct GemmSmem {
     static constexpr int kTotal = kBars + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
 };
 
-template <int BN, int STAGES, bool H16 = false>   // H16: bfloat16 operands, 64 elements per swizzle row
+template <int BN, int STAGES, int H16 = 0>   // H16: 16-bit operands, 64 elements per swizzle row (1: bfloat16, 2: binary16)
 __global__ void __launch_bounds__(kGemmThreads)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
                  const float* __restrict__ bias, float* __restrict__ D, int M, int N, int K, int ldd, int relu,
@@ -108,7 +109,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {
             // instruction descriptor: fp32 accumulate, tf32 x tf32 (H16: bfloat16 x bfloat16 -- measured: mixing bfloat16 and
             // binary16 operands in one tcgen05.mma.kind::f16 is an illegal instruction), both K-major, N = BN, M = 128
-            const unsigned idesc = (1u << 4) | ((H16 ? 1u : 2u) << 7) | ((H16 ? 1u : 2u) << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(kGemmBM >> 4) << 24);
+            // (operand format field: kind::tf32 2 = TF32; kind::f16 1 = bfloat16, 0 = binary16)
+            constexpr unsigned kFmt = H16 == 0 ? 2u : (H16 == 1 ? 1u : 0u);
+            const unsigned idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(kGemmBM >> 4) << 24);
             for (int k = 0; k < nk; ++k) {
                 const int s = k % STAGES;
                 g_mbar_wait(bar_full + s * 8, (k / STAGES) & 1);
@@ -246,7 +249,7 @@ int gemm_set_tma_store(int on) {
 }
 }  // namespace ocr
 
-template <int BN, int STAGES, bool H16 = false>
+template <int BN, int STAGES, int H16 = 0>
 static int launch_planned(const GemmPlan& p, cudaStream_t st)
 {
     using S = GemmSmem<BN, STAGES>;
@@ -323,6 +326,37 @@ int gemm_plan(GemmPlan* p, const float* A, int lda, const float* W, int ldw, con
     return tma_map_2d(&p->tmB, W, N, K, ldw, bn);
 }
 
+// gemm_plan with binary16 operands A [M, K], W [N, K] (row pitches in elements, multiples of 8): tcgen05.mma.kind::f16, float32
+// sums, bias, output and epilogue as gemm_plan.  binary16 carries the 10 mantissa bits TF32 keeps, so for operands inside its
+// range (|v| < 65504, steps of 6e-8 near zero) the products are the TF32 products at twice the tensor rate and half the bytes.
+int gemm_plan_f16(GemmPlan* p, const void* A, int lda, const void* W, int ldw, const float* bias, float* D, int ldd, int M, int N, int K, int relu)
+{
+    OCR_CHECK_ARG(M >= 1 && N >= 1 && K >= 1, "gemm_f16: bad shape M=%d N=%d K=%d", M, N, K);
+    OCR_CHECK_ARG(A && W && D, "gemm_f16: NULL argument");
+    OCR_CHECK_ARG(lda >= K && ldw >= K && ldd >= N, "gemm_f16: leading dimensions too small");
+    OCR_CHECK_ARG((lda % 8) == 0 && (ldw % 8) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0,
+                  "gemm_f16: A and W need 16-byte aligned rows (pointer and leading dimension * 2 bytes)");
+    const long long mt = (M + kGemmBM - 1) / kGemmBM;
+    int bn = 32;
+    long long best = -1;
+    for (int cand = 32; cand <= 256; cand *= 2) {
+        if (cand > 32 && cand / 2 >= N) break;
+        const long long tiles = mt * ((N + cand - 1) / cand);
+        const long long cost = ((tiles + 147) / 148) * (128 + cand);
+        if (best < 0 || cost < best) { best = cost; bn = cand; }
+    }
+    p->bn = bn; p->bias = bias; p->D = D; p->M = M; p->N = N; p->K = K; p->ldd = ldd; p->relu = relu; p->h16 = 2;
+    int rc = tma_map_2d_h(&p->tmA, A, M, K, lda, kGemmBM);
+    if (rc != OCR_OK) return rc;
+    p->tma_store = 0;
+    if ((ldd % 4) == 0 && (N % 4) == 0 && ((uintptr_t)D % 16) == 0) {
+        rc = tma_map_out(&p->tmD, D, M, N, ldd);
+        if (rc != OCR_OK) return rc;
+        p->tma_store = 1;
+    }
+    return tma_map_2d_h(&p->tmB, W, N, K, ldw, bn);
+}
+
 // The two directions of a recurrent layer as ONE launch: batch d multiplies rows [d*M, (d+1)*M) of A with rows
 // [d*N, (d+1)*N) of W; outputs are dense [M, N] tiles batch_stride apart; optional split over K (partials split_stride apart).
 int gemm_plan_dirs(GemmPlan* p, const float* A, int lda, const float* W, int ldw, float* D, int M, int N, int K, int ndir, int splits, int bn)
@@ -363,7 +397,15 @@ int gemm_plan_dirs_h16(GemmPlan* p, const void* A, int lda, const void* W, int l
 
 int gemm_run(const GemmPlan& p, cudaStream_t st)
 {
-    if (p.h16) return p.bn == 32 ? launch_planned<32, 8, true>(p, st) : launch_planned<64, 6, true>(p, st);
+    if (p.h16 == 1) return p.bn == 32 ? launch_planned<32, 8, 1>(p, st) : launch_planned<64, 6, 1>(p, st);
+    if (p.h16 == 2) {             // binary16 operands (gemm_plan_f16): the many-tile projections, shallow rings as below
+        switch (p.bn) {
+            case 32: return launch_planned<32, 3, 2>(p, st);
+            case 64: return launch_planned<64, 3, 2>(p, st);
+            case 128: return launch_planned<128, 3, 2>(p, st);
+            default: return launch_planned<256, 2, 2>(p, st);
+        }
+    }
     // Two shapes of pipeline.  Grids that put at most one CTA on an SM (split-K contractions, the small per-frame
     // products) get a deep TMA ring: the k loop is all there is.  Grids of many short tiles get a shallow ring so that
     // 2-3 CTAs share an SM (shared memory and the 512 TMEM columns allow it) and the epilogue of one tile -- one thread per
@@ -478,6 +520,38 @@ extern "C" int ocr_debug_gemm_tma_store(int on) {
     g_wgrad_stack = (on & 2) ? 0 : 1;
     g_tma_promo256 = (on & 4) ? 1 : 0;
     return gemm_set_tma_store(on & 1);
+}
+
+__global__ void __launch_bounds__(256) float_to_half_kernel(const float4* __restrict__ in, uint2* __restrict__ out, long long n4)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = in[i];
+        const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+        out[i] = make_uint2(*reinterpret_cast<const unsigned*>(&lo), *reinterpret_cast<const unsigned*>(&hi));
+    }
+}
+
+extern "C" int ocr_float_to_half(const float* in, void* out, long long n, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(n >= 0 && (n % 4) == 0, "ocr_float_to_half: n must be a multiple of 4");
+    if (n == 0) return OCR_OK;
+    OCR_CHECK_ARG(in && out && ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 8) == 0, "ocr_float_to_half: NULL or misaligned argument");
+    long long g = (n / 4 + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    float_to_half_kernel<<<(unsigned)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<uint2*>(out), n / 4);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+extern "C" int ocr_gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, float* D, int ldd, int M, int N, int K, int relu,
+                            ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(M >= 0 && N >= 0 && K >= 1, "ocr_gemm_f16: bad shape M=%d N=%d K=%d", M, N, K);
+    if (M == 0 || N == 0) return OCR_OK;
+    GemmPlan p;
+    int rc = gemm_plan_f16(&p, A, lda, W, ldw, bias, D, ldd, M, N, K, relu);
+    if (rc != OCR_OK) return rc;
+    return gemm_run(p, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ocr_gemm_tf32(const float* A, int lda, const float* W, int ldw, const float* bias, float* D, int ldd, int M, int N,

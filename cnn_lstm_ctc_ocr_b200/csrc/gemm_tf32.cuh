@@ -17,7 +17,7 @@ struct GemmPlan {
     // split-K / shifted-operand form used by the weight-gradient contractions (gemm_plan_wgrad):
     //   D[batch][split] (M x N) = sum over the split's k range of A[m, k + a_shift[batch]] * W[n, k]
     int splits = 1, ksteps_per_split = 0, nbatch = 1, a_box_rows = 128;
-    int h16 = 0;             // 1: bfloat16 operands (gemm_plan_dirs_h16), K counted in elements of 64 per 128-byte row
+    int h16 = 0;             // 1: bfloat16 operands (gemm_plan_dirs_h16), 2: binary16 (gemm_plan_f16); K counted in elements of 64 per 128-byte row
     int tp = 1, ntaps = 0;   // stacked views (gemm_wgrad, shallow layers): tp views of a_box_rows rows per A tile, ntaps views in all
     int pdl = 0;       // 1: launch with programmatic stream serialization (the kernel orders itself with griddepcontrol.wait after its prologue)
     int shallow = 0;   // 1: take the shallow pipeline (small shared-memory footprint) even for a one-wave grid, to leave room for co-running kernels
@@ -34,6 +34,8 @@ int gemm_plan_dirs(GemmPlan* p, const float* A, int lda, const float* W, int ldw
 // the same with bfloat16 operands (gradients need float32's exponent range): A [ndir*M, K], W [ndir*N, K] bfloat16, float32 sums
 // (tcgen05.mma.kind::f16, K = 16 per instruction; half the operand bytes through L2 -> shared memory); bn is 32 or 64
 int gemm_plan_dirs_h16(GemmPlan* p, const void* A, int lda, const void* W, int ldw, float* D, int M, int N, int K, int ndir, int splits, int bn);
+// binary16 operands, otherwise gemm_plan (bias, ReLU, TMA-store epilogue)
+int gemm_plan_f16(GemmPlan* p, const void* A, int lda, const void* W, int ldw, const float* bias, float* D, int ldd, int M, int N, int K, int relu);
 // Weight-gradient contraction over a long row dimension R (both operands R-contiguous, i.e. transposed activations):
 //   D[batch] (M x N, row pitch ldd, batches batch_stride apart) = sum_r A[a_row[batch] + m, r + a_shift[batch]] * W[n, r]
 // (A has a_rows rows in total; a_shift must be a multiple of 4: TMA box origins are 16-byte aligned)

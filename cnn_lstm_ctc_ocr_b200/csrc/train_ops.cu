@@ -1296,6 +1296,9 @@ static int recurrent_bn(int M, int N, int splits) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // bidirectional LSTM layer, training form (frame by frame; keeps gate activations and cell states)
+static int g_proj_f16 = 1;   // binary16 operands in the training-side input projections (0: TF32)
+extern "C" int ocr_debug_proj_f16(int on) { g_proj_f16 = on ? 1 : 0; return OCR_OK; }
+
 extern "C" int ocr_birnn_lstm_train_workspace_bytes(int T, int B, int H, size_t* bytes)
 {
     OCR_CHECK_ARG(bytes && T >= 0 && B >= 0 && H >= 1, "ocr_birnn_lstm_train_workspace_bytes: bad argument");
@@ -1304,6 +1307,10 @@ extern "C" int ocr_birnn_lstm_train_workspace_bytes(int T, int B, int H, size_t*
     size_t fl = (size_t)2 * B * 8 * H + (size_t)2 * B * H * 4 + (size_t)2 * B * 4 * H + (size_t)4 * H * H + 64;
     if (T >= 1 && B >= 1 && lstm_persistent_supported(T, B, H) && lstm_persistent_workspace_floats(B, H) > fl) fl = lstm_persistent_workspace_floats(B, H);
     if (T >= 1 && B >= 1 && lstm_bptt_supported(T, B, H) && lstm_bptt_workspace_floats(B, H) > fl) fl = lstm_bptt_workspace_floats(B, H);
+    // binary16 copies of the layer input [T*B, I] and of the input kernels [8H, I] for the input projection (I <= 2H: the
+    // recognizer's layers; wider inputs take the TF32 product): (T*B + 8H) * 2H halves, used before anything else touches the workspace
+    const size_t f16 = ((size_t)T * B + (size_t)8 * H) * H + 64;
+    if (f16 > fl) fl = f16;
     *bytes = sizeof(float) * fl + 256;
     return OCR_OK;
 }
@@ -1322,7 +1329,21 @@ extern "C" int ocr_birnn_lstm_train_fwd(const float* x, int T, int B, int I, int
     float* gh = ws;
     float* h = gh + (size_t)2 * B * 8 * H;
     float* c = h + (size_t)2 * B * H;
-    int rc = ocr_gemm_tf32(x, I, wx, I, bias, gates, 8 * H, T * B, 8 * H, I, 0, stream);
+    int rc;
+    if (g_proj_f16 && I <= 2 * H && (I % 8) == 0) {
+        // input projection with binary16 operands (the 10 mantissa bits TF32 keeps; layer inputs are ReLU outputs / tanh-bounded
+        // layer outputs, far inside binary16's range): twice the tensor rate, half the operand bytes.  The copies live at the
+        // head of the workspace, which nothing else uses before the product has run (same stream).
+        unsigned short* x16 = reinterpret_cast<unsigned short*>(ws);
+        unsigned short* w16 = x16 + (size_t)T * B * I;
+        rc = ocr_float_to_half(x, x16, (long long)T * B * I, stream);
+        if (rc != OCR_OK) return rc;
+        rc = ocr_float_to_half(wx, w16, (long long)8 * H * I, stream);
+        if (rc != OCR_OK) return rc;
+        rc = ocr_gemm_f16(x16, I, w16, I, bias, gates, 8 * H, T * B, 8 * H, I, 0, stream);
+    } else {
+        rc = ocr_gemm_tf32(x, I, wx, I, bias, gates, 8 * H, T * B, 8 * H, I, 0, stream);
+    }
     if (rc != OCR_OK) return rc;
     if ((g_birnn_path == 0 || g_birnn_path == 2 || g_birnn_path == 3) && lstm_persistent_supported(T, B, H)) {
         // all T frames of both directions in ONE cooperative launch, W_h resident in shared memory (lstm_persistent.cu)

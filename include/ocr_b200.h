@@ -141,6 +141,16 @@ int ocr_edit_distance(const int64_t* hyp, int hyp_stride, const int32_t* hyp_len
 int ocr_debug_gemm_tma_store(int on);
 int ocr_gemm_tf32(const float* A, int lda, const float* W, int ldw, const float* bias, float* D, int ldd, int M,
                   int N, int K, int relu, ocr_stream_t stream);
+/* ocr_gemm_f16: ocr_gemm_tf32 with BINARY16 operands A [M, K], W [N, K] (row pitches in elements, multiples of 8; 16-byte
+ * aligned): tcgen05.mma.kind::f16 with float32 sums, bias, output and epilogue as ocr_gemm_tf32.  binary16 keeps the 10 mantissa
+ * bits TF32 keeps: for operands inside its range the products are the TF32 products at twice the tensor rate and half the
+ * operand bytes.  Used by the training-side input projections of the recurrent layers (tf.nn.bidirectional_dynamic_rnn's
+ * x * W_x, model.py:167-199); ocr_debug_proj_f16(0) selects TF32 there.  ocr_float_to_half: n (a multiple of 4) floats ->
+ * binary16, round to nearest even. */
+int ocr_float_to_half(const float* in, void* out, long long n, ocr_stream_t stream);
+int ocr_gemm_f16(const void* A, int lda, const void* W, int ldw, const float* bias, float* D, int ldd, int M, int N, int K,
+                 int relu, ocr_stream_t stream);
+int ocr_debug_proj_f16(int on);
 
 /* ---------------------------------------------------------------------------------------------
  * Recognizer layers around the GEMM (INFER mode; batch-norm folded into filters/biases by the caller).

@@ -90,3 +90,48 @@ def test_gemm_tma_store_epilogue_equals_stg_epilogue(M, N, K, relu, ldd):
     if relu:
         ref = ref.clamp(min=0)
     assert (res[0][:M, :N].double() - ref).abs().max() <= 5e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K,relu,use_bias", [
+    (128, 32, 64, False, False),      # one tile, one k-step of 64 halves
+    (32000, 4096, 512, False, True),  # cfg3 layer-1 input projection (T=125, B=256)
+    (4000, 4096, 1024, False, True),  # layer 2 (B=32)
+    (1952, 96, 1024, True, True),
+    (200, 130, 40, False, True),      # ragged M / N, K tail zero-filled by TMA
+])
+def test_gemm_f16_matches_reference(M, N, K, relu, use_bias):
+    """ocr_gemm_f16 (binary16 operands, float32 sums): exact products of the ROUNDED operands up to float32 accumulation
+    (1e-5 of sum |a||w|), and the TF32 bar of this file (2e-3) against the unrounded float32 operands; ocr_float_to_half is
+    round-to-nearest-even (torch's .half())."""
+    from cnn_lstm_ctc_ocr_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(M * 7 + N + 1)
+    A = torch.randn((M, K), device="cuda", generator=g).abs()      # layer inputs are ReLU / bounded outputs
+    W = torch.randn((N, K), device="cuda", generator=g) * 0.1
+    bias = torch.randn((N,), device="cuda", generator=g) if use_bias else None
+    A16 = torch.empty((M, K), dtype=torch.float16, device="cuda")
+    W16 = torch.empty((N, K), dtype=torch.float16, device="cuda")
+    sh = _lib.stream_handle()
+    if (M * K) % 4 == 0 and (N * K) % 4 == 0:
+        _lib.check(lib.ocr_float_to_half(_lib.ptr(A), _lib.ptr(A16), M * K, sh), "to_half")
+        _lib.check(lib.ocr_float_to_half(_lib.ptr(W), _lib.ptr(W16), N * K, sh), "to_half")
+        torch.cuda.synchronize()
+        assert torch.equal(A16, A.half()) and torch.equal(W16, W.half())
+    else:
+        A16, W16 = A.half(), W.half()
+    D = torch.full((M, N), float("nan"), device="cuda")
+    _lib.check(lib.ocr_gemm_f16(_lib.ptr(A16), K, _lib.ptr(W16), K, _lib.ptr(bias), _lib.ptr(D), N, M, N, K, int(relu), sh), "ocr_gemm_f16")
+    torch.cuda.synchronize()
+    assert torch.isfinite(D).all()
+    rows = slice(0, M) if M <= 4000 else torch.arange(0, M, 37, device="cuda")       # float64 reference on a row subsample
+    def ref_of(a, w):
+        r = a[rows].double() @ w.double().t()
+        if use_bias:
+            r = r + bias.double()
+        return r.clamp_min(0) if relu else r
+    mag = A[rows].abs().double() @ W.abs().double().t() + 1e-6
+    err16 = (D[rows].double() - ref_of(A16, W16)).abs()
+    assert bool((err16 <= 1e-5 * mag).all()), "vs rounded operands: max %.3g" % (err16 / mag).max().item()
+    err32 = (D[rows].double() - ref_of(A, W)).abs()
+    assert bool((err32 <= 2e-3 * mag).all()), "vs float32 operands: max %.3g" % (err32 / mag).max().item()
