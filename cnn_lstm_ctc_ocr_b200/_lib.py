@@ -59,6 +59,9 @@ SIGNATURES = {
     "ocr_nhwc_to_planar_pad": (_i, [_vp, _i, _i, _i, _i, _vp, _ll, _i, _ll, _vp]),
     "ocr_gemm_wgrad_scratch_bytes": (_i, [_i, _i, _ll, _i, _c.POINTER(_sz)]),
     "ocr_gemm_tf32_wgrad": (_i, [_vp, _ll, _vp, _ll, _vp, _i, _ll, _i, _i, _ll, _i, _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32), _ll, _vp, _sz, _vp]),
+    "ocr_planar_pad_pitch32": (_i, [_i]),
+    "ocr_nhwc_to_planar_blocked": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
+    "ocr_gemm_tf32_wgrad_blocked": (_i, [_vp, _ll, _vp, _ll, _vp, _i, _ll, _i, _i, _ll, _i, _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32), _vp, _sz, _vp]),
     "ocr_bn_batch_sums": (_i, [_vp, _ll, _i, _vp, _vp]),
     "ocr_bn_finalize": (_i, [_vp, _ll, _i, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "ocr_bn_relu_apply": (_i, [_vp, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -29,6 +29,7 @@ struct GemmSplit {
     int a_box_bytes;   // bytes one A box delivers (boxes shorter than 128 rows when M < 128: no over-fetch of foreign rows)
     int tma_store;     // 1: TMA-store epilogue through tmD
     int tp, ntaps;     // tp > 1: a tile stacks the a_box_rows-row slices of tp consecutive views (of ntaps in all) in its 128 rows
+    int blocked;       // 1: K-blocked operands, 3-D tensor maps [K/32][rows][32]; a_shift counts blocks
     long long split_stride, batch_stride;
 };
 
@@ -99,6 +100,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int s = k % STAGES;
                 if (k >= STAGES) g_mbar_wait(bar_empty + s * 8, ((k / STAGES) - 1) & 1);
                 g_mbar_expect_tx(bar_full + s * 8, (unsigned)(nview * sp.a_box_bytes + S::kB));
+                if (sp.blocked) {     // K-blocked operands: a box is one contiguous run of box_rows x 128 bytes
+                    for (int i = 0; i < nview; ++i)
+                        tma_load_3d(s_base + s * S::kStage + i * sp.a_box_bytes, &tmA, 0, m0 + sp.a_row[v0 + i], k_begin + k + sp.a_shift[v0 + i],
+                                    bar_full + s * 8);
+                    tma_load_3d(s_base + s * S::kStage + S::kA, &tmB, 0, n0 + b_row, k_begin + k, bar_full + s * 8);
+                    continue;
+                }
                 for (int i = 0; i < nview; ++i)
                     tma_load_2d(s_base + s * S::kStage + i * sp.a_box_bytes, &tmA, (k_begin + k) * kBKe + sp.a_shift[v0 + i], m0 + sp.a_row[v0 + i],
                                 bar_full + s * 8);
@@ -177,6 +185,22 @@ int tma_map_2d(CUtensorMap* tm, const float* base, long long rows, long long K, 
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      g_tma_promo256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld K=%lld ld=%lld", (int)r, rows, K, ld); return OCR_ECUDA; }
+    return OCR_OK;
+}
+}  // namespace ocr
+
+namespace ocr {
+// K-blocked fp32 operand [nblk][rows][32]: box = [1][box_rows][32 floats] = box_rows x 128 contiguous bytes, 128-byte swizzle
+int tma_map_blocked(CUtensorMap* tm, const float* base, long long rows, long long nblk, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (enc == nullptr) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return OCR_ECUDA; }
+    cuuint64_t dims[3] = {(cuuint64_t)kGemmBK, (cuuint64_t)rows, (cuuint64_t)nblk};
+    cuuint64_t strides[2] = {(cuuint64_t)kGemmBK * 4, (cuuint64_t)rows * kGemmBK * 4};
+    cuuint32_t box[3] = {(cuuint32_t)kGemmBK, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (blocked) failed (%d) rows=%lld nblk=%lld", (int)r, rows, nblk); return OCR_ECUDA; }
     return OCR_OK;
 }
 }  // namespace ocr
@@ -271,6 +295,7 @@ static int launch_planned(const GemmPlan& p, cudaStream_t st)
     sp.tma_store = (p.tma_store && g_gemm_tma_store && p.nbatch == 1 && p.splits == 1) ? 1 : 0;
     sp.tp = p.tp;
     sp.ntaps = p.ntaps;
+    sp.blocked = p.blocked;
     if (p.pdl) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid;
@@ -470,18 +495,30 @@ size_t gemm_wgrad_scratch_floats(int M, int N, long long R, int nbatch) {
 }
 
 int gemm_wgrad(const float* A, long long lda, const float* W, long long ldw, float* D, int ldd, long long batch_stride, int M, int N,
-               long long R, int nbatch, const int* a_shift, const int* a_row, long long a_rows, float* partials, cudaStream_t st)
+               long long R, int nbatch, const int* a_shift, const int* a_row, long long a_rows, float* partials, cudaStream_t st,
+               int blocked, long long w_rows)
 {
     OCR_CHECK_ARG(M >= 1 && N >= 1 && R >= 1 && nbatch >= 1 && nbatch <= 9, "gemm_wgrad: bad shape M=%d N=%d R=%lld nbatch=%d", M, N, R, nbatch);
     OCR_CHECK_ARG(A && W && D && partials, "gemm_wgrad: NULL argument");
-    OCR_CHECK_ARG((lda % 4) == 0 && (ldw % 4) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0 && R < 0x7fffffffLL,
-                  "gemm_wgrad: operands need 16-byte aligned rows");
+    if (blocked) {
+        OCR_CHECK_ARG((R % kGemmBK) == 0 && w_rows >= N && ((uintptr_t)A % 128) == 0 && ((uintptr_t)W % 128) == 0 && R < 0x7fffffffLL,
+                      "gemm_wgrad: blocked operands need R %% 32 == 0 and 128-byte aligned bases");
+    } else {
+        OCR_CHECK_ARG((lda % 4) == 0 && (ldw % 4) == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0 && R < 0x7fffffffLL,
+                      "gemm_wgrad: operands need 16-byte aligned rows");
+    }
     GemmPlan p;
+    p.blocked = blocked ? 1 : 0;
     p.bn = N > 128 ? 256 : (N > 64 ? 128 : (N > 32 ? 64 : 32));
     p.bias = nullptr; p.M = M; p.N = N; p.K = (int)R; p.relu = 0;
     p.splits = wgrad_splits(M, N, R, nbatch, &p.ksteps_per_split);
     p.nbatch = nbatch;
     for (int i = 0; i < nbatch; ++i) { p.a_shift[i] = a_shift ? a_shift[i] : 0; p.a_row[i] = a_row ? a_row[i] : 0; }
+    if (blocked)
+        for (int i = 0; i < nbatch; ++i) {
+            OCR_CHECK_ARG((p.a_shift[i] % kGemmBK) == 0, "gemm_wgrad: blocked operands need shifts that are multiples of 32 (a_shift[%d] = %d)", i, p.a_shift[i]);
+            p.a_shift[i] /= kGemmBK;
+        }
     // partial tiles are dense M x N
     p.D = partials; p.ldd = N;
     p.split_stride = (long long)M * N;
@@ -498,9 +535,9 @@ int gemm_wgrad(const float* A, long long lda, const float* W, long long ldw, flo
         in_batch_stride = (long long)M * N;
         in_split_stride = p.split_stride;
     }
-    int rc = tma_map_2d(&p.tmA, A, a_rows, R, lda, p.a_box_rows);
+    int rc = blocked ? tma_map_blocked(&p.tmA, A, a_rows, R / kGemmBK, p.a_box_rows) : tma_map_2d(&p.tmA, A, a_rows, R, lda, p.a_box_rows);
     if (rc != OCR_OK) return rc;
-    rc = tma_map_2d(&p.tmB, W, N, R, ldw, p.bn);
+    rc = blocked ? tma_map_blocked(&p.tmB, W, w_rows, R / kGemmBK, p.bn) : tma_map_2d(&p.tmB, W, N, R, ldw, p.bn);
     if (rc != OCR_OK) return rc;
     if (p.splits == 1) p.ksteps_per_split = 0;
     rc = gemm_run(p, st);

@@ -20,6 +20,7 @@ struct GemmPlan {
     int h16 = 0;             // 1: bfloat16 operands (gemm_plan_dirs_h16), 2: binary16 (gemm_plan_f16); K counted in elements of 64 per 128-byte row
     int tp = 1, ntaps = 0;   // stacked views (gemm_wgrad, shallow layers): tp views of a_box_rows rows per A tile, ntaps views in all
     int pdl = 0;       // 1: launch with programmatic stream serialization (the kernel orders itself with griddepcontrol.wait after its prologue)
+    int blocked = 0;   // 1: K-blocked operands (gemm_wgrad, blocked != 0): 3-D tensor maps [K/32][rows][32], a_shift in blocks of 32
     int shallow = 0;   // 1: take the shallow pipeline (small shared-memory footprint) even for a one-wave grid, to leave room for co-running kernels
     int a_shift[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, a_row[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, b_row[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long split_stride = 0, batch_stride = 0;   // elements between the partial outputs of consecutive splits / batches
@@ -43,7 +44,13 @@ int gemm_plan_f16(GemmPlan* p, const void* A, int lda, const void* W, int ldw, c
 // kernel adds them up in a fixed order (deterministic).  Out-of-range r (negative too) reads as zero (TMA fill).
 size_t gemm_wgrad_scratch_floats(int M, int N, long long R, int nbatch);
 int gemm_wgrad(const float* A, long long lda, const float* W, long long ldw, float* D, int ldd, long long batch_stride, int M, int N,
-               long long R, int nbatch, const int* a_shift, const int* a_row, long long a_rows, float* partials, cudaStream_t st);
+               long long R, int nbatch, const int* a_shift, const int* a_row, long long a_rows, float* partials, cudaStream_t st,
+               int blocked = 0, long long w_rows = 0);
+// blocked != 0: the operands are K-BLOCKED -- element (row, r) of A lies at ((r / 32) * a_rows + row) * 32 + r % 32 (W likewise
+// with w_rows rows), R and every a_shift are multiples of 32, lda / ldw are unused.  The 128 bytes x box_rows a k-step needs of
+// an operand are then ONE contiguous run of memory instead of box_rows runs a whole row pitch apart (channel planes of the
+// shallow layers lie 2-8 MB apart: a k-step touched 160 pages, and conv2's filter gradient moved 25 GB/s per SM).
+int tma_map_blocked(CUtensorMap* tm, const float* base, long long rows, long long nblk, int box_rows);
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 32;  // fp32 elements = one 128-byte swizzle row

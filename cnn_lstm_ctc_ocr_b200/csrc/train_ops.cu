@@ -72,7 +72,9 @@ transpose_kernel(const float* __restrict__ in, long long rows, int cols, int ld_
 // Zero-ringed channel-planar copies, the fast path of ocr_nhwc_to_planar_pad: one CTA = 128 padded pixels x 32 channels.
 // The tile (with a one-pixel halo on both sides) is read ONCE with float4 loads along the channels and written NCOPY
 // times (pixel shifts -1, 0, +1, or just 0) as 512-byte runs along the pixels.
-template <int NCOPY>
+// BLOCKED: the K-blocked layout of gemm_wgrad(blocked) -- element (channel row, r) at ((r / 32) * ld + row) * 32 + r % 32, where ld
+// is then the operand's total row count and copy k starts copy_stride ROWS further down.
+template <int NCOPY, bool BLOCKED = false>
 __global__ void __launch_bounds__(256)
 planar_pad_kernel(const float* __restrict__ in, unsigned rows, int C, float* __restrict__ out, long long ld, int H, int W, int Wp,
                   long long copy_stride)
@@ -103,7 +105,7 @@ planar_pad_kernel(const float* __restrict__ in, unsigned rows, int C, float* __r
 #pragma unroll
     for (int k = 0; k < NCOPY; ++k) {
         const int sh = (NCOPY == 3) ? k : 1;     // copy k holds pixel r + k - 1 at r  -> tile column (r - r0) + k
-        float* o = out + (size_t)k * copy_stride;
+        float* o = BLOCKED ? out : out + (size_t)k * copy_stride;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int c = warp + 8 * i;
@@ -111,7 +113,11 @@ planar_pad_kernel(const float* __restrict__ in, unsigned rows, int C, float* __r
 #pragma unroll
             for (int j = 0; j < TP / 32; ++j) {
                 const unsigned r = r0 + j * 32 + lane;
-                if (r < rows) o[(size_t)(c0 + c) * ld + r] = tile[c][j * 32 + lane + sh];
+                if (BLOCKED) {
+                    if (r < rows) o[((size_t)(r >> 5) * ld + (size_t)k * copy_stride + c0 + c) * 32 + lane] = tile[c][j * 32 + lane + sh];
+                } else {
+                    if (r < rows) o[(size_t)(c0 + c) * ld + r] = tile[c][j * 32 + lane + sh];
+                }
             }
         }
     }
@@ -993,6 +999,49 @@ extern "C" int ocr_nhwc_to_planar_pad(const float* in, int B, int H, int W, int 
     }
     OCR_CHECK_LAUNCH();
     return OCR_OK;
+}
+
+// K-blocked form of the planar copies (ocr_gemm_tf32_wgrad_blocked): pitch = W + 1 rounded up to 32 -- ONE zero column between
+// image rows serves as the right ring of one row and the left ring of the next, and the vertical taps (+- one pitch) are whole
+// blocks of 32 pixels.  out: [R / 32][rows_total][32] with R = B * (H + 2) * pitch; copy k (pixel shift k - 1; ncopies 1 or 3)
+// occupies rows row0 + k * C .. of the rows_total rows.
+extern "C" int ocr_planar_pad_pitch32(int W) { return (W + 1 + 31) & ~31; }
+
+extern "C" int ocr_nhwc_to_planar_blocked(const float* in, int B, int H, int W, int C, float* out, int rows_total, int row0, int ncopies,
+                                          ocr_stream_t stream)
+{
+    const int Wp = ocr_planar_pad_pitch32(W);
+    const long long rows = (long long)B * (H + 2) * Wp;
+    OCR_CHECK_ARG(rows < 0x7fffffffLL, "ocr_nhwc_to_planar_blocked: too many pixels");
+    OCR_CHECK_ARG(B >= 0 && H >= 1 && W >= 1 && C >= 4 && (C % 4) == 0 && (ncopies == 1 || ncopies == 3) && row0 >= 0 && row0 + ncopies * C <= rows_total,
+                  "ocr_nhwc_to_planar_blocked: bad shape B=%d H=%d W=%d C=%d rows_total=%d row0=%d ncopies=%d", B, H, W, C, rows_total, row0, ncopies);
+    if (B == 0) return OCR_OK;
+    OCR_CHECK_ARG(in && out && ((uintptr_t)in % 16) == 0, "ocr_nhwc_to_planar_blocked: NULL or misaligned argument");
+    dim3 grid((unsigned)((rows + 127) / 128), (unsigned)((C + 31) / 32));
+    float* o = out + (size_t)row0 * 32;
+    if (ncopies == 3) planar_pad_kernel<3, true><<<grid, 256, 0, ST(stream)>>>(in, (unsigned)rows, C, o, rows_total, H, W, Wp, C);
+    else planar_pad_kernel<1, true><<<grid, 256, 0, ST(stream)>>>(in, (unsigned)rows, C, o, rows_total, H, W, Wp, C);
+    OCR_CHECK_LAUNCH();
+    return OCR_OK;
+}
+
+extern "C" int ocr_gemm_tf32_wgrad_blocked(const float* At, long long a_rows, const float* Wt, long long w_rows, float* D, int ldd,
+                                           long long batch_stride, int M, int N, long long R, int nbatch, const int32_t* a_shift_host,
+                                           const int32_t* a_row_host, void* scratch, size_t scratch_bytes, ocr_stream_t stream)
+{
+    OCR_CHECK_ARG(M >= 1 && N >= 1 && R >= 1 && nbatch >= 1 && nbatch <= 9 && a_rows >= M && w_rows >= N, "ocr_gemm_tf32_wgrad_blocked: bad shape");
+    if (scratch == nullptr || scratch_bytes < gemm_wgrad_scratch_floats(M, N, R, nbatch) * sizeof(float)) {
+        set_error("ocr_gemm_tf32_wgrad_blocked: scratch too small");
+        return OCR_EWORKSPACE;
+    }
+    int sh[9] = {0}, ar[9] = {0};
+    for (int i = 0; i < nbatch; ++i) {
+        sh[i] = a_shift_host ? a_shift_host[i] : 0;
+        ar[i] = a_row_host ? a_row_host[i] : 0;
+        OCR_CHECK_ARG((sh[i] % 32) == 0, "ocr_gemm_tf32_wgrad_blocked: a_shift[%d] = %d is not a multiple of 32", i, sh[i]);
+        OCR_CHECK_ARG(ar[i] >= 0 && ar[i] + M <= a_rows, "ocr_gemm_tf32_wgrad_blocked: a_row[%d] = %d outside the operand", i, ar[i]);
+    }
+    return gemm_wgrad(At, 0, Wt, 0, D, ldd, batch_stride, M, N, R, nbatch, sh, ar, a_rows, reinterpret_cast<float*>(scratch), ST(stream), 1, w_rows);
 }
 
 extern "C" int ocr_gemm_wgrad_scratch_bytes(int M, int N, long long R, int nbatch, size_t* bytes)

@@ -137,6 +137,7 @@ class Trainer:
         # pooled batch-norm layers keep the arguments of the pool's maxima instead of the full-size activation (tests switch it
         # off to compare with the separate max-pool gradient)
         self.pool_arg = True
+        self.blocked_planar = True   # K-blocked planar operands for the conv filter gradients (ocr_gemm_tf32_wgrad_blocked)
         self.early_planar = True     # planar copies of the conv inputs (weight-gradient operands) made during the recurrent layers
         self.side = torch.cuda.Stream(device=dev) if self.overlap else None
         self.scratch_side = torch.zeros_like(self.scratch)
@@ -386,12 +387,37 @@ class Trainer:
         self._c(self.lib.ocr_nhwc_to_planar_pad(_lib.ptr(x), B, H, W, C, _lib.ptr(out), R, ncopies, C * R, self._sh()), "ocr_nhwc_to_planar_pad")
         return out, R
 
+    def _planar_blocked(self, x, ncopies=1):
+        """Zero-ringed K-blocked planar copies [R/32][ncopies*C][32] (ocr_nhwc_to_planar_blocked)."""
+        B, H, W, C = x.shape
+        R = B * (H + 2) * self.lib.ocr_planar_pad_pitch32(W)     # a multiple of 32
+        out = self._new(R // 32, ncopies * C, 32)
+        self._c(self.lib.ocr_nhwc_to_planar_blocked(_lib.ptr(x), B, H, W, C, _lib.ptr(out), ncopies * C, 0, ncopies, self._sh()), "ocr_nhwc_to_planar_blocked")
+        return out, R
+
     def _conv_wgrad(self, x, dy, name, xp=None):
         """d kernel [3,3,C,Cout] = sum over pixels of (3x3 patch of x) x dy.  Tap (i, j) is the zero-ringed planar copy of x
         shifted by j-1 pixels (three copies: TMA box origins must be 16-byte aligned) and by i-1 padded rows (a multiple of
         four elements): nine views, one launch."""
         B, H, W, C = x.shape
         Co = dy.shape[3]
+        if getattr(self, "blocked_planar", True) and C % 4 == 0 and Co % 4 == 0:
+            # K-blocked operands: a k-step's 128 bytes x C rows are one contiguous run (the channel planes of the plain planar copy
+            # lie megabytes apart)
+            Wp = self.lib.ocr_planar_pad_pitch32(W)
+            xp, R = xp if xp is not None else self._planar_blocked(x, 3)
+            dyp, _ = self._planar_blocked(dy, 1)
+            shifts = [(i - 1) * Wp for i in range(3) for j in range(3)]
+            a_row = [j * C for i in range(3) for j in range(3)]
+            need = ctypes.c_size_t(0)
+            self._c(self.lib.ocr_gemm_wgrad_scratch_bytes(C, Co, R, 9, ctypes.byref(need)), "ocr_gemm_wgrad_scratch_bytes")
+            if self.wscratch is None or self.wscratch.numel() < need.value:
+                self.wscratch = torch.empty(max(need.value, 1 << 24), dtype=torch.uint8, device=self.device)
+            arr, rows = (ctypes.c_int32 * 9)(*shifts), (ctypes.c_int32 * 9)(*a_row)
+            self._c(self.lib.ocr_gemm_tf32_wgrad_blocked(_lib.ptr(xp), 3 * C, _lib.ptr(dyp), Co, _lib.ptr(self.grads["convnet/%s/kernel" % name]), Co, C * Co,
+                                                         C, Co, R, 9, arr, rows, _lib.ptr(self.wscratch), self.wscratch.numel(), self._sh()),
+                    "ocr_gemm_tf32_wgrad_blocked")
+            return
         Wp = self.lib.ocr_planar_pad_pitch(W)
         xp, R = xp if xp is not None else self._planar(x, 3)
         dyp, _ = self._planar(dy, 1)
@@ -541,7 +567,7 @@ class Trainer:
             # optimizer waits for (0.6 ms of copies at B = 256)
             with self._on_side(*[saved[n]["x"] for n in names[1:]]):
                 for n in names[1:]:
-                    saved[n]["xp"] = self._planar(saved[n]["x"], 3)
+                    saved[n]["xp"] = (self._planar_blocked if self.blocked_planar else self._planar)(saved[n]["x"], 3)
         Bn, Hn, Wn, Cn = a.shape
         seq = self._new(Wn, Bn, Cn)
         self._c(lib.ocr_rows_max_to_seq(_lib.ptr(a), Bn, Hn, Wn, Cn, _lib.ptr(seq), sh), "ocr_rows_max_to_seq")

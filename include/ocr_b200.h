@@ -254,6 +254,20 @@ int ocr_gemm_wgrad_scratch_bytes(int M, int N, long long R, int nbatch, size_t* 
 int ocr_gemm_tf32_wgrad(const float* At, long long lda, const float* Wt, long long ldw, float* D, int ldd, long long batch_stride,
                         int M, int N, long long R, int nbatch, const int32_t* a_shift_host, const int32_t* a_row_host,
                         long long a_rows, void* scratch, size_t scratch_bytes, ocr_stream_t stream);
+/* K-blocked operands for the filter gradients of the convolutions (the 128 bytes x rows a k-step needs are one contiguous run
+ * instead of one run per channel plane, planes lying megabytes apart):
+ *   ocr_planar_pad_pitch32          padded row pitch: W + 1 rounded up to 32 (one zero column between image rows is the right
+ *                                   ring of one row and the left ring of the next; +- one pitch = whole blocks of 32 pixels)
+ *   ocr_nhwc_to_planar_blocked      x [B,H,W,C] -> out [R/32][rows_total][32], R = B*(H+2)*pitch32, zero-ringed; copy k (pixel
+ *                                   shift k-1, ncopies 1 or 3) in rows row0 + k*C ..
+ *   ocr_gemm_tf32_wgrad_blocked     ocr_gemm_tf32_wgrad over such operands (At with a_rows rows, Wt with w_rows rows; R and
+ *                                   every a_shift multiples of 32; bases 128-byte aligned) */
+int ocr_planar_pad_pitch32(int W);
+int ocr_nhwc_to_planar_blocked(const float* in, int B, int H, int W, int C, float* out, int rows_total, int row0, int ncopies,
+                               ocr_stream_t stream);
+int ocr_gemm_tf32_wgrad_blocked(const float* At, long long a_rows, const float* Wt, long long w_rows, float* D, int ldd,
+                                long long batch_stride, int M, int N, long long R, int nbatch, const int32_t* a_shift_host,
+                                const int32_t* a_row_host, void* scratch, size_t scratch_bytes, ocr_stream_t stream);
 /* tf.layers.batch_normalization(training=True) (model.py:118-123) over y [rows, C] (rows = B*H*W of this replica):
  *   ocr_bn_batch_sums      sums [2][C] DOUBLES: per-channel sum and sum of squares (a data-parallel job may all-reduce them)
  *   ocr_bn_finalize        n = rows behind `sums` -> batch mean and 1/sqrt(biased variance + eps); moving_mean / moving_var

@@ -287,9 +287,11 @@ def test_conv_gradients():
     from cnn_lstm_ctc_ocr_b200 import train
     tr = object.__new__(train.Trainer)
     tr.lib, tr.device, tr.wscratch = lib, torch.device(DEV), None
-    tr.grads = {"convnet/convX/kernel": torch.zeros((3, 3, C, Co), device=DEV)}
-    tr._conv_wgrad(_t(x), _t(dy), "convX")
-    _close(tr.grads["convnet/convX/kernel"].cpu().numpy(), wt.grad.numpy(), 3e-3, "conv wgrad")
+    for blocked in (True, False):       # K-blocked planar operands (default) and the plain planar copies
+        tr.blocked_planar = blocked
+        tr.grads = {"convnet/convX/kernel": torch.zeros((3, 3, C, Co), device=DEV)}
+        tr._conv_wgrad(_t(x), _t(dy), "convX")
+        _close(tr.grads["convnet/convX/kernel"].cpu().numpy(), wt.grad.numpy(), 3e-3, "conv wgrad (blocked=%s)" % blocked)
     # conv1: one input channel, 'valid'
     img = rng.integers(0, 256, (B, 12, 23)).astype(np.uint8)
     Co1 = 32
@@ -302,6 +304,30 @@ def test_conv_gradients():
     scr = torch.zeros(1 << 16, dtype=torch.uint8, device=DEV)
     L.check(lib.ocr_conv1_wgrad(L.ptr(dimg), 1, B, 12, 23, L.ptr(_t(dy1)), Co1, L.ptr(dw1), L.ptr(scr), sh), "c1")
     _close(dw1.cpu().numpy(), w1.grad.numpy(), 1e-5, "conv1 wgrad")
+
+
+@pytest.mark.parametrize("B,H,W,C,Co", [(3, 5, 31, 32, 32), (2, 6, 63, 64, 128), (2, 3, 126, 128, 128), (1, 30, 254, 32, 32)])
+def test_conv_wgrad_blocked_operands(B, H, W, C, Co):
+    """Filter gradient over K-blocked planar operands (pitch = W + 1 rounded to 32: the zero column between rows is shared;
+    W = 31 and 63 give pitch == W + 1 exactly) against float64 autograd, and against the plain planar path."""
+    from cnn_lstm_ctc_ocr_b200 import train
+    L, lib, sh = _lib()
+    rng = np.random.default_rng(B * 100 + W)
+    x = rng.standard_normal((B, H, W, C)).astype(np.float32)
+    dy = rng.standard_normal((B, H, W, Co)).astype(np.float32)
+    xt = torch.tensor(x, dtype=torch.float64).permute(0, 3, 1, 2)
+    wt = torch.zeros((3, 3, C, Co), dtype=torch.float64, requires_grad=True)
+    F.conv2d(xt, wt.permute(3, 2, 0, 1), padding=1).backward(torch.tensor(dy, dtype=torch.float64).permute(0, 3, 1, 2))
+    tr = object.__new__(train.Trainer)
+    tr.lib, tr.device, tr.wscratch = lib, torch.device(DEV), None
+    got = {}
+    for blocked in (True, False):
+        tr.blocked_planar = blocked
+        tr.grads = {"convnet/convX/kernel": torch.zeros((3, 3, C, Co), device=DEV)}
+        tr._conv_wgrad(_t(x), _t(dy), "convX")
+        got[blocked] = tr.grads["convnet/convX/kernel"].cpu().numpy()
+        _close(got[blocked], wt.grad.numpy(), 3e-3, "conv wgrad (blocked=%s)" % blocked)
+    _close(got[True], got[False], 1e-4, "blocked vs planar")      # same TF32 products, different split-K partition
 
 
 def test_adam_matches_oracle():
