@@ -657,27 +657,32 @@ lstm_cell_bwd_kernel(float* __restrict__ act, const float* __restrict__ cs, cons
         const int len = min(seq_len[b], T);
         GS* gs = dgs + (size_t)r * 4 * H;
         const size_t e = (size_t)r * H + j;          // element index in dh / dc
-        // gradient flowing into h_s from step s+1 (only if that step was live for this example)
-        float4 dhv = make_float4(0.f, 0.f, 0.f, 0.f), dcv = dhv;
-        if (!last && s + 1 < len) {
-            const float* pr = dh_rec + ((size_t)dir * splits * B + b) * H + j;     // [2][splits][B][H] split-K partials
-            for (int z = 0; z < splits; ++z) {
-                const float4 p4 = *reinterpret_cast<const float4*>(pr + (size_t)z * B * H);
-                dhv.x += p4.x; dhv.y += p4.y; dhv.z += p4.z; dhv.w += p4.w;
-            }
-            dcv = *reinterpret_cast<const float4*>(dc + e);
-        }
+        // Every load of the frame is issued before the first use: the split-K partials as eight predicated loads (a loop over a
+        // run-time `splits` kept one load in flight per trip), the activations of a live row beside them -- the kernel is a chain of
+        // memory round trips (6.5 us per frame at B = 256 for 20 MB), and there were five of them in a row.
         const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (s >= len) { st4(gs + j, zero); st4(gs + H + j, zero); st4(gs + 2 * H + j, zero); st4(gs + 3 * H + j, zero); continue; }
-        const int t = dir ? len - 1 - s : s;
+        const bool live = s < len, rec = !last && s + 1 < len;
+        const int t = live ? (dir ? len - 1 - s : s) : 0;
         const size_t o = ((size_t)t * B + b) * 2 * H + dir * H + j;
         float* a = act + ((size_t)t * B + b) * 8 * H + dir * 4 * H;
-        const float4 gi = *reinterpret_cast<const float4*>(a + j), gj = *reinterpret_cast<const float4*>(a + H + j);
-        const float4 gf = *reinterpret_cast<const float4*>(a + 2 * H + j), go = *reinterpret_cast<const float4*>(a + 3 * H + j);
-        const float4 cn = *reinterpret_cast<const float4*>(cs + o), dO = *reinterpret_cast<const float4*>(dout + o);
-        float4 cp = zero;
-        if (s > 0) { const int tp = dir ? t + 1 : t - 1; cp = *reinterpret_cast<const float4*>(cs + ((size_t)tp * B + b) * 2 * H + dir * H + j); }
-        float4 d_i, d_j, d_f, d_o, ndc, ndh;
+        const float* pr = dh_rec + ((size_t)dir * splits * B + b) * H + j;     // [2][splits][B][H] split-K partials
+        float4 part[8];
+#pragma unroll
+        for (int z = 0; z < 8; ++z) part[z] = (rec && z < splits) ? *reinterpret_cast<const float4*>(pr + (size_t)z * B * H) : zero;
+        const float4 dcv = rec ? *reinterpret_cast<const float4*>(dc + e) : zero;
+        float4 gi = zero, gj = zero, gf = zero, go = zero, cn = zero, dO = zero, cp = zero;
+        if (live) {
+            gi = *reinterpret_cast<const float4*>(a + j); gj = *reinterpret_cast<const float4*>(a + H + j);
+            gf = *reinterpret_cast<const float4*>(a + 2 * H + j); go = *reinterpret_cast<const float4*>(a + 3 * H + j);
+            cn = *reinterpret_cast<const float4*>(cs + o); dO = *reinterpret_cast<const float4*>(dout + o);
+            if (s > 0) { const int tp = dir ? t + 1 : t - 1; cp = *reinterpret_cast<const float4*>(cs + ((size_t)tp * B + b) * 2 * H + dir * H + j); }
+        }
+        // gradient flowing into h_s from step s+1 (only if that step was live for this example): the partials in split order
+        float4 dhv = zero;
+#pragma unroll
+        for (int z = 0; z < 8; ++z) { dhv.x += part[z].x; dhv.y += part[z].y; dhv.z += part[z].z; dhv.w += part[z].w; }
+        if (!live) { st4(gs + j, zero); st4(gs + H + j, zero); st4(gs + 2 * H + j, zero); st4(gs + 3 * H + j, zero); continue; }
+        float4 d_i, d_j, d_f, d_o, ndc;
 #define OCR_CB1(f_)                                                   \
         {                                                             \
             const float tc = tanhf(cn.f_);                            \
@@ -688,7 +693,6 @@ lstm_cell_bwd_kernel(float* __restrict__ act, const float* __restrict__ cs, cons
             d_j.f_ = dct * gi.f_ * (1.f - gj.f_ * gj.f_);             \
             d_f.f_ = dct * cp.f_ * gf.f_ * (1.f - gf.f_);             \
             ndc.f_ = dct * gf.f_;                                     \
-            ndh.f_ = dht;                                             \
         }
         OCR_CB1(x) OCR_CB1(y) OCR_CB1(z) OCR_CB1(w)
 #undef OCR_CB1
@@ -696,7 +700,7 @@ lstm_cell_bwd_kernel(float* __restrict__ act, const float* __restrict__ cs, cons
         *reinterpret_cast<float4*>(a + 2 * H + j) = d_f; *reinterpret_cast<float4*>(a + 3 * H + j) = d_o;
         st4(gs + j, d_i); st4(gs + H + j, d_j); st4(gs + 2 * H + j, d_f); st4(gs + 3 * H + j, d_o);
         *reinterpret_cast<float4*>(dc + e) = ndc;
-        *reinterpret_cast<float4*>(dh + e) = ndh;   // kept for inspection; the recurrent product is taken from dgs
+        // (d h_t itself is not stored: the recurrent product is taken from dgs; the store was 1 MB per frame at B = 256)
     }
 }
 
