@@ -403,7 +403,7 @@ def run_ours(args, cfg):
         line = {
             "metric": METRIC, "value": training["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": training["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "tf32 products (binary16 operands in the recurrent and input-projection products, bfloat16 in the BPTT product), fp32 accumulate/storage/optimizer", "data": "synthetic",
+            "dtype": "tf32 products (16-bit operands in the recurrent, projection and BPTT products), fp32 accumulate/storage/optimizer", "data": "synthetic",
             "config": dict(cfg["config"], per_gpu_batch=cfg["B"] // world, timed_region=training["timed_region"],
                            l2="per-step working set (activations + 43 MB of weights, gradients and Adam slots) >> 126 MB L2"),
             "e2e": training["e2e"], "gpu_launches": training["gpu_launches_per_step"] * K,
